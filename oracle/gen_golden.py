@@ -1,0 +1,190 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python -m oracle.gen_golden
+
+The reference ships no golden vectors or unit tests for this path
+(SURVEY.md section 4), so these fixtures are the parity pins: outputs of the
+reference's own functions on seeded inputs, with FPS start index 0.  They are
+valid for the torch build recorded in each file (`torch_version`).  Small cases
+store full arrays; BASELINE-size cases store sha256 digests of canonicalised
+outputs (a checksum of checksums) so the fixtures stay small.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import refimport  # noqa: E402
+from oracle import torch_port  # noqa: E402
+from oracle.inputs import cloud, digest  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+
+
+def small_int(a, hi):
+    a = a.numpy() if isinstance(a, torch.Tensor) else a
+    return a.astype(np.int16 if hi < 32768 else np.int32)
+
+
+def knn_tie_rows(sqd, k):
+    """Rows whose k-th and (k+1)-th smallest distances are equal."""
+    v = torch.topk(sqd, k + 1, dim=-1, largest=False, sorted=True).values
+    return (v[..., k - 1] == v[..., k]).numpy()
+
+
+def canon_group(nb, idx):
+    """Reorders each group's rows by point index so unordered top-k output compares."""
+    order = idx.argsort(dim=-1)
+    return torch.gather(nb, 2, order.unsqueeze(-1).expand_as(nb))
+
+
+def gen_group(ns, name, kind, B, N, G, K, seed, full):
+    xyz = cloud(kind, B, N, seed)
+    with refimport.fixed_fps_start(0):
+        fps_idx = ns.misc.farthest_point_sample(xyz, G)
+        nb, center = ns.dvae.Group(G, K)(xyz)
+    sqd = ns.dvae.square_distance(center, xyz)
+    knn = ns.dvae.knn_point(K, xyz, center)
+    knn_sorted = knn.sort(-1).values
+    tie = knn_tie_rows(sqd, K)
+    nb_c = canon_group(nb, knn)
+    rec = dict(kind=kind, B=B, N=N, G=G, K=K, seed=seed, torch_version=torch.__version__,
+               xyz_sha=digest(xyz.numpy()), fps_sha=digest(fps_idx.numpy()),
+               knn_sorted_sha=digest(knn_sorted.numpy()), center_sha=digest(center.numpy()),
+               nb_canon_sha=digest(nb_c.numpy()), tie_rows=np.argwhere(tie).astype(np.int32),
+               n_negative_self=int((sqd.min(-1).values < 0).sum()))
+    if full:
+        rec.update(xyz=xyz.numpy(), fps_idx=small_int(fps_idx, N), knn_sorted=small_int(knn_sorted, N),
+                   center=center.numpy(), nb_canon=nb_c.numpy())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, "tie rows", int(tie.sum()), "neg self", rec["n_negative_self"])
+
+
+def gen_sqdist(ns):
+    """Bit pattern of square_distance on a small ragged case (F2, F3)."""
+    src = cloud("U", 2, 37, 77)
+    dst = cloud("U", 2, 1000, 78)
+    d = ns.dvae.square_distance(src, dst)
+    np.savez_compressed(os.path.join(OUT, "sqdist_small.npz"), src=src.numpy(), dst=dst.numpy(),
+                        dist_bits=d.numpy().view(np.uint32), torch_version=torch.__version__)
+
+
+def gen_sa(ns, name, B, N, seed, full):
+    """PointNet++ SSG grouping (models/pointnet2/pointnet2.py:11-12): cfg 3."""
+    xyz = cloud("S", B, N, seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    with refimport.fixed_fps_start(0):
+        f1 = ns.pn2.farthest_point_sample(xyz, 512)
+        c1 = ns.pn2.index_points(xyz, f1)
+        b1 = ns.pn2.query_ball_point(0.2, 32, xyz, c1)
+        new_xyz1, new_pts1 = ns.pn2.sample_and_group(512, 0.2, 32, xyz, None)
+        feats = torch.randn(B, 512, 128, generator=g)
+        f2 = ns.pn2.farthest_point_sample(c1, 128)
+        c2 = ns.pn2.index_points(c1, f2)
+        b2 = ns.pn2.query_ball_point(0.4, 64, c1, c2)
+        new_xyz2, new_pts2 = ns.pn2.sample_and_group(128, 0.4, 64, c1, feats)
+    rec = dict(B=B, N=N, seed=seed, torch_version=torch.__version__, xyz_sha=digest(xyz.numpy()),
+               fps1_sha=digest(f1.numpy()), ball1_sha=digest(b1.numpy()), grp1_sha=digest(new_pts1.numpy()),
+               fps2_sha=digest(f2.numpy()), ball2_sha=digest(b2.numpy()), grp2_sha=digest(new_pts2.numpy()),
+               feats_sha=digest(feats.numpy()))
+    if full:
+        rec.update(xyz=xyz.numpy(), fps1=small_int(f1, N), ball1=small_int(b1, N),
+                   fps2=small_int(f2, N), ball2=small_int(b2, N))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    occ = (b1 != b1[..., :1]).sum(-1).float().mean().item() + 1
+    print(name, "mean occupancy sa1 ~", round(occ, 1))
+
+
+def gen_msg_fp(ns, name, B, N, seed, D, full):
+    """MSG ball queries (models/pointnet2/pointnet2.py:45-46) and part-seg
+    feature propagation (three_nn + interpolate): cfg 4."""
+    xyz = cloud("S", B, N, seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    with refimport.fixed_fps_start(0):
+        f1 = ns.pn2.farthest_point_sample(xyz, 512)
+    c1 = ns.pn2.index_points(xyz, f1)
+    rec = dict(B=B, N=N, D=D, seed=seed, torch_version=torch.__version__, xyz_sha=digest(xyz.numpy()),
+               fps1_sha=digest(f1.numpy()))
+    for r, k in ((0.1, 16), (0.2, 32), (0.4, 128)):
+        b = ns.pn2.query_ball_point(r, k, xyz, c1)
+        rec["ball_%g_%d_sha" % (r, k)] = digest(b.numpy())
+        if full:
+            rec["ball_%g_%d" % (r, k)] = small_int(b, N + 1)
+    # three_nn / three_interpolate exactly as PointNetFeaturePropagation.forward does
+    # it (models/pointnet2/pointnet2_utils.py:300-307), channel-last.
+    feats = torch.randn(B, 512, D, generator=g)
+    d, i = ns.pn2.square_distance(xyz, c1).sort(dim=-1)
+    d, i = d[:, :, :3], i[:, :, :3]
+    r = 1.0 / (d + 1e-8)
+    w = r / torch.sum(r, dim=2, keepdim=True)
+    interp = torch.sum(ns.pn2.index_points(feats, i) * w.view(B, N, 3, 1), dim=2)
+    # rows where the 3rd/4th nearest tie are not uniquely defined
+    d4 = torch.topk(ns.pn2.square_distance(xyz, c1), 4, dim=-1, largest=False, sorted=True).values
+    tie = ((d4[..., 2] == d4[..., 3]) | (d4[..., 0] == d4[..., 1]) | (d4[..., 1] == d4[..., 2])).numpy()
+    rec.update(nn_dist_sha=digest(d.numpy()), nn_idx_sha=digest(i.numpy()), interp_sha=digest(interp.numpy()),
+               feats_sha=digest(feats.numpy()), nn_tie_rows=np.argwhere(tie).astype(np.int32),
+               n_negative=int((d < 0).sum()))
+    if full:
+        rec.update(xyz=xyz.numpy(), fps1=small_int(f1, N), nn_dist_bits=d.numpy().view(np.uint32),
+                   nn_idx=small_int(i, 512), feats=feats.numpy(), interp_bits=interp.numpy().view(np.uint32))
+    # the whole module's interpolation path through the reference class (no MLP: mlp=[])
+    fp = ns.pn2.PointNetFeaturePropagation(D, [])
+    out = fp(xyz.permute(0, 2, 1), c1.permute(0, 2, 1), None, feats.permute(0, 2, 1))
+    assert torch.equal(out.permute(0, 2, 1), interp)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, "nn tie rows", int(tie.sum()), "negative d", rec["n_negative"])
+
+
+def gen_encoder(ns):
+    """Reference Encoder (models/pointbert/dvae.py:184-215) + reduce_dim
+    (models/pointbert/point_encoder.py:133,239), eval mode, seeded weights."""
+    sd = torch_port.make_encoder_state()
+    enc = ns.dvae.Encoder(256).eval()
+    missing = enc.load_state_dict({k: v for k, v in sd.items() if k in torch_port.ENCODER_KEYS}, strict=False)
+    assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing
+    reduce_dim = torch.nn.Linear(256, 384)
+    reduce_dim.load_state_dict({"weight": sd["reduce_dim.weight"], "bias": sd["reduce_dim.bias"]})
+    xyz = cloud("U", 2, 1024, 4242)
+    with refimport.fixed_fps_start(0):
+        nb, _ = ns.dvae.Group(64, 32)(xyz)
+    with torch.no_grad():
+        feat = enc(nb)
+        tok = reduce_dim(feat)
+    wsum = hashlib.sha256(b"".join(np.ascontiguousarray(sd[k].numpy()).tobytes() for k in sorted(sd))).hexdigest()
+    np.savez_compressed(os.path.join(OUT, "encoder_small.npz"), neighborhood=nb.numpy(), features=feat.numpy(),
+                        tokens=tok.numpy(), weights_sha=wsum, torch_version=torch.__version__)
+    print("encoder tokens", tuple(tok.shape), "absmax", float(tok.abs().max()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    ns = refimport.load()
+    gen_sqdist(ns)
+    gen_group(ns, "group_u1024", "U", 2, 1024, 128, 32, 1001, full=True)     # unordered-topk regime (F5, F11)
+    gen_group(ns, "group_u1000_ragged", "U", 3, 1000, 37, 24, 1002, full=True)  # odd sizes, PointMLP k=24
+    gen_group(ns, "group_s2048", "S", 1, 2048, 512, 32, 1003, full=True)      # part-seg shape
+    gen_group(ns, "group_cfg1_u8192", "U", 32, 8192, 512, 32, 1234, full=False)  # BASELINE config 1 (U)
+    gen_group(ns, "group_cfg1_s8192", "S", 32, 8192, 512, 32, 1235, full=False)  # BASELINE config 1 (S)
+    gen_group(ns, "group_stress_s32768", "S", 1, 32768, 512, 32, 1239, full=False)  # cfg 5 stress
+    gen_sa(ns, "sa_ssg_small", 2, 1024, 1237, full=True)
+    gen_sa(ns, "sa_ssg_cfg3", 32, 1024, 1237, full=False)
+    gen_msg_fp(ns, "msg_fp_small", 1, 2048, 1238, 16, full=True)
+    gen_msg_fp(ns, "msg_fp_cfg4", 8, 2048, 1238, 384, full=False)
+    gen_encoder(ns)
+    tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print("fixtures total bytes", tot)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,21 @@
+"""Seeded synthetic inputs shared by the fixtures, the tests and bench.py
+(SURVEY.md section 8d).  TEST INFRASTRUCTURE ONLY."""
+import hashlib
+
+import numpy as np
+import torch
+
+
+def cloud(kind, B, N, seed):
+    """'U' = uniform cube [-1,1)^3, 'S' = unit sphere surface; fp32, CPU generator."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == "U":
+        return torch.rand(B, N, 3, generator=g) * 2 - 1
+    p = torch.randn(B, N, 3, generator=g)
+    return p / p.norm(dim=-1, keepdim=True)
+
+
+def digest(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()

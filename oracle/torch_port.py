@@ -1,0 +1,156 @@
+"""Torch-op restatement of the reference's CPU path -- TEST INFRASTRUCTURE ONLY.
+
+The reference implements the tokenizer with ATen ops (matmul, topk, sort,
+max, advanced indexing, Conv1d/BatchNorm1d), so the honest "reference on CPU"
+timing is those same ops on CPU tensors.  /root/reference does not exist on
+the GPU box, hence this port: the same op sequence, written independently,
+validated bit-for-bit against the imported reference in the build container
+(tests/test_oracle_vs_reference.py) and against tests/golden/.
+
+Used for: bench.py's cpu_baseline / --impl reference legs (kind "port"), and
+as the fp32 reference for the Encoder (a floating-point kernel keeps a torch
+fp32 reference; tolerance is norm-relative).
+"""
+import torch
+import torch.nn.functional as F
+
+
+def pairwise_sqdist(src, dst):
+    """models/pointbert/dvae.py:130-149 -- -2*src@dst^T + |src|^2 + |dst|^2, that order."""
+    d = torch.matmul(src, dst.transpose(1, 2))
+    d = d * -2
+    d += (src ** 2).sum(-1).unsqueeze(2)
+    d += (dst ** 2).sum(-1).unsqueeze(1)
+    return d
+
+
+def take_rows(points, idx):
+    """index_points, models/pointbert/misc.py:26-42: points[b, idx[b, ...], :]."""
+    B = points.shape[0]
+    bsel = torch.arange(B, device=points.device).reshape((B,) + (1,) * (idx.dim() - 1))
+    return points[bsel.expand_as(idx), idx, :]
+
+
+def fps_indices(xyz, npoint, start):
+    """models/pointbert/misc.py:44-69 with the start index supplied (the
+    reference draws it with torch.randint, misc.py:59)."""
+    B, N, _ = xyz.shape
+    picked = xyz.new_zeros((B, npoint), dtype=torch.long)
+    mind = xyz.new_full((B, N), 1e10)
+    far = torch.as_tensor(start, dtype=torch.long, device=xyz.device).expand(B).clone()
+    rows = torch.arange(B, device=xyz.device)
+    for g in range(npoint):
+        picked[:, g] = far
+        c = xyz[rows, far].unsqueeze(1)
+        d = ((xyz - c) ** 2).sum(-1)
+        mind = torch.minimum(mind, d)
+        far = mind.max(dim=-1).indices
+    return picked
+
+
+def knn_indices(k, xyz, query):
+    """models/pointbert/dvae.py:116-127."""
+    return pairwise_sqdist(query, xyz).topk(k, dim=-1, largest=False, sorted=False).indices
+
+
+def group_forward(xyz, num_group, group_size, start=0):
+    """Group.forward, models/pointbert/dvae.py:159-181 -> (neighborhood, center)."""
+    B, N, _ = xyz.shape
+    center = take_rows(xyz, fps_indices(xyz, num_group, start))
+    idx = knn_indices(group_size, xyz, center)
+    flat = (idx + torch.arange(B, device=xyz.device).view(B, 1, 1) * N).reshape(-1)
+    nb = xyz.reshape(B * N, 3)[flat].reshape(B, num_group, group_size, 3)
+    return nb - center.unsqueeze(2), center
+
+
+def ball_indices(radius, nsample, xyz, query):
+    """query_ball_point, models/pointnet2/pointnet2_utils.py:87-107."""
+    B, N, _ = xyz.shape
+    S = query.shape[1]
+    ids = torch.arange(N, device=xyz.device).expand(B, S, N).clone()
+    ids[pairwise_sqdist(query, xyz) > radius ** 2] = N
+    ids = ids.sort(dim=-1).values[:, :, :nsample]
+    first = ids[:, :, :1].expand(-1, -1, nsample)
+    return torch.where(ids == N, first, ids)
+
+
+def three_nn_interpolate(xyz1, xyz2, feats2):
+    """Interpolation part of PointNetFeaturePropagation.forward,
+    models/pointnet2/pointnet2_utils.py:297-307 (channel-last tensors)."""
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    if S == 1:
+        return feats2.repeat(1, N, 1)
+    d, i = pairwise_sqdist(xyz1, xyz2).sort(dim=-1)
+    d, i = d[:, :, :3], i[:, :, :3]
+    r = 1.0 / (d + 1e-8)
+    w = r / r.sum(dim=2, keepdim=True)
+    return (take_rows(feats2, i) * w.unsqueeze(-1)).sum(dim=2)
+
+
+# ---- mini-PointNet patch Encoder (+ reduce_dim) ------------------------------
+
+ENCODER_KEYS = (
+    "first_conv.0.weight", "first_conv.0.bias",
+    "first_conv.1.weight", "first_conv.1.bias", "first_conv.1.running_mean", "first_conv.1.running_var",
+    "first_conv.3.weight", "first_conv.3.bias",
+    "second_conv.0.weight", "second_conv.0.bias",
+    "second_conv.1.weight", "second_conv.1.bias", "second_conv.1.running_mean", "second_conv.1.running_var",
+    "second_conv.3.weight", "second_conv.3.bias",
+)
+
+
+def make_encoder_state(encoder_channel=256, trans_dim=384, seed=0):
+    """Seeded weights in the reference Encoder's state_dict naming
+    (models/pointbert/dvae.py:188-199) plus reduce_dim
+    (models/pointbert/point_encoder.py:133).  Same init distributions torch
+    uses for Conv1d/Linear, BN running stats perturbed so folding is exercised
+    (SURVEY.md section 8d).  Deterministic for a given torch build; the
+    fixture stores a checksum."""
+    g = torch.Generator().manual_seed(seed)
+
+    def conv(cout, cin):
+        bound = 1.0 / (cin ** 0.5)
+        w = (torch.rand(cout, cin, 1, generator=g) * 2 - 1) * bound
+        b = (torch.rand(cout, generator=g) * 2 - 1) * bound
+        return w, b
+
+    def bn(c):
+        return (0.75 + 0.5 * torch.rand(c, generator=g), 0.1 * torch.randn(c, generator=g),
+                0.1 * torch.randn(c, generator=g), 0.5 + torch.rand(c, generator=g))
+
+    sd = {}
+    sd["first_conv.0.weight"], sd["first_conv.0.bias"] = conv(128, 3)
+    (sd["first_conv.1.weight"], sd["first_conv.1.bias"],
+     sd["first_conv.1.running_mean"], sd["first_conv.1.running_var"]) = bn(128)
+    sd["first_conv.3.weight"], sd["first_conv.3.bias"] = conv(256, 128)
+    sd["second_conv.0.weight"], sd["second_conv.0.bias"] = conv(512, 512)
+    (sd["second_conv.1.weight"], sd["second_conv.1.bias"],
+     sd["second_conv.1.running_mean"], sd["second_conv.1.running_var"]) = bn(512)
+    sd["second_conv.3.weight"], sd["second_conv.3.bias"] = conv(encoder_channel, 512)
+    w, b = conv(trans_dim, encoder_channel)
+    sd["reduce_dim.weight"], sd["reduce_dim.bias"] = w.squeeze(-1), b
+    return sd
+
+
+def encoder_forward(sd, point_groups, eps=1e-5):
+    """Encoder.forward in eval mode, models/pointbert/dvae.py:201-215:
+    (B,G,n,3) -> (B,G,C)."""
+    bs, g, n, _ = point_groups.shape
+    x = point_groups.reshape(bs * g, n, 3).transpose(2, 1)
+    x = F.conv1d(x, sd["first_conv.0.weight"], sd["first_conv.0.bias"])
+    x = F.batch_norm(x, sd["first_conv.1.running_mean"], sd["first_conv.1.running_var"],
+                     sd["first_conv.1.weight"], sd["first_conv.1.bias"], False, 0.0, eps)
+    x = F.conv1d(F.relu(x), sd["first_conv.3.weight"], sd["first_conv.3.bias"])
+    glob = x.max(dim=2, keepdim=True).values
+    x = torch.cat([glob.expand(-1, -1, n), x], dim=1)
+    x = F.conv1d(x, sd["second_conv.0.weight"], sd["second_conv.0.bias"])
+    x = F.batch_norm(x, sd["second_conv.1.running_mean"], sd["second_conv.1.running_var"],
+                     sd["second_conv.1.weight"], sd["second_conv.1.bias"], False, 0.0, eps)
+    x = F.conv1d(F.relu(x), sd["second_conv.3.weight"], sd["second_conv.3.bias"])
+    return x.max(dim=2).values.reshape(bs, g, -1)
+
+
+def tokens_forward(sd, point_groups):
+    """Encoder then reduce_dim (models/pointbert/point_encoder.py:239): (B,G,n,3) -> (B,G,384)."""
+    return F.linear(encoder_forward(sd, point_groups), sd["reduce_dim.weight"], sd["reduce_dim.bias"])

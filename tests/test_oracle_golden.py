@@ -1,0 +1,156 @@
+"""The CPU oracle (oracle/ppt_oracle.c, oracle/torch_port.py) against the
+fixtures generated from the unmodified reference (oracle/gen_golden.py).
+This is what makes the oracle's parity PINNED."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu, torch_port
+from oracle.inputs import cloud, digest
+
+SMALL_GROUP = ["group_u1024", "group_u1000_ragged", "group_s2048"]
+BIG_GROUP = ["group_cfg1_u8192", "group_cfg1_s8192", "group_stress_s32768"]
+
+
+def _mask_rows(shape, rows):
+    m = np.zeros(shape, dtype=bool)
+    for r in rows:
+        m[tuple(r)] = True
+    return m
+
+
+def _canon(nb, idx):
+    order = np.argsort(idx, axis=-1, kind="stable")
+    return np.take_along_axis(nb, order[..., None], axis=2)
+
+
+@pytest.mark.parametrize("name", SMALL_GROUP)
+def test_group_small_cases_match_reference(golden, name):
+    f = golden(name)
+    xyz, G, K = f["xyz"], int(f["G"]), int(f["K"])
+    assert digest(xyz) == str(f["xyz_sha"])
+    nb, center, fidx, kidx = cpu.group_forward(xyz, G, K, start=0)
+    assert np.array_equal(fidx, f["fps_idx"].astype(np.int64))
+    assert np.array_equal(center.view(np.uint32), f["center"].view(np.uint32))
+    tie = _mask_rows(kidx.shape[:2], f["tie_rows"])
+    ks = np.sort(kidx, -1)
+    assert np.array_equal(ks[~tie], f["knn_sorted"].astype(np.int64)[~tie])
+    nbc = _canon(nb, kidx)
+    assert np.array_equal(nbc[~tie].view(np.uint32), f["nb_canon"][~tie].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", BIG_GROUP)
+def test_group_baseline_sizes_match_reference_digests(golden, name):
+    f = golden(name)
+    B, N, G, K = (int(f[k]) for k in "BNGK")
+    xyz = cloud(str(f["kind"]), B, N, int(f["seed"])).numpy()
+    assert digest(xyz) == str(f["xyz_sha"]), "torch RNG stream differs from the fixture's"
+    nb, center, fidx, kidx = cpu.group_forward(xyz, G, K, start=0)
+    assert digest(fidx) == str(f["fps_sha"])
+    assert digest(center) == str(f["center_sha"])
+    tie = _mask_rows(kidx.shape[:2], f["tie_rows"])
+    if not tie.any():
+        assert digest(np.sort(kidx, -1)) == str(f["knn_sorted_sha"])
+        assert digest(_canon(nb, kidx)) == str(f["nb_canon_sha"])
+    else:
+        # F6: the reference resolves k-boundary ties arbitrarily; on those rows
+        # compare the selected distance multiset, elsewhere demand the digest
+        # after substituting the reference-agnostic rows out of both sides.
+        t = torch.from_numpy(xyz)
+        ref_idx = torch_port.knn_indices(K, t, torch.from_numpy(center)).numpy()
+        ks, rs = np.sort(kidx, -1), np.sort(ref_idx, -1)
+        assert digest(rs) == str(f["knn_sorted_sha"])  # the port reproduces the reference here
+        assert np.array_equal(ks[~tie], rs[~tie])
+        sd = cpu.square_distance(center, xyz)
+        for b, g in np.argwhere(tie):
+            assert np.array_equal(np.sort(sd[b, g, kidx[b, g]]), np.sort(sd[b, g, ref_idx[b, g]]))
+
+
+def test_square_distance_bits(golden):
+    f = golden("sqdist_small")
+    d = cpu.square_distance(f["src"], f["dst"])
+    assert np.array_equal(d.view(np.uint32), f["dist_bits"])
+    dp = torch_port.pairwise_sqdist(torch.from_numpy(f["src"]), torch.from_numpy(f["dst"])).numpy()
+    assert np.array_equal(dp.view(np.uint32), f["dist_bits"])
+    assert (d < 0).any() or True  # negatives are legal (F3)
+
+
+def _ssg(xyz, feats):
+    f1 = cpu.farthest_point_sample(xyz, 512, 0)
+    c1 = cpu.index_points(xyz, f1)
+    b1 = cpu.query_ball_point(0.2, 32, xyz, c1)
+    g1 = cpu.group_center(xyz, b1, c1)
+    f2 = cpu.farthest_point_sample(c1, 128, 0)
+    c2 = cpu.index_points(c1, f2)
+    b2 = cpu.query_ball_point(0.4, 64, c1, c2)
+    g2 = np.concatenate([cpu.group_center(c1, b2, c2), cpu.index_points(feats, b2)], -1)
+    return f1, b1, g1, f2, b2, g2
+
+
+@pytest.mark.parametrize("name", ["sa_ssg_small", "sa_ssg_cfg3"])
+def test_set_abstraction_grouping_matches_reference(golden, name):
+    f = golden(name)
+    B, N, seed = int(f["B"]), int(f["N"]), int(f["seed"])
+    xyz = cloud("S", B, N, seed).numpy()
+    assert digest(xyz) == str(f["xyz_sha"])
+    feats = torch.randn(B, 512, 128, generator=torch.Generator().manual_seed(seed + 100)).numpy()
+    assert digest(feats) == str(f["feats_sha"])
+    f1, b1, g1, f2, b2, g2 = _ssg(xyz, feats)
+    for got, key in ((f1, "fps1"), (b1, "ball1"), (g1, "grp1"), (f2, "fps2"), (b2, "ball2"), (g2, "grp2")):
+        assert digest(got) == str(f[key + "_sha"]), key
+    if "ball1" in f.files:
+        assert np.array_equal(b1, f["ball1"].astype(np.int64))
+
+
+@pytest.mark.parametrize("name", ["msg_fp_small", "msg_fp_cfg4"])
+def test_msg_ball_and_feature_propagation_match_reference(golden, name):
+    f = golden(name)
+    B, N, D, seed = int(f["B"]), int(f["N"]), int(f["D"]), int(f["seed"])
+    xyz = cloud("S", B, N, seed).numpy()
+    assert digest(xyz) == str(f["xyz_sha"])
+    f1 = cpu.farthest_point_sample(xyz, 512, 0)
+    assert digest(f1) == str(f["fps1_sha"])
+    c1 = cpu.index_points(xyz, f1)
+    for r, k in ((0.1, 16), (0.2, 32), (0.4, 128)):
+        assert digest(cpu.query_ball_point(r, k, xyz, c1)) == str(f["ball_%g_%d_sha" % (r, k)])
+    feats = torch.randn(B, 512, D, generator=torch.Generator().manual_seed(seed + 100)).numpy()
+    assert digest(feats) == str(f["feats_sha"])
+    dist, idx = cpu.three_nn(xyz, c1)
+    assert len(f["nn_tie_rows"]) == 0
+    assert digest(dist) == str(f["nn_dist_sha"])
+    assert digest(idx) == str(f["nn_idx_sha"])
+    out = cpu.three_interpolate(feats, idx, dist)
+    assert digest(out) == str(f["interp_sha"])  # bit-exact (F8), including negative-d rows (F3)
+    assert int(f["n_negative"]) > 0
+    outp = torch_port.three_nn_interpolate(torch.from_numpy(xyz), torch.from_numpy(c1), torch.from_numpy(feats))
+    assert digest(outp) == str(f["interp_sha"])
+
+
+def test_ball_query_without_survivor_pads_with_N():
+    xyz = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], dtype=np.float32)
+    q = np.array([[[10, 10, 10]]], dtype=np.float32)
+    assert (cpu.query_ball_point(0.1, 4, xyz, q) == 3).all()  # reference sentinel N
+
+
+def test_fps_tie_breaks_on_first_index():
+    # four corners of a square: after picking corner 0, corners 1 and 2 tie; torch.max keeps the first
+    xyz = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]]], dtype=np.float32)
+    got = cpu.farthest_point_sample(xyz, 4, 0)
+    ref = torch_port.fps_indices(torch.from_numpy(xyz), 4, 0).numpy()
+    assert np.array_equal(got, ref)
+    assert got[0, 1] == 3 and got[0, 2] == 1
+
+
+def test_encoder_port_matches_reference_tokens(golden):
+    f = golden("encoder_small")
+    sd = torch_port.make_encoder_state()
+    import hashlib
+    wsum = hashlib.sha256(b"".join(np.ascontiguousarray(sd[k].numpy()).tobytes() for k in sorted(sd))).hexdigest()
+    assert wsum == str(f["weights_sha"]), "seeded weights differ from the fixture's (torch build changed?)"
+    with torch.no_grad():
+        nb = torch.from_numpy(f["neighborhood"])
+        feat = torch_port.encoder_forward(sd, nb).numpy()
+        tok = torch_port.tokens_forward(sd, nb).numpy()
+    for got, ref in ((feat, f["features"]), (tok, f["tokens"])):
+        rel = np.abs(got - ref).max() / np.abs(ref).max()
+        assert rel <= 1e-6, rel
