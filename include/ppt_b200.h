@@ -1,0 +1,138 @@
+/*
+ * ppt_b200.h -- C ABI of libppt_b200.so: the B200 (sm_100a) point-cloud
+ * tokenizer behind auniquesun/PPT's Python hot path.
+ *
+ * The reference has no FFI for this path: its "operator interface" is a set
+ * of Python functions / nn.Modules built from ATen ops.  Each entry point
+ * below replaces one of them; the reference lines are cited per function
+ * (paths relative to the reference root) and INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer into memory owned by the caller; the
+ *     library never allocates, frees or synchronises, and keeps no state
+ *     except cached cudaFuncSetAttribute calls;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and
+ *     the call returns immediately;
+ *   - tensors are dense row-major, fp32 coordinates/features, int64 indices
+ *     (the dtypes of the reference API);
+ *   - return value: 0 on success, a cudaError_t (> 0) for a CUDA failure, or
+ *     a negative PPT_E* code for an argument the kernels do not support.
+ */
+#ifndef PPT_B200_H_
+#define PPT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPT_B200_ABI_VERSION 1
+
+#define PPT_EINVAL (-1) /* bad shape / null pointer */
+#define PPT_ERANGE (-2) /* size outside what the kernel supports */
+
+/* Precision modes of the patch Encoder. */
+#define PPT_ENC_FP16 0   /* fp16 operands, fp32 accumulate (tcgen05 kind::f16) */
+#define PPT_ENC_BF16 1   /* bf16 operands, fp32 accumulate */
+#define PPT_ENC_BF16X3 2 /* bf16 hi/lo split, 3 MMAs per product: fp32-parity mode */
+
+int ppt_abi_version(void);
+
+/* Human-readable text for a return code (static storage). */
+const char *ppt_strerror(int code);
+
+/* farthest_point_sample -- models/pointbert/misc.py:44-69,
+ * models/pointbert/pointnet2_utils.py:95-116, models/pointnet2/pointnet2_utils.py:63-84,
+ * models/pointmlp/pointMLP.py:64-84 (identical results).
+ * The caller draws `start` with the reference's own torch.randint call.
+ *   xyz [B,N,3] f32; start [B] i64; idx_out [B,G] i64;
+ *   centers_out [B,G,3] f32 or NULL (= index_points(xyz, idx), misc.py:12-24 `fps`).
+ * N <= 65536. */
+int ppt_fps(const float *xyz, const int64_t *start, int64_t *idx_out, float *centers_out,
+            int B, int N, int G, void *stream);
+
+/* square_distance -- models/pointbert/dvae.py:130-149 (same text in both
+ * pointnet2_utils.py copies and pointMLP.py:23-42).
+ *   src [B,S,3], dst [B,N,3] -> out [B,S,N] f32, bit pattern of the reference's CPU path. */
+int ppt_square_distance(const float *src, const float *dst, float *out, int B, int S, int N, void *stream);
+
+/* knn_point -- models/pointbert/dvae.py:116-127 (pointnet2_utils.py:20-34, pointMLP.py:110-121).
+ *   xyz [B,N,3]; query [B,S,3] -> idx_out [B,S,k] i64, the k nearest under
+ *   (distance, index), ascending; dist_out [B,S,k] f32 or NULL.  1 <= k <= 32, k <= N. */
+int ppt_knn(const float *xyz, const float *query, int64_t *idx_out, float *dist_out,
+            int B, int N, int S, int k, void *stream);
+
+/* Group.forward after FPS -- models/pointbert/dvae.py:159-181: kNN of each
+ * centre, flat gather of the neighbours, subtraction of the centre.
+ *   xyz [B,N,3]; center [B,G,3] -> neighborhood_out [B,G,k,3] f32;
+ *   idx_out [B,G,k] i64 or NULL.  1 <= k <= 32. */
+int ppt_knn_group(const float *xyz, const float *center, float *neighborhood_out, int64_t *idx_out,
+                  int B, int N, int G, int k, void *stream);
+
+/* query_ball_point -- models/pointnet2/pointnet2_utils.py:87-107
+ * (pointbert/pointnet2_utils.py:119-139, pointMLP.py:87-107).
+ * `radius2` is (float)(radius**2): torch compares in fp32.
+ *   xyz [B,N,3]; new_xyz [B,S,3] -> idx_out [B,S,nsample] i64. */
+int ppt_ball_query(const float *xyz, const float *new_xyz, int64_t *idx_out, float radius2,
+                   int B, int N, int S, int nsample, void *stream);
+
+/* index_points -- models/pointbert/misc.py:26-42 (and the three copies):
+ *   points [B,N,C]; idx [B,M] i64 (M = product of the trailing idx dims) -> out [B,M,C]. */
+int ppt_gather(const float *points, const int64_t *idx, float *out, int B, int N, int C, int M, void *stream);
+
+/* Grouping tail of sample_and_group / PointNetSetAbstractionMsg.forward --
+ * models/pointnet2/pointnet2_utils.py:127-134 and :244-254:
+ *   out[b,s,j,:] = cat(xyz[b,idx] - new_xyz[b,s], points[b,idx])   (xyz_first = 1, SSG order)
+ *                = cat(points[b,idx], xyz[b,idx] - new_xyz[b,s])   (xyz_first = 0, MSG order)
+ *   xyz [B,N,3]; new_xyz [B,S,3]; points [B,N,D] or NULL (D = 0); idx [B,S,K] i64;
+ *   out [B,S,K,3+D]. */
+int ppt_group_concat(const float *xyz, const float *new_xyz, const float *points, const int64_t *idx,
+                     float *out, int B, int N, int S, int K, int D, int xyz_first, void *stream);
+
+/* three_nn part of PointNetFeaturePropagation.forward --
+ * models/pointnet2/pointnet2_utils.py:300-302 (pointbert/pointnet2_utils.py:340-342):
+ * squared distances (not sqrt), three nearest under (distance, index).
+ *   unknown [B,N,3]; known [B,S,3], S >= 3 -> dist_out [B,N,3] f32; idx_out [B,N,3] i64. */
+int ppt_three_nn(const float *unknown, const float *known, float *dist_out, int64_t *idx_out,
+                 int B, int N, int S, void *stream);
+
+/* three_interpolate -- models/pointnet2/pointnet2_utils.py:304-307:
+ * weights 1/(d+1e-8) normalised, ((w0*f0 + w1*f1) + w2*f2).
+ *   feats [B,S,D]; idx [B,N,3] i64; dist [B,N,3] -> out [B,N,D]. */
+int ppt_three_interpolate(const float *feats, const int64_t *idx, const float *dist, float *out,
+                          int B, int N, int S, int D, void *stream);
+
+/* Gradient of three_interpolate w.r.t. feats (the part-seg head trains through
+ * it, models/pointbert/point_encoder.py:404-413).  grad_feats [B,S,D] must be
+ * zero-filled by the caller; contributions are accumulated with red.global.add. */
+int ppt_three_interpolate_grad(const float *grad_out, const int64_t *idx, const float *dist,
+                               float *grad_feats, int B, int N, int S, int D, void *stream);
+
+/* ---- mini-PointNet patch Encoder + reduce_dim (tcgen05) ---------------------
+ * Encoder.forward in eval mode, models/pointbert/dvae.py:201-215, followed by
+ * reduce_dim, models/pointbert/point_encoder.py:133,239.
+ *
+ * The host folds BatchNorm into the convolutions, splits second_conv.0 into
+ * its global-feature and per-point halves and packs everything into one device
+ * blob (ppt_b200/encoder_pack.py documents the layout); the blob is opaque here.
+ *   packed_bytes = ppt_encoder_packed_bytes(mode);
+ *   workspace    = ppt_encoder_workspace_bytes(num_groups, mode) bytes of scratch.
+ *   neighborhood [num_groups, 32, 3] f32 -> tokens_out [num_groups, 384] f32,
+ *   features_out [num_groups, 256] f32 or NULL (the Encoder's own output).
+ * num_groups = B*G; any value >= 1. */
+int64_t ppt_encoder_packed_bytes(int mode);
+int64_t ppt_encoder_workspace_bytes(int64_t num_groups, int mode);
+int ppt_encoder_forward(const float *neighborhood, const void *packed, void *workspace,
+                        float *features_out, float *tokens_out, int64_t num_groups, int mode, void *stream);
+
+/* Self-test of the tcgen05 building blocks (one 128 x N x K GEMM through the
+ * same smem layouts, descriptors and epilogue the Encoder uses).
+ *   a [128,K] f32, b [N,K] f32 -> d [128,N] f32 = a * b^T with operands rounded to `mode`'s type. */
+int ppt_selftest_umma(const float *a, const float *b, float *d, int N, int K, int mode, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPT_B200_H_ */

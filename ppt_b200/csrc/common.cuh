@@ -1,0 +1,45 @@
+// Shared helpers for the sm_100a kernels of libppt_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ppt_b200.h"
+
+#define PPT_FULL_MASK 0xffffffffu
+#define PPT_EXPORT __attribute__((visibility("default")))
+
+// Launch-site error capture: the C ABI returns the cudaError_t, never exits
+// (contrast the reference's vendored kernels, which exit(-1):
+// models/pointnext/PointNeXt/openpoints/cpp/pointnet2_batch/src/sampling_gpu.cu:255-259).
+#define PPT_RETURN_IF_CUDA(expr)                    \
+  do {                                              \
+    cudaError_t _e = (expr);                        \
+    if (_e != cudaSuccess) return (int)_e;          \
+  } while (0)
+
+static inline int ppt_launch_status() { return (int)cudaPeekAtLastError(); }
+
+// ---- exact fp32 arithmetic of the reference's CPU path ----
+// Intrinsics with explicit rounding are never contracted into FMAs by nvcc,
+// whatever -fmad says.
+
+// models/pointbert/misc.py:65  torch.sum((xyz - centroid) ** 2, -1) = (dx*dx + dy*dy) + dz*dz
+__device__ __forceinline__ float ppt_fps_dist(float x, float y, float z, float cx, float cy, float cz) {
+  const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy), dz = __fsub_rn(z, cz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// torch.sum(p ** 2, -1) for a 3-vector
+__device__ __forceinline__ float ppt_sqnorm3(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// models/pointbert/dvae.py:146-148: K=3 sgemm is an FMA chain in k order, then
+// (-2*dot + |src|^2) + |dst|^2.
+__device__ __forceinline__ float ppt_pair_sqdist(float sx, float sy, float sz, float ns,
+                                                 float dx, float dy, float dz, float nd) {
+  const float dot = __fmaf_rn(sz, dz, __fmaf_rn(sy, dy, __fmul_rn(sx, dx)));
+  return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), ns), nd);
+}
+
+__device__ __forceinline__ int ppt_lane() { return threadIdx.x & 31; }

@@ -1,0 +1,107 @@
+// Index gathers for sm_100a: index_points and the grouping tail of
+// sample_and_group / PointNetSetAbstractionMsg.  Pure HBM/L2 traffic: every
+// thread produces four consecutive output floats (one 16-byte store when the
+// output is 16-byte aligned) and reads the gathered rows with coalesced loads.
+#include "common.cuh"
+
+namespace {
+
+// index_points (models/pointbert/misc.py:26-42): out[b,m,:] = points[b,idx[b,m],:]
+__global__ void gather_kernel(const float* __restrict__ points, const int64_t* __restrict__ idx,
+                              float* __restrict__ out, int N, int C, int M) {
+  const int b = blockIdx.y;
+  const size_t total = (size_t)M * C;
+  const size_t e0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e0 >= total) return;
+  const float* src = points + (size_t)b * N * C;
+  const int64_t* ib = idx + (size_t)b * M;
+  float* dst = out + (size_t)b * total;
+  float v[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const size_t e = e0 + t;
+    if (e < total) {
+      const int m = (int)(e / C), c = (int)(e - (size_t)m * C);
+      v[t] = __ldg(src + (size_t)ib[m] * C + c);
+    } else {
+      v[t] = 0.f;
+    }
+  }
+  if (e0 + 3 < total && ((reinterpret_cast<uintptr_t>(dst + e0) & 15) == 0)) {
+    *reinterpret_cast<float4*>(dst + e0) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (e0 + t < total) dst[e0 + t] = v[t];
+  }
+}
+
+// models/pointnet2/pointnet2_utils.py:127-134 (SSG: [xyz - centre, feats]) and
+// :244-254 (MSG: [feats, xyz - centre]).  Row = one (b, s, j) neighbour, 3 + D floats.
+__global__ void group_concat_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                                    const float* __restrict__ points, const int64_t* __restrict__ idx,
+                                    float* __restrict__ out, int N, int S, int K, int D, int xyz_first) {
+  const int b = blockIdx.y;
+  const int C = 3 + D;
+  const size_t total = (size_t)S * K * C;
+  const size_t e0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e0 >= total) return;
+  const float* cloud = xyz + (size_t)b * N * 3;
+  const float* ctr = new_xyz + (size_t)b * S * 3;
+  const float* feat = points ? points + (size_t)b * N * D : nullptr;
+  const int64_t* ib = idx + (size_t)b * S * K;
+  float* dst = out + (size_t)b * total;
+  const int xyz_lo = xyz_first ? 0 : D;  // first column of the coordinate block
+  float v[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const size_t e = e0 + t;
+    if (e < total) {
+      const int row = (int)(e / C), c = (int)(e - (size_t)row * C);
+      const int64_t n = ib[row];
+      const int cx = c - xyz_lo;
+      if (cx >= 0 && cx < 3) {
+        const int s = row / K;
+        v[t] = __fsub_rn(__ldg(cloud + (size_t)n * 3 + cx), __ldg(ctr + (size_t)s * 3 + cx));
+      } else {
+        const int cf = xyz_first ? c - 3 : c;
+        v[t] = __ldg(feat + (size_t)n * D + cf);
+      }
+    } else {
+      v[t] = 0.f;
+    }
+  }
+  if (e0 + 3 < total && ((reinterpret_cast<uintptr_t>(dst + e0) & 15) == 0)) {
+    *reinterpret_cast<float4*>(dst + e0) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (e0 + t < total) dst[e0 + t] = v[t];
+  }
+}
+
+}  // namespace
+
+extern "C" PPT_EXPORT int ppt_gather(const float* points, const int64_t* idx, float* out, int B, int N, int C, int M,
+                          void* stream) {
+  if (!points || !idx || !out || B < 0 || N < 1 || C < 1 || M < 0) return PPT_EINVAL;
+  if (B == 0 || M == 0) return 0;
+  if (B > 65535) return PPT_ERANGE;
+  const size_t quads = ((size_t)M * C + 3) / 4;
+  dim3 grid((unsigned)((quads + 255) / 256), B);
+  gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, idx, out, N, C, M);
+  return ppt_launch_status();
+}
+
+extern "C" PPT_EXPORT int ppt_group_concat(const float* xyz, const float* new_xyz, const float* points, const int64_t* idx,
+                                float* out, int B, int N, int S, int K, int D, int xyz_first, void* stream) {
+  if (!xyz || !new_xyz || !idx || !out || B < 0 || N < 1 || S < 1 || K < 1 || D < 0) return PPT_EINVAL;
+  if (D > 0 && !points) return PPT_EINVAL;
+  if (B == 0) return 0;
+  if (B > 65535) return PPT_ERANGE;
+  const size_t quads = ((size_t)S * K * (3 + D) + 3) / 4;
+  dim3 grid((unsigned)((quads + 255) / 256), B);
+  group_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, new_xyz, D ? points : nullptr, idx, out, N, S, K, D,
+                                                             xyz_first);
+  return ppt_launch_status();
+}

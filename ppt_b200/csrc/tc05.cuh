@@ -1,0 +1,168 @@
+// Thin PTX wrappers for the Blackwell (sm_100a) tensor path used by the patch
+// Encoder: mbarrier, 1-D bulk async copy (TMA engine, UBLKCP), tcgen05
+// alloc / mma / commit / ld, and the 128-byte-swizzled shared-memory operand
+// layout with its matrix descriptors.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace tc05 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier -----------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Spins on try_wait (which itself sleeps in hardware for a bounded time).  A pipeline bug would
+// otherwise hang the GPU: after ~2^26 failed probes (seconds) the kernel traps, so the host sees an
+// error instead of a stuck stream.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+// Generic-proxy shared-memory writes -> visible to the async proxy (tensor core, bulk copies).
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- 1-D bulk async copy global -> shared, completion on an mbarrier (SASS: UBLKCP) ----
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- tensor memory ---------------------------------------------------------------
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp
+  static_assert(NCOLS >= 32 && NCOLS <= 512 && (NCOLS & (NCOLS - 1)) == 0, "TMEM columns: power of two in [32,512]");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp, same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 columns of fp32: thread i of the warp receives lane (base_lane + i), columns c..c+31.
+// A warp may only touch the 32-lane quadrant (warp_id % 4).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- UMMA descriptors ---------------------------------------------------------------
+// Operand formats of tcgen05.mma.kind::f16 (instruction descriptor bits [7,10) / [10,13)).
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1;
+
+// Instruction descriptor: fp32 accumulate, both operands `fmt`, A K-major,
+// B K-major (b_mn = 0) or MN-major (b_mn = 1), shape M x N (K = 16 per instruction).
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, int M, int N, int b_mn) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor, 128-byte swizzle (layout type 2), sm_100 version bit set.
+//   K-major : rows (M or N index) are 128 B apart inside an 8-row, 1024-byte atom;
+//             stride_bytes = distance between consecutive 8-row atoms; leading offset unused (1).
+//   MN-major: an atom is 8 K-rows of 64 contiguous MN elements; stride_bytes = distance between
+//             K-atoms, leading_bytes = distance between 64-element MN blocks.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t leading_bytes, uint32_t stride_bytes) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)((leading_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((stride_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues for the CTA.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Arrives on `bar` once every tcgen05 op issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- operand layout in shared memory ---------------------------------------------------
+// K-major, 128-byte swizzle.  A "chunk" is ROWS x 64 16-bit elements = ROWS x 128 B; row r lives at
+// r * 128 and its 16-byte piece c is stored at position c ^ (r & 7).  Chunks must be 1024-byte aligned.
+__device__ __forceinline__ uint32_t sw128_kmajor_off(int row, int k_in_chunk /*0..63*/) {
+  const uint32_t piece = (uint32_t)(k_in_chunk >> 3) ^ (uint32_t)(row & 7);
+  return (uint32_t)row * 128u + piece * 16u + (uint32_t)(k_in_chunk & 7) * 2u;
+}
+// MN-major, 128-byte swizzle: 1024-byte atoms of 8 K-rows x 64 MN elements; K-atoms are 1024 B apart
+// (stride), 64-element MN blocks are `mn_block_bytes` apart (leading).
+__device__ __forceinline__ uint32_t sw128_mnmajor_off(int mn, int k, uint32_t mn_block_bytes) {
+  const uint32_t piece = (uint32_t)((mn & 63) >> 3) ^ (uint32_t)(k & 7);
+  return (uint32_t)(mn >> 6) * mn_block_bytes + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + piece * 16u +
+         (uint32_t)(mn & 7) * 2u;
+}
+
+// ---- fp32 -> operand conversion -----------------------------------------------------------
+template <uint32_t FMT>
+__device__ __forceinline__ uint16_t to_operand(float v) {
+  if (FMT == FMT_F16) {
+    // saturate instead of producing inf: fp16 tops out at 65504 (SURVEY.md F15 range guard)
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    return __half_as_ushort(__float2half_rn(v));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+template <uint32_t FMT>
+__device__ __forceinline__ float from_operand(uint16_t b) {
+  if (FMT == FMT_F16) return __half2float(__ushort_as_half(b));
+  return __bfloat162float(__ushort_as_bfloat16(b));
+}
+
+}  // namespace tc05

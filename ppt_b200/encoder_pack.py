@@ -1,0 +1,103 @@
+"""Host-side preparation of the patch Encoder's weights for the tcgen05 kernels.
+
+Done once per weight version (the Encoder is frozen in PPT, models/ULIP_models.py:505):
+
+1. BatchNorm folding (eval mode, eps 1e-5):  W' = W * g/sqrt(v+eps),  b' = (b - m) * g/sqrt(v+eps) + beta
+   for first_conv.{0,1} and second_conv.{0,1}  (models/pointbert/dvae.py:188-199).
+2. second_conv.0 consumes cat([global.expand, feature]) (dvae.py:212): its weight splits into
+   W3a (columns 0..255, applied to the per-group max) and W3b (columns 256..511, per point).
+   first_conv.3 (128->256, no activation after it) and W3b are both linear, so they compose:
+       W32 = W3b' @ W2   (512 x 128, computed in fp64)
+   which halves the per-point work of that layer.  The per-group term becomes
+       c = W3a' @ max_pts(W2 @ h1) + [ (W3a' + W3b') @ b2 + b3' ].
+3. Biases of max-pooled layers move behind the max; reduce_dim's input bias folds into
+   its own: tokens = Wr @ max_pts(W4 @ h3) + (Wr @ b4 + br)   (models/pointbert/point_encoder.py:133,239).
+4. Every tensor-core weight is cut into 128-row x 64-column operand images in the K-major,
+   128-byte-swizzled layout tcgen05.mma reads from shared memory (csrc/tc05.cuh: sw128_kmajor_off),
+   so a pipeline stage is one contiguous 16 KB bulk copy.  Order: [unit][k-chunk][split][16 KB];
+   split = 2 stores bf16 hi and lo parts for the 3-MMA fp32-parity mode.
+
+Blob layout (bytes), mirrored by csrc/encoder.cu (EncoderBlob):
+    [0, 8192)            fp32 section: W1' rows {w0,w1,w2,b} [128][4], bias_c [512], b4 [256], bias_tok [384]
+    then W2 (2 units x 2 chunks), W3A (4 x 4), W32 (4 x 2), W4 (2 x 8), WR (3 x 4) operand images.
+"""
+import torch
+
+ENC_FP16, ENC_BF16, ENC_BF16X3 = 0, 1, 2
+F32_SECTION_BYTES = 8192
+IMAGE_BYTES = 16384
+# (name, rows, cols)
+SECTIONS = (("W2", 256, 128), ("W3A", 512, 256), ("W32", 512, 128), ("W4", 256, 512), ("WR", 384, 256))
+
+
+def operand_dtype(mode):
+    return torch.float16 if mode == ENC_FP16 else torch.bfloat16
+
+
+def split_of(mode):
+    return 2 if mode == ENC_BF16X3 else 1
+
+
+def packed_bytes(mode):
+    n = sum((r // 128) * (c // 64) for _, r, c in SECTIONS)
+    return F32_SECTION_BYTES + n * split_of(mode) * IMAGE_BYTES
+
+
+def pack_kmajor(w, dtype, split=1):
+    """w [R, K] fp32 (R % 128 == 0, K % 64 == 0) -> uint8 tensor of operand images
+    [R/128][K/64][split][128 rows x 128 B], 16-byte pieces XOR-swizzled by (row & 7)."""
+    R, K = w.shape
+    assert R % 128 == 0 and K % 64 == 0
+    w = w.detach().to(torch.float32).cpu()
+    parts = [w.to(dtype)]
+    if split == 2:
+        parts.append((w - parts[0].to(torch.float32)).to(dtype))
+    elif dtype == torch.float16:
+        parts[0] = w.clamp(-65504.0, 65504.0).to(dtype)
+    r = torch.arange(128).view(128, 1)
+    q = torch.arange(8).view(1, 8)
+    src_piece = (q ^ (r & 7)).view(1, 1, 128, 8, 1).expand(R // 128, K // 64, 128, 8, 8)
+    imgs = []
+    for p in parts:
+        t = p.view(torch.int16).view(R // 128, 128, K // 64, 8, 8).permute(0, 2, 1, 3, 4)  # [u][kc][row][piece][8]
+        imgs.append(torch.gather(t, 3, src_piece))  # physical piece q holds logical piece q ^ (row & 7)
+    out = torch.stack(imgs, dim=2).contiguous()  # [u][kc][split][128][8][8] int16
+    return out.view(torch.uint8).reshape(-1)
+
+
+def fold(sd, eps=1e-5):
+    """State dict (reference naming, + reduce_dim.{weight,bias}) -> folded fp64 matrices."""
+    d = {k: v.detach().to(torch.float64).cpu() for k, v in sd.items() if not k.endswith("num_batches_tracked")}
+    s1 = d["first_conv.1.weight"] / torch.sqrt(d["first_conv.1.running_var"] + eps)
+    w1 = d["first_conv.0.weight"].reshape(128, 3) * s1[:, None]
+    b1 = (d["first_conv.0.bias"] - d["first_conv.1.running_mean"]) * s1 + d["first_conv.1.bias"]
+    w2 = d["first_conv.3.weight"].reshape(256, 128)
+    b2 = d["first_conv.3.bias"]
+    s3 = d["second_conv.1.weight"] / torch.sqrt(d["second_conv.1.running_var"] + eps)
+    w3 = d["second_conv.0.weight"].reshape(512, 512) * s3[:, None]
+    b3 = (d["second_conv.0.bias"] - d["second_conv.1.running_mean"]) * s3 + d["second_conv.1.bias"]
+    w3a, w3b = w3[:, :256], w3[:, 256:]
+    w4 = d["second_conv.3.weight"].reshape(-1, 512)
+    b4 = d["second_conv.3.bias"]
+    wr, br = d["reduce_dim.weight"], d["reduce_dim.bias"]
+    if w4.shape[0] != 256 or tuple(wr.shape) != (384, 256):
+        raise ValueError("kernels are specialised for encoder_dims=256, trans_dim=384 "
+                         "(models/pointbert/PointTransformer_8192point.yaml:17-24)")
+    return {
+        "W1": torch.cat([w1, b1[:, None]], dim=1),  # [128,4]
+        "W2": w2, "W3A": w3a, "W32": w3b @ w2, "W4": w4, "WR": wr,
+        "bias_c": (w3a + w3b) @ b2 + b3, "b4": b4, "bias_tok": wr @ b4 + br,
+    }
+
+
+def pack_encoder(sd, mode):
+    """-> uint8 CPU tensor of packed_bytes(mode) bytes."""
+    f = fold(sd)
+    dtype, split = operand_dtype(mode), split_of(mode)
+    f32 = torch.cat([f["W1"].reshape(-1), f["bias_c"], f["b4"], f["bias_tok"]]).to(torch.float32)
+    head = torch.zeros(F32_SECTION_BYTES, dtype=torch.uint8)
+    head[: f32.numel() * 4] = f32.view(torch.uint8)
+    parts = [head] + [pack_kmajor(f[name].to(torch.float32), dtype, split) for name, _, _ in SECTIONS]
+    blob = torch.cat(parts)
+    assert blob.numel() == packed_bytes(mode), (blob.numel(), packed_bytes(mode))
+    return blob

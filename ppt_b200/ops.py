@@ -1,0 +1,197 @@
+"""Tensor-level front end of the C ABI: validates, allocates outputs with torch,
+launches on torch's current stream.  One function per entry point of
+include/ppt_b200.h.  CUDA tensors only -- there is no CPU path here.
+"""
+import torch
+
+from . import _lib
+
+ENC_FP16, ENC_BF16, ENC_BF16X3 = 0, 1, 2
+ENC_MODES = {"fp16": ENC_FP16, "bf16": ENC_BF16, "fp32": ENC_BF16X3, "bf16x3": ENC_BF16X3}
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ppt_b200 ops need CUDA tensors (got device %s); there is no CPU fallback" % t.device)
+
+
+def _f32(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _i64(t):
+    return t.contiguous() if t.dtype == torch.int64 else t.long().contiguous()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def fps(xyz, npoint, start, return_centers=False):
+    """farthest_point_sample with a given start index tensor [B] -> idx [B,npoint] (int64)."""
+    _need_cuda(xyz, start)
+    xyz = _f32(xyz)
+    B, N, C = xyz.shape
+    if C != 3:
+        raise ValueError("xyz must be [B,N,3]")
+    start = _i64(start)
+    idx = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    centers = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device) if return_centers else None
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().ppt_fps(_ptr(xyz), _ptr(start), _ptr(idx), _ptr(centers), B, N, npoint, _stream(xyz)),
+                   "ppt_fps")
+    return (idx, centers) if return_centers else idx
+
+
+def square_distance(src, dst):
+    _need_cuda(src, dst)
+    src, dst = _f32(src), _f32(dst)
+    B, S, _ = src.shape
+    N = dst.shape[1]
+    out = torch.empty((B, S, N), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().ppt_square_distance(_ptr(src), _ptr(dst), _ptr(out), B, S, N, _stream(src)),
+                   "ppt_square_distance")
+    return out
+
+
+def knn(k, xyz, query, return_dist=False):
+    _need_cuda(xyz, query)
+    xyz, query = _f32(xyz), _f32(query)
+    B, N, _ = xyz.shape
+    S = query.shape[1]
+    idx = torch.empty((B, S, k), dtype=torch.int64, device=xyz.device)
+    dist = torch.empty((B, S, k), dtype=torch.float32, device=xyz.device) if return_dist else None
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().ppt_knn(_ptr(xyz), _ptr(query), _ptr(idx), _ptr(dist), B, N, S, k, _stream(xyz)),
+                   "ppt_knn")
+    return (idx, dist) if return_dist else idx
+
+
+def knn_group(xyz, center, k, return_idx=False):
+    _need_cuda(xyz, center)
+    xyz, center = _f32(xyz), _f32(center)
+    B, N, _ = xyz.shape
+    G = center.shape[1]
+    nb = torch.empty((B, G, k, 3), dtype=torch.float32, device=xyz.device)
+    idx = torch.empty((B, G, k), dtype=torch.int64, device=xyz.device) if return_idx else None
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().ppt_knn_group(_ptr(xyz), _ptr(center), _ptr(nb), _ptr(idx), B, N, G, k, _stream(xyz)),
+                   "ppt_knn_group")
+    return (nb, idx) if return_idx else nb
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    _need_cuda(xyz, new_xyz)
+    xyz, new_xyz = _f32(xyz), _f32(new_xyz)
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    # torch compares the fp32 distances with the Python double radius**2 cast to fp32
+    thr = float(torch.tensor(float(radius) ** 2, dtype=torch.float32))
+    idx = torch.empty((B, S, nsample), dtype=torch.int64, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().ppt_ball_query(_ptr(xyz), _ptr(new_xyz), _ptr(idx), thr, B, N, S, nsample, _stream(xyz)),
+                   "ppt_ball_query")
+    return idx
+
+
+def gather(points, idx):
+    """index_points: points [B,N,C], idx [B,...] -> [B,...,C]."""
+    _need_cuda(points, idx)
+    points, idx = _f32(points), _i64(idx)
+    B, N, C = points.shape
+    M = idx[0].numel() if B else 0
+    out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.check(_lib.load().ppt_gather(_ptr(points), _ptr(idx), _ptr(out), B, N, C, M, _stream(points)),
+                   "ppt_gather")
+    return out
+
+
+def group_concat(xyz, new_xyz, points, idx, xyz_first=True):
+    _need_cuda(xyz, new_xyz, points, idx)
+    xyz, new_xyz, idx = _f32(xyz), _f32(new_xyz), _i64(idx)
+    B, N, _ = xyz.shape
+    _, S, K = idx.shape
+    D = 0
+    if points is not None:
+        points = _f32(points)
+        D = points.shape[2]
+    out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().ppt_group_concat(_ptr(xyz), _ptr(new_xyz), _ptr(points), _ptr(idx), _ptr(out), B, N, S,
+                                                K, D, 1 if xyz_first else 0, _stream(xyz)), "ppt_group_concat")
+    return out
+
+
+def three_nn(unknown, known):
+    _need_cuda(unknown, known)
+    unknown, known = _f32(unknown), _f32(known)
+    B, N, _ = unknown.shape
+    S = known.shape[1]
+    dist = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
+    idx = torch.empty((B, N, 3), dtype=torch.int64, device=unknown.device)
+    with torch.cuda.device(unknown.device):
+        _lib.check(_lib.load().ppt_three_nn(_ptr(unknown), _ptr(known), _ptr(dist), _ptr(idx), B, N, S,
+                                            _stream(unknown)), "ppt_three_nn")
+    return dist, idx
+
+
+def _interp_fwd(feats, idx, dist):
+    B, S, D = feats.shape
+    N = idx.shape[1]
+    out = torch.empty((B, N, D), dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.load().ppt_three_interpolate(_ptr(feats), _ptr(idx), _ptr(dist), _ptr(out), B, N, S, D,
+                                                     _stream(feats)), "ppt_three_interpolate")
+    return out
+
+
+class _ThreeInterpolate(torch.autograd.Function):
+    """Differentiable w.r.t. feats only (the part-seg head trains through it)."""
+
+    @staticmethod
+    def forward(ctx, feats, idx, dist):
+        ctx.save_for_backward(idx, dist)
+        ctx.S = feats.shape[1]
+        return _interp_fwd(feats, idx, dist)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, dist = ctx.saved_tensors
+        grad_out = _f32(grad_out)
+        B, N, D = grad_out.shape
+        grad_feats = torch.zeros((B, ctx.S, D), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _lib.check(_lib.load().ppt_three_interpolate_grad(_ptr(grad_out), _ptr(idx), _ptr(dist), _ptr(grad_feats),
+                                                              B, N, ctx.S, D, _stream(grad_out)),
+                       "ppt_three_interpolate_grad")
+        return grad_feats, None, None
+
+
+def three_interpolate(feats, idx, dist):
+    """feats [B,S,D], idx/dist [B,N,3] -> [B,N,D]."""
+    _need_cuda(feats, idx, dist)
+    feats, idx, dist = _f32(feats), _i64(idx), _f32(dist)
+    if feats.requires_grad and torch.is_grad_enabled():
+        return _ThreeInterpolate.apply(feats, idx, dist)
+    return _interp_fwd(feats, idx, dist)
+
+
+def selftest_umma(a, b, mode=ENC_FP16, b_mn_major=False, a_packed=None):
+    """D[128,N] = A[128,K] @ B[N,K]^T through the Encoder's tcgen05 building blocks."""
+    _need_cuda(a, b)
+    a, b = _f32(a), _f32(b)
+    N, K = b.shape
+    d = torch.empty((128, N), dtype=torch.float32, device=a.device)
+    flags = mode | (4 if b_mn_major else 0) | (8 if a_packed is not None else 0)
+    src = a if a_packed is None else a_packed
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().ppt_selftest_umma(_ptr(src), _ptr(b), _ptr(d), N, K, flags, _stream(a)),
+                   "ppt_selftest_umma")
+    return d
