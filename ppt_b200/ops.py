@@ -195,3 +195,46 @@ def selftest_umma(a, b, mode=ENC_FP16, b_mn_major=False, a_packed=None):
         _lib.check(_lib.load().ppt_selftest_umma(_ptr(src), _ptr(b), _ptr(d), N, K, flags, _stream(a)),
                    "ppt_selftest_umma")
     return d
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Scratch owned by the host layer (the C ABI never allocates); grown on demand, one per device."""
+    buf = _workspaces.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[device] = buf
+    return buf
+
+
+def encoder_packed_bytes(mode):
+    return int(_lib.load().ppt_encoder_packed_bytes(mode))
+
+
+def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False):
+    """neighborhood [..., 32, 3] fp32 (CUDA) -> tokens [..., 384] (and Encoder features [..., 256]).
+
+    `packed` is the uint8 CUDA blob from ppt_b200.encoder_pack.pack_encoder(state_dict, mode)."""
+    _need_cuda(neighborhood, packed)
+    nb = _f32(neighborhood)
+    if nb.dim() < 3 or nb.shape[-1] != 3 or nb.shape[-2] != 32:
+        raise ValueError("neighborhood must be [..., 32, 3]; the kernels are specialised for group_size 32 "
+                         "(models/pointbert/PointTransformer_8192point.yaml:17-24)")
+    lead = tuple(nb.shape[:-2])
+    groups = 1
+    for d in lead:
+        groups *= d
+    lib = _lib.load()
+    if packed.dtype != torch.uint8 or packed.numel() != lib.ppt_encoder_packed_bytes(mode):
+        raise ValueError("packed weight blob does not match mode %d" % mode)
+    tokens = torch.empty(lead + (384,), dtype=torch.float32, device=nb.device)
+    feats = torch.empty(lead + (256,), dtype=torch.float32, device=nb.device) if return_features else None
+    if groups == 0:
+        return (tokens, feats) if return_features else tokens
+    ws = _workspace(nb.device, lib.ppt_encoder_workspace_bytes(groups, mode))
+    with torch.cuda.device(nb.device):
+        _lib.check(lib.ppt_encoder_forward(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens), groups, mode,
+                                           _stream(nb)), "ppt_encoder_forward")
+    return (tokens, feats) if return_features else tokens
