@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- tokenized clouds/sec of the PPT point-cloud tokenizer hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic clouds: FPS -> kNN + gather +
+centre (Group.forward) -> mini-PointNet Encoder -> reduce_dim, i.e. 128 clouds x 8192 points ->
+128 x 512 tokens x 384 per GPU (BASELINE.json configs[1]).  Clouds are independent, so N GPUs
+each take their own 128-cloud batch (weak scaling, no collective in the timed loop).
+
+Prints ONE JSON line (rank 0).  `value` has the inputs resident in HBM; `e2e` goes through the
+public API with pinned HOST buffers (H2D of the clouds and D2H of the tokens inside the timed
+region); `roofline` describes the dominant kernel (Encoder stage 2 on the tensor pipe), timed
+with CUDA events on its own stream during the same timed steps; `cpu_baseline` is the
+reference's CPU path (torch-op port, oracle/torch_port.py) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tokenized clouds/sec (8192 pts->512x32 patches->512x384 tokens)"
+UNIT = "clouds/s"
+N_POINTS, N_GROUP, GROUP_SIZE = 8192, 512, 32
+BATCH_PER_GPU = 128
+ROTATE = 12  # distinct resident input batches (12 x 12.6 MB > 126 MB L2)
+
+# Algorithmic work (DESIGN.md "Measurement"): executed FLOPs of Encoder stage 2 per point
+STAGE2_FLOP_PER_POINT = 2 * 128 * 512 + 2 * 512 * 256
+ENC_FLOP_PER_POINT = 2 * 3 * 128 + 2 * 128 * 256 + STAGE2_FLOP_PER_POINT  # + per-group terms below
+ENC_FLOP_PER_GROUP = 2 * 256 * 512 + 2 * 256 * 384
+FPS_LANE_INSTR_PER_CLOUD = 512 * 8192 * 11
+KNN_LANE_INSTR_PER_CLOUD = 512 * 8192 * 7
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_clouds_per_s(clouds, points, repeats, threads):
+    """The reference's CPU path (torch-op port) on `clouds` clouds: median of `repeats` after one warm-up."""
+    import torch
+    from oracle import torch_port
+    from oracle.inputs import cloud
+    torch.set_num_threads(threads)
+    sd = torch_port.make_encoder_state()
+    xyz = cloud("U", clouds, points, 1234)
+    times = []
+    with torch.no_grad():
+        for i in range(repeats + 1):
+            t = time.perf_counter()
+            nb, _ = torch_port.group_forward(xyz, N_GROUP, GROUP_SIZE, 0)
+            torch_port.tokens_forward(sd, nb)
+            if i:
+                times.append(time.perf_counter() - t)
+    return clouds / statistics.median(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.
+    The reference is Python/PyTorch and /root/reference does not travel to the GPU box, so this
+    is the torch-op port (same ATen ops, validated bit-for-bit against the reference where it exists)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_port
+    from oracle.inputs import cloud
+    threads = len(os.sched_getaffinity(0))
+    torch.set_num_threads(threads)
+    clouds = int(os.environ.get("PPT_BENCH_REF_CLOUDS", "8"))
+    points = int(os.environ.get("PPT_BENCH_REF_POINTS", str(N_POINTS)))
+    sd = torch_port.make_encoder_state()
+    xyz = cloud("U", clouds, points, 1234)
+
+    def step():
+        with torch.no_grad():
+            nb, _ = torch_port.group_forward(xyz, N_GROUP, GROUP_SIZE, 0)
+            return torch_port.tokens_forward(sd, nb)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = clouds * args.steps / dt
+    sample = "%d clouds x %d pts per step (torch-op port of Group+Encoder+reduce_dim, fp32)" % (clouds, points)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def config_block(args):
+    return {"workload": "BASELINE configs[1]: Group tokenizer (FPS 8192->512, 32-NN, gather+centre) + mini-PointNet "
+                        "patch Encoder + reduce_dim -> 512x384 tokens, batch %d per GPU" % BATCH_PER_GPU,
+            "clouds_per_gpu_per_step": BATCH_PER_GPU, "points": N_POINTS, "groups": N_GROUP, "group_size": GROUP_SIZE,
+            "encoder_precision": args.precision, "fps_start_index": 0, "parallelism": "batch shard x%d, no collective"
+            % args.gpus, "l2": "inputs larger than L2: %d distinct resident batches rotate (%.0f MB)"
+            % (ROTATE, ROTATE * BATCH_PER_GPU * N_POINTS * 12 / 1e6)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import torch_port  # seeded Encoder weights only (no compute from oracle/ on this path)
+    from ppt_b200.tokenizer import PointTokenizer
+    from ppt_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    tok = PointTokenizer(N_GROUP, GROUP_SIZE, precision=args.precision).to(dev).eval()
+    tok.load_reference_state(torch_port.make_encoder_state())
+    tok.start_idx = 0
+    B = BATCH_PER_GPU
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [(torch.rand(B, N_POINTS, 3, generator=g) * 2 - 1).pin_memory() for _ in range(ROTATE)]
+    resident = [h.to(dev) for h in host]
+    zeros = torch.zeros(B, dtype=torch.int64, device=dev)
+
+    def step(i, phase_events=None):
+        xyz = resident[i % ROTATE]
+        _, center = ops.fps(xyz, N_GROUP, zeros, return_centers=True)
+        nb = ops.knn_group(xyz, center, GROUP_SIZE)
+        blob, mode = tok.encoder._blob(dev)
+        return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events), center
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    phase_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i, phase_events)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    per_phase = {}
+    for name, a, b in phase_events:
+        per_phase.setdefault(name, []).append(a.elapsed_time(b))
+
+    # ---- timed region 2: end to end through the public API with pinned host buffers ----
+    out_host = torch.empty((B, N_GROUP, 384), dtype=torch.float32).pin_memory()
+    ctr_host = torch.empty((B, N_GROUP, 3), dtype=torch.float32).pin_memory()
+    stage_dev = torch.empty((B, N_POINTS, 3), dtype=torch.float32, device=dev)
+
+    def step_e2e(i):
+        stage_dev.copy_(host[i % ROTATE], non_blocking=True)
+        tokens, center = tok(stage_dev)
+        out_host.copy_(tokens, non_blocking=True)
+        ctr_host.copy_(center, non_blocking=True)
+
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    f1.record()
+    barrier()
+    ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+    checksum = float(out_host.double().abs().sum())
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peaks = load_peaks()
+    clouds_total = B * world * args.steps
+    value = clouds_total / (ms_total * 1e-3)
+    e2e_value = clouds_total / (ms_e2e * 1e-3)
+    s2_ms = statistics.mean(per_phase["stage2"])
+    points = B * N_GROUP * GROUP_SIZE
+    achieved_tf = points * STAGE2_FLOP_PER_POINT / (s2_ms * 1e-3) / 1e12
+    roofline = {"kernel": "encoder_stage_kernel<stage 2> (relu(W32 h1 + c) -> h3 -> W4 h3 -> group max)",
+                "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["bf16_tflops"], "traffic": None,
+                "peak_source": "%s cuBLAS bf16 burst (MEASURED_PEAKS.json)" % peaks["source"],
+                "flops_per_launch": points * STAGE2_FLOP_PER_POINT, "ms_per_launch": s2_ms,
+                "phase_ms": {k: statistics.mean(v) for k, v in per_phase.items()}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        sample_clouds = 16
+        v = cpu_reference_clouds_per_s(sample_clouds, N_POINTS, 2, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d clouds x %d pts, torch-op port of Group+Encoder+reduce_dim (fp32), median of 2 after 1 "
+                         "warm-up" % (sample_clouds, N_POINTS)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 operands / fp32 accumulate" if args.precision == "fp16" else args.precision,
+        "data": "synthetic (uniform cube clouds, seeded random-init Encoder weights)",
+        "config": config_block(args), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_POINTS * 12,
+                "d2h_bytes_per_step": B * N_GROUP * (384 + 3) * 4, "ms_per_step": ms_e2e / args.steps,
+                "checksum": checksum},
+        "gpu_launches": 6 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,13 +119,21 @@ int ppt_three_interpolate_grad(const float *grad_out, const int64_t *idx, const 
  * blob (ppt_b200/encoder_pack.py documents the layout); the blob is opaque here.
  *   packed_bytes = ppt_encoder_packed_bytes(mode);
  *   workspace    = ppt_encoder_workspace_bytes(num_groups, mode) bytes of scratch.
- *   neighborhood [num_groups, 32, 3] f32 -> tokens_out [num_groups, 384] f32,
- *   features_out [num_groups, 256] f32 or NULL (the Encoder's own output).
+ *   neighborhood [num_groups, 32, 3] f32 -> tokens_out [num_groups, 384] f32 (or NULL),
+ *   features_out [num_groups, 256] f32 or NULL (the Encoder's own output); not both NULL.
  * num_groups = B*G; any value >= 1. */
 int64_t ppt_encoder_packed_bytes(int mode);
 int64_t ppt_encoder_workspace_bytes(int64_t num_groups, int mode);
 int ppt_encoder_forward(const float *neighborhood, const void *packed, void *workspace,
                         float *features_out, float *tokens_out, int64_t num_groups, int mode, void *stream);
+
+/* Same pipeline, one or more of its four launches at a time (bit 0 stage1, bit 1 per-group
+ * linear -> c, bit 2 stage2, bit 3 per-group linear -> tokens), in order, sharing `workspace`.
+ * Lets a caller bracket one launch with events; tokens_out may be NULL if features_out is given
+ * (plain Encoder.forward without reduce_dim). */
+int ppt_encoder_forward_phases(const float *neighborhood, const void *packed, void *workspace,
+                               float *features_out, float *tokens_out, int64_t num_groups, int mode,
+                               int phases, void *stream);
 
 /* Self-test of the tcgen05 building blocks (one 128 x N x K GEMM through the
  * same smem layouts, descriptors and epilogue the Encoder uses).

@@ -470,9 +470,10 @@ struct Workspace {
   }
 };
 
+// phases: bit 0 stage1, bit 1 group_linear(c), bit 2 stage2, bit 3 group_linear(tokens)
 template <uint32_t FMT, int SPLIT, int NT>
 int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws, float* features_out,
-                float* tokens_out, long long groups, cudaStream_t st) {
+                float* tokens_out, long long groups, int phases, cudaStream_t st) {
   const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
   auto k1 = encoder_stage_kernel<FMT, SPLIT, NT, 1>;
@@ -498,12 +499,15 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   // The tail tile of the operand images is only partly written by the stage kernels; the unwritten rows
   // feed MMA columns that are never stored, but they must not hold NaN patterns that trap nothing -- any
   // bit pattern is fine for unused columns, so no clearing is needed.
-  k1<<<grid_t, ENC_THREADS, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
-  kb<<<grid_g, ENC_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
-                                      cbuf, groups, tiles128);
-  k2<<<grid_t, ENC_THREADS, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
-  kd<<<grid_g, ENC_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(), reinterpret_cast<const float*>(blob + L.bias_tok()),
-                                      tokens_out, groups, tiles128);
+  if (phases & 1) k1<<<grid_t, ENC_THREADS, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
+  if (phases & 2)
+    kb<<<grid_g, ENC_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(),
+                                        reinterpret_cast<const float*>(blob + L.bias_c()), cbuf, groups, tiles128);
+  if (phases & 4) k2<<<grid_t, ENC_THREADS, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
+  if ((phases & 8) && tokens_out)
+    kd<<<grid_g, ENC_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(),
+                                        reinterpret_cast<const float*>(blob + L.bias_tok()), tokens_out, groups,
+                                        tiles128);
   return ppt_launch_status();
 }
 
@@ -519,10 +523,10 @@ extern "C" PPT_EXPORT int64_t ppt_encoder_workspace_bytes(int64_t num_groups, in
   return (int64_t)Workspace(num_groups, mode == PPT_ENC_BF16X3 ? 2 : 1).total;
 }
 
-extern "C" PPT_EXPORT int ppt_encoder_forward(const float* neighborhood, const void* packed, void* workspace,
-                                              float* features_out, float* tokens_out, int64_t num_groups, int mode,
-                                              void* stream) {
-  if (!neighborhood || !packed || !workspace || !tokens_out || num_groups < 1) return PPT_EINVAL;
+extern "C" PPT_EXPORT int ppt_encoder_forward_phases(const float* neighborhood, const void* packed, void* workspace,
+                                                     float* features_out, float* tokens_out, int64_t num_groups,
+                                                     int mode, int phases, void* stream) {
+  if (!neighborhood || !packed || !workspace || (!tokens_out && !features_out) || num_groups < 1) return PPT_EINVAL;
   if (num_groups > (1ll << 31) / 32) return PPT_ERANGE;
   if ((reinterpret_cast<uintptr_t>(packed) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PPT_EINVAL;
   const unsigned char* blob = static_cast<const unsigned char*>(packed);
@@ -530,12 +534,22 @@ extern "C" PPT_EXPORT int ppt_encoder_forward(const float* neighborhood, const v
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {
     case PPT_ENC_FP16:
-      return run_encoder<tc05::FMT_F16, 1, 128>(neighborhood, blob, ws, features_out, tokens_out, num_groups, st);
+      return run_encoder<tc05::FMT_F16, 1, 128>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
+                                                st);
     case PPT_ENC_BF16:
-      return run_encoder<tc05::FMT_BF16, 1, 128>(neighborhood, blob, ws, features_out, tokens_out, num_groups, st);
+      return run_encoder<tc05::FMT_BF16, 1, 128>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
+                                                 st);
     case PPT_ENC_BF16X3:
-      return run_encoder<tc05::FMT_BF16, 2, 64>(neighborhood, blob, ws, features_out, tokens_out, num_groups, st);
+      return run_encoder<tc05::FMT_BF16, 2, 64>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
+                                                st);
     default:
       return PPT_EINVAL;
   }
+}
+
+extern "C" PPT_EXPORT int ppt_encoder_forward(const float* neighborhood, const void* packed, void* workspace,
+                                              float* features_out, float* tokens_out, int64_t num_groups, int mode,
+                                              void* stream) {
+  return ppt_encoder_forward_phases(neighborhood, packed, workspace, features_out, tokens_out, num_groups, mode, 15,
+                                    stream);
 }

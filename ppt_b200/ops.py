@@ -213,10 +213,16 @@ def encoder_packed_bytes(mode):
     return int(_lib.load().ppt_encoder_packed_bytes(mode))
 
 
-def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False):
+ENC_PHASE_NAMES = ("stage1", "group_linear_c", "stage2", "group_linear_tokens")
+
+
+def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, want_tokens=True, phase_events=None):
     """neighborhood [..., 32, 3] fp32 (CUDA) -> tokens [..., 384] (and Encoder features [..., 256]).
 
-    `packed` is the uint8 CUDA blob from ppt_b200.encoder_pack.pack_encoder(state_dict, mode)."""
+    `packed` is the uint8 CUDA blob from ppt_b200.encoder_pack.pack_encoder(state_dict, mode).
+    `phase_events`: optional list; when given, the four launches are issued one by one and a
+    (name, start_event, end_event) triple per launch is appended (for per-kernel timing on
+    the launching stream)."""
     _need_cuda(neighborhood, packed)
     nb = _f32(neighborhood)
     if nb.dim() < 3 or nb.shape[-1] != 3 or nb.shape[-2] != 32:
@@ -229,12 +235,23 @@ def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False):
     lib = _lib.load()
     if packed.dtype != torch.uint8 or packed.numel() != lib.ppt_encoder_packed_bytes(mode):
         raise ValueError("packed weight blob does not match mode %d" % mode)
-    tokens = torch.empty(lead + (384,), dtype=torch.float32, device=nb.device)
+    if not (want_tokens or return_features):
+        raise ValueError("nothing to compute")
+    tokens = torch.empty(lead + (384,), dtype=torch.float32, device=nb.device) if want_tokens else None
     feats = torch.empty(lead + (256,), dtype=torch.float32, device=nb.device) if return_features else None
     if groups == 0:
         return (tokens, feats) if return_features else tokens
     ws = _workspace(nb.device, lib.ppt_encoder_workspace_bytes(groups, mode))
     with torch.cuda.device(nb.device):
-        _lib.check(lib.ppt_encoder_forward(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens), groups, mode,
-                                           _stream(nb)), "ppt_encoder_forward")
+        if phase_events is None:
+            _lib.check(lib.ppt_encoder_forward_phases(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens),
+                                                      groups, mode, 15, _stream(nb)), "ppt_encoder_forward")
+        else:
+            for bit, name in enumerate(ENC_PHASE_NAMES):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(lib.ppt_encoder_forward_phases(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens),
+                                                          groups, mode, 1 << bit, _stream(nb)), "ppt_encoder_" + name)
+                e1.record()
+                phase_events.append((name, e0, e1))
     return (tokens, feats) if return_features else tokens

@@ -1,0 +1,152 @@
+"""patch_reference(): install the B200 kernels behind an imported auniquesun/PPT tree.
+
+The reference has no operator registry; its boundary is Python names.
+Module-level functions are rebound on the reference modules (intra-module calls resolve
+through module globals at call time, so `sample_and_group` picks up the new
+`farthest_point_sample`), and the nn.Module classes get their `forward` replaced in place,
+which is import-order-proof (`from models.pointbert.dvae import Group` elsewhere keeps working).
+
+CPU tensors keep running the reference's own code: the wrappers only divert CUDA tensors.
+"""
+import functools
+import importlib
+import sys
+
+import torch
+
+from . import encoder_pack, ops, pointbert, pointnet2
+
+_FUNCTIONS = {
+    # reference module -> {attribute: replacement}
+    "models.pointbert.misc": {
+        "fps": pointbert.fps, "farthest_point_sample": pointbert.farthest_point_sample,
+        "index_points": pointbert.index_points,
+    },
+    "models.pointbert.dvae": {"knn_point": pointbert.knn_point, "square_distance": pointbert.square_distance},
+    "models.pointbert.pointnet2_utils": {
+        "farthest_point_sample": pointnet2.farthest_point_sample, "index_points": pointbert.index_points,
+        "knn_point": pointbert.knn_point, "square_distance": pointbert.square_distance,
+        "query_ball_point": pointnet2.query_ball_point, "sample_and_group": pointnet2.sample_and_group,
+    },
+    "models.pointnet2.pointnet2_utils": {
+        "farthest_point_sample": pointnet2.farthest_point_sample, "index_points": pointbert.index_points,
+        "square_distance": pointbert.square_distance, "query_ball_point": pointnet2.query_ball_point,
+        "sample_and_group": pointnet2.sample_and_group,
+    },
+    "models.pointmlp.pointMLP": {
+        "farthest_point_sample": pointbert.farthest_point_sample, "index_points": pointbert.index_points,
+        "knn_point": pointbert.knn_point, "square_distance": pointbert.square_distance,
+        "query_ball_point": pointnet2.query_ball_point,
+    },
+}
+
+_installed = []  # (owner, attribute, original)
+
+
+def _first_tensor(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            return a
+    return None
+
+
+def _divert_cuda(original, replacement):
+    @functools.wraps(original)
+    def wrapper(*args, **kwargs):
+        t = _first_tensor(args, kwargs)
+        if t is not None and t.is_cuda:
+            return replacement(*args, **kwargs)
+        return original(*args, **kwargs)
+
+    wrapper.__ppt_b200_original__ = original
+    return wrapper
+
+
+def _set(owner, name, value):
+    _installed.append((owner, name, getattr(owner, name)))
+    setattr(owner, name, value)
+
+
+def _group_forward(self, xyz):
+    """Group.forward, models/pointbert/dvae.py:159-181."""
+    start = pointbert._draw_start(xyz)
+    _, center = ops.fps(xyz, self.num_group, start, return_centers=True)
+    return ops.knn_group(xyz, center, self.group_size), center
+
+
+def _encoder_forward(self, point_groups):
+    """Encoder.forward (eval), models/pointbert/dvae.py:201-215, on the reference's own module instance."""
+    mode = ops.ENC_MODES[getattr(self, "ppt_precision", "fp16")]
+    tensors = list(self.parameters()) + list(self.buffers())
+    key = (mode, str(point_groups.device)) + tuple((t.data_ptr(), t._version) for t in tensors)
+    if getattr(self, "_ppt_key", None) != key:
+        sd = dict(self.state_dict())
+        ref = sd["first_conv.0.weight"]
+        sd["reduce_dim.weight"], sd["reduce_dim.bias"] = ref.new_zeros((384, 256)), ref.new_zeros((384,))
+        object.__setattr__(self, "_ppt_blob", encoder_pack.pack_encoder(sd, mode).to(point_groups.device))
+        object.__setattr__(self, "_ppt_key", key)
+    return ops.encoder_forward(point_groups, self._ppt_blob, mode=mode, return_features=True, want_tokens=False)[1]
+
+
+def _fp_forward(self, xyz1, xyz2, points1, points2):
+    return pointnet2.PointNetFeaturePropagation.forward(self, xyz1, xyz2, points1, points2)
+
+
+def patch_reference(modules=None):
+    """Rebinds the hot-path names on every reference module that is importable.
+    Returns the list of patched 'module.attribute' names.  Idempotent."""
+    if _installed:
+        return [getattr(o, "__name__", repr(o)) + "." + n for o, n, _ in _installed]
+    names = modules if modules is not None else list(_FUNCTIONS)
+    for modname in names:
+        mod = sys.modules.get(modname)
+        if mod is None:
+            try:
+                mod = importlib.import_module(modname)
+            except Exception:
+                continue  # optional backbone whose imports are unavailable
+        for attr, repl in _FUNCTIONS.get(modname, {}).items():
+            if hasattr(mod, attr):
+                _set(mod, attr, _divert_cuda(getattr(mod, attr), repl))
+        if modname == "models.pointbert.dvae":
+            orig_g, orig_e = mod.Group.forward, mod.Encoder.forward
+
+            def group_fwd(self, xyz, _o=orig_g):
+                return _group_forward(self, xyz) if xyz.is_cuda else _o(self, xyz)
+
+            def enc_fwd(self, pg, _o=orig_e):
+                fused = pg.is_cuda and not self.training and pg.shape[2] == 32 and self.encoder_channel == 256
+                return _encoder_forward(self, pg) if fused else _o(self, pg)
+
+            _set(mod.Group, "forward", group_fwd)
+            _set(mod.Encoder, "forward", enc_fwd)
+        if modname in ("models.pointnet2.pointnet2_utils", "models.pointbert.pointnet2_utils"):
+            cls = getattr(mod, "PointNetFeaturePropagation", None)
+            if cls is not None:
+                orig_f = cls.forward
+
+                def fp_fwd(self, xyz1, xyz2, points1, points2, _o=orig_f):
+                    if xyz1.is_cuda:
+                        return _fp_forward(self, xyz1, xyz2, points1, points2)
+                    return _o(self, xyz1, xyz2, points1, points2)
+
+                _set(cls, "forward", fp_fwd)
+            msg = getattr(mod, "PointNetSetAbstractionMsg", None)
+            if msg is not None:
+                orig_m = msg.forward
+
+                def msg_fwd(self, xyz, points, _o=orig_m):
+                    if xyz.is_cuda:
+                        if not hasattr(self, "start_idx"):
+                            self.start_idx = None
+                        return pointnet2.PointNetSetAbstractionMsg.forward(self, xyz, points)
+                    return _o(self, xyz, points)
+
+                _set(msg, "forward", msg_fwd)
+    return [getattr(o, "__name__", repr(o)) + "." + n for o, n, _ in _installed]
+
+
+def unpatch_reference():
+    while _installed:
+        owner, name, original = _installed.pop()
+        setattr(owner, name, original)

@@ -1,0 +1,145 @@
+"""Drop-in counterparts of models/pointbert/misc.py and models/pointbert/dvae.py (reference tree).
+
+Same names, argument order, dtypes and return shapes as the reference; the bodies launch
+the sm_100a kernels through ppt_b200.ops.  Additive keywords (never required): `start_idx`
+to pin the FPS start instead of drawing it.
+"""
+import torch
+import torch.nn as nn
+
+from . import encoder_pack, ops
+
+
+def _draw_start(xyz):
+    """The reference's own draw (models/pointbert/misc.py:59), so a seeded run consumes
+    the RNG stream exactly as it does with the reference."""
+    B, N, _ = xyz.shape
+    return torch.randint(0, N, (B,), dtype=torch.long, device=xyz.device)
+
+
+def farthest_point_sample(xyz, npoint, start_idx=None):
+    """models/pointbert/misc.py:44-69.  xyz [B,N,3] -> centroids [B,npoint] int64."""
+    start = _draw_start(xyz) if start_idx is None else _as_start(start_idx, xyz)
+    return ops.fps(xyz, npoint, start)
+
+
+def _as_start(start_idx, xyz):
+    s = torch.as_tensor(start_idx, dtype=torch.long, device=xyz.device)
+    return s.expand(xyz.shape[0]).contiguous() if s.dim() == 0 else s
+
+
+def index_points(points, idx):
+    """models/pointbert/misc.py:26-42.  points [B,N,C], idx [B,S] or [B,S,K] -> [B,S(,K),C]."""
+    return ops.gather(points, idx)
+
+
+def fps(data, number, start_idx=None):
+    """models/pointbert/misc.py:12-24.  data [B,N,3] -> fps_data [B,number,3]."""
+    start = _draw_start(data) if start_idx is None else _as_start(start_idx, data)
+    return ops.fps(data, number, start, return_centers=True)[1]
+
+
+def square_distance(src, dst):
+    """models/pointbert/dvae.py:130-149.  src [B,N,C], dst [B,M,C] -> [B,N,M] (C = 3)."""
+    return ops.square_distance(src, dst)
+
+
+def knn_point(nsample, xyz, new_xyz):
+    """models/pointbert/dvae.py:116-127.  -> group_idx [B,S,nsample] int64.  The reference's
+    topk(sorted=False) leaves the order unspecified; here it is ascending (distance, index)."""
+    return ops.knn(nsample, xyz, new_xyz)
+
+
+class Group(nn.Module):
+    """models/pointbert/dvae.py:152-181: FPS centres, kNN patches, centred coordinates."""
+
+    def __init__(self, num_group, group_size):
+        super().__init__()
+        self.num_group = num_group
+        self.group_size = group_size
+        self.start_idx = None  # additive: set to an int / [B] tensor for a deterministic start
+
+    def forward(self, xyz):
+        """xyz [B,N,3] -> neighborhood [B,G,M,3], center [B,G,3]."""
+        start = _draw_start(xyz) if self.start_idx is None else _as_start(self.start_idx, xyz)
+        _, center = ops.fps(xyz, self.num_group, start, return_centers=True)
+        neighborhood = ops.knn_group(xyz, center, self.group_size)
+        return neighborhood, center
+
+
+class Encoder(nn.Module):
+    """models/pointbert/dvae.py:184-215 -- same sub-module / state_dict names, so the ULIP
+    checkpoints keep loading (models/ULIP_models.py:487-507).
+
+    eval(): BatchNorm is folded and the whole stack runs in the tcgen05 kernels.
+    train(): the reference puts the frozen Encoder's BatchNorm in batch-statistics mode
+    (main_cls.py:169); that path runs the module's own torch layers on the GPU.
+    """
+
+    def __init__(self, encoder_channel, precision="fp16"):
+        super().__init__()
+        self.encoder_channel = encoder_channel
+        self.first_conv = nn.Sequential(nn.Conv1d(3, 128, 1), nn.BatchNorm1d(128), nn.ReLU(inplace=True),
+                                        nn.Conv1d(128, 256, 1))
+        self.second_conv = nn.Sequential(nn.Conv1d(512, 512, 1), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
+                                         nn.Conv1d(512, self.encoder_channel, 1))
+        self.precision = precision
+        self._reduce_dim = None  # optional nn.Linear fused behind the Encoder (point_encoder.py:133)
+        self._packed = None
+        self._packed_key = None
+
+    # -- additive API -----------------------------------------------------------------------------
+    def attach_reduce_dim(self, linear):
+        """Registers the caller's reduce_dim Linear (not as a sub-module: its parameters stay
+        owned by the caller) so forward_tokens() can fuse it."""
+        object.__setattr__(self, "_reduce_dim", linear)
+        self._packed = None
+        return self
+
+    def _state_for_pack(self):
+        sd = {k: v for k, v in self.state_dict().items()}
+        if self._reduce_dim is not None:
+            sd["reduce_dim.weight"], sd["reduce_dim.bias"] = self._reduce_dim.weight, self._reduce_dim.bias
+        else:
+            ref = sd["first_conv.0.weight"]
+            sd["reduce_dim.weight"] = ref.new_zeros((384, 256))
+            sd["reduce_dim.bias"] = ref.new_zeros((384,))
+        return sd
+
+    def _blob(self, device):
+        mode = ops.ENC_MODES[self.precision]
+        tensors = list(self.parameters()) + list(self.buffers())
+        if self._reduce_dim is not None:
+            tensors += [self._reduce_dim.weight, self._reduce_dim.bias]
+        key = (mode, str(device)) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._packed is None or self._packed_key != key:
+            self._packed = encoder_pack.pack_encoder(self._state_for_pack(), mode).to(device)
+            self._packed_key = key
+        return self._packed, mode
+
+    def _forward_torch(self, point_groups):
+        bs, g, n, _ = point_groups.shape
+        feature = self.first_conv(point_groups.reshape(bs * g, n, 3).transpose(2, 1))
+        glob = torch.max(feature, dim=2, keepdim=True)[0]
+        feature = self.second_conv(torch.cat([glob.expand(-1, -1, n), feature], dim=1))
+        return torch.max(feature, dim=2, keepdim=False)[0].reshape(bs, g, self.encoder_channel)
+
+    def forward_tokens(self, point_groups):
+        """(B,G,32,3) -> reduce_dim(Encoder(point_groups)) : (B,G,384), one fused pipeline."""
+        if self._reduce_dim is None:
+            raise RuntimeError("attach_reduce_dim() first")
+        if self.training:
+            return self._reduce_dim(self._forward_torch(point_groups))
+        blob, mode = self._blob(point_groups.device)
+        return ops.encoder_forward(point_groups, blob, mode=mode)
+
+    # -- reference API ----------------------------------------------------------------------------
+    def forward(self, point_groups):
+        """point_groups [B,G,N,3] -> feature_global [B,G,C]."""
+        if self.training:
+            return self._forward_torch(point_groups)
+        if point_groups.shape[2] != 32 or self.encoder_channel != 256:
+            raise RuntimeError("fused Encoder is specialised for 32-point groups and encoder_dims=256 "
+                               "(models/pointbert/PointTransformer_8192point.yaml:17-24)")
+        blob, mode = self._blob(point_groups.device)
+        return ops.encoder_forward(point_groups, blob, mode=mode, return_features=True, want_tokens=False)[1]

@@ -1,0 +1,164 @@
+"""Drop-in counterparts of models/pointnet2/pointnet2_utils.py (and the copy in
+models/pointbert/pointnet2_utils.py) of the reference tree.
+
+The geometry (FPS, ball query, grouping, three_nn / three_interpolate) runs in the sm_100a
+kernels; the shared MLPs of the set-abstraction / feature-propagation modules stay the
+module's own Conv/BatchNorm layers (SURVEY.md section 8f lists fusing them as the next
+step), so state dicts and outputs keep the reference's layout: channel-first in, channel-first out.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .pointbert import _as_start, index_points, knn_point, square_distance  # noqa: F401  (same functions)
+
+
+def farthest_point_sample(xyz, npoint, start_idx=None):
+    """models/pointnet2/pointnet2_utils.py:63-84.  This copy draws the start index on the
+    CPU and moves it (:75); the draw is repeated here so seeded runs stay aligned."""
+    B, N, _ = xyz.shape
+    if start_idx is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
+    else:
+        start = _as_start(start_idx, xyz)
+    return ops.fps(xyz, npoint, start)
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """models/pointnet2/pointnet2_utils.py:87-107.  -> group_idx [B,S,nsample] int64."""
+    return ops.ball_query(radius, nsample, xyz, new_xyz)
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, start_idx=None):
+    """models/pointnet2/pointnet2_utils.py:110-138.
+    -> new_xyz [B,npoint,3], new_points [B,npoint,nsample,3+D] (SSG order: [xyz - centre, feats])."""
+    fps_idx = farthest_point_sample(xyz, npoint, start_idx)
+    new_xyz = ops.gather(xyz, fps_idx)
+    idx = ops.ball_query(radius, nsample, xyz, new_xyz)
+    new_points = ops.group_concat(xyz, new_xyz, points, idx, xyz_first=True)
+    if returnfps:
+        return new_xyz, new_points, ops.gather(xyz, idx), fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """models/pointnet2/pointnet2_utils.py:141-158 (no geometry: a view and a concat)."""
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device)
+    grouped_xyz = xyz.view(B, 1, N, C)
+    if points is not None:
+        return new_xyz, torch.cat([grouped_xyz, points.view(B, 1, N, -1)], dim=-1)
+    return new_xyz, grouped_xyz
+
+
+def _shared_mlp_max(new_points, convs, bns):
+    # [B, S, K, C] -> [B, C, K, S] -> Conv2d/BN/ReLU stack -> max over K  (:196-201)
+    x = new_points.permute(0, 3, 2, 1)
+    for conv, bn in zip(convs, bns):
+        x = F.relu(bn(conv(x)))
+    return torch.max(x, 2)[0]
+
+
+class PointNetSetAbstraction(nn.Module):
+    """models/pointnet2/pointnet2_utils.py:161-206."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all, remove_last=False):
+        super().__init__()
+        self.npoint, self.radius, self.nsample = npoint, radius, nsample
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last = out_channel
+        self.group_all = group_all
+        self.remove_last = remove_last
+        self.start_idx = None
+
+    def forward(self, xyz, points):
+        """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,D',S]."""
+        xyz = xyz.permute(0, 2, 1).contiguous()
+        if points is not None:
+            points = points.permute(0, 2, 1).contiguous()
+        if self.group_all:
+            new_xyz, new_points = sample_and_group_all(xyz, points)
+        else:
+            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points,
+                                                   start_idx=self.start_idx)
+        new_points = _shared_mlp_max(new_points, self.mlp_convs, self.mlp_bns)
+        if self.remove_last:
+            return new_points
+        return new_xyz.permute(0, 2, 1), new_points
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """models/pointnet2/pointnet2_utils.py:209-266: one FPS, one ball query + grouping + MLP per radius;
+    grouped features come first, centred coordinates last (:252)."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for widths in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            last = in_channel + 3
+            for out_channel in widths:
+                convs.append(nn.Conv2d(last, out_channel, 1))
+                bns.append(nn.BatchNorm2d(out_channel))
+                last = out_channel
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self.start_idx = None
+
+    def forward(self, xyz, points):
+        xyz = xyz.permute(0, 2, 1).contiguous()
+        if points is not None:
+            points = points.permute(0, 2, 1).contiguous()
+        new_xyz = ops.gather(xyz, farthest_point_sample(xyz, self.npoint, self.start_idx))
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            idx = ops.ball_query(radius, self.nsample_list[i], xyz, new_xyz)
+            grouped = ops.group_concat(xyz, new_xyz, points, idx, xyz_first=False)
+            outs.append(_shared_mlp_max(grouped, self.conv_blocks[i], self.bn_blocks[i]))
+        return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=1)
+
+
+def three_nn_interpolate(xyz1, xyz2, points2):
+    """Interpolation part of PointNetFeaturePropagation.forward (:297-307), channel-last:
+    xyz1 [B,N,3], xyz2 [B,S,3], points2 [B,S,D] -> [B,N,D].  Differentiable w.r.t. points2."""
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    if S == 1:
+        return points2.repeat(1, N, 1)
+    dist, idx = ops.three_nn(xyz1, xyz2)
+    return ops.three_interpolate(points2, idx, dist)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """models/pointnet2/pointnet2_utils.py:269-319."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last = out_channel
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        interpolated = three_nn_interpolate(xyz1.permute(0, 2, 1).contiguous(), xyz2.permute(0, 2, 1).contiguous(),
+                                            points2.permute(0, 2, 1).contiguous())
+        if points1 is not None:
+            new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)
+        else:
+            new_points = interpolated
+        new_points = new_points.permute(0, 2, 1)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            new_points = F.relu(bn(conv(new_points)))
+        return new_points

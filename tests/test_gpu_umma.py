@@ -13,9 +13,9 @@ CHILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_umma_child.py
 
 # N, K, mode (0 fp16, 1 bf16, 2 bf16x3), B MN-major, A from packed image
 VARIANTS = [
-    (128, 64, 0, 0, 0), (128, 128, 0, 0, 0), (128, 512, 0, 0, 0), (64, 256, 0, 0, 0), (32, 128, 0, 0, 0),
-    (256, 128, 0, 0, 0), (128, 128, 1, 0, 0), (128, 128, 0, 0, 1), (128, 512, 1, 0, 1), (64, 128, 2, 0, 0),
-    (64, 256, 2, 0, 1), (128, 128, 0, 1, 0), (128, 512, 0, 1, 1), (64, 128, 1, 1, 0),
+    (128, 64, 0, 0, 0), (128, 128, 0, 0, 0), (64, 512, 0, 0, 0), (64, 256, 0, 0, 0), (32, 128, 0, 0, 0),
+    (256, 128, 0, 0, 0), (128, 128, 1, 0, 0), (128, 128, 0, 0, 1), (64, 512, 1, 0, 1), (64, 128, 2, 0, 0),
+    (64, 256, 2, 0, 1), (128, 128, 0, 1, 0), (64, 512, 0, 1, 1), (64, 128, 1, 1, 0),
 ]
 
 

@@ -1,0 +1,163 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/ppt_b200.h declares, the
+host logic (weight folding / packing, sharding, gloo gather, patching) behaves, and nothing
+silently falls back to a CPU implementation."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ppt_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "ppt_b200.h")).read()
+    declared = set(re.findall(r"\b(ppt_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # raises if any symbol is missing
+    assert lib.ppt_abi_version() == _lib.ABI_VERSION
+    assert b"invalid" in lib.ppt_strerror(-1)
+    assert lib.ppt_encoder_packed_bytes(0) == 925696
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (\w+)", nm))
+    assert declared <= exported
+    assert not [s for s in exported if not s.startswith("ppt_")], "only the C ABI may be exported"
+
+
+def test_ops_refuse_cpu_tensors():
+    from ppt_b200 import ops, pointbert
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.knn(4, torch.zeros(1, 8, 3), torch.zeros(1, 2, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pointbert.Group(4, 2)(torch.zeros(1, 8, 3))
+
+
+def test_product_code_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ppt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle's rule", ""), (f, "product code mentions oracle/")
+
+
+def test_fold_and_pack():
+    from oracle import torch_port
+    from ppt_b200 import encoder_pack as ep
+    sd = torch_port.make_encoder_state()
+    f = ep.fold(sd)
+    x = (torch.rand(5, 32, 3, dtype=torch.float64) - 0.5) * 0.3
+    h1 = torch.relu(x @ f["W1"][:, :3].T + f["W1"][:, 3])
+    graw = (h1 @ f["W2"].T).max(1).values
+    h3 = torch.relu(h1 @ f["W32"].T + (graw @ f["W3A"].T + f["bias_c"])[:, None, :])
+    tok = (h3 @ f["W4"].T).max(1).values @ f["WR"].T + f["bias_tok"]
+    ref = torch_port.tokens_forward({k: v.double() for k, v in sd.items()}, x[None])[0]
+    assert float((tok - ref).abs().max() / ref.abs().max()) < 1e-12
+    for mode in (0, 1, 2):
+        assert ep.pack_encoder(sd, mode).numel() == ep.packed_bytes(mode)
+    # operand image layout == csrc/tc05.cuh sw128_kmajor_off
+    w = (torch.arange(256 * 128) % 1999).float().reshape(256, 128)
+    img = ep.pack_kmajor(w, torch.float16).view(torch.float16).reshape(2, 2, 128 * 64)
+    for r in (0, 3, 8, 77, 127, 128, 255):
+        for k in (0, 7, 8, 63, 64, 127):
+            off = (r % 128) * 128 + ((((k % 64) >> 3) ^ (r & 7)) * 16) + (k & 7) * 2
+            assert float(img[r // 128, k // 64, off // 2]) == float(w[r, k])
+    hi_lo = ep.pack_kmajor(torch.full((128, 64), 1.001), torch.bfloat16, split=2).view(torch.bfloat16).reshape(2, -1)
+    assert abs(float(hi_lo[0, 0]) + float(hi_lo[1, 0]) - 1.001) < 1e-5
+
+
+def test_shard_bounds_cover_everything_once():
+    from ppt_b200.tokenizer import shard_bounds
+    for total in (0, 1, 7, 128, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from ppt_b200.tokenizer import gather_tokens, shard_bounds
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    full = torch.arange(6 * 4 * 5, dtype=torch.float32).reshape(6, 4, 5)
+    lo, hi = shard_bounds(6, rank, world)
+    out = gather_tokens(full[lo:hi] * 1.0)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+def test_batch_shard_and_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference prints one JSON line with the contract's keys (tiny sample)."""
+    import json
+    env = dict(os.environ, PPT_BENCH_REF_CLOUDS="2", PPT_BENCH_REF_POINTS="1024")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "impl", "cpu_baseline", "e2e", "config", "n_gpus", "steps", "warmup"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0
+
+
+refonly = pytest.mark.skipif(not os.path.isdir("/root/reference/models/pointbert"),
+                             reason="reference tree only exists in the build container")
+
+
+@refonly
+def test_torch_port_is_bit_identical_to_the_reference():
+    from oracle import refimport, torch_port
+    from oracle.inputs import cloud
+    ns = refimport.load()
+    xyz = cloud("U", 2, 1500, 31)
+    with refimport.fixed_fps_start(0):
+        ref_nb, ref_c = ns.dvae.Group(64, 32)(xyz)
+    nb, c = torch_port.group_forward(xyz, 64, 32, 0)
+    assert torch.equal(nb, ref_nb) and torch.equal(c, ref_c)
+    q = xyz[:, :50].contiguous()
+    assert torch.equal(torch_port.ball_indices(0.3, 16, xyz, q), ns.pn2.query_ball_point(0.3, 16, xyz, q))
+    sd = torch_port.make_encoder_state()
+    enc = ns.dvae.Encoder(256).eval()
+    enc.load_state_dict({k: v for k, v in sd.items() if k in torch_port.ENCODER_KEYS}, strict=False)
+    with torch.no_grad():
+        assert torch.equal(enc(nb), torch_port.encoder_forward(sd, nb))
+
+
+@refonly
+def test_patch_reference_keeps_cpu_behaviour_and_is_reversible():
+    from oracle import refimport
+    from oracle.inputs import cloud
+    from ppt_b200 import patch
+    ns = refimport.load()
+    xyz = cloud("U", 1, 300, 5)
+    with refimport.fixed_fps_start(0):
+        before = ns.dvae.Group(16, 8)(xyz)
+    names = patch.patch_reference()
+    try:
+        assert "models.pointbert.dvae.knn_point" in names and "Group.forward" in names
+        assert hasattr(ns.dvae.knn_point, "__ppt_b200_original__")
+        with refimport.fixed_fps_start(0):
+            after = ns.dvae.Group(16, 8)(xyz)  # CPU tensors still take the reference's own code
+        assert torch.equal(before[0], after[0]) and torch.equal(before[1], after[1])
+    finally:
+        patch.unpatch_reference()
+    assert not hasattr(ns.dvae.knn_point, "__ppt_b200_original__")
