@@ -1,0 +1,213 @@
+"""The reference-facing layer (ppt_b200.pointbert / pointnet2 / patch / tokenizer) on the GPU:
+same signatures and results as the reference's functions and modules."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu, torch_port
+from oracle.inputs import cloud
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(t):
+    return np.ascontiguousarray(t.detach().cpu().numpy()).view(np.uint32)
+
+
+def test_group_module_matches_oracle_and_consumes_rng_like_the_reference():
+    from ppt_b200 import pointbert
+    xyz = cloud("U", 3, 2048, 77)
+    grp = pointbert.Group(128, 32)
+    grp.start_idx = 0
+    nb, center = grp(xyz.cuda())
+    o_nb, o_c, _, _ = cpu.group_forward(xyz.numpy(), 128, 32, 0)
+    assert nb.shape == (3, 128, 32, 3) and center.shape == (3, 128, 3)
+    assert np.array_equal(bits(nb), o_nb.view(np.uint32)) and np.array_equal(bits(center), o_c.view(np.uint32))
+    # default start: the reference's own torch.randint call on the device (misc.py:59)
+    grp.start_idx = None
+    torch.manual_seed(11)
+    nb2, c2 = grp(xyz.cuda())
+    torch.manual_seed(11)
+    start = torch.randint(0, 2048, (3,), dtype=torch.long, device="cuda")
+    want = np.stack([cpu.group_forward(xyz[i:i + 1].numpy(), 128, 32, int(start[i]))[1][0] for i in range(3)])
+    assert np.array_equal(bits(c2), want.view(np.uint32))
+    # function forms
+    idx = pointbert.farthest_point_sample(xyz.cuda(), 64, start_idx=0)
+    assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), cpu.farthest_point_sample(xyz.numpy(), 64, 0))
+    assert torch.equal(pointbert.fps(xyz.cuda(), 64, start_idx=0), pointbert.index_points(xyz.cuda(), idx))
+    k = pointbert.knn_point(8, xyz.cuda(), xyz[:, :10].contiguous().cuda())
+    assert np.array_equal(k.cpu().numpy(), cpu.knn_point(8, xyz.numpy(), xyz[:, :10].numpy()))
+    d = pointbert.square_distance(xyz[:, :10].contiguous().cuda(), xyz.cuda())
+    assert np.array_equal(bits(d), cpu.square_distance(xyz[:, :10].numpy(), xyz.numpy()).view(np.uint32))
+
+
+def test_encoder_module_state_dict_names_and_eval_output():
+    from ppt_b200 import pointbert
+    enc = pointbert.Encoder(256)
+    keys = set(enc.state_dict())
+    assert set(torch_port.ENCODER_KEYS) <= keys
+    assert keys - set(torch_port.ENCODER_KEYS) == {"first_conv.1.num_batches_tracked",
+                                                   "second_conv.1.num_batches_tracked"}
+    sd = torch_port.make_encoder_state()
+    enc.load_state_dict({k: v for k, v in sd.items() if k in torch_port.ENCODER_KEYS}, strict=False)
+    enc = enc.cuda().eval()
+    nb = (torch.rand(2, 70, 32, 3, generator=torch.Generator().manual_seed(5)) - 0.5) * 0.5
+    with torch.no_grad():
+        got = enc(nb.cuda())
+        ref = torch_port.encoder_forward(sd, nb)
+    assert got.shape == (2, 70, 256)
+    assert float((got.cpu() - ref).abs().max() / ref.abs().max()) <= 1e-3
+    # weights change -> repack (version counter), not a stale blob
+    with torch.no_grad():
+        enc.second_conv[3].bias.add_(1.0)
+        got2 = enc(nb.cuda())
+    assert float((got2 - got - 1.0).abs().max()) < 1e-3
+    # train(): batch-statistics BatchNorm through the module's own layers
+    enc.train()
+    before = enc.first_conv[1].running_mean.clone()
+    out = enc(nb.cuda())
+    assert out.shape == (2, 70, 256) and not torch.equal(before, enc.first_conv[1].running_mean)
+
+
+def test_tokenizer_end_to_end_and_fp32_parity_mode():
+    from ppt_b200.tokenizer import PointTokenizer
+    sd = torch_port.make_encoder_state()
+    xyz = cloud("S", 2, 4096, 21)
+    o_nb, o_c, _, _ = cpu.group_forward(xyz.numpy(), 256, 32, 0)
+    with torch.no_grad():
+        ref = torch_port.tokens_forward(sd, torch.from_numpy(o_nb))
+    for precision, tol in (("fp16", 1e-3), ("fp32", 2e-5)):
+        tok = PointTokenizer(256, 32, precision=precision).cuda().eval().load_reference_state(sd)
+        tok.start_idx = 0
+        tokens, center, nb = tok(xyz.cuda(), return_neighborhood=True)
+        assert tokens.shape == (2, 256, 384)
+        assert np.array_equal(bits(nb), o_nb.view(np.uint32)) and np.array_equal(bits(center), o_c.view(np.uint32))
+        err = float((tokens.cpu() - ref).abs().max() / ref.abs().max())
+        assert err <= tol, (precision, err)
+
+
+def _ssg_reference(sa, xyz, feats):
+    """Same module arithmetic on CPU with the oracle's grouping."""
+    f = cpu.farthest_point_sample(xyz.numpy(), sa.npoint, 0)
+    c = cpu.index_points(xyz.numpy(), f)
+    b = cpu.query_ball_point(sa.radius, sa.nsample, xyz.numpy(), c)
+    g = cpu.group_center(xyz.numpy(), b, c)
+    if feats is not None:
+        g = np.concatenate([g, cpu.index_points(feats.numpy(), b)], -1)
+    x = torch.from_numpy(g).permute(0, 3, 2, 1)
+    for conv, bn in zip(sa.mlp_convs, sa.mlp_bns):
+        x = torch.relu(bn(conv(x)))
+    return torch.from_numpy(c).permute(0, 2, 1), x.max(2)[0]
+
+
+def test_set_abstraction_modules():
+    from ppt_b200 import pointnet2
+    torch.manual_seed(0)
+    xyz = cloud("S", 2, 1024, 3)
+    feats = torch.randn(2, 1024, 16)
+    sa = pointnet2.PointNetSetAbstraction(128, 0.3, 32, 16 + 3, [32, 64], False).eval()
+    sa.start_idx = 0
+    with torch.no_grad():
+        want_xyz, want = _ssg_reference(sa, xyz, feats)
+        sa.cuda()
+        got_xyz, got = sa(xyz.permute(0, 2, 1).cuda(), feats.permute(0, 2, 1).cuda())
+    assert got_xyz.shape == (2, 3, 128) and got.shape == (2, 64, 128)
+    assert torch.equal(got_xyz.cpu(), want_xyz)
+    assert float((got.cpu() - want).abs().max()) < 1e-4
+    # MSG: [feats, xyz - centre] order, one FPS
+    msg = pointnet2.PointNetSetAbstractionMsg(64, [0.2, 0.4], [8, 16], 16, [[16, 32], [16, 48]]).eval()
+    msg.start_idx = 0
+    with torch.no_grad():
+        f = cpu.farthest_point_sample(xyz.numpy(), 64, 0)
+        c = cpu.index_points(xyz.numpy(), f)
+        outs = []
+        for i, (r, k) in enumerate(((0.2, 8), (0.4, 16))):
+            b = cpu.query_ball_point(r, k, xyz.numpy(), c)
+            g = np.concatenate([cpu.index_points(feats.numpy(), b), cpu.group_center(xyz.numpy(), b, c)], -1)
+            x = torch.from_numpy(g).permute(0, 3, 2, 1)
+            for conv, bn in zip(msg.conv_blocks[i], msg.bn_blocks[i]):
+                x = torch.relu(bn(conv(x)))
+            outs.append(x.max(2)[0])
+        want = torch.cat(outs, 1)
+        msg.cuda()
+        _, got = msg(xyz.permute(0, 2, 1).cuda(), feats.permute(0, 2, 1).cuda())
+    assert got.shape == (2, 80, 64) and float((got.cpu() - want).abs().max()) < 1e-4
+    # function form and returnfps
+    nx, npts, gx, fi = pointnet2.sample_and_group(128, 0.3, 32, xyz.cuda(), feats.cuda(), returnfps=True, start_idx=0)
+    assert npts.shape == (2, 128, 32, 19) and gx.shape == (2, 128, 32, 3) and fi.shape == (2, 128)
+    assert torch.equal(npts[..., :3], gx - nx.unsqueeze(2))
+
+
+def test_feature_propagation_module_forward_and_backward():
+    from ppt_b200 import pointnet2
+    torch.manual_seed(1)
+    xyz1, xyz2 = cloud("S", 2, 512, 8), cloud("S", 2, 64, 9)
+    p1, p2 = torch.randn(2, 5, 512), torch.randn(2, 24, 64)
+    fp = pointnet2.PointNetFeaturePropagation(5 + 24, [32]).eval()
+    with torch.no_grad():
+        interp = torch_port.three_nn_interpolate(xyz1, xyz2, p2.permute(0, 2, 1))
+        x = torch.cat([p1.permute(0, 2, 1), interp], -1).permute(0, 2, 1)
+        want = torch.relu(fp.mlp_bns[0](fp.mlp_convs[0](x)))
+    fp.cuda()
+    p2g = p2.cuda().requires_grad_(True)
+    got = fp(xyz1.permute(0, 2, 1).cuda(), xyz2.permute(0, 2, 1).cuda(), p1.cuda(), p2g)
+    assert got.shape == (2, 32, 512) and float((got.detach().cpu() - want).abs().max()) < 1e-4
+    got.sum().backward()
+    assert p2g.grad is not None and p2g.grad.shape == p2.shape and float(p2g.grad.abs().sum()) > 0
+    # S == 1 branch: plain repeat (pointnet2_utils.py:297-298)
+    one = pointnet2.three_nn_interpolate(xyz1.cuda(), xyz2[:, :1].contiguous().cuda(), p2[:, :, :1].permute(0, 2, 1).cuda())
+    assert one.shape == (2, 512, 24) and torch.equal(one[:, 0], one[:, 100])
+
+
+def test_patch_reference_diverts_cuda_tensors_on_a_stand_in_tree():
+    """The reference tree does not exist on the GPU box: a stand-in with the reference's module
+    and attribute names (bodies from the torch-op port) shows the rebinding works on CUDA tensors."""
+    from ppt_b200 import patch
+
+    class Group(torch.nn.Module):
+        def __init__(self, num_group, group_size):
+            super().__init__()
+            self.num_group, self.group_size = num_group, group_size
+
+        def forward(self, xyz):
+            return torch_port.group_forward(xyz, self.num_group, self.group_size, 0)
+
+    class Encoder(torch.nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.encoder_channel = c
+
+        def forward(self, pg):
+            raise AssertionError("reference body must not run for CUDA eval input")
+
+    mods = {}
+    for name in ("models", "models.pointbert", "models.pointbert.dvae"):
+        mods[name] = types.ModuleType(name)
+    dvae = mods["models.pointbert.dvae"]
+    dvae.knn_point = lambda k, xyz, q: torch_port.knn_indices(k, xyz, q)
+    dvae.square_distance = torch_port.pairwise_sqdist
+    dvae.Group, dvae.Encoder = Group, Encoder
+    saved = {n: sys.modules.get(n) for n in mods}
+    sys.modules.update(mods)
+    try:
+        names = patch.patch_reference(["models.pointbert.dvae"])
+        assert "models.pointbert.dvae.knn_point" in names
+        xyz = cloud("U", 2, 1024, 1)
+        q = xyz[:, :20].contiguous()
+        got = dvae.knn_point(16, xyz.cuda(), q.cuda())  # CUDA -> kernels
+        assert got.is_cuda and np.array_equal(got.cpu().numpy(), cpu.knn_point(16, xyz.numpy(), q.numpy()))
+        cpu_got = dvae.knn_point(16, xyz, q)             # CPU -> the tree's own code
+        assert not cpu_got.is_cuda
+        torch.manual_seed(0)
+        nb, c = dvae.Group(32, 8)(xyz.cuda())
+        assert nb.is_cuda and nb.shape == (2, 32, 8, 3)
+    finally:
+        patch.unpatch_reference()
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
