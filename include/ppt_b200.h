@@ -36,7 +36,7 @@ extern "C" {
 /* Precision modes of the patch Encoder. */
 #define PPT_ENC_FP16 0   /* fp16 operands, fp32 accumulate (tcgen05 kind::f16) */
 #define PPT_ENC_BF16 1   /* bf16 operands, fp32 accumulate */
-#define PPT_ENC_BF16X3 2 /* bf16 hi/lo split, 3 MMAs per product: fp32-parity mode */
+#define PPT_ENC_FP16X3 2 /* fp16 hi/lo split (power-of-two pre-scaled), 3 MMAs per product: fp32-parity mode */
 
 int ppt_abi_version(void);
 

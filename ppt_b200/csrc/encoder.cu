@@ -16,10 +16,14 @@
 // and the ACTIVATIONS the B operand (points = TMEM columns).  A thread of the
 // epilogue therefore owns one output channel: its bias is one register and the
 // max over a 32-point group is a max over 32 of its own registers -- no shuffles.
+// h1 is written by point-owning threads as a K-major operand (16-byte stores along the
+// channels); h3 is written by channel-owning threads as an MN-major operand (16-byte
+// stores along the points), each pair of values converted, ReLU'd and saturated by one
+// F2FP instruction.
 //
 // Pipeline per CTA (persistent over tiles): warp 0 streams 16 KB weight images from
 // L2 with 1-D bulk async copies into a ring (full/empty mbarriers); warp 1 issues
-// tcgen05.mma into two alternating TMEM accumulators; warps 2-5 build h1, drain the
+// tcgen05.mma into two alternating TMEM accumulators; warps 2-9 build h1, drain the
 // accumulators (tcgen05.ld), apply bias/ReLU/max and write the next operand.
 #include "common.cuh"
 #include "tc05.cuh"
@@ -28,9 +32,12 @@ namespace {
 
 using namespace tc05;
 
-constexpr int ENC_THREADS = 192;      // producer warp, MMA warp, 4 epilogue warps
-constexpr int EPI_THREADS = 128;
+constexpr int ENC_THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps
+constexpr int EPI_THREADS = 256;
+constexpr int LIN_THREADS = 192;      // group_linear: producer, MMA, 4 epilogue warps
+constexpr int LIN_EPI = 128;
 constexpr uint32_t IMG = 16384;       // one operand image: 128 rows x 64 K x 2 B
+constexpr uint32_t MNBLK = 65536;     // MN-major h3: bytes between 64-point blocks (64 K-atoms x 1 KB)
 
 // ---- packed weight blob (ppt_b200/encoder_pack.py) -----------------------------------
 struct BlobLayout {
@@ -39,6 +46,9 @@ struct BlobLayout {
   __host__ __device__ uint32_t bias_c() const { return 2048; }   // [512]
   __host__ __device__ uint32_t b4() const { return 4096; }       // [256]
   __host__ __device__ uint32_t bias_tok() const { return 5120; } // [384]
+  // [8] powers of two: 1/scale of {stage1, linear c, stage2 W32, stage2 W4, linear tokens} accumulators,
+  // scale of the point activations (h1, h3), scale of the group operands (g, t), unused
+  __host__ __device__ uint32_t scales() const { return 6656; }
   __host__ __device__ uint32_t W2() const { return 8192; }                       // 2 units x 2 chunks
   __host__ __device__ uint32_t W3A() const { return W2() + 4 * split * IMG; }    // 4 x 4
   __host__ __device__ uint32_t W32() const { return W3A() + 16 * split * IMG; }  // 4 x 2
@@ -53,17 +63,25 @@ struct Ring {  // position in a ring of mbarrier-guarded stages
   template <int NSTAGE> __device__ uint32_t parity() const { return (it / NSTAGE) & 1u; }
 };
 
-template <uint32_t FMT, int SPLIT>
+// One 64-wide K chunk = four K=16 instructions (x3 passes in the hi/lo split mode: hi*hi, hi*lo, lo*hi).
+// B_MN = false: B is K-major, `b_addr` points at the chunk (rows 128 B apart).
+// B_MN = true : B is MN-major, `b_addr` points at the operand base, `kc` selects the K-atoms.
+template <int SPLIT, bool B_MN>
 __device__ __forceinline__ void issue_k64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t b_split_bytes,
-                                          uint32_t idesc, bool first) {
-  // One 64-wide K chunk = four K=16 instructions (x3 passes in the hi/lo split mode).
+                                          int kc, uint32_t idesc, bool first) {
 #pragma unroll
   for (int k16 = 0; k16 < 4; ++k16) {
 #pragma unroll
     for (int pass = 0; pass < (SPLIT == 2 ? 3 : 1); ++pass) {
-      const uint32_t sa = pass == 2 ? 1 : 0, sb = pass == 1 ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+      const uint32_t sa = pass == 2 ? 1 : 0, sb = pass == 1 ? 1 : 0;
       const uint64_t ad = make_sdesc(a_addr + sa * IMG + k16 * 32u, 16u, 1024u);
-      const uint64_t bd = make_sdesc(b_addr + sb * b_split_bytes + k16 * 32u, 16u, 1024u);
+      uint64_t bd;
+      if (B_MN) {
+        const uint32_t atom = (uint32_t)kc * 8u + (uint32_t)k16 * 2u;  // K index / 8
+        bd = make_sdesc(b_addr + sb * b_split_bytes + atom * 1024u, MNBLK, 1024u);
+      } else {
+        bd = make_sdesc(b_addr + sb * b_split_bytes + k16 * 32u, 16u, 1024u);
+      }
       umma_f16(d_tmem, ad, bd, idesc, (first && k16 == 0 && pass == 0) ? 0u : 1u);
     }
   }
@@ -75,6 +93,24 @@ __device__ __forceinline__ void store_operand(unsigned char* base, uint32_t off,
   const uint16_t hi = to_operand<FMT>(v);
   *reinterpret_cast<uint16_t*>(base + off) = hi;
   if (SPLIT == 2) *reinterpret_cast<uint16_t*>(base + split_bytes + off) = to_operand<FMT>(v - from_operand<FMT>(hi));
+}
+
+// Eight consecutive operand elements (16 bytes) from eight fp32 values, ReLU fused; lo parts in split mode.
+template <uint32_t FMT, int SPLIT>
+__device__ __forceinline__ void store_relu8(unsigned char* base, uint32_t off, uint32_t split_bytes, const float* v) {
+  uint32_t hi[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) hi[t] = pack2<FMT, true>(v[2 * t], v[2 * t + 1]);
+  *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (SPLIT == 2) {
+    uint32_t lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 h = unpack2<FMT>(hi[t]);
+      lo[t] = pack2<FMT, false>(fmaxf(v[2 * t], 0.f) - h.x, fmaxf(v[2 * t + 1], 0.f) - h.y);
+    }
+    *reinterpret_cast<uint4*>(base + split_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
 // ======================================================================================
@@ -90,34 +126,46 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int GPT = NT / 32;                       // groups per tile
   constexpr int NUNITS = STAGE == 1 ? 2 : 6;
-  constexpr uint32_t H1_BYTES = 2u * NT * 128u;      // per split copy: 2 chunks
-  constexpr uint32_t H3_BYTES = STAGE == 2 ? 8u * NT * 128u : 0u;
+  constexpr int NH1 = STAGE == 1 ? 2 : 1;            // h1 buffers (stage 1 builds one tile ahead)
+  constexpr uint32_t H1_BYTES = 2u * NT * 128u;      // one split part of one buffer: 2 K-chunks, K-major
+  constexpr uint32_t H1_BUF = SPLIT * H1_BYTES;
+  constexpr uint32_t H3_BYTES = STAGE == 2 ? (NT / 64) * MNBLK : 0u;  // one split part, MN-major
   constexpr uint32_t STAGE_BYTES = SPLIT * IMG;
   constexpr int TCOLS = 2 * NT;
+  constexpr int CPW = NT / 2;                        // accumulator columns per epilogue thread
+  constexpr int GH = CPW / 32;                       // groups per epilogue thread
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* h1buf = smem;                                   // [SPLIT][2][NT x 128 B]
-  unsigned char* h3buf = h1buf + SPLIT * H1_BYTES;               // [SPLIT][8][NT x 128 B]
+  unsigned char* h1buf = smem;                                   // [NH1][SPLIT][2][NT x 128 B]
+  unsigned char* h3buf = h1buf + NH1 * H1_BUF;                   // [SPLIT][NT/64][64][1 KB]
   unsigned char* ring = h3buf + SPLIT * H3_BYTES;                // [NSTAGE][SPLIT][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_BYTES);
   uint64_t* full = bars;                   // [NSTAGE]
   uint64_t* empty = full + NSTAGE;         // [NSTAGE]
   uint64_t* acc_full = empty + NSTAGE;     // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
-  uint64_t* h1_ready = acc_empty + 2;      // [1]
-  uint64_t* h3_ready = h1_ready + 1;       // [4]
+  uint64_t* h1_ready = acc_empty + 2;      // [2]
+  uint64_t* h3_ready = h1_ready + 2;       // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h3_ready + 4);
+  float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [128]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BlobLayout L{(uint32_t)SPLIT};
+  const float* sc = reinterpret_cast<const float*>(blob + L.scales());
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_THREADS); }
-    mbar_init(h1_ready, EPI_THREADS);
+    for (int i = 0; i < 2; ++i) mbar_init(&h1_ready[i], EPI_THREADS);
     for (int i = 0; i < 4; ++i) mbar_init(&h3_ready[i], EPI_THREADS);
     mbar_fence_init();
+  }
+  if (tid < 128) {  // W1' rows pre-multiplied by the activation scale (a power of two: exact)
+    float4 w = __ldg(reinterpret_cast<const float4*>(blob + L.w1()) + tid);
+    const float s = __ldg(sc + 5);
+    w.x *= s; w.y *= s; w.z *= s; w.w *= s;
+    w1s[tid] = w;
   }
   if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
   fence_before_sync();
@@ -138,7 +186,7 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
           const int blk = g3 ? u - 4 : u;
           for (int kc = 0; kc < nkc; ++kc) {
             const uint32_t s = r.stage<NSTAGE>();
-            mbar_wait(&empty[s], r.parity<NSTAGE>() ^ 1u);
+            mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
             mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
             bulk_g2s(ring + s * STAGE_BYTES, blob + sec + (size_t)(blk * nkc + kc) * STAGE_BYTES, STAGE_BYTES,
                      &full[s]);
@@ -150,11 +198,12 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     Ring r;
-    const uint32_t idesc = make_idesc(FMT, 128, NT, 0);
+    const uint32_t idesc_k = make_idesc(FMT, 128, NT, 0), idesc_mn = make_idesc(FMT, 128, NT, 1);
     const uint32_t ring_addr = smem_u32(ring), h1_addr = smem_u32(h1buf), h3_addr = smem_u32(h3buf);
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      mbar_wait(h1_ready, tile_it & 1u);
+      mbar_wait(&h1_ready[tile_it % NH1], (tile_it / NH1) & 1u);
+      const uint32_t h1_cur = h1_addr + (tile_it % NH1) * H1_BUF;
 #pragma unroll 1
       for (int u = 0; u < NUNITS; ++u) {
         const bool g3 = STAGE == 2 && u >= 4;
@@ -166,16 +215,18 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
         fence_after_sync();
         const uint32_t d_tmem = tbase + (uint32_t)(buf * NT);
         for (int kc = 0; kc < nkc; ++kc) {
-          if (STAGE == 2 && u == 4 && (kc & 1) == 0) {  // h3 K-chunks 2i, 2i+1 come from unit i's epilogue
+          if (STAGE == 2 && u == 4 && (kc & 1) == 0) {  // h3 channels of K-chunks 2i, 2i+1 come from unit i
             mbar_wait(&h3_ready[kc >> 1], tile_it & 1u);
           }
           const uint32_t s = r.stage<NSTAGE>();
           mbar_wait(&full[s], r.parity<NSTAGE>());
           fence_after_sync();
           if (lane == 0) {
-            const uint32_t b_addr = (g3 ? h3_addr : h1_addr) + (uint32_t)kc * (NT * 128u);
-            issue_k64<FMT, SPLIT>(d_tmem, ring_addr + s * STAGE_BYTES, b_addr, g3 ? H3_BYTES : H1_BYTES, idesc,
-                                  kc == 0);
+            if (g3)
+              issue_k64<SPLIT, true>(d_tmem, ring_addr + s * STAGE_BYTES, h3_addr, H3_BYTES, kc, idesc_mn, kc == 0);
+            else
+              issue_k64<SPLIT, false>(d_tmem, ring_addr + s * STAGE_BYTES, h1_cur + (uint32_t)kc * (NT * 128u),
+                                      H1_BYTES, kc, idesc_k, kc == 0);
             umma_commit(&empty[s]);
           }
           __syncwarp();
@@ -186,105 +237,121 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int e = tid - 64;                 // 0..127
+    // ===================== epilogue warps (2..9) =====================
+    const int e = tid - 64;                 // 0..255
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;       // which half of the accumulator columns
     const int m = quad * 32 + lane;         // output-channel row inside a 128-row unit
-    const float4* w1 = reinterpret_cast<const float4*>(blob + L.w1());
+    const int col0 = half * CPW;
     const float* bias_b4 = reinterpret_cast<const float*>(blob + L.b4());
+    const float inv_p1 = __ldg(sc + 0), inv_g3 = __ldg(sc + 3);
+    const float act_scale = __ldg(sc + 5), grp_scale = __ldg(sc + 6);
+    const float inv_p2s = __ldg(sc + 2) * act_scale;  // accumulator -> scaled activation, one FFMA per element
 
-    auto build_h1 = [&](int tile) {
+    auto build_h1 = [&](int tile, uint32_t slot) {
       // h1[p][ch] = relu(w.x + b), K = 3 on CUDA cores; written as the K-major B operand.
       constexpr int TPP = EPI_THREADS / NT;          // threads per point
       constexpr int CH = 128 / TPP;                  // channels per thread
-      const int p = e % NT, ch0 = (e / NT) * CH;
+      const int p = e % NT, ch0 = (e / NT) * CH;     // ch0 is warp-uniform: w1s reads broadcast
+      unsigned char* dst = h1buf + slot * H1_BUF;
       const long long gp = (long long)tile * NT + p;
       float x = 0.f, y = 0.f, z = 0.f;
       if (gp < num_groups * 32) {
         const float* src = nbhd + gp * 3;
         x = src[0]; y = src[1]; z = src[2];
       }
-#pragma unroll 2
+#pragma unroll 4
       for (int c8 = 0; c8 < CH; c8 += 8) {
-        uint32_t hi[4], lo[4];
+        float v[8];
 #pragma unroll
-        for (int t = 0; t < 8; t += 2) {
-          float v[2];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 w = __ldg(w1 + ch0 + c8 + t + q);
-            v[q] = fmaxf(fmaf(w.z, z, fmaf(w.y, y, fmaf(w.x, x, w.w))), 0.f);
-          }
-          const uint16_t h0 = to_operand<FMT>(v[0]), h1v = to_operand<FMT>(v[1]);
-          hi[t >> 1] = (uint32_t)h0 | ((uint32_t)h1v << 16);
-          if (SPLIT == 2)
-            lo[t >> 1] = (uint32_t)to_operand<FMT>(v[0] - from_operand<FMT>(h0)) |
-                         ((uint32_t)to_operand<FMT>(v[1] - from_operand<FMT>(h1v)) << 16);
+        for (int t = 0; t < 8; ++t) {
+          const float4 w = w1s[ch0 + c8 + t];
+          v[t] = fmaf(w.z, z, fmaf(w.y, y, fmaf(w.x, x, w.w)));
         }
         const int ch = ch0 + c8;
-        const uint32_t off = (uint32_t)(ch >> 6) * (NT * 128u) + sw128_kmajor_off(p, ch & 63);
-        *reinterpret_cast<uint4*>(h1buf + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (SPLIT == 2) *reinterpret_cast<uint4*>(h1buf + H1_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        store_relu8<FMT, SPLIT>(dst, (uint32_t)(ch >> 6) * (NT * 128u) + sw128_kmajor_off(p, ch & 63), H1_BYTES, v);
       }
       fence_proxy_async_smem();
-      mbar_arrive(h1_ready);
+      mbar_arrive(&h1_ready[slot]);
     };
 
-    if ((int)blockIdx.x < num_tiles) build_h1(blockIdx.x);
+    float cnext[4][GH];
+    auto load_c = [&](int tile) {
+      if (STAGE != 2) return;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int jj = 0; jj < GH; ++jj) {
+          const long long g = (long long)tile * GPT + half * GH + jj;
+          cnext[u][jj] = g < num_groups ? __ldg(cbuf + g * 512 + u * 128 + m) * act_scale : 0.f;
+        }
+    };
+
+    if ((int)blockIdx.x < num_tiles) {
+      load_c(blockIdx.x);
+      build_h1(blockIdx.x, 0);
+      if (STAGE == 1 && (int)(blockIdx.x + gridDim.x) < num_tiles) build_h1(blockIdx.x + gridDim.x, 1);
+    }
 
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      const long long g0 = (long long)tile * GPT;  // first group of this tile
-#pragma unroll 1
+      const long long g0 = (long long)tile * GPT + half * GH;  // first group this thread touches
+      float ccur[4][GH];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int jj = 0; jj < GH; ++jj) ccur[u][jj] = STAGE == 2 ? cnext[u][jj] : 0.f;
+
+#pragma unroll
       for (int u = 0; u < NUNITS; ++u) {
         const int buf = u & 1;
         const bool relu_unit = STAGE == 2 && u < 4;
-        float cval[GPT];
-        if (relu_unit) {
-#pragma unroll
-          for (int j = 0; j < GPT; ++j)
-            cval[j] = (g0 + j < num_groups) ? __ldg(cbuf + (g0 + j) * 512 + u * 128 + m) : 0.f;
-        }
         mbar_wait(&acc_full[buf], (tile_it * (NUNITS / 2) + (uint32_t)(u >> 1)) & 1u);
         fence_after_sync();
-        const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * NT);
+        const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * NT + col0);
 
         if (relu_unit) {
-          // h3[p][ch] = relu(acc + c[group][ch]); ch = u*128 + m is this thread's K index.
+          // h3[p][ch] = relu(acc + c[group][ch]); ch = u*128 + m is this thread's K index (MN-major B).
           const int ch = u * 128 + m;
-          const uint32_t kbase = (uint32_t)(ch >> 6) * (NT * 128u) + (uint32_t)(ch & 7) * 2u;
-          const uint32_t piece = (uint32_t)((ch & 63) >> 3);
+          const uint32_t krow = (uint32_t)(ch >> 3) * 1024u + (uint32_t)(ch & 7) * 128u;
+          const uint32_t sw = (uint32_t)(ch & 7);
 #pragma unroll
-          for (int j = 0; j < GPT; ++j) {
+          for (int jj = 0; jj < GH; ++jj) {
             float v[32];
-            tmem_ld32(t_addr + j * 32, v);
+            tmem_ld32(t_addr + jj * 32, v);
+            const float cv = ccur[u < 4 ? u : 0][jj];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int p = j * 32 + i;
-              const uint32_t off = kbase + (uint32_t)p * 128u + ((piece ^ (uint32_t)(i & 7)) << 4);
-              store_operand<FMT, SPLIT>(h3buf, off, H3_BYTES, fmaxf(v[i] + cval[j], 0.f));
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], inv_p2s, cv);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int n = col0 + jj * 32 + q * 8;
+              const uint32_t off = (uint32_t)(n >> 6) * MNBLK + krow + ((((uint32_t)(n & 63) >> 3) ^ sw) << 4);
+              store_relu8<FMT, SPLIT>(h3buf, off, H3_BYTES, v + q * 8);
             }
           }
           fence_proxy_async_smem();
           fence_before_sync();
           mbar_arrive(&acc_empty[buf]);
-          mbar_arrive(&h3_ready[u]);
+          mbar_arrive(&h3_ready[u & 3]);
         } else {
           // per-group max over the 32 points (columns) this thread holds for its channel
           const int blk = STAGE == 1 ? u : u - 4;
           const int ch = blk * 128 + m;  // 0..255
+          const float inv = STAGE == 1 ? inv_p1 : inv_g3;
 #pragma unroll
-          for (int j = 0; j < GPT; ++j) {
+          for (int jj = 0; jj < GH; ++jj) {
             float v[32];
-            tmem_ld32(t_addr + j * 32, v);
+            tmem_ld32(t_addr + jj * 32, v);
             float mx = v[0];
 #pragma unroll
             for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
-            const long long g = g0 + j;
+            mx *= inv;  // exact: power of two
+            const long long g = g0 + jj;
             if (g < num_groups) {
               // operand image for group_linear: tile of 128 groups, K = 256 -> 4 chunks
               const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * (SPLIT * IMG);
-              store_operand<FMT, SPLIT>(out_img + img, sw128_kmajor_off((int)(g & 127), ch & 63), IMG, mx);
+              store_operand<FMT, SPLIT>(out_img + img, sw128_kmajor_off((int)(g & 127), ch & 63), IMG,
+                                        mx * grp_scale);
               if (STAGE == 2 && features_out) features_out[g * 256 + ch] = mx + __ldg(bias_b4 + ch);
             }
           }
@@ -292,11 +359,20 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
           mbar_arrive(&acc_empty[buf]);
         }
 
-        // every MMA that reads h1 has completed once the last h1-consuming unit's accumulator is full
-        if (u == (STAGE == 1 ? 1 : 3)) {
+        // Stage 2: every MMA that reads h1 has completed once unit 3's accumulator is full -> rebuild it
+        // for the next tile while the tensor pipe runs the W4 units; fetch that tile's c values too.
+        if (STAGE == 2 && u == 3) {
           const int next = tile + gridDim.x;
-          if (next < num_tiles) build_h1(next);
+          if (next < num_tiles) {
+            load_c(next);
+            build_h1(next, 0);
+          }
         }
+      }
+      // Stage 1: both units of this tile are drained, so its h1 buffer is free for tile + 2.
+      if (STAGE == 1) {
+        const int next2 = tile + 2 * gridDim.x;
+        if (next2 < num_tiles) build_h1(next2, tile_it & 1u);
       }
     }
   }
@@ -310,9 +386,10 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 // group_linear: out[g][o] = sum_k W[o][k] * act[g][k] + bias[o], act given as operand images
 // ======================================================================================
 template <uint32_t FMT, int SPLIT, int NUNITS>
-__global__ void __launch_bounds__(ENC_THREADS, 1)
+__global__ void __launch_bounds__(LIN_THREADS, 1)
 group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned char* __restrict__ wsec,
-                    const float* __restrict__ bias, float* __restrict__ out, long long num_groups, int num_tiles) {
+                    const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ out,
+                    long long num_groups, int num_tiles) {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int NT = 128;                      // groups per tile (MMA N)
   constexpr int NOUT = NUNITS * 128;
@@ -336,7 +413,7 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], LIN_EPI); }
     mbar_init(b_full, 1);
     mbar_init(b_empty, 1);
     mbar_fence_init();
@@ -352,7 +429,7 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
       Ring r;
       uint32_t tile_it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-        mbar_wait(b_empty, (tile_it & 1u) ^ 1u);
+        mbar_wait_relaxed(b_empty, (tile_it & 1u) ^ 1u);
         mbar_arrive_expect_tx(b_full, B_BYTES);
         for (int kc = 0; kc < 4; ++kc)
           bulk_g2s(bbuf + kc * STAGE_BYTES, act_img + ((size_t)tile * 4 + kc) * STAGE_BYTES, STAGE_BYTES, b_full);
@@ -360,7 +437,7 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
         for (int u = 0; u < NUNITS; ++u)
           for (int kc = 0; kc < 4; ++kc) {
             const uint32_t s = r.stage<NSTAGE>();
-            mbar_wait(&empty[s], r.parity<NSTAGE>() ^ 1u);
+            mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
             mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
             bulk_g2s(ring + s * STAGE_BYTES, wsec + (size_t)(u * 4 + kc) * STAGE_BYTES, STAGE_BYTES, &full[s]);
             ++r.it;
@@ -385,8 +462,8 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
           fence_after_sync();
           if (lane == 0) {
             // activation image order is [kc][split]: the lo copy sits IMG bytes after the hi copy
-            issue_k64<FMT, SPLIT>(tbase + (uint32_t)(buf * NT), ring_addr + s * STAGE_BYTES,
-                                  b_addr0 + kc * STAGE_BYTES, IMG, idesc, kc == 0);
+            issue_k64<SPLIT, false>(tbase + (uint32_t)(buf * NT), ring_addr + s * STAGE_BYTES,
+                                    b_addr0 + kc * STAGE_BYTES, IMG, kc, idesc, kc == 0);
             umma_commit(&empty[s]);
           }
           __syncwarp();
@@ -402,6 +479,7 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
   } else {
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
+    const float inv_scale = __ldg(inv_scale_ptr);
     uint32_t unit_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -419,7 +497,7 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
           const long long g0 = (long long)tile * NT + j * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (g0 + i < num_groups) out[(g0 + i) * NOUT + o] = v[i] + bo;
+            if (g0 + i < num_groups) out[(g0 + i) * NOUT + o] = fmaf(v[i], inv_scale, bo);
         }
         fence_before_sync();
         mbar_arrive(&acc_empty[buf]);
@@ -438,13 +516,13 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
 template <int SPLIT, int NT, int STAGE>
 constexpr size_t stage_smem_bytes() {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
-  return (size_t)SPLIT * (2u * NT * 128u) + (STAGE == 2 ? (size_t)SPLIT * (8u * NT * 128u) : 0) +
-         (size_t)NSTAGE * SPLIT * IMG + (2 * NSTAGE + 9) * 8 + 16;
+  return (size_t)(STAGE == 1 ? 2 : 1) * SPLIT * (2u * NT * 128u) + (STAGE == 2 ? (size_t)SPLIT * (NT / 64) * MNBLK : 0) +
+         (size_t)NSTAGE * SPLIT * IMG + 256 + 2048;
 }
 template <int SPLIT>
 constexpr size_t linear_smem_bytes() {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
-  return (size_t)4 * SPLIT * IMG + (size_t)NSTAGE * SPLIT * IMG + (2 * NSTAGE + 6) * 8 + 16;
+  return (size_t)4 * SPLIT * IMG + (size_t)NSTAGE * SPLIT * IMG + 256;
 }
 
 int num_sms() {
@@ -482,6 +560,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
   constexpr size_t s1 = stage_smem_bytes<SPLIT, NT, 1>(), s2 = stage_smem_bytes<SPLIT, NT, 2>(),
                    sl = linear_smem_bytes<SPLIT>();
+  static_assert(s2 <= 232448 && s1 <= 232448 && sl <= 232448, "shared memory budget (227 KB per CTA)");
   static bool configured = false;
   if (!configured) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
@@ -496,31 +575,31 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   const int sms = num_sms();
   const int grid_t = tiles < sms ? tiles : sms, grid_g = tiles128 < sms ? tiles128 : sms;
   float* cbuf = reinterpret_cast<float*>(ws + W.c_buf);
-  // The tail tile of the operand images is only partly written by the stage kernels; the unwritten rows
-  // feed MMA columns that are never stored, but they must not hold NaN patterns that trap nothing -- any
-  // bit pattern is fine for unused columns, so no clearing is needed.
+  const float* scales = reinterpret_cast<const float*>(blob + L.scales());
+  // Rows of the last operand-image tile beyond `groups` are never written; they only feed accumulator
+  // columns that are never stored.
   if (phases & 1) k1<<<grid_t, ENC_THREADS, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
   if (phases & 2)
-    kb<<<grid_g, ENC_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(),
-                                        reinterpret_cast<const float*>(blob + L.bias_c()), cbuf, groups, tiles128);
+    kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
+                                        scales + 1, cbuf, groups, tiles128);
   if (phases & 4) k2<<<grid_t, ENC_THREADS, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
   if ((phases & 8) && tokens_out)
-    kd<<<grid_g, ENC_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(),
-                                        reinterpret_cast<const float*>(blob + L.bias_tok()), tokens_out, groups,
-                                        tiles128);
+    kd<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(),
+                                        reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,
+                                        groups, tiles128);
   return ppt_launch_status();
 }
 
 }  // namespace
 
 extern "C" PPT_EXPORT int64_t ppt_encoder_packed_bytes(int mode) {
-  if (mode < PPT_ENC_FP16 || mode > PPT_ENC_BF16X3) return PPT_EINVAL;
-  return (int64_t)BlobLayout{mode == PPT_ENC_BF16X3 ? 2u : 1u}.total();
+  if (mode < PPT_ENC_FP16 || mode > PPT_ENC_FP16X3) return PPT_EINVAL;
+  return (int64_t)BlobLayout{mode == PPT_ENC_FP16X3 ? 2u : 1u}.total();
 }
 
 extern "C" PPT_EXPORT int64_t ppt_encoder_workspace_bytes(int64_t num_groups, int mode) {
-  if (mode < PPT_ENC_FP16 || mode > PPT_ENC_BF16X3 || num_groups < 1) return PPT_EINVAL;
-  return (int64_t)Workspace(num_groups, mode == PPT_ENC_BF16X3 ? 2 : 1).total;
+  if (mode < PPT_ENC_FP16 || mode > PPT_ENC_FP16X3 || num_groups < 1) return PPT_EINVAL;
+  return (int64_t)Workspace(num_groups, mode == PPT_ENC_FP16X3 ? 2 : 1).total;
 }
 
 extern "C" PPT_EXPORT int ppt_encoder_forward_phases(const float* neighborhood, const void* packed, void* workspace,
@@ -539,9 +618,9 @@ extern "C" PPT_EXPORT int ppt_encoder_forward_phases(const float* neighborhood, 
     case PPT_ENC_BF16:
       return run_encoder<tc05::FMT_BF16, 1, 128>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
                                                  st);
-    case PPT_ENC_BF16X3:
-      return run_encoder<tc05::FMT_BF16, 2, 64>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
-                                                st);
+    case PPT_ENC_FP16X3:
+      return run_encoder<tc05::FMT_F16, 2, 64>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
+                                               st);
     default:
       return PPT_EINVAL;
   }

@@ -46,6 +46,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+// Same, for a single long-waiting thread (the copy producer): sleeps between probes so that its spin
+// does not take issue slots from the warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 
 // Generic-proxy shared-memory writes -> visible to the async proxy (tensor core, bulk copies).
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -150,14 +159,29 @@ __device__ __forceinline__ uint32_t sw128_mnmajor_off(int mn, int k, uint32_t mn
 }
 
 // ---- fp32 -> operand conversion -----------------------------------------------------------
+// Two fp32 values -> one packed pair of operand elements (a in the low half = lower address), with an
+// optional fused ReLU.  fp16 saturates to +-65504 instead of producing inf (SURVEY.md F15 range guard).
+// One F2FP instruction either way.
+template <uint32_t FMT, bool RELU>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  uint32_t r;
+  if (FMT == FMT_F16) {
+    if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  } else {
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  }
+  return r;
+}
+template <uint32_t FMT>
+__device__ __forceinline__ float2 unpack2(uint32_t r) {
+  if (FMT == FMT_F16) return __half22float2(*reinterpret_cast<const __half2*>(&r));
+  return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+}
 template <uint32_t FMT>
 __device__ __forceinline__ uint16_t to_operand(float v) {
-  if (FMT == FMT_F16) {
-    // saturate instead of producing inf: fp16 tops out at 65504 (SURVEY.md F15 range guard)
-    v = fminf(fmaxf(v, -65504.f), 65504.f);
-    return __half_as_ushort(__float2half_rn(v));
-  }
-  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return (uint16_t)(pack2<FMT, false>(v, 0.f) & 0xffffu);
 }
 template <uint32_t FMT>
 __device__ __forceinline__ float from_operand(uint16_t b) {

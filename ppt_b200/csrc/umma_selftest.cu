@@ -115,22 +115,22 @@ umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restric
 
 }  // namespace
 
-// mode: bits [0,2) = PPT_ENC_FP16 / PPT_ENC_BF16 / PPT_ENC_BF16X3; bit 2 = B operand MN-major;
+// mode: bits [0,2) = PPT_ENC_FP16 / PPT_ENC_BF16 / PPT_ENC_FP16X3; bit 2 = B operand MN-major;
 // bit 3 = `a` points at a packed operand image (ppt_b200/encoder_pack.py: pack_kmajor) instead of fp32.
 extern "C" PPT_EXPORT int ppt_selftest_umma(const float* a, const float* b, float* d, int N, int K, int mode,
                                             void* stream) {
   if (!a || !b || !d) return PPT_EINVAL;
   const int prec = mode & 3, b_mn = (mode >> 2) & 1, packed = (mode >> 3) & 1;
-  if (prec > PPT_ENC_BF16X3) return PPT_EINVAL;
+  if (prec > PPT_ENC_FP16X3) return PPT_EINVAL;
   if (N < 32 || N > 256 || (N % 32) != 0 || K < 64 || (K % 64) != 0) return PPT_ERANGE;
   if (b_mn && (N % 64) != 0) return PPT_ERANGE;
-  const int split = prec == PPT_ENC_BF16X3 ? 2 : 1;
+  const int split = prec == PPT_ENC_FP16X3 ? 2 : 1;
   const size_t smem = (size_t)split * ((size_t)(K / 64) * 16384 + (size_t)N * K * 2) + 64;
   if (smem > 220 * 1024) return PPT_ERANGE;
   const float* af = packed ? nullptr : a;
   const unsigned char* ap = packed ? reinterpret_cast<const unsigned char*>(a) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  if (prec == PPT_ENC_FP16) {
+  if (prec != PPT_ENC_BF16) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel<tc05::FMT_F16>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     umma_selftest_kernel<tc05::FMT_F16><<<1, ST_THREADS, smem, st>>>(af, ap, b, d, N, K, b_mn, split);

@@ -14,16 +14,25 @@ Done once per weight version (the Encoder is frozen in PPT, models/ULIP_models.p
    its own: tokens = Wr @ max_pts(W4 @ h3) + (Wr @ b4 + br)   (models/pointbert/point_encoder.py:133,239).
 4. Every tensor-core weight is cut into 128-row x 64-column operand images in the K-major,
    128-byte-swizzled layout tcgen05.mma reads from shared memory (csrc/tc05.cuh: sw128_kmajor_off),
-   so a pipeline stage is one contiguous 16 KB bulk copy.  Order: [unit][k-chunk][split][16 KB];
-   split = 2 stores bf16 hi and lo parts for the 3-MMA fp32-parity mode.
+   so a pipeline stage is one contiguous 16 KB bulk copy.  Order: [unit][k-chunk][split][16 KB].
+5. fp32-parity mode (ENC_FP16X3): every operand is split into fp16 hi + fp16 lo and each product is
+   three MMAs (hi*hi, hi*lo, lo*hi).  fp16 carries 11 significant bits, so hi+lo carries ~22 -- but only
+   inside fp16's narrow exponent range -- so weights and activations are pre-multiplied by powers of two
+   (exact) that centre them in that range, and the accumulators are multiplied back in the epilogue.
+   bf16 hi/lo (16 bits) measured 1.2e-5 on B200, fp16 hi/lo with scaling reaches the fp32 reference's
+   own rounding noise.
 
 Blob layout (bytes), mirrored by csrc/encoder.cu (EncoderBlob):
-    [0, 8192)            fp32 section: W1' rows {w0,w1,w2,b} [128][4], bias_c [512], b4 [256], bias_tok [384]
+    [0, 8192)            fp32 section: W1' rows {w0,w1,w2,b} [128][4], bias_c [512], b4 [256], bias_tok [384],
+                         scales [8] = 1/(weight scale * operand scale) of the five GEMMs, point-activation
+                         scale, group-operand scale, 0   (all 1.0 outside the fp32-parity mode)
     then W2 (2 units x 2 chunks), W3A (4 x 4), W32 (4 x 2), W4 (2 x 8), WR (3 x 4) operand images.
 """
 import torch
 
-ENC_FP16, ENC_BF16, ENC_BF16X3 = 0, 1, 2
+ENC_FP16, ENC_BF16, ENC_FP16X3 = 0, 1, 2
+ACT_SCALE = 64.0   # fp32-parity mode: h1/h3 operands (values up to 1023 before fp16 saturates)
+GRP_SCALE = 64.0   # fp32-parity mode: g/t operands
 F32_SECTION_BYTES = 8192
 IMAGE_BYTES = 16384
 # (name, rows, cols)
@@ -31,11 +40,20 @@ SECTIONS = (("W2", 256, 128), ("W3A", 512, 256), ("W32", 512, 128), ("W4", 256, 
 
 
 def operand_dtype(mode):
-    return torch.float16 if mode == ENC_FP16 else torch.bfloat16
+    return torch.bfloat16 if mode == ENC_BF16 else torch.float16
 
 
 def split_of(mode):
-    return 2 if mode == ENC_BF16X3 else 1
+    return 2 if mode == ENC_FP16X3 else 1
+
+
+def weight_scale(w):
+    """Power of two that puts max|w| in [4096, 8192): hi keeps 11 bits, lo stays a normal fp16."""
+    m = float(w.abs().max())
+    if m == 0.0 or not torch.isfinite(torch.tensor(m)):
+        return 1.0
+    import math
+    return 2.0 ** (12 - math.floor(math.log2(m)) )
 
 
 def packed_bytes(mode):
@@ -94,10 +112,21 @@ def pack_encoder(sd, mode):
     """-> uint8 CPU tensor of packed_bytes(mode) bytes."""
     f = fold(sd)
     dtype, split = operand_dtype(mode), split_of(mode)
-    f32 = torch.cat([f["W1"].reshape(-1), f["bias_c"], f["b4"], f["bias_tok"]]).to(torch.float32)
+    if mode == ENC_FP16X3:
+        ws = {name: weight_scale(f[name]) for name, _, _ in SECTIONS}
+        act, grp = ACT_SCALE, GRP_SCALE
+    else:
+        ws = {name: 1.0 for name, _, _ in SECTIONS}
+        act = grp = 1.0
+    # inverse accumulator scales in launch order: stage1 (W2 x h1), linear c (W3A x g), stage2 (W32 x h1),
+    # stage2 (W4 x h3), linear tokens (WR x t); then the two operand scales
+    scales = torch.tensor([1.0 / (ws["W2"] * act), 1.0 / (ws["W3A"] * grp), 1.0 / (ws["W32"] * act),
+                           1.0 / (ws["W4"] * act), 1.0 / (ws["WR"] * grp), act, grp, 0.0], dtype=torch.float64)
+    f32 = torch.cat([f["W1"].reshape(-1), f["bias_c"], f["b4"], f["bias_tok"], scales]).to(torch.float32)
+    assert f32.numel() * 4 <= F32_SECTION_BYTES
     head = torch.zeros(F32_SECTION_BYTES, dtype=torch.uint8)
     head[: f32.numel() * 4] = f32.view(torch.uint8)
-    parts = [head] + [pack_kmajor(f[name].to(torch.float32), dtype, split) for name, _, _ in SECTIONS]
+    parts = [head] + [pack_kmajor((f[name] * ws[name]).to(torch.float32), dtype, split) for name, _, _ in SECTIONS]
     blob = torch.cat(parts)
     assert blob.numel() == packed_bytes(mode), (blob.numel(), packed_bytes(mode))
     return blob

@@ -6,8 +6,8 @@ import torch
 
 from . import _lib
 
-ENC_FP16, ENC_BF16, ENC_BF16X3 = 0, 1, 2
-ENC_MODES = {"fp16": ENC_FP16, "bf16": ENC_BF16, "fp32": ENC_BF16X3, "bf16x3": ENC_BF16X3}
+ENC_FP16, ENC_BF16, ENC_FP16X3 = 0, 1, 2
+ENC_MODES = {"fp16": ENC_FP16, "bf16": ENC_BF16, "fp32": ENC_FP16X3, "fp16x3": ENC_FP16X3}
 
 
 def _need_cuda(*tensors):

@@ -23,7 +23,7 @@ def main():
         ap = encoder_pack.pack_kmajor(a, dt, encoder_pack.split_of(mode)).cuda()
     d = ops.selftest_umma(a.cuda(), b.cuda(), mode=mode, b_mn_major=bool(b_mn), a_packed=ap)
     torch.cuda.synchronize()
-    if mode == ops.ENC_BF16X3:
+    if mode == ops.ENC_FP16X3:
         ref = a.double() @ b.double().T
     else:
         ref = a.to(dt).double() @ b.to(dt).double().T

@@ -66,8 +66,10 @@ def test_fold_and_pack():
         for k in (0, 7, 8, 63, 64, 127):
             off = (r % 128) * 128 + ((((k % 64) >> 3) ^ (r & 7)) * 16) + (k & 7) * 2
             assert float(img[r // 128, k // 64, off // 2]) == float(w[r, k])
-    hi_lo = ep.pack_kmajor(torch.full((128, 64), 1.001), torch.bfloat16, split=2).view(torch.bfloat16).reshape(2, -1)
-    assert abs(float(hi_lo[0, 0]) + float(hi_lo[1, 0]) - 1.001) < 1e-5
+    hi_lo = ep.pack_kmajor(torch.full((128, 64), 1.001), torch.float16, split=2).view(torch.float16).reshape(2, -1)
+    assert abs(float(hi_lo[0, 0]) + float(hi_lo[1, 0]) - 1.001) < 1e-6
+    s = ep.weight_scale(torch.tensor([0.3, -0.07]))
+    assert 4096 <= 0.3 * s < 8192 and s == 2.0 ** round(__import__('math').log2(s))
 
 
 def test_shard_bounds_cover_everything_once():
