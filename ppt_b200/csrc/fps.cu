@@ -20,6 +20,39 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// round(a*a) per lane.  ptxas 12.9 contracts an f32x2 multiply feeding an f32x2 add into FFMA2 even
+// with explicit .rn and --fmad=false (checked in SASS), which would change the reference's rounding
+// (SURVEY.md F1).  So only the subtractions and the squares are packed; the two additions are
+// scalar add.rn.f32 (__fadd_rn), which ptxas never contracts.
+__device__ __forceinline__ unsigned long long sqr_f32x2(unsigned long long a) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(a));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3_f32(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 struct FpsRecord {  // one per CTA of a cluster, exchanged through DSMEM
   int val;          // float bits of the CTA-local maximum
   unsigned idx;     // its global point index
@@ -54,15 +87,21 @@ fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int
   }
   __syncthreads();
 
-  float px[PPT], py[PPT], pz[PPT], mind[PPT];
+  // Coordinates live in registers as packed pairs (slot j, slot j+1) for the f32x2 pipe:
+  // sub/mul/add.rn.f32x2 round each lane like the scalar instruction, so the distance is still
+  // exactly (dx*dx + dy*dy) + dz*dz -- two points per instruction.
+  static_assert(PPT % 2 == 0, "points per thread must be even");
+  unsigned long long px[PPT / 2], py[PPT / 2], pz[PPT / 2];
+  float mind[PPT];
 #pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int l = j * THREADS + tid;
-    const bool ok = base + l < N;
-    px[j] = ok ? sx[l] : 0.f;
-    py[j] = ok ? sy[l] : 0.f;
-    pz[j] = ok ? sz[l] : 0.f;
-    mind[j] = ok ? 1e10f : -1.0f;
+  for (int j = 0; j < PPT; j += 2) {
+    const int l0 = j * THREADS + tid, l1 = (j + 1) * THREADS + tid;
+    const bool ok0 = base + l0 < N, ok1 = base + l1 < N;
+    px[j / 2] = pack_f32x2(ok0 ? sx[l0] : 0.f, ok1 ? sx[l1] : 0.f);
+    py[j / 2] = pack_f32x2(ok0 ? sy[l0] : 0.f, ok1 ? sy[l1] : 0.f);
+    pz[j / 2] = pack_f32x2(ok0 ? sz[l0] : 0.f, ok1 ? sz[l1] : 0.f);
+    mind[j] = ok0 ? 1e10f : -1.0f;
+    mind[j + 1] = ok1 ? 1e10f : -1.0f;
   }
 
   unsigned far = (unsigned)start[b];
@@ -77,15 +116,28 @@ fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int
     }
     if (g == G - 1) break;
 
-    float best = -1.0f;
-    int bj = 0;
+    const unsigned long long cx2 = pack_f32x2(cx, cx), cy2 = pack_f32x2(cy, cy), cz2 = pack_f32x2(cz, cz);
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      const float d = ppt_fps_dist(px[j], py[j], pz[j], cx, cy, cz);
-      const float m = d < mind[j] ? d : mind[j];  // torch.min(distance, dist)
-      mind[j] = m;
-      if (m > best) { best = m; bj = j; }
+    for (int j = 0; j < PPT; j += 2) {
+      const unsigned long long dx = sub_f32x2(px[j / 2], cx2), dy = sub_f32x2(py[j / 2], cy2),
+                               dz = sub_f32x2(pz[j / 2], cz2);
+      float x0, x1, y0, y1, z0, z1;
+      unpack_f32x2(sqr_f32x2(dx), x0, x1);
+      unpack_f32x2(sqr_f32x2(dy), y0, y1);
+      unpack_f32x2(sqr_f32x2(dz), z0, z1);
+      const float d0 = __fadd_rn(__fadd_rn(x0, y0), z0), d1 = __fadd_rn(__fadd_rn(x1, y1), z1);
+      mind[j] = fminf(mind[j], d0);        // torch.min(distance, dist) for finite input
+      mind[j + 1] = fminf(mind[j + 1], d1);
     }
+    // Thread-local maximum with 3-input max, then the first slot that holds it (ascending slot =
+    // ascending point index inside a thread), instead of carrying an index through every compare.
+    float best = mind[0];
+#pragma unroll
+    for (int j = 1; j + 1 < PPT; j += 2) best = max3_f32(best, mind[j], mind[j + 1]);
+    if ((PPT & 1) == 0) best = fmaxf(best, mind[PPT - 1]);
+    int bj = PPT - 1;
+#pragma unroll
+    for (int j = PPT - 2; j >= 0; --j) bj = mind[j] == best ? j : bj;
     const int vb = __float_as_int(best);
     const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
     const unsigned cand = vb == wmax ? (unsigned)(base + bj * THREADS + tid) : 0xffffffffu;

