@@ -64,25 +64,25 @@ struct Ring {  // position in a ring of mbarrier-guarded stages
 };
 
 // One 64-wide K chunk = four K=16 instructions (x3 passes in the hi/lo split mode: hi*hi, hi*lo, lo*hi).
-// B_MN = false: B is K-major, `b_addr` points at the chunk (rows 128 B apart).
-// B_MN = true : B is MN-major, `b_addr` points at the operand base, `kc` selects the K-atoms.
+// The issuing thread's own instruction stream is the critical path of the tensor pipe, so descriptors
+// are stepped as 32-bit words (tc05.cuh: sdesc_lo / sdesc_hi): `a_lo` / `b_lo` describe the first K=16
+// slice of the chunk, each further slice adds a constant (in 16-byte units) to the start-address field.
+//   A (weights, K-major):      +2 per slice (32 B),  lo part +IMG/16
+//   B K-major  (h1, g, t):     +2 per slice
+//   B MN-major (h3):           +128 per slice (two 1 KB K-atoms)
 template <int SPLIT, bool B_MN>
-__device__ __forceinline__ void issue_k64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t b_split_bytes,
-                                          int kc, uint32_t idesc, bool first) {
+__device__ __forceinline__ void issue_k64(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t b_split_step,
+                                          uint32_t idesc, bool first) {
+  constexpr uint32_t HI = sdesc_hi(1024u);
+  constexpr uint32_t B_STEP = B_MN ? 128u : 2u;
 #pragma unroll
   for (int k16 = 0; k16 < 4; ++k16) {
 #pragma unroll
     for (int pass = 0; pass < (SPLIT == 2 ? 3 : 1); ++pass) {
       const uint32_t sa = pass == 2 ? 1 : 0, sb = pass == 1 ? 1 : 0;
-      const uint64_t ad = make_sdesc(a_addr + sa * IMG + k16 * 32u, 16u, 1024u);
-      uint64_t bd;
-      if (B_MN) {
-        const uint32_t atom = (uint32_t)kc * 8u + (uint32_t)k16 * 2u;  // K index / 8
-        bd = make_sdesc(b_addr + sb * b_split_bytes + atom * 1024u, MNBLK, 1024u);
-      } else {
-        bd = make_sdesc(b_addr + sb * b_split_bytes + k16 * 32u, 16u, 1024u);
-      }
-      umma_f16(d_tmem, ad, bd, idesc, (first && k16 == 0 && pass == 0) ? 0u : 1u);
+      const uint64_t ad = sdesc_join(a_lo + sa * (IMG >> 4) + (uint32_t)k16 * 2u, HI);
+      const uint64_t bd = sdesc_join(b_lo + sb * b_split_step + (uint32_t)k16 * B_STEP, HI);
+      umma_f16_elect(d_tmem, ad, bd, idesc, (first && k16 == 0 && pass == 0) ? 0u : 1u);
     }
   }
 }
@@ -196,44 +196,44 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    Ring r;
-    const uint32_t idesc_k = make_idesc(FMT, 128, NT, 0), idesc_mn = make_idesc(FMT, 128, NT, 1);
-    const uint32_t ring_addr = smem_u32(ring), h1_addr = smem_u32(h1buf), h3_addr = smem_u32(h3buf);
-    uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      mbar_wait(&h1_ready[tile_it % NH1], (tile_it / NH1) & 1u);
-      const uint32_t h1_cur = h1_addr + (tile_it % NH1) * H1_BUF;
-#pragma unroll 1
-      for (int u = 0; u < NUNITS; ++u) {
-        const bool g3 = STAGE == 2 && u >= 4;
-        const int nkc = g3 ? 8 : 2;
-        const int buf = u & 1;
-        // accumulator `buf` is used NUNITS/2 times per tile: its n-th use has parity n & 1
-        const uint32_t use = tile_it * (NUNITS / 2) + (uint32_t)(u >> 1);
-        mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
-        fence_after_sync();
-        const uint32_t d_tmem = tbase + (uint32_t)(buf * NT);
-        for (int kc = 0; kc < nkc; ++kc) {
-          if (STAGE == 2 && u == 4 && (kc & 1) == 0) {  // h3 channels of K-chunks 2i, 2i+1 come from unit i
-            mbar_wait(&h3_ready[kc >> 1], tile_it & 1u);
-          }
-          const uint32_t s = r.stage<NSTAGE>();
-          mbar_wait(&full[s], r.parity<NSTAGE>());
+    // ===================== MMA issuer: converged warp, one elected lane issues =====================
+    {
+      const uint32_t idesc_k = make_idesc(FMT, 128, NT, 0), idesc_mn = make_idesc(FMT, 128, NT, 1);
+      const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u);            // stage s: + s * STAGE_BYTES/16
+      const uint32_t h1_lo0 = sdesc_lo(smem_u32(h1buf), 16u);          // K-major: chunk kc: + kc * NT*128/16
+      const uint32_t h3_lo0 = sdesc_lo(smem_u32(h3buf), MNBLK);        // MN-major: chunk kc: + kc * 8 KB/16
+      uint32_t it = 0, tile_it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        mbar_wait(&h1_ready[tile_it % NH1], (tile_it / NH1) & 1u);
+        const uint32_t h1_lo = h1_lo0 + (tile_it % NH1) * (H1_BUF >> 4);
+#pragma unroll
+        for (int u = 0; u < NUNITS; ++u) {
+          const bool g3 = STAGE == 2 && u >= 4;
+          const int nkc = g3 ? 8 : 2;
+          const int buf = u & 1;
+          // accumulator `buf` is used NUNITS/2 times per tile: its n-th use has parity n & 1
+          const uint32_t use = tile_it * (NUNITS / 2) + (uint32_t)(u >> 1);
+          mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
           fence_after_sync();
-          if (lane == 0) {
+          const uint32_t d_tmem = tbase + (uint32_t)(buf * NT);
+#pragma unroll
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            if (STAGE == 2 && u == 4 && (kc & 1) == 0) {  // h3 channels of K-chunks 2i, 2i+1 come from unit i
+              mbar_wait(&h3_ready[kc >> 1], tile_it & 1u);
+            }
+            const uint32_t s = it % NSTAGE;
+            mbar_wait(&full[s], (it / NSTAGE) & 1u);
+            fence_after_sync();
+            const uint32_t a_lo = a_lo0 + s * (STAGE_BYTES >> 4);
             if (g3)
-              issue_k64<SPLIT, true>(d_tmem, ring_addr + s * STAGE_BYTES, h3_addr, H3_BYTES, kc, idesc_mn, kc == 0);
+              issue_k64<SPLIT, true>(d_tmem, a_lo, h3_lo0 + (uint32_t)kc * 512u, H3_BYTES >> 4, idesc_mn, kc == 0);
             else
-              issue_k64<SPLIT, false>(d_tmem, ring_addr + s * STAGE_BYTES, h1_cur + (uint32_t)kc * (NT * 128u),
-                                      H1_BYTES, kc, idesc_k, kc == 0);
-            umma_commit(&empty[s]);
+              issue_k64<SPLIT, false>(d_tmem, a_lo, h1_lo + (uint32_t)kc * ((NT * 128u) >> 4), H1_BYTES >> 4,
+                                      idesc_k, kc == 0);
+            umma_commit_elect(&empty[s]);
           }
-          __syncwarp();
-          ++r.it;
+          umma_commit_elect(&acc_full[buf]);
         }
-        if (lane == 0) umma_commit(&acc_full[buf]);
-        __syncwarp();
       }
     }
   } else {
@@ -445,35 +445,30 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
       }
     }
   } else if (warp == 1) {
-    Ring r;
-    const uint32_t idesc = make_idesc(FMT, 128, NT, 0);
-    const uint32_t ring_addr = smem_u32(ring), b_addr0 = smem_u32(bbuf);
-    uint32_t tile_it = 0, unit_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      mbar_wait(b_full, tile_it & 1u);
+    {  // converged warp, one elected lane issues
+      const uint32_t idesc = make_idesc(FMT, 128, NT, 0);
+      const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u), b_lo0 = sdesc_lo(smem_u32(bbuf), 16u);
+      uint32_t it = 0, tile_it = 0, unit_it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        mbar_wait(b_full, tile_it & 1u);
 #pragma unroll 1
-      for (int u = 0; u < NUNITS; ++u, ++unit_it) {
-        const int buf = unit_it & 1;
-        mbar_wait(&acc_empty[buf], ((unit_it >> 1) & 1u) ^ 1u);
-        fence_after_sync();
-        for (int kc = 0; kc < 4; ++kc) {
-          const uint32_t s = r.stage<NSTAGE>();
-          mbar_wait(&full[s], r.parity<NSTAGE>());
+        for (int u = 0; u < NUNITS; ++u, ++unit_it) {
+          const int buf = unit_it & 1;
+          mbar_wait(&acc_empty[buf], ((unit_it >> 1) & 1u) ^ 1u);
           fence_after_sync();
-          if (lane == 0) {
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc, ++it) {
+            const uint32_t s = it % NSTAGE;
+            mbar_wait(&full[s], (it / NSTAGE) & 1u);
+            fence_after_sync();
             // activation image order is [kc][split]: the lo copy sits IMG bytes after the hi copy
-            issue_k64<SPLIT, false>(tbase + (uint32_t)(buf * NT), ring_addr + s * STAGE_BYTES,
-                                    b_addr0 + kc * STAGE_BYTES, IMG, kc, idesc, kc == 0);
-            umma_commit(&empty[s]);
+            issue_k64<SPLIT, false>(tbase + (uint32_t)(buf * NT), a_lo0 + s * (STAGE_BYTES >> 4),
+                                    b_lo0 + (uint32_t)kc * (STAGE_BYTES >> 4), IMG >> 4, idesc, kc == 0);
+            umma_commit_elect(&empty[s]);
           }
-          __syncwarp();
-          ++r.it;
+          umma_commit_elect(&acc_full[buf]);
+          if (u == NUNITS - 1) umma_commit_elect(b_empty);  // all MMAs reading this tile's activations are done
         }
-        if (lane == 0) {
-          umma_commit(&acc_full[buf]);
-          if (u == NUNITS - 1) umma_commit(b_empty);  // all MMAs reading this tile's activations are done
-        }
-        __syncwarp();
       }
     }
   } else {

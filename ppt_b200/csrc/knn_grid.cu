@@ -1,0 +1,365 @@
+// Exact kNN with spatial pruning for clouds of up to 8192 points (sm_100a).
+//
+// Same contract as the brute-force scan in knn.cu (the k nearest under (distance, index) with the
+// reference's fp32 distance formula) -- but most of the cloud is never touched:
+//
+//   knn_prepare_kernel  one CTA per cloud: bounding box -> 16x16x16 Morton cells -> counting sort in
+//                       shared memory -> the cloud in cell order as float4 {x,y,z,|p|^2} + original
+//                       indices, one bounding box (+ max |p|^2) per row of 32 consecutive sorted points,
+//                       and the first sorted position of every cell.
+//   knn_search_kernel   CTA = (cloud, 64 queries), the sorted cloud resident in shared memory; a warp
+//                       takes one query at a time: seeds its sorted top-k list from the three rows
+//                       around the query's own cell, then visits only rows whose box can still hold a
+//                       point closer than the current k-th distance.
+//
+// Pruning is conservative in floating point: the reference distance d_ref = fl(fl(-2 q.p + |q|^2) + |p|^2)
+// differs from the exact squared distance by at most ~10 ulp of (|q|^2 + |p|^2); a row is skipped only
+// if its box distance exceeds tau + 2e-6 (|q|^2 + max|p|^2 + |tau|), a bound three times wider than
+// that.  Hence the result is bit-identical to the full scan; the order inside a cell (atomics) cannot
+// matter because candidates are ordered by (distance, original index) explicitly.
+#include "common.cuh"
+
+namespace {
+
+constexpr int GRID_MAX_N = 8192;
+constexpr int CELLS = 4096;              // 16^3
+constexpr int PREP_THREADS = 1024;
+constexpr int SEARCH_THREADS = 512;
+constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;
+constexpr int SEARCH_QPB = 64;           // queries per CTA
+
+struct CloudHeader {  // 32 bytes at the start of each cloud's workspace record
+  float lo[3];
+  float inv[3];       // cells per unit length
+  int rows;
+  int pad;
+};
+
+struct RowBox {       // 32 bytes
+  float lo[3];
+  float npmax;        // max |p|^2 in the row
+  float hi[3];
+  float unused;
+};
+
+__host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct GridLayout {   // byte offsets inside one cloud's workspace record
+  size_t pts, idx, boxes, cells, total;
+  __host__ __device__ explicit GridLayout(int N) {
+    const size_t np = (size_t)((N + 31) / 32) * 32;
+    pts = align256(sizeof(CloudHeader));
+    idx = pts + np * sizeof(float4);
+    boxes = idx + np * sizeof(int);
+    cells = boxes + (np / 32) * sizeof(RowBox);
+    total = align256(cells + (CELLS + 1) * sizeof(int));
+  }
+};
+
+__device__ __forceinline__ unsigned spread4(unsigned v) {  // 4 bits -> every third bit
+  return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+}
+__device__ __forceinline__ int cell_of(float x, float y, float z, const float* lo, const float* inv) {
+  const int cx = min(15, max(0, (int)((x - lo[0]) * inv[0])));
+  const int cy = min(15, max(0, (int)((y - lo[1]) * inv[1])));
+  const int cz = min(15, max(0, (int)((z - lo[2]) * inv[2])));
+  return (int)(spread4((unsigned)cx) | (spread4((unsigned)cy) << 1) | (spread4((unsigned)cz) << 2));
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(PPT_FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(PPT_FULL_MASK, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PREP_THREADS, 1)
+knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ workspace, int N) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int np = ((N + 31) / 32) * 32, rows = np / 32;
+  float4* spts = reinterpret_cast<float4*>(smem_raw);                  // [np]
+  int* sidx = reinterpret_cast<int*>(spts + np);                       // [np]
+  int* hist = sidx + np;                                               // [CELLS]  counts, then cursors
+  int* warp_tot = hist + CELLS;                                        // [32]
+  float* red = reinterpret_cast<float*>(warp_tot + 32);                // [6][32]
+  float* box = red + 6 * 32;                                           // lo[3], inv[3]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float* cloud = xyz + (size_t)b * N * 3;
+  const GridLayout L(N);
+  unsigned char* rec = workspace + (size_t)b * L.total;
+
+  // 1. bounding box of the cloud
+  const float inf = __int_as_float(0x7f800000);
+  float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+  for (int n = tid; n < N; n += PREP_THREADS) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = cloud[(size_t)n * 3 + c];
+      mn[c] = fminf(mn[c], v);
+      mx[c] = fmaxf(mx[c], v);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float a = warp_min(mn[c]), z = warp_max(mx[c]);
+    if (lane == 0) { red[c * 32 + warp] = a; red[(3 + c) * 32 + warp] = z; }
+  }
+  for (int i = tid; i < CELLS; i += PREP_THREADS) hist[i] = 0;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = warp_min(red[c * 32 + lane]), z = warp_max(red[(3 + c) * 32 + lane]);
+      if (lane == 0) {
+        const float ext = z - a;
+        box[c] = a;
+        box[3 + c] = ext > 0.f ? 16.0f / ext : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const float lo[3] = {box[0], box[1], box[2]}, inv[3] = {box[3], box[4], box[5]};
+
+  // 2. histogram of cells
+  for (int n = tid; n < N; n += PREP_THREADS) {
+    const float x = cloud[(size_t)n * 3], y = cloud[(size_t)n * 3 + 1], z = cloud[(size_t)n * 3 + 2];
+    atomicAdd(&hist[cell_of(x, y, z, lo, inv)], 1);
+  }
+  __syncthreads();
+
+  // 3. exclusive scan of the 4096 counts (4 per thread); cell starts go to the workspace
+  int c4[4], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { c4[i] = hist[tid * 4 + i]; sum += c4[i]; }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(PPT_FULL_MASK, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(PPT_FULL_MASK, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  int run = warp_tot[warp] + incl - sum;
+  int* cells_out = reinterpret_cast<int*>(rec + L.cells);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hist[tid * 4 + i] = run;       // becomes the scatter cursor
+    cells_out[tid * 4 + i] = run;
+    run += c4[i];
+  }
+  if (tid == PREP_THREADS - 1) cells_out[CELLS] = run;  // = N
+  __syncthreads();
+
+  // 4. scatter into cell order (order inside a cell is whatever the atomics give; see header comment)
+  for (int n = tid; n < N; n += PREP_THREADS) {
+    const float x = cloud[(size_t)n * 3], y = cloud[(size_t)n * 3 + 1], z = cloud[(size_t)n * 3 + 2];
+    const int pos = atomicAdd(&hist[cell_of(x, y, z, lo, inv)], 1);
+    spts[pos] = make_float4(x, y, z, ppt_sqnorm3(x, y, z));
+    sidx[pos] = n;
+  }
+  for (int n = N + tid; n < np; n += PREP_THREADS) {
+    spts[n] = make_float4(0.f, 0.f, 0.f, inf);  // padding: distance +inf, never selected
+    sidx[n] = 0x7fffffff;
+  }
+  __syncthreads();
+
+  // 5. sorted cloud, indices, per-row boxes and the header to the workspace
+  float4* pts_out = reinterpret_cast<float4*>(rec + L.pts);
+  int* idx_out = reinterpret_cast<int*>(rec + L.idx);
+  for (int n = tid; n < np; n += PREP_THREADS) { pts_out[n] = spts[n]; idx_out[n] = sidx[n]; }
+  RowBox* boxes = reinterpret_cast<RowBox*>(rec + L.boxes);
+  for (int r = warp; r < rows; r += PREP_THREADS / 32) {
+    const float4 p = spts[r * 32 + lane];
+    const bool ok = r * 32 + lane < N;
+    const float bx0 = warp_min(ok ? p.x : inf), by0 = warp_min(ok ? p.y : inf), bz0 = warp_min(ok ? p.z : inf);
+    const float bx1 = warp_max(ok ? p.x : -inf), by1 = warp_max(ok ? p.y : -inf), bz1 = warp_max(ok ? p.z : -inf);
+    const float nmax = warp_max(ok ? p.w : 0.f);
+    if (lane == 0) {
+      RowBox rb;
+      rb.lo[0] = bx0; rb.lo[1] = by0; rb.lo[2] = bz0; rb.npmax = nmax;
+      rb.hi[0] = bx1; rb.hi[1] = by1; rb.hi[2] = bz1; rb.unused = 0.f;
+      boxes[r] = rb;
+    }
+  }
+  if (tid == 0) {
+    CloudHeader h;
+    for (int c = 0; c < 3; ++c) { h.lo[c] = lo[c]; h.inv[c] = inv[c]; }
+    h.rows = rows;
+    h.pad = 0;
+    *reinterpret_cast<CloudHeader*>(rec) = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TopList {  // lane i holds the i-th smallest (d, idx); tau = entry k-1 (warp-uniform)
+  float d;
+  int i;
+  float tau_d;
+  int tau_i;
+};
+
+__device__ __forceinline__ bool pair_less(float da, int ia, float db, int ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+__device__ __forceinline__ void scan_row(TopList& t, const float4* __restrict__ pts, const int* __restrict__ sidx,
+                                         int row, float qx, float qy, float qz, float qn, int k, int lane) {
+  const float4 p = pts[row * 32 + lane];
+  const int pi = sidx[row * 32 + lane];
+  const float d = ppt_pair_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
+  unsigned bal = __ballot_sync(PPT_FULL_MASK, pair_less(d, pi, t.tau_d, t.tau_i));
+  while (bal) {
+    const int src = __ffs(bal) - 1;
+    bal &= bal - 1;
+    const float cd = __shfl_sync(PPT_FULL_MASK, d, src);
+    const int ci = __shfl_sync(PPT_FULL_MASK, pi, src);
+    if (!pair_less(cd, ci, t.tau_d, t.tau_i)) continue;  // tau tightened since the vote (warp-uniform)
+    const int pos = __popc(__ballot_sync(PPT_FULL_MASK, pair_less(t.d, t.i, cd, ci)));
+    const float ud = __shfl_up_sync(PPT_FULL_MASK, t.d, 1);
+    const int ui = __shfl_up_sync(PPT_FULL_MASK, t.i, 1);
+    if (lane == pos) { t.d = cd; t.i = ci; }
+    else if (lane > pos) { t.d = ud; t.i = ui; }
+    t.tau_d = __shfl_sync(PPT_FULL_MASK, t.d, k - 1);
+    t.tau_i = __shfl_sync(PPT_FULL_MASK, t.i, k - 1);
+  }
+}
+
+template <bool GROUP>
+__global__ void __launch_bounds__(SEARCH_THREADS, 1)
+knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query,
+                  const unsigned char* __restrict__ workspace, int64_t* __restrict__ idx_out,
+                  float* __restrict__ dist_out, float* __restrict__ nb_out, int N, int S, int k,
+                  int tiles_per_cloud) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int np = ((N + 31) / 32) * 32, rows = np / 32;
+  float4* pts = reinterpret_cast<float4*>(smem_raw);     // [np]
+  int* sidx = reinterpret_cast<int*>(pts + np);          // [np]
+  RowBox* boxes = reinterpret_cast<RowBox*>(sidx + np);  // [rows]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / tiles_per_cloud;
+  const int tile = blockIdx.x - b * tiles_per_cloud;
+  const GridLayout L(N);
+  const unsigned char* rec = workspace + (size_t)b * L.total;
+  const float* cloud = xyz + (size_t)b * N * 3;
+
+  {  // contiguous in the record: pts | idx | boxes
+    const uint4* src = reinterpret_cast<const uint4*>(rec + L.pts);
+    uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+    const int n16 = (int)((L.cells - L.pts) / 16);
+    for (int i = tid; i < n16; i += SEARCH_THREADS) dst[i] = __ldg(src + i);
+  }
+  const CloudHeader hdr = *reinterpret_cast<const CloudHeader*>(rec);
+  const int* cell_start = reinterpret_cast<const int*>(rec + L.cells);
+  __syncthreads();
+
+  const float inf = __int_as_float(0x7f800000);
+  for (int qq = warp; qq < SEARCH_QPB; qq += SEARCH_WARPS) {
+    const int q = tile * SEARCH_QPB + qq;
+    if (q >= S) break;  // warp-uniform
+    const float* qp = query + ((size_t)b * S + q) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    const float qn = ppt_sqnorm3(qx, qy, qz);
+    TopList t;
+    t.d = inf; t.i = 0x7fffffff; t.tau_d = inf; t.tau_i = 0x7fffffff;
+
+    // seed: the rows around the query's own cell
+    const int r0 = min(rows - 1, __ldg(cell_start + cell_of(qx, qy, qz, hdr.lo, hdr.inv)) >> 5);
+    const int ra = max(0, r0 - 1), rz = min(rows - 1, r0 + 1);
+    for (int r = ra; r <= rz; ++r) scan_row(t, pts, sidx, r, qx, qy, qz, qn, k, lane);
+
+    // every other row whose box may still contain a closer point
+    for (int rb = 0; rb < rows; rb += 32) {
+      const int r = rb + lane;
+      float lb = inf, slack = 0.f;
+      if (r < rows && (r < ra || r > rz)) {
+        const RowBox bx = boxes[r];
+        const float dx = fmaxf(fmaxf(bx.lo[0] - qx, qx - bx.hi[0]), 0.f);
+        const float dy = fmaxf(fmaxf(bx.lo[1] - qy, qy - bx.hi[1]), 0.f);
+        const float dz = fmaxf(fmaxf(bx.lo[2] - qz, qz - bx.hi[2]), 0.f);
+        lb = dx * dx + dy * dy + dz * dz;
+        slack = 2e-6f * (qn + bx.npmax);
+      }
+      // conservative: keep the row unless lb > tau + 2e-6 (|q|^2 + max|p|^2 + |tau|)
+      unsigned bal = __ballot_sync(PPT_FULL_MASK, !(lb > t.tau_d + slack + 2e-6f * fabsf(t.tau_d)));
+      while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const float lbr = __shfl_sync(PPT_FULL_MASK, lb, src);
+        const float slr = __shfl_sync(PPT_FULL_MASK, slack, src);
+        if (lbr > t.tau_d + slr + 2e-6f * fabsf(t.tau_d)) continue;  // tau tightened meanwhile
+        scan_row(t, pts, sidx, rb + src, qx, qy, qz, qn, k, lane);
+      }
+    }
+
+    if (lane < k) {
+      const size_t o = ((size_t)b * S + q) * k + lane;
+      if (idx_out) idx_out[o] = (int64_t)t.i;
+      if (dist_out) dist_out[o] = t.d;
+      if (GROUP) {
+        const float* p = cloud + (size_t)t.i * 3;
+        nb_out[o * 3 + 0] = __fsub_rn(p[0], qx);
+        nb_out[o * 3 + 1] = __fsub_rn(p[1], qy);
+        nb_out[o * 3 + 2] = __fsub_rn(p[2], qz);
+      }
+    }
+  }
+}
+
+size_t prep_smem(int N) {
+  const size_t np = (size_t)((N + 31) / 32) * 32;
+  return np * 20 + (CELLS + 32) * sizeof(int) + (6 * 32 + 8) * sizeof(float);
+}
+size_t search_smem(int N) {
+  const size_t np = (size_t)((N + 31) / 32) * 32;
+  return np * 20 + (np / 32) * sizeof(RowBox);
+}
+
+}  // namespace
+
+// Internal entry points used by knn.cu (not part of the C ABI).
+size_t ppt_knn_grid_workspace_bytes(int B, int N) {
+  if (N > GRID_MAX_N) return 0;
+  return (size_t)B * GridLayout(N).total;
+}
+
+int ppt_knn_grid_launch(const float* xyz, const float* query, void* workspace, int64_t* idx_out, float* dist_out,
+                        float* nb_out, int B, int N, int S, int k, bool group, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)prep_smem(GRID_MAX_N)));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)search_smem(GRID_MAX_N)));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)search_smem(GRID_MAX_N)));
+    configured = true;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  knn_prepare_kernel<<<B, PREP_THREADS, prep_smem(N), st>>>(xyz, ws, N);
+  const int tiles = (S + SEARCH_QPB - 1) / SEARCH_QPB;
+  if (group)
+    knn_search_kernel<true><<<B * tiles, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out,
+                                                                              nb_out, N, S, k, tiles);
+  else
+    knn_search_kernel<false><<<B * tiles, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out,
+                                                                               nb_out, N, S, k, tiles);
+  return ppt_launch_status();
+}

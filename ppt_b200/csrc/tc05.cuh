@@ -125,6 +125,20 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lead
          ((uint64_t)((stride_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// The same descriptor as two 32-bit words, so that an issue loop can step the start address (and keep
+// everything else) with one 32-bit add: lo = start>>4 | leading>>4 << 16, hi = stride>>4 | version | layout.
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr, uint32_t leading_bytes) {
+  return ((smem_addr & 0x3ffffu) >> 4) | (((leading_bytes >> 4) & 0x3fffu) << 16);
+}
+__host__ __device__ constexpr uint32_t sdesc_hi(uint32_t stride_bytes) {
+  return ((stride_bytes >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t sdesc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; one thread issues for the CTA.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -133,6 +147,27 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Warp-converged variants: every lane executes the call with warp-uniform operands (so ptxas keeps the
+// descriptor arithmetic in uniform registers), one elected lane issues.  The elected lane is the same
+// for every call of a converged warp, so "ops issued so far by this thread" stays meaningful for commit.
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
 
