@@ -60,16 +60,19 @@ int ppt_square_distance(const float *src, const float *dst, float *out, int B, i
 
 /* knn_point -- models/pointbert/dvae.py:116-127 (pointnet2_utils.py:20-34, pointMLP.py:110-121).
  *   xyz [B,N,3]; query [B,S,3] -> idx_out [B,S,k] i64, the k nearest under
- *   (distance, index), ascending; dist_out [B,S,k] f32 or NULL.  1 <= k <= 32, k <= N. */
-int ppt_knn(const float *xyz, const float *query, int64_t *idx_out, float *dist_out,
+ *   (distance, index), ascending; dist_out [B,S,k] f32 or NULL.  1 <= k <= 32, k <= N.
+ *   workspace: NULL (full scan of the cloud per query), or ppt_knn_workspace_bytes(B, N) bytes of
+ *   scratch, which enables the exact spatially-pruned search for 512 <= N <= 8192 (same results). */
+int64_t ppt_knn_workspace_bytes(int B, int N);
+int ppt_knn(const float *xyz, const float *query, int64_t *idx_out, float *dist_out, void *workspace,
             int B, int N, int S, int k, void *stream);
 
 /* Group.forward after FPS -- models/pointbert/dvae.py:159-181: kNN of each
  * centre, flat gather of the neighbours, subtraction of the centre.
  *   xyz [B,N,3]; center [B,G,3] -> neighborhood_out [B,G,k,3] f32;
- *   idx_out [B,G,k] i64 or NULL.  1 <= k <= 32. */
+ *   idx_out [B,G,k] i64 or NULL.  1 <= k <= 32.  workspace as for ppt_knn. */
 int ppt_knn_group(const float *xyz, const float *center, float *neighborhood_out, int64_t *idx_out,
-                  int B, int N, int G, int k, void *stream);
+                  void *workspace, int B, int N, int G, int k, void *stream);
 
 /* query_ball_point -- models/pointnet2/pointnet2_utils.py:87-107
  * (pointbert/pointnet2_utils.py:119-139, pointMLP.py:87-107).

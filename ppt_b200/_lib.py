@@ -15,8 +15,9 @@ SIGNATURES = {
     "ppt_strerror": (_c.c_char_p, [_i]),
     "ppt_fps": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "ppt_square_distance": (_i, [_p, _p, _p, _i, _i, _i, _p]),
-    "ppt_knn": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "ppt_knn_group": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ppt_knn_workspace_bytes": (_i64, [_i, _i]),
+    "ppt_knn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ppt_knn_group": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ppt_ball_query": (_i, [_p, _p, _p, _f, _i, _i, _i, _i, _p]),
     "ppt_gather": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "ppt_group_concat": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

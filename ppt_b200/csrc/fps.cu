@@ -42,11 +42,6 @@ __device__ __forceinline__ unsigned long long sqr_f32x2(unsigned long long a) {
   asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(a));
   return r;
 }
-__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 __device__ __forceinline__ float max3_f32(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));

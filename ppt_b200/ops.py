@@ -60,29 +60,37 @@ def square_distance(src, dst):
     return out
 
 
-def knn(k, xyz, query, return_dist=False):
+def _knn_workspace(device, B, N, pruned):
+    """Scratch for the spatially-pruned search (None -> the kernels scan the whole cloud per query)."""
+    nbytes = _lib.load().ppt_knn_workspace_bytes(B, N) if pruned else 0
+    return _workspace((device, "knn"), nbytes) if nbytes > 0 else None
+
+
+def knn(k, xyz, query, return_dist=False, pruned=True):
     _need_cuda(xyz, query)
     xyz, query = _f32(xyz), _f32(query)
     B, N, _ = xyz.shape
     S = query.shape[1]
     idx = torch.empty((B, S, k), dtype=torch.int64, device=xyz.device)
     dist = torch.empty((B, S, k), dtype=torch.float32, device=xyz.device) if return_dist else None
+    ws = _knn_workspace(xyz.device, B, N, pruned)
     with torch.cuda.device(xyz.device):
-        _lib.check(_lib.load().ppt_knn(_ptr(xyz), _ptr(query), _ptr(idx), _ptr(dist), B, N, S, k, _stream(xyz)),
-                   "ppt_knn")
+        _lib.check(_lib.load().ppt_knn(_ptr(xyz), _ptr(query), _ptr(idx), _ptr(dist), _ptr(ws), B, N, S, k,
+                                       _stream(xyz)), "ppt_knn")
     return (idx, dist) if return_dist else idx
 
 
-def knn_group(xyz, center, k, return_idx=False):
+def knn_group(xyz, center, k, return_idx=False, pruned=True):
     _need_cuda(xyz, center)
     xyz, center = _f32(xyz), _f32(center)
     B, N, _ = xyz.shape
     G = center.shape[1]
     nb = torch.empty((B, G, k, 3), dtype=torch.float32, device=xyz.device)
     idx = torch.empty((B, G, k), dtype=torch.int64, device=xyz.device) if return_idx else None
+    ws = _knn_workspace(xyz.device, B, N, pruned)
     with torch.cuda.device(xyz.device):
-        _lib.check(_lib.load().ppt_knn_group(_ptr(xyz), _ptr(center), _ptr(nb), _ptr(idx), B, N, G, k, _stream(xyz)),
-                   "ppt_knn_group")
+        _lib.check(_lib.load().ppt_knn_group(_ptr(xyz), _ptr(center), _ptr(nb), _ptr(idx), _ptr(ws), B, N, G, k,
+                                             _stream(xyz)), "ppt_knn_group")
     return (nb, idx) if return_idx else nb
 
 
@@ -241,7 +249,7 @@ def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, 
     feats = torch.empty(lead + (256,), dtype=torch.float32, device=nb.device) if return_features else None
     if groups == 0:
         return (tokens, feats) if return_features else tokens
-    ws = _workspace(nb.device, lib.ppt_encoder_workspace_bytes(groups, mode))
+    ws = _workspace((nb.device, "encoder"), lib.ppt_encoder_workspace_bytes(groups, mode))
     with torch.cuda.device(nb.device):
         if phase_events is None:
             _lib.check(lib.ppt_encoder_forward_phases(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens),

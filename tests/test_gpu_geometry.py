@@ -57,22 +57,24 @@ def test_fps_per_cloud_start_and_first_index_ties(ops):
 
 KNN_CASES = [  # kind, B, N, S, k
     ("U", 2, 1024, 128, 32), ("U", 3, 1000, 37, 24), ("S", 1, 2048, 512, 32), ("U", 2, 8192, 512, 32),
+    ("S", 3, 8192, 512, 32), ("U", 2, 8191, 100, 7), ("C", 2, 4096, 300, 32),
     ("U", 2, 256, 256, 4), ("S", 1, 512, 256, 4), ("U", 1, 32, 5, 32), ("U", 1, 33, 70, 1), ("S", 1, 20000, 65, 32),
 ]
 
 
+@pytest.mark.parametrize("pruned", [True, False])
 @pytest.mark.parametrize("kind,B,N,S,k", KNN_CASES)
-def test_knn_matches_oracle_order_and_bits(ops, kind, B, N, S, k):
+def test_knn_matches_oracle_order_and_bits(ops, kind, B, N, S, k, pruned):
     xyz = cloud(kind, B, N, 900 + N)
     # queries are members of the cloud, as in Group.forward (self-distance can be negative, F3)
     sel = torch.stack([torch.randperm(N, generator=torch.Generator().manual_seed(b))[:S] if S <= N
                        else torch.arange(S) % N for b in range(B)])
     query = torch.gather(xyz, 1, sel.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     want_i, want_d = cpu.knn_point(k, xyz.numpy(), query.numpy(), return_dist=True)
-    got_i, got_d = ops.knn(k, dev(xyz), dev(query), return_dist=True)
+    got_i, got_d = ops.knn(k, dev(xyz), dev(query), return_dist=True, pruned=pruned)
     assert np.array_equal(got_i.cpu().numpy(), want_i)
     assert np.array_equal(bits(got_d), bits(want_d))
-    nb, gi = ops.knn_group(dev(xyz), dev(query), k, return_idx=True)
+    nb, gi = ops.knn_group(dev(xyz), dev(query), k, return_idx=True, pruned=pruned)
     assert np.array_equal(gi.cpu().numpy(), want_i)
     assert np.array_equal(bits(nb), bits(cpu.group_center(xyz.numpy(), want_i, query.numpy())))
 
