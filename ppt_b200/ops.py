@@ -208,12 +208,13 @@ def selftest_umma(a, b, mode=ENC_FP16, b_mn_major=False, a_packed=None):
 _workspaces = {}
 
 
-def _workspace(device, nbytes):
-    """Scratch owned by the host layer (the C ABI never allocates); grown on demand, one per device."""
-    buf = _workspaces.get(device)
+def _workspace(key, nbytes):
+    """Scratch owned by the host layer (the C ABI never allocates); grown on demand, one per
+    (device, purpose) key."""
+    buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _workspaces[device] = buf
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=key[0])
+        _workspaces[key] = buf
     return buf
 
 

@@ -47,6 +47,69 @@ class PointTokenizer(nn.Module):
         return tokens, center
 
 
+class HostPipeline:
+    """Host-to-host tokenization of a stream of batches: pinned host clouds in, pinned host tokens out.
+
+    Three CUDA streams (H2D copy, kernels, D2H copy) and `depth` rotating slots, so the copy of
+    batch i+1 and the read-back of batch i-1 overlap the kernels of batch i.  This is the path a
+    data-loader-fed caller uses (pc.to(gpu) ... features.cpu(), main_cls.py:188-189,
+    lp_feat_extractor.py:53-56), and what bench.py reports as `e2e`."""
+
+    def __init__(self, tokenizer, batch, points, depth=2, device=None):
+        self.tok = tokenizer
+        self.device = device or next(tokenizer.parameters()).device
+        self.depth = depth
+        G = tokenizer.num_group
+        D = tokenizer.reduce_dim.out_features
+        self.dev_in = [torch.empty((batch, points, 3), dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.out_tokens = [torch.empty((batch, G, D), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.out_center = [torch.empty((batch, G, 3), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_consumed = [torch.cuda.Event() for _ in range(depth)]  # kernels done reading dev_in[slot]
+
+    def run(self, host_batches, on_result=None):
+        """host_batches: iterable of pinned [B,N,3] fp32 tensors.  `on_result(i, tokens, center)` is
+        called with the pinned output buffers of batch i once they are complete (they are reused
+        `depth` batches later).  Returns the number of batches processed."""
+        pending = []
+        n = 0
+        for i, h in enumerate(host_batches):
+            slot = i % self.depth
+            if i >= self.depth:  # slot reuse: its previous outputs must have reached the host
+                self.ev_out[slot].synchronize()
+                if on_result is not None:
+                    j = pending.pop(0)
+                    on_result(j, self.out_tokens[slot], self.out_center[slot])
+            with torch.cuda.stream(self.s_in):
+                if i >= self.depth:
+                    self.s_in.wait_event(self.ev_consumed[slot])
+                self.dev_in[slot].copy_(h, non_blocking=True)
+                self.ev_in[slot].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[slot])
+                tokens, center = self.tok(self.dev_in[slot])
+                self.ev_consumed[slot].record(self.s_run)
+                self.ev_run[slot].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[slot])
+                tokens.record_stream(self.s_out)
+                center.record_stream(self.s_out)
+                self.out_tokens[slot].copy_(tokens, non_blocking=True)
+                self.out_center[slot].copy_(center, non_blocking=True)
+                self.ev_out[slot].record(self.s_out)
+            pending.append(i)
+            n += 1
+        for j in pending:
+            slot = j % self.depth
+            self.ev_out[slot].synchronize()
+            if on_result is not None:
+                on_result(j, self.out_tokens[slot], self.out_center[slot])
+        return n
+
+
 def shard_bounds(total, rank, world_size):
     """Contiguous [lo, hi) slice of `total` clouds for `rank` (mirrors DistributedSampler's even split,
     main_cls.py:74-76, but contiguous and without padding)."""
