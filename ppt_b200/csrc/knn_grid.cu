@@ -24,9 +24,10 @@ namespace {
 constexpr int GRID_MAX_N = 8192;
 constexpr int CELLS = 4096;              // 16^3
 constexpr int PREP_THREADS = 1024;
-constexpr int SEARCH_THREADS = 512;
-constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;
-constexpr int SEARCH_QPB = 64;           // queries per CTA
+constexpr int SEARCH_THREADS = 1024;     // 32 warps: the per-query work is latency-bound (shuffles), so
+constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;  // occupancy is what hides it
+constexpr int SEARCH_QPB = 128;          // queries per CTA
+constexpr int MERGE_MIN = 5;             // candidates in a row from which sort+merge beats serial insertion
 
 struct CloudHeader {  // 32 bytes at the start of each cloud's workspace record
   float lo[3];
@@ -219,12 +220,43 @@ __device__ __forceinline__ bool pair_less(float da, int ia, float db, int ib) {
   return da < db || (da == db && ia < ib);
 }
 
+// One compare-exchange stage of a bitonic network across the warp: partner = lane ^ j.
+__device__ __forceinline__ void bitonic_stage(float& d, int& i, int j, bool want_min, int lane) {
+  const float od = __shfl_xor_sync(PPT_FULL_MASK, d, j);
+  const int oi = __shfl_xor_sync(PPT_FULL_MASK, i, j);
+  const bool other_less = pair_less(od, oi, d, i);
+  if (other_less == want_min) { d = od; i = oi; }
+}
+// Full ascending sort of one (d, idx) pair per lane: 15 stages.
+__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+      bitonic_stage(d, i, j, ((lane & j) == 0) == ((lane & k) == 0), lane);
+}
+// list := the 32 smallest of (list U row), ascending.  Both inputs one pair per lane; the row need not be sorted.
+__device__ __forceinline__ void merge_row(TopList& t, float d, int i, int k, int lane) {
+  bitonic_sort32(d, i, lane);
+  const float rd = __shfl_sync(PPT_FULL_MASK, d, 31 - lane);  // descending copy of the row
+  const int ri = __shfl_sync(PPT_FULL_MASK, i, 31 - lane);
+  if (pair_less(rd, ri, t.d, t.i)) { t.d = rd; t.i = ri; }      // element-wise min: a bitonic sequence
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) bitonic_stage(t.d, t.i, j, (lane & j) == 0, lane);
+  t.tau_d = __shfl_sync(PPT_FULL_MASK, t.d, k - 1);
+  t.tau_i = __shfl_sync(PPT_FULL_MASK, t.i, k - 1);
+}
+
 __device__ __forceinline__ void scan_row(TopList& t, const float4* __restrict__ pts, const int* __restrict__ sidx,
                                          int row, float qx, float qy, float qz, float qn, int k, int lane) {
   const float4 p = pts[row * 32 + lane];
   const int pi = sidx[row * 32 + lane];
   const float d = ppt_pair_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
   unsigned bal = __ballot_sync(PPT_FULL_MASK, pair_less(d, pi, t.tau_d, t.tau_i));
+  if (__popc(bal) >= MERGE_MIN) {  // many candidates (seed rows, loose tau): one sort + merge
+    merge_row(t, d, pi, k, lane);
+    return;
+  }
   while (bal) {
     const int src = __ffs(bal) - 1;
     bal &= bal - 1;
