@@ -43,15 +43,24 @@ int ppt_abi_version(void);
 /* Human-readable text for a return code (static storage). */
 const char *ppt_strerror(int code);
 
+/* Spatial index of a batch of clouds (Morton-cell order + per-row bounding boxes), shared by
+ * ppt_fps and ppt_knn / ppt_knn_group: with it they skip the parts of a cloud that cannot change the
+ * result -- the outputs are bit-identical with and without it.  Supported for 512 <= N <= 8192
+ * (ppt_spatial_index_bytes returns 0 otherwise; pass index = NULL then).
+ *   index: ppt_spatial_index_bytes(B, N) bytes of caller-owned scratch, valid until xyz changes. */
+int64_t ppt_spatial_index_bytes(int B, int N);
+int ppt_spatial_index_build(const float *xyz, void *index, int B, int N, void *stream);
+
 /* farthest_point_sample -- models/pointbert/misc.py:44-69,
  * models/pointbert/pointnet2_utils.py:95-116, models/pointnet2/pointnet2_utils.py:63-84,
  * models/pointmlp/pointMLP.py:64-84 (identical results).
  * The caller draws `start` with the reference's own torch.randint call.
  *   xyz [B,N,3] f32; start [B] i64; idx_out [B,G] i64;
- *   centers_out [B,G,3] f32 or NULL (= index_points(xyz, idx), misc.py:12-24 `fps`).
+ *   centers_out [B,G,3] f32 or NULL (= index_points(xyz, idx), misc.py:12-24 `fps`);
+ *   index: NULL or a built spatial index of xyz.
  * N <= 65536. */
 int ppt_fps(const float *xyz, const int64_t *start, int64_t *idx_out, float *centers_out,
-            int B, int N, int G, void *stream);
+            const void *index, int B, int N, int G, void *stream);
 
 /* square_distance -- models/pointbert/dvae.py:130-149 (same text in both
  * pointnet2_utils.py copies and pointMLP.py:23-42).
@@ -61,18 +70,16 @@ int ppt_square_distance(const float *src, const float *dst, float *out, int B, i
 /* knn_point -- models/pointbert/dvae.py:116-127 (pointnet2_utils.py:20-34, pointMLP.py:110-121).
  *   xyz [B,N,3]; query [B,S,3] -> idx_out [B,S,k] i64, the k nearest under
  *   (distance, index), ascending; dist_out [B,S,k] f32 or NULL.  1 <= k <= 32, k <= N.
- *   workspace: NULL (full scan of the cloud per query), or ppt_knn_workspace_bytes(B, N) bytes of
- *   scratch, which enables the exact spatially-pruned search for 512 <= N <= 8192 (same results). */
-int64_t ppt_knn_workspace_bytes(int B, int N);
-int ppt_knn(const float *xyz, const float *query, int64_t *idx_out, float *dist_out, void *workspace,
+ *   index: NULL (full scan of the cloud per query) or a built spatial index of xyz (pruned search). */
+int ppt_knn(const float *xyz, const float *query, int64_t *idx_out, float *dist_out, const void *index,
             int B, int N, int S, int k, void *stream);
 
 /* Group.forward after FPS -- models/pointbert/dvae.py:159-181: kNN of each
  * centre, flat gather of the neighbours, subtraction of the centre.
  *   xyz [B,N,3]; center [B,G,3] -> neighborhood_out [B,G,k,3] f32;
- *   idx_out [B,G,k] i64 or NULL.  1 <= k <= 32.  workspace as for ppt_knn. */
+ *   idx_out [B,G,k] i64 or NULL.  1 <= k <= 32.  index as for ppt_knn. */
 int ppt_knn_group(const float *xyz, const float *center, float *neighborhood_out, int64_t *idx_out,
-                  void *workspace, int B, int N, int G, int k, void *stream);
+                  const void *index, int B, int N, int G, int k, void *stream);
 
 /* query_ball_point -- models/pointnet2/pointnet2_utils.py:87-107
  * (pointbert/pointnet2_utils.py:119-139, pointMLP.py:87-107).

@@ -13,9 +13,10 @@ _p, _i, _f, _i64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64
 SIGNATURES = {
     "ppt_abi_version": (_i, []),
     "ppt_strerror": (_c.c_char_p, [_i]),
-    "ppt_fps": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "ppt_spatial_index_bytes": (_i64, [_i, _i]),
+    "ppt_spatial_index_build": (_i, [_p, _p, _i, _i, _p]),
+    "ppt_fps": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "ppt_square_distance": (_i, [_p, _p, _p, _i, _i, _i, _p]),
-    "ppt_knn_workspace_bytes": (_i64, [_i, _i]),
     "ppt_knn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ppt_knn_group": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ppt_ball_query": (_i, [_p, _p, _p, _f, _i, _i, _i, _i, _p]),

@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "spatial_index.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -203,11 +204,12 @@ int launch_fps(const float* xyz, const int64_t* start, int64_t* idx_out, float* 
 
 }  // namespace
 
-extern "C" PPT_EXPORT int ppt_fps(const float* xyz, const int64_t* start, int64_t* idx_out, float* centers_out, int B, int N,
-                       int G, void* stream) {
+extern "C" PPT_EXPORT int ppt_fps(const float* xyz, const int64_t* start, int64_t* idx_out, float* centers_out,
+                                  const void* index, int B, int N, int G, void* stream) {
   if (!xyz || !start || !idx_out || B < 0 || N < 1 || G < 1) return PPT_EINVAL;
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (index && spidx::supported(N)) return ppt_fps_grid(xyz, start, index, idx_out, centers_out, B, N, G, st);
   if (N <= 512) return launch_fps<128, 4, 1>(xyz, start, idx_out, centers_out, B, N, G, st);
   if (N <= 1024) return launch_fps<256, 4, 1>(xyz, start, idx_out, centers_out, B, N, G, st);
   if (N <= 2048) return launch_fps<512, 4, 1>(xyz, start, idx_out, centers_out, B, N, G, st);

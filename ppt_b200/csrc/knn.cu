@@ -18,6 +18,7 @@
 // (SURVEY.md F6).  Distances use the reference's exact formula (F2) and may be
 // negative (F3).
 #include "common.cuh"
+#include "spatial_index.cuh"
 
 namespace {
 
@@ -130,23 +131,16 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ query, int64
 
 }  // namespace
 
-// knn_grid.cu: exact search with spatial pruning for clouds that fit in shared memory
-size_t ppt_knn_grid_workspace_bytes(int B, int N);
-int ppt_knn_grid_launch(const float* xyz, const float* query, void* workspace, int64_t* idx_out, float* dist_out,
-                        float* nb_out, int B, int N, int S, int k, bool group, cudaStream_t st);
-
 namespace {
-
-constexpr int KNN_GRID_MIN_N = 512;  // below this the full scan is already cheap
 
 template <bool GROUP>
 int launch_knn(const float* xyz, const float* query, int64_t* idx_out, float* dist_out, float* nb_out,
-               void* workspace, int B, int N, int S, int k, cudaStream_t st) {
+               const void* index, int B, int N, int S, int k, cudaStream_t st) {
   if (!xyz || !query || B < 0 || N < 1 || S < 1) return PPT_EINVAL;
   if (k < 1 || k > 32 || k > N) return PPT_ERANGE;
   if (B == 0) return 0;
-  if (workspace && N >= KNN_GRID_MIN_N && ppt_knn_grid_workspace_bytes(B, N) > 0)
-    return ppt_knn_grid_launch(xyz, query, workspace, idx_out, dist_out, nb_out, B, N, S, k, GROUP, st);
+  if (index && spidx::supported(N))
+    return ppt_knn_grid_search(xyz, query, index, idx_out, dist_out, nb_out, B, N, S, k, GROUP, st);
   auto kern = knn_kernel<GROUP>;
   const int resident = N < KNN_CHUNK ? ((N + 31) / 32) * 32 : KNN_CHUNK;
   const size_t smem = (size_t)resident * sizeof(float4);
@@ -178,22 +172,29 @@ __global__ void square_distance_kernel(const float* __restrict__ src, const floa
 
 }  // namespace
 
-extern "C" PPT_EXPORT int64_t ppt_knn_workspace_bytes(int B, int N) {
+extern "C" PPT_EXPORT int64_t ppt_spatial_index_bytes(int B, int N) {
   if (B < 0 || N < 1) return PPT_EINVAL;
-  return N >= KNN_GRID_MIN_N ? (int64_t)ppt_knn_grid_workspace_bytes(B, N) : 0;
+  return (int64_t)ppt_index_bytes(B, N);
+}
+
+extern "C" PPT_EXPORT int ppt_spatial_index_build(const float* xyz, void* index, int B, int N, void* stream) {
+  if (!xyz || !index || B < 0 || N < 1) return PPT_EINVAL;
+  if (!spidx::supported(N)) return PPT_ERANGE;
+  if (B == 0) return 0;
+  return ppt_index_build(xyz, index, B, N, (cudaStream_t)stream);
 }
 
 extern "C" PPT_EXPORT int ppt_knn(const float* xyz, const float* query, int64_t* idx_out, float* dist_out,
-                                  void* workspace, int B, int N, int S, int k, void* stream) {
+                                  const void* index, int B, int N, int S, int k, void* stream) {
   if (!idx_out) return PPT_EINVAL;
-  return launch_knn<false>(xyz, query, idx_out, dist_out, nullptr, workspace, B, N, S, k, (cudaStream_t)stream);
+  return launch_knn<false>(xyz, query, idx_out, dist_out, nullptr, index, B, N, S, k, (cudaStream_t)stream);
 }
 
 extern "C" PPT_EXPORT int ppt_knn_group(const float* xyz, const float* center, float* neighborhood_out,
-                                        int64_t* idx_out, void* workspace, int B, int N, int G, int k, void* stream) {
+                                        int64_t* idx_out, const void* index, int B, int N, int G, int k,
+                                        void* stream) {
   if (!neighborhood_out) return PPT_EINVAL;
-  return launch_knn<true>(xyz, center, idx_out, nullptr, neighborhood_out, workspace, B, N, G, k,
-                          (cudaStream_t)stream);
+  return launch_knn<true>(xyz, center, idx_out, nullptr, neighborhood_out, index, B, N, G, k, (cudaStream_t)stream);
 }
 
 extern "C" PPT_EXPORT int ppt_square_distance(const float* src, const float* dst, float* out, int B, int S, int N, void* stream) {

@@ -7,7 +7,7 @@
 //                       shared memory -> the cloud in cell order as float4 {x,y,z,|p|^2} + original
 //                       indices, one bounding box (+ max |p|^2) per row of 32 consecutive sorted points,
 //                       and the first sorted position of every cell.
-//   knn_search_kernel   CTA = (cloud, 64 queries), the sorted cloud resident in shared memory; a warp
+//   knn_search_kernel   CTA = (cloud, 128 queries), the sorted cloud resident in shared memory; a warp
 //                       takes one query at a time: seeds its sorted top-k list from the three rows
 //                       around the query's own cell, then visits only rows whose box can still hold a
 //                       point closer than the current k-th distance.
@@ -18,44 +18,20 @@
 // that.  Hence the result is bit-identical to the full scan; the order inside a cell (atomics) cannot
 // matter because candidates are ordered by (distance, original index) explicitly.
 #include "common.cuh"
+#include "spatial_index.cuh"
 
 namespace {
 
-constexpr int GRID_MAX_N = 8192;
-constexpr int CELLS = 4096;              // 16^3
+using spidx::CELLS;
+using spidx::CloudHeader;
+using spidx::RowBox;
+using GridLayout = spidx::Layout;
+constexpr int GRID_MAX_N = spidx::MAX_N;
 constexpr int PREP_THREADS = 1024;
 constexpr int SEARCH_THREADS = 1024;     // 32 warps: the per-query work is latency-bound (shuffles), so
 constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;  // occupancy is what hides it
 constexpr int SEARCH_QPB = 128;          // queries per CTA
 constexpr int MERGE_MIN = 5;             // candidates in a row from which sort+merge beats serial insertion
-
-struct CloudHeader {  // 32 bytes at the start of each cloud's workspace record
-  float lo[3];
-  float inv[3];       // cells per unit length
-  int rows;
-  int pad;
-};
-
-struct RowBox {       // 32 bytes
-  float lo[3];
-  float npmax;        // max |p|^2 in the row
-  float hi[3];
-  float unused;
-};
-
-__host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-
-struct GridLayout {   // byte offsets inside one cloud's workspace record
-  size_t pts, idx, boxes, cells, total;
-  __host__ __device__ explicit GridLayout(int N) {
-    const size_t np = (size_t)((N + 31) / 32) * 32;
-    pts = align256(sizeof(CloudHeader));
-    idx = pts + np * sizeof(float4);
-    boxes = idx + np * sizeof(int);
-    cells = boxes + (np / 32) * sizeof(RowBox);
-    total = align256(cells + (CELLS + 1) * sizeof(int));
-  }
-};
 
 __device__ __forceinline__ unsigned spread4(unsigned v) {  // 4 bits -> every third bit
   return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
@@ -366,26 +342,33 @@ size_t search_smem(int N) {
 
 }  // namespace
 
-// Internal entry points used by knn.cu (not part of the C ABI).
-size_t ppt_knn_grid_workspace_bytes(int B, int N) {
-  if (N > GRID_MAX_N) return 0;
+size_t ppt_index_bytes(int B, int N) {
+  if (!spidx::supported(N)) return 0;
   return (size_t)B * GridLayout(N).total;
 }
 
-int ppt_knn_grid_launch(const float* xyz, const float* query, void* workspace, int64_t* idx_out, float* dist_out,
-                        float* nb_out, int B, int N, int S, int k, bool group, cudaStream_t st) {
+int ppt_index_build(const float* xyz, void* index, int B, int N, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)prep_smem(GRID_MAX_N)));
+    configured = true;
+  }
+  knn_prepare_kernel<<<B, PREP_THREADS, prep_smem(N), st>>>(xyz, static_cast<unsigned char*>(index), N);
+  return ppt_launch_status();
+}
+
+int ppt_knn_grid_search(const float* xyz, const float* query, const void* index, int64_t* idx_out, float* dist_out,
+                        float* nb_out, int B, int N, int S, int k, bool group, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)search_smem(GRID_MAX_N)));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)search_smem(GRID_MAX_N)));
     configured = true;
   }
-  unsigned char* ws = static_cast<unsigned char*>(workspace);
-  knn_prepare_kernel<<<B, PREP_THREADS, prep_smem(N), st>>>(xyz, ws, N);
+  const unsigned char* ws = static_cast<const unsigned char*>(index);
   const int tiles = (S + SEARCH_QPB - 1) / SEARCH_QPB;
   if (group)
     knn_search_kernel<true><<<B * tiles, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out,

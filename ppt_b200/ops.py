@@ -32,8 +32,33 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def fps(xyz, npoint, start, return_centers=False):
-    """farthest_point_sample with a given start index tensor [B] -> idx [B,npoint] (int64)."""
+AUTO = "auto"
+
+
+def spatial_index(xyz):
+    """Builds the per-cloud spatial index used by fps / knn / knn_group to skip far-away rows of the
+    cloud (results are bit-identical with and without it).  Returns None where it does not apply
+    (N outside [512, 8192]).  The buffer is reused by the next call on the same device: build, use, discard."""
+    _need_cuda(xyz)
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    lib = _lib.load()
+    nbytes = lib.ppt_spatial_index_bytes(B, N)
+    if nbytes <= 0:
+        return None
+    buf = _workspace((xyz.device, "index"), nbytes)
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.ppt_spatial_index_build(_ptr(xyz), _ptr(buf), B, N, _stream(xyz)), "ppt_spatial_index_build")
+    return buf
+
+
+def _resolve_index(index, xyz):
+    return spatial_index(xyz) if isinstance(index, str) and index == AUTO else index
+
+
+def fps(xyz, npoint, start, return_centers=False, index=AUTO):
+    """farthest_point_sample with a given start index tensor [B] -> idx [B,npoint] (int64).
+    index: AUTO (build one if it applies), None (plain kernel), or the result of spatial_index(xyz)."""
     _need_cuda(xyz, start)
     xyz = _f32(xyz)
     B, N, C = xyz.shape
@@ -42,9 +67,10 @@ def fps(xyz, npoint, start, return_centers=False):
     start = _i64(start)
     idx = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
     centers = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device) if return_centers else None
+    index = _resolve_index(index, xyz) if npoint > 8 else (None if isinstance(index, str) else index)
     with torch.cuda.device(xyz.device):
-        _lib.check(_lib.load().ppt_fps(_ptr(xyz), _ptr(start), _ptr(idx), _ptr(centers), B, N, npoint, _stream(xyz)),
-                   "ppt_fps")
+        _lib.check(_lib.load().ppt_fps(_ptr(xyz), _ptr(start), _ptr(idx), _ptr(centers), _ptr(index), B, N, npoint,
+                                       _stream(xyz)), "ppt_fps")
     return (idx, centers) if return_centers else idx
 
 
@@ -60,36 +86,30 @@ def square_distance(src, dst):
     return out
 
 
-def _knn_workspace(device, B, N, pruned):
-    """Scratch for the spatially-pruned search (None -> the kernels scan the whole cloud per query)."""
-    nbytes = _lib.load().ppt_knn_workspace_bytes(B, N) if pruned else 0
-    return _workspace((device, "knn"), nbytes) if nbytes > 0 else None
-
-
-def knn(k, xyz, query, return_dist=False, pruned=True):
+def knn(k, xyz, query, return_dist=False, index=AUTO):
     _need_cuda(xyz, query)
     xyz, query = _f32(xyz), _f32(query)
     B, N, _ = xyz.shape
     S = query.shape[1]
     idx = torch.empty((B, S, k), dtype=torch.int64, device=xyz.device)
     dist = torch.empty((B, S, k), dtype=torch.float32, device=xyz.device) if return_dist else None
-    ws = _knn_workspace(xyz.device, B, N, pruned)
+    index = _resolve_index(index, xyz)
     with torch.cuda.device(xyz.device):
-        _lib.check(_lib.load().ppt_knn(_ptr(xyz), _ptr(query), _ptr(idx), _ptr(dist), _ptr(ws), B, N, S, k,
+        _lib.check(_lib.load().ppt_knn(_ptr(xyz), _ptr(query), _ptr(idx), _ptr(dist), _ptr(index), B, N, S, k,
                                        _stream(xyz)), "ppt_knn")
     return (idx, dist) if return_dist else idx
 
 
-def knn_group(xyz, center, k, return_idx=False, pruned=True):
+def knn_group(xyz, center, k, return_idx=False, index=AUTO):
     _need_cuda(xyz, center)
     xyz, center = _f32(xyz), _f32(center)
     B, N, _ = xyz.shape
     G = center.shape[1]
     nb = torch.empty((B, G, k, 3), dtype=torch.float32, device=xyz.device)
     idx = torch.empty((B, G, k), dtype=torch.int64, device=xyz.device) if return_idx else None
-    ws = _knn_workspace(xyz.device, B, N, pruned)
+    index = _resolve_index(index, xyz)
     with torch.cuda.device(xyz.device):
-        _lib.check(_lib.load().ppt_knn_group(_ptr(xyz), _ptr(center), _ptr(nb), _ptr(idx), _ptr(ws), B, N, G, k,
+        _lib.check(_lib.load().ppt_knn_group(_ptr(xyz), _ptr(center), _ptr(nb), _ptr(idx), _ptr(index), B, N, G, k,
                                              _stream(xyz)), "ppt_knn_group")
     return (nb, idx) if return_idx else nb
 

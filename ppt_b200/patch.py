@@ -70,8 +70,9 @@ def _set(owner, name, value):
 def _group_forward(self, xyz):
     """Group.forward, models/pointbert/dvae.py:159-181."""
     start = pointbert._draw_start(xyz)
-    _, center = ops.fps(xyz, self.num_group, start, return_centers=True)
-    return ops.knn_group(xyz, center, self.group_size), center
+    index = ops.spatial_index(xyz)
+    _, center = ops.fps(xyz, self.num_group, start, return_centers=True, index=index)
+    return ops.knn_group(xyz, center, self.group_size, index=index), center
 
 
 def _encoder_forward(self, point_groups):

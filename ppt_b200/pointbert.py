@@ -62,8 +62,9 @@ class Group(nn.Module):
     def forward(self, xyz):
         """xyz [B,N,3] -> neighborhood [B,G,M,3], center [B,G,3]."""
         start = _draw_start(xyz) if self.start_idx is None else _as_start(self.start_idx, xyz)
-        _, center = ops.fps(xyz, self.num_group, start, return_centers=True)
-        neighborhood = ops.knn_group(xyz, center, self.group_size)
+        index = ops.spatial_index(xyz)  # one index serves both FPS and kNN
+        _, center = ops.fps(xyz, self.num_group, start, return_centers=True, index=index)
+        neighborhood = ops.knn_group(xyz, center, self.group_size, index=index)
         return neighborhood, center
 
 

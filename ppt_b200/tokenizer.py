@@ -34,8 +34,9 @@ class PointTokenizer(nn.Module):
 
     def group(self, xyz):
         start = _draw_start(xyz) if self.start_idx is None else _as_start(self.start_idx, xyz)
-        _, center = ops.fps(xyz, self.num_group, start, return_centers=True)
-        return ops.knn_group(xyz, center, self.group_size), center
+        index = ops.spatial_index(xyz)  # one index serves both FPS and kNN
+        _, center = ops.fps(xyz, self.num_group, start, return_centers=True, index=index)
+        return ops.knn_group(xyz, center, self.group_size, index=index), center
 
     @torch.no_grad()
     def forward(self, xyz, return_neighborhood=False):

@@ -30,15 +30,17 @@ FPS_CASES = [  # kind, B, N, G, start
     ("U", 2, 1024, 128, 0), ("U", 3, 1000, 37, 5), ("S", 1, 2048, 512, 0), ("U", 4, 8192, 512, 0),
     ("S", 2, 512, 128, 7), ("U", 2, 100, 100, 3), ("U", 1, 4096, 256, 0), ("U", 2, 3, 3, 1),
     ("S", 1, 32768, 512, 0), ("U", 1, 20000, 64, 11), ("U", 1, 65536, 32, 0), ("S", 2, 12000, 128, 0),
+    ("S", 3, 8192, 512, 0), ("C", 2, 4096, 300, 2), ("U", 2, 8191, 1024, 8190), ("C", 1, 600, 600, 0),
 ]
 
 
+@pytest.mark.parametrize("indexed", [True, False])
 @pytest.mark.parametrize("kind,B,N,G,start", FPS_CASES)
-def test_fps_indices_bit_exact(ops, kind, B, N, G, start):
+def test_fps_indices_bit_exact(ops, kind, B, N, G, start, indexed):
     xyz = cloud(kind, B, N, 500 + N)
     want = cpu.farthest_point_sample(xyz.numpy(), G, start)
     st = torch.full((B,), start, dtype=torch.int64)
-    got, centers = ops.fps(dev(xyz), G, dev(st), return_centers=True)
+    got, centers = ops.fps(dev(xyz), G, dev(st), return_centers=True, index=ops.AUTO if indexed else None)
     assert np.array_equal(got.cpu().numpy(), want)
     assert np.array_equal(bits(centers), bits(cpu.index_points(xyz.numpy(), want)))
 
@@ -71,10 +73,11 @@ def test_knn_matches_oracle_order_and_bits(ops, kind, B, N, S, k, pruned):
                        else torch.arange(S) % N for b in range(B)])
     query = torch.gather(xyz, 1, sel.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     want_i, want_d = cpu.knn_point(k, xyz.numpy(), query.numpy(), return_dist=True)
-    got_i, got_d = ops.knn(k, dev(xyz), dev(query), return_dist=True, pruned=pruned)
+    ix = ops.AUTO if pruned else None
+    got_i, got_d = ops.knn(k, dev(xyz), dev(query), return_dist=True, index=ix)
     assert np.array_equal(got_i.cpu().numpy(), want_i)
     assert np.array_equal(bits(got_d), bits(want_d))
-    nb, gi = ops.knn_group(dev(xyz), dev(query), k, return_idx=True, pruned=pruned)
+    nb, gi = ops.knn_group(dev(xyz), dev(query), k, return_idx=True, index=ix)
     assert np.array_equal(gi.cpu().numpy(), want_i)
     assert np.array_equal(bits(nb), bits(cpu.group_center(xyz.numpy(), want_i, query.numpy())))
 
