@@ -248,18 +248,27 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
     const float act_scale = __ldg(sc + 5), grp_scale = __ldg(sc + 6);
     const float inv_p2s = __ldg(sc + 2) * act_scale;  // accumulator -> scaled activation, one FFMA per element
 
-    auto build_h1 = [&](int tile, uint32_t slot) {
-      // h1[p][ch] = relu(w.x + b), K = 3 on CUDA cores; written as the K-major B operand.
-      constexpr int TPP = EPI_THREADS / NT;          // threads per point
-      constexpr int CH = 128 / TPP;                  // channels per thread
-      const int p = e % NT, ch0 = (e / NT) * CH;     // ch0 is warp-uniform: w1s reads broadcast
-      unsigned char* dst = h1buf + slot * H1_BUF;
+    // This thread's point of a tile, fetched one build ahead: the load comes from HBM (the neighbourhoods
+    // are read here for the first time) and would otherwise stall the first FFMA of every build.
+    constexpr int TPP = EPI_THREADS / NT;            // threads per point
+    constexpr int CH = 128 / TPP;                    // channels per thread
+    const int p = e % NT, ch0 = (e / NT) * CH;       // ch0 is warp-uniform: w1s reads broadcast
+    float nx = 0.f, ny = 0.f, nz = 0.f;              // coordinates for the NEXT build_h1 call
+    auto fetch_point = [&](int tile) {
+      nx = ny = nz = 0.f;
       const long long gp = (long long)tile * NT + p;
-      float x = 0.f, y = 0.f, z = 0.f;
-      if (gp < num_groups * 32) {
+      if (tile < num_tiles && gp < num_groups * 32) {
         const float* src = nbhd + gp * 3;
-        x = src[0]; y = src[1]; z = src[2];
+        nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
       }
+    };
+    // builds h1 of `tile` from the prefetched point, then prefetches the point of `tile_after`
+    auto build_h1 = [&](int tile, uint32_t slot, int tile_after) {
+      // h1[p][ch] = relu(w.x + b), K = 3 on CUDA cores; written as the K-major B operand.
+      unsigned char* dst = h1buf + slot * H1_BUF;
+      const float x = nx, y = ny, z = nz;
+      fetch_point(tile_after);
+      (void)tile;
 #pragma unroll 4
       for (int c8 = 0; c8 < CH; c8 += 8) {
         float v[8];
@@ -288,9 +297,11 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
     };
 
     if ((int)blockIdx.x < num_tiles) {
+      fetch_point(blockIdx.x);
       load_c(blockIdx.x);
-      build_h1(blockIdx.x, 0);
-      if (STAGE == 1 && (int)(blockIdx.x + gridDim.x) < num_tiles) build_h1(blockIdx.x + gridDim.x, 1);
+      build_h1(blockIdx.x, 0, blockIdx.x + gridDim.x);
+      if (STAGE == 1 && (int)(blockIdx.x + gridDim.x) < num_tiles)
+        build_h1(blockIdx.x + gridDim.x, 1, blockIdx.x + 2 * gridDim.x);
     }
 
     uint32_t tile_it = 0;
@@ -365,14 +376,14 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
           const int next = tile + gridDim.x;
           if (next < num_tiles) {
             load_c(next);
-            build_h1(next, 0);
+            build_h1(next, 0, next + gridDim.x);
           }
         }
       }
       // Stage 1: both units of this tile are drained, so its h1 buffer is free for tile + 2.
       if (STAGE == 1) {
         const int next2 = tile + 2 * gridDim.x;
-        if (next2 < num_tiles) build_h1(next2, tile_it & 1u);
+        if (next2 < num_tiles) build_h1(next2, tile_it & 1u, next2 + gridDim.x);
       }
     }
   }

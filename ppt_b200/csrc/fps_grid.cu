@@ -8,28 +8,31 @@
 // evaluated with the very same rounded operations.  If lb >= the row's largest running min-distance,
 // min(mind, d) leaves every point of the row unchanged and the row (and its cached argmax) is skipped.
 //
-// One CTA per cloud, 32 warps; warp w owns rows w, w+32, ... (a centre's neighbourhood is a run of
-// consecutive Morton rows, so interleaving spreads the affected rows over the warps).  Lane j of a warp
-// also keeps row (w + 32 j)'s box, max and argmax, so the skip test of all rows of a warp is ONE pass
-// over 8 lanes.  Ties: (max value, smallest ORIGINAL index), as torch.max.
+// One CTA per cloud, 16 warps.  The sorted cloud, the running min-distances and the original indices
+// live in shared memory (one point per lane per row: conflict-free), so the rows a centre touches are
+// visited with a plain loop over the set bits of a ballot.  Warp w owns rows w, w+16, ... (a centre's
+// neighbourhood is a run of consecutive Morton rows, so interleaving spreads them over the warps) and
+// lane j keeps row (w + 16 j)'s box, max, argmax index and argmax position, so the skip test of all
+// rows of a warp is ONE pass.  Ties: (max value, smallest ORIGINAL index), as torch.max.
 #include "common.cuh"
 #include "spatial_index.cuh"
 
 namespace {
 
-constexpr int FG_THREADS = 1024;
-constexpr int FG_WARPS = 32;
+constexpr int FG_WARPS = 16;
+constexpr int FG_THREADS = FG_WARPS * 32;
+constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most: 16
 
-template <int RPW>  // rows per warp: rows <= 32 * RPW
 __global__ void __launch_bounds__(FG_THREADS, 1)
 fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start,
                 const unsigned char* __restrict__ index, int64_t* __restrict__ idx_out,
                 float* __restrict__ centers_out, int N, int G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sx = reinterpret_cast<float*>(smem_raw);   // unsorted cloud, SoA: centroid lookup by original index
-  float* sy = sx + N;
-  float* sz = sy + N;
-  int2* slot = reinterpret_cast<int2*>(sz + N);     // [2][32]
+  const int np = (N + 31) & ~31, rows = np / 32;
+  float4* spts = reinterpret_cast<float4*>(smem_raw);       // [np] sorted {x,y,z,|p|^2}
+  float* smind = reinterpret_cast<float*>(spts + np);       // [np] running min-distance (-1: padding)
+  unsigned* soid = reinterpret_cast<unsigned*>(smind + np); // [np] original index
+  int4* slot = reinterpret_cast<int4*>(soid + np);          // [2][FG_WARPS] (value bits, index, position, -)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -39,47 +42,31 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   const float4* pts = reinterpret_cast<const float4*>(rec + L.pts);
   const int* sidx = reinterpret_cast<const int*>(rec + L.idx);
   const spidx::RowBox* boxes = reinterpret_cast<const spidx::RowBox*>(rec + L.boxes);
-  const int rows = (N + 31) / 32;
 
-  for (int i = tid; i < 3 * N; i += FG_THREADS) {
-    const float v = cloud[i];
-    const int n = i / 3, c = i - n * 3;
-    (c == 0 ? sx : c == 1 ? sy : sz)[n] = v;
+  for (int i = tid; i < np; i += FG_THREADS) {
+    spts[i] = __ldg(pts + i);
+    const int o = __ldg(sidx + i);
+    soid[i] = (unsigned)o;
+    smind[i] = o != 0x7fffffff ? 1e10f : -1.0f;
   }
 
-  // this lane's point of each owned row
-  float px[RPW], py[RPW], pz[RPW], mind[RPW];
-  unsigned oid[RPW];
-#pragma unroll
-  for (int j = 0; j < RPW; ++j) {
-    const int row = warp + FG_WARPS * j;
-    px[j] = py[j] = pz[j] = 0.f;
-    mind[j] = -1.0f;
-    oid[j] = 0xffffffffu;
-    if (row < rows) {
-      const float4 p = __ldg(pts + row * 32 + lane);
-      const int o = __ldg(sidx + row * 32 + lane);
-      px[j] = p.x; py[j] = p.y; pz[j] = p.z;
-      if (o != 0x7fffffff) { mind[j] = 1e10f; oid[j] = (unsigned)o; }
-    }
-  }
-  // lane j < RPW: state of row (warp + 32 j)
+  // lane j: state of row (warp + FG_WARPS * j)
+  const int myrow = warp + FG_WARPS * lane;
+  const bool owner = lane < FG_RPW && myrow < rows;
   float blo0 = 0.f, blo1 = 0.f, blo2 = 0.f, bhi0 = 0.f, bhi1 = 0.f, bhi2 = 0.f;
-  float rmax = -1.0f;         // largest running min-distance in the row (-1: no real point)
-  unsigned rarg = 0xffffffffu;
-  {
-    const int myrow = warp + FG_WARPS * lane;
-    if (lane < RPW && myrow < rows) {
-      const spidx::RowBox bx = boxes[myrow];
-      blo0 = bx.lo[0]; blo1 = bx.lo[1]; blo2 = bx.lo[2];
-      bhi0 = bx.hi[0]; bhi1 = bx.hi[1]; bhi2 = bx.hi[2];
-      rmax = 1e10f;  // forces the first iteration to visit the row
-    }
+  float rmax = -1.0f;          // largest running min-distance in the row (-1: nothing to pick)
+  unsigned rarg = 0xffffffffu; // original index of that point (smallest among equals)
+  int rpos = 0;                // its sorted position
+  if (owner) {
+    const spidx::RowBox bx = boxes[myrow];
+    blo0 = bx.lo[0]; blo1 = bx.lo[1]; blo2 = bx.lo[2];
+    bhi0 = bx.hi[0]; bhi1 = bx.hi[1]; bhi2 = bx.hi[2];
+    rmax = 1e10f;  // forces the first iteration to visit the row
   }
   __syncthreads();
 
   unsigned far = (unsigned)start[b];
-  float cx = sx[far], cy = sy[far], cz = sz[far];
+  float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
   int64_t* out = idx_out + (size_t)b * G;
   float* cout = centers_out ? centers_out + (size_t)b * G * 3 : nullptr;
   const int neg1 = __float_as_int(-1.0f);
@@ -96,57 +83,58 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
     const float gy = fmaxf(fmaxf(__fsub_rn(blo1, cy), __fsub_rn(cy, bhi1)), 0.f);
     const float gz = fmaxf(fmaxf(__fsub_rn(blo2, cz), __fsub_rn(cz, bhi2)), 0.f);
     const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-    const unsigned mask = __ballot_sync(PPT_FULL_MASK, lane < RPW && lb < rmax);
+    unsigned mask = __ballot_sync(PPT_FULL_MASK, owner && lb < rmax);
 
-#pragma unroll
-    for (int j = 0; j < RPW; ++j) {
-      if (mask & (1u << j)) {  // warp-uniform
-        const float d = ppt_fps_dist(px[j], py[j], pz[j], cx, cy, cz);
-        const float m = fminf(mind[j], d);  // torch.min(distance, dist)
-        mind[j] = m;
-        const int vb = __float_as_int(m);
-        const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
-        const unsigned widx = __reduce_min_sync(PPT_FULL_MASK, vb == wmax ? oid[j] : 0xffffffffu);
-        if (lane == j) { rmax = __int_as_float(wmax); rarg = widx; }
-      }
+    while (mask) {  // warp-uniform
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int pos = (warp + FG_WARPS * j) * 32 + lane;
+      const float4 p = spts[pos];
+      const float d = ppt_fps_dist(p.x, p.y, p.z, cx, cy, cz);
+      const float m = fminf(smind[pos], d);  // torch.min(distance, dist); padding stays -1
+      smind[pos] = m;
+      const int vb = __float_as_int(m);
+      const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
+      const unsigned cand = vb == wmax ? soid[pos] : 0xffffffffu;
+      const unsigned widx = __reduce_min_sync(PPT_FULL_MASK, cand);
+      const int wl = __ffs(__ballot_sync(PPT_FULL_MASK, cand == widx)) - 1;
+      if (lane == j) { rmax = __int_as_float(wmax); rarg = widx; rpos = pos - lane + wl; }
     }
 
     // best row of this warp, then of the block (one barrier per iteration, double-buffered slots)
-    const int vb = lane < RPW ? __float_as_int(rmax) : neg1;
+    const int vb = owner ? __float_as_int(rmax) : neg1;
     const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
-    const unsigned widx = __reduce_min_sync(PPT_FULL_MASK, (lane < RPW && vb == wmax) ? rarg : 0xffffffffu);
+    const unsigned cand = (owner && vb == wmax) ? rarg : 0xffffffffu;
+    const unsigned widx = __reduce_min_sync(PPT_FULL_MASK, cand);
+    const int wl = __ffs(__ballot_sync(PPT_FULL_MASK, owner && vb == wmax && rarg == widx)) - 1;
+    const int wpos = __shfl_sync(PPT_FULL_MASK, rpos, wl < 0 ? 0 : wl);
     const int par = g & 1;
-    if (lane == 0) slot[par * 32 + warp] = make_int2(wmax, (int)widx);
+    if (lane == 0) slot[par * FG_WARPS + warp] = make_int4(wmax, (int)widx, wpos, 0);
     __syncthreads();
-    const int2 s = slot[par * 32 + lane];
+    const int4 s = lane < FG_WARPS ? slot[par * FG_WARPS + lane] : make_int4(neg1, -1, 0, 0);
     const int cmax = __reduce_max_sync(PPT_FULL_MASK, s.x);
-    far = __reduce_min_sync(PPT_FULL_MASK, s.x == cmax ? (unsigned)s.y : 0xffffffffu);
-    cx = sx[far]; cy = sy[far]; cz = sz[far];
+    const unsigned ccand = s.x == cmax ? (unsigned)s.y : 0xffffffffu;
+    far = __reduce_min_sync(PPT_FULL_MASK, ccand);
+    const int cl = __ffs(__ballot_sync(PPT_FULL_MASK, s.x == cmax && (unsigned)s.y == far)) - 1;
+    const int cpos = __shfl_sync(PPT_FULL_MASK, s.z, cl < 0 ? 0 : cl);
+    const float4 c = spts[cpos];
+    cx = c.x; cy = c.y; cz = c.z;
   }
-}
-
-template <int RPW>
-int launch(const float* xyz, const int64_t* start, const unsigned char* index, int64_t* idx_out, float* centers_out,
-           int B, int N, int G, cudaStream_t st) {
-  auto kern = fps_grid_kernel<RPW>;
-  static bool configured = false;
-  if (!configured) {
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(spidx::MAX_N * 12 + 64 * sizeof(int2))));
-    configured = true;
-  }
-  const size_t smem = (size_t)N * 12 + 64 * sizeof(int2);
-  kern<<<B, FG_THREADS, smem, st>>>(xyz, start, index, idx_out, centers_out, N, G);
-  return ppt_launch_status();
 }
 
 }  // namespace
 
 int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                  int B, int N, int G, cudaStream_t st) {
-  const unsigned char* ix = static_cast<const unsigned char*>(index);
-  const int rows = (N + 31) / 32;
-  if (rows <= 64) return launch<2>(xyz, start, ix, idx_out, centers_out, B, N, G, st);
-  if (rows <= 128) return launch<4>(xyz, start, ix, idx_out, centers_out, B, N, G, st);
-  return launch<8>(xyz, start, ix, idx_out, centers_out, B, N, G, st);
+  static bool configured = false;
+  const size_t slots = 2 * FG_WARPS * sizeof(int4);
+  if (!configured) {
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)spidx::MAX_N * 24 + slots)));
+    configured = true;
+  }
+  const size_t smem = (size_t)((N + 31) & ~31) * 24 + slots;
+  fps_grid_kernel<<<B, FG_THREADS, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,
+                                              centers_out, N, G);
+  return ppt_launch_status();
 }
