@@ -8,20 +8,23 @@
 // evaluated with the very same rounded operations.  If lb >= the row's largest running min-distance,
 // min(mind, d) leaves every point of the row unchanged and the row (and its cached argmax) is skipped.
 //
-// One CTA per cloud, 16 warps.  The sorted cloud, the running min-distances and the original indices
-// live in shared memory (one point per lane per row: conflict-free), so the rows a centre touches are
-// visited with a plain loop over the set bits of a ballot.  Warp w owns rows w, w+16, ... (a centre's
-// neighbourhood is a run of consecutive Morton rows, so interleaving spreads them over the warps) and
-// lane j keeps row (w + 16 j)'s box, max, argmax index and argmax position, so the skip test of all
-// rows of a warp is ONE pass.  Ties: (max value, smallest ORIGINAL index), as torch.max.
+// One CTA per cloud, 32 warps.  The kernel is bound by the dependent-latency chain of one iteration
+// (skip test -> row updates -> warp argmax -> barrier -> block argmax -> centroid), not by work, so:
+//  * the sorted cloud, running min-distances and original indices live in shared memory (one point
+//    per lane per row: conflict-free) and the rows a centre touches are visited with a loop over the
+//    set bits of a ballot; warp w owns rows w, w+32, ... (a centre's neighbourhood is a run of
+//    consecutive Morton rows, so interleaving leaves at most one or two per warp);
+//  * lane j keeps row (w + 32 j)'s box, max and argmax POSITION, so the skip test of all rows of a
+//    warp is one pass and every argmax level is ONE max-reduction plus a ballot; the original-index
+//    tie-break (torch.max keeps the first index, F4) runs only when the ballot shows an actual tie.
 #include "common.cuh"
 #include "spatial_index.cuh"
 
 namespace {
 
-constexpr int FG_WARPS = 16;
+constexpr int FG_WARPS = 32;
 constexpr int FG_THREADS = FG_WARPS * 32;
-constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most: 16
+constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most: 8
 
 __global__ void __launch_bounds__(FG_THREADS, 1)
 fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start,
@@ -32,7 +35,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   float4* spts = reinterpret_cast<float4*>(smem_raw);       // [np] sorted {x,y,z,|p|^2}
   float* smind = reinterpret_cast<float*>(spts + np);       // [np] running min-distance (-1: padding)
   unsigned* soid = reinterpret_cast<unsigned*>(smind + np); // [np] original index
-  int4* slot = reinterpret_cast<int4*>(soid + np);          // [2][FG_WARPS] (value bits, index, position, -)
+  int2* slot = reinterpret_cast<int2*>(soid + np);          // [2][FG_WARPS] (value bits, sorted position)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -55,8 +58,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   const bool owner = lane < FG_RPW && myrow < rows;
   float blo0 = 0.f, blo1 = 0.f, blo2 = 0.f, bhi0 = 0.f, bhi1 = 0.f, bhi2 = 0.f;
   float rmax = -1.0f;          // largest running min-distance in the row (-1: nothing to pick)
-  unsigned rarg = 0xffffffffu; // original index of that point (smallest among equals)
-  int rpos = 0;                // its sorted position
+  int rpos = 0;                // sorted position of that point (smallest original index among equals)
   if (owner) {
     const spidx::RowBox bx = boxes[myrow];
     blo0 = bx.lo[0]; blo1 = bx.lo[1]; blo2 = bx.lo[2];
@@ -95,28 +97,35 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
       smind[pos] = m;
       const int vb = __float_as_int(m);
       const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
-      const unsigned cand = vb == wmax ? soid[pos] : 0xffffffffu;
-      const unsigned widx = __reduce_min_sync(PPT_FULL_MASK, cand);
-      const int wl = __ffs(__ballot_sync(PPT_FULL_MASK, cand == widx)) - 1;
-      if (lane == j) { rmax = __int_as_float(wmax); rarg = widx; rpos = pos - lane + wl; }
+      unsigned eq = __ballot_sync(PPT_FULL_MASK, vb == wmax);
+      if (eq & (eq - 1)) {  // several lanes hold the maximum: the smallest original index wins
+        const unsigned cand = vb == wmax ? soid[pos] : 0xffffffffu;
+        eq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+      }
+      if (lane == j) { rmax = __int_as_float(wmax); rpos = pos - lane + __ffs(eq) - 1; }
     }
 
     // best row of this warp, then of the block (one barrier per iteration, double-buffered slots)
     const int vb = owner ? __float_as_int(rmax) : neg1;
     const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
-    const unsigned cand = (owner && vb == wmax) ? rarg : 0xffffffffu;
-    const unsigned widx = __reduce_min_sync(PPT_FULL_MASK, cand);
-    const int wl = __ffs(__ballot_sync(PPT_FULL_MASK, owner && vb == wmax && rarg == widx)) - 1;
-    const int wpos = __shfl_sync(PPT_FULL_MASK, rpos, wl < 0 ? 0 : wl);
+    unsigned eq = __ballot_sync(PPT_FULL_MASK, owner && vb == wmax);
+    if (eq & (eq - 1)) {
+      const unsigned cand = (owner && vb == wmax) ? soid[rpos] : 0xffffffffu;
+      eq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+    }
+    const int wpos = __shfl_sync(PPT_FULL_MASK, rpos, eq ? __ffs(eq) - 1 : 0);
     const int par = g & 1;
-    if (lane == 0) slot[par * FG_WARPS + warp] = make_int4(wmax, (int)widx, wpos, 0);
+    if (lane == 0) slot[par * FG_WARPS + warp] = make_int2(wmax, wpos);
     __syncthreads();
-    const int4 s = lane < FG_WARPS ? slot[par * FG_WARPS + lane] : make_int4(neg1, -1, 0, 0);
+    const int2 s = slot[par * FG_WARPS + lane];
     const int cmax = __reduce_max_sync(PPT_FULL_MASK, s.x);
-    const unsigned ccand = s.x == cmax ? (unsigned)s.y : 0xffffffffu;
-    far = __reduce_min_sync(PPT_FULL_MASK, ccand);
-    const int cl = __ffs(__ballot_sync(PPT_FULL_MASK, s.x == cmax && (unsigned)s.y == far)) - 1;
-    const int cpos = __shfl_sync(PPT_FULL_MASK, s.z, cl < 0 ? 0 : cl);
+    unsigned ceq = __ballot_sync(PPT_FULL_MASK, s.x == cmax);
+    if (ceq & (ceq - 1)) {
+      const unsigned cand = s.x == cmax ? soid[s.y] : 0xffffffffu;
+      ceq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+    }
+    const int cpos = __shfl_sync(PPT_FULL_MASK, s.y, __ffs(ceq) - 1);
+    far = soid[cpos];
     const float4 c = spts[cpos];
     cx = c.x; cy = c.y; cz = c.z;
   }
@@ -127,7 +136,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
 int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                  int B, int N, int G, cudaStream_t st) {
   static bool configured = false;
-  const size_t slots = 2 * FG_WARPS * sizeof(int4);
+  const size_t slots = 2 * FG_WARPS * sizeof(int2);
   if (!configured) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)spidx::MAX_N * 24 + slots)));
