@@ -17,19 +17,20 @@
 //  * lane j keeps row (w + 32 j)'s box, max and argmax POSITION, so the skip test of all rows of a
 //    warp is one pass and every argmax level is ONE max-reduction plus a ballot; the original-index
 //    tie-break (torch.max keeps the first index, F4) runs only when the ballot shows an actual tie.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "spatial_index.cuh"
 
 namespace {
 
-constexpr int FG_WARPS = 32;
-constexpr int FG_THREADS = FG_WARPS * 32;
-constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most: 8
-
-__global__ void __launch_bounds__(FG_THREADS, 1)
+template <int FG_WARPS>
+__global__ void __launch_bounds__(FG_WARPS * 32, 1)
 fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start,
                 const unsigned char* __restrict__ index, int64_t* __restrict__ idx_out,
                 float* __restrict__ centers_out, int N, int G) {
+  constexpr int FG_THREADS = FG_WARPS * 32;
+  constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = (N + 31) & ~31, rows = np / 32;
   float4* spts = reinterpret_cast<float4*>(smem_raw);       // [np] sorted {x,y,z,|p|^2}
@@ -87,22 +88,32 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
     const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
     unsigned mask = __ballot_sync(PPT_FULL_MASK, owner && lb < rmax);
 
+    // Two rows per pass: their load -> distance -> reduce chains are independent and overlap.
     while (mask) {  // warp-uniform
-      const int j = __ffs(mask) - 1;
+      const int j0 = __ffs(mask) - 1;
       mask &= mask - 1;
-      const int pos = (warp + FG_WARPS * j) * 32 + lane;
-      const float4 p = spts[pos];
-      const float d = ppt_fps_dist(p.x, p.y, p.z, cx, cy, cz);
-      const float m = fminf(smind[pos], d);  // torch.min(distance, dist); padding stays -1
-      smind[pos] = m;
-      const int vb = __float_as_int(m);
-      const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
-      unsigned eq = __ballot_sync(PPT_FULL_MASK, vb == wmax);
-      if (eq & (eq - 1)) {  // several lanes hold the maximum: the smallest original index wins
-        const unsigned cand = vb == wmax ? soid[pos] : 0xffffffffu;
-        eq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+      const bool two = mask != 0;
+      const int j1 = two ? __ffs(mask) - 1 : j0;
+      mask &= mask - 1;  // no-op when it is already 0
+      const int pos0 = (warp + FG_WARPS * j0) * 32 + lane, pos1 = (warp + FG_WARPS * j1) * 32 + lane;
+      const float4 p0 = spts[pos0], p1 = spts[pos1];
+      const float m0 = fminf(smind[pos0], ppt_fps_dist(p0.x, p0.y, p0.z, cx, cy, cz));  // torch.min(distance, dist)
+      const float m1 = fminf(smind[pos1], ppt_fps_dist(p1.x, p1.y, p1.z, cx, cy, cz));  // padding stays -1
+      smind[pos0] = m0;
+      if (two) smind[pos1] = m1;
+      const int vb0 = __float_as_int(m0), vb1 = __float_as_int(m1);
+      const int w0 = __reduce_max_sync(PPT_FULL_MASK, vb0), w1 = __reduce_max_sync(PPT_FULL_MASK, vb1);
+      unsigned eq0 = __ballot_sync(PPT_FULL_MASK, vb0 == w0), eq1 = __ballot_sync(PPT_FULL_MASK, vb1 == w1);
+      if (eq0 & (eq0 - 1)) {  // several lanes hold the maximum: the smallest original index wins
+        const unsigned cand = vb0 == w0 ? soid[pos0] : 0xffffffffu;
+        eq0 = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
       }
-      if (lane == j) { rmax = __int_as_float(wmax); rpos = pos - lane + __ffs(eq) - 1; }
+      if (eq1 & (eq1 - 1)) {
+        const unsigned cand = vb1 == w1 ? soid[pos1] : 0xffffffffu;
+        eq1 = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+      }
+      if (lane == j0) { rmax = __int_as_float(w0); rpos = pos0 - lane + __ffs(eq0) - 1; }
+      if (two && lane == j1) { rmax = __int_as_float(w1); rpos = pos1 - lane + __ffs(eq1) - 1; }
     }
 
     // best row of this warp, then of the block (one barrier per iteration, double-buffered slots)
@@ -117,7 +128,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
     const int par = g & 1;
     if (lane == 0) slot[par * FG_WARPS + warp] = make_int2(wmax, wpos);
     __syncthreads();
-    const int2 s = slot[par * FG_WARPS + lane];
+    const int2 s = lane < FG_WARPS ? slot[par * FG_WARPS + lane] : make_int2(neg1, 0);
     const int cmax = __reduce_max_sync(PPT_FULL_MASK, s.x);
     unsigned ceq = __ballot_sync(PPT_FULL_MASK, s.x == cmax);
     if (ceq & (ceq - 1)) {
@@ -131,19 +142,33 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   }
 }
 
-}  // namespace
-
-int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
-                 int B, int N, int G, cudaStream_t st) {
+template <int W>
+int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
+                    int B, int N, int G, cudaStream_t st) {
   static bool configured = false;
-  const size_t slots = 2 * FG_WARPS * sizeof(int2);
+  const size_t slots = 2 * W * sizeof(int2);
   if (!configured) {
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)spidx::MAX_N * 24 + slots)));
     configured = true;
   }
   const size_t smem = (size_t)((N + 31) & ~31) * 24 + slots;
-  fps_grid_kernel<<<B, FG_THREADS, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,
-                                              centers_out, N, G);
+  fps_grid_kernel<W><<<B, W * 32, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,
+                                             centers_out, N, G);
   return ppt_launch_status();
+}
+
+}  // namespace
+
+int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
+                 int B, int N, int G, cudaStream_t st) {
+  static int warps = 0;
+  if (!warps) {  // tuning knob; the default is what measured best on B200
+    const char* e = getenv("PPT_FPS_GRID_WARPS");
+    warps = e ? atoi(e) : 32;
+    if (warps != 8 && warps != 16 && warps != 32) warps = 32;
+  }
+  if (warps == 8) return launch_fps_grid<8>(xyz, start, index, idx_out, centers_out, B, N, G, st);
+  if (warps == 16) return launch_fps_grid<16>(xyz, start, index, idx_out, centers_out, B, N, G, st);
+  return launch_fps_grid<32>(xyz, start, index, idx_out, centers_out, B, N, G, st);
 }
