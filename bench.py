@@ -187,11 +187,23 @@ def run_ours(args):
     resident = [h.to(dev) for h in host]
     zeros = torch.zeros(B, dtype=torch.int64, device=dev)
 
+    def timed_op(events, name, fn):
+        if events is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        events.append((name, a, b))
+        return out
+
     def step(i, phase_events=None):
+        # identical to PointTokenizer.forward, with an event pair around every launch when asked
         xyz = resident[i % ROTATE]
-        index = ops.spatial_index(xyz)
-        _, center = ops.fps(xyz, N_GROUP, zeros, return_centers=True, index=index)
-        nb = ops.knn_group(xyz, center, GROUP_SIZE, index=index)
+        index = timed_op(phase_events, "spatial_index", lambda: ops.spatial_index(xyz))
+        _, center = timed_op(phase_events, "fps",
+                             lambda: ops.fps(xyz, N_GROUP, zeros, return_centers=True, index=index))
+        nb = timed_op(phase_events, "knn_group", lambda: ops.knn_group(xyz, center, GROUP_SIZE, index=index))
         blob, mode = tok.encoder._blob(dev)
         return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events), center
 
@@ -271,6 +283,28 @@ def run_ours(args):
                 "peak_source": "%s cuBLAS bf16 burst (MEASURED_PEAKS.json)" % peaks["source"],
                 "flops_per_launch": points * STAGE2_FLOP_PER_POINT, "ms_per_launch": s2_ms,
                 "phase_ms": {k: statistics.mean(v) for k, v in per_phase.items()}}
+    # Every kernel of the step against the roofline that bounds it.  FPS / kNN:
+    # algorithmic lane-instructions of the full scan over the SM issue peak at the clock
+    # seen during the run -- the bucketed / pruned kernels execute far fewer, so this is an effective rate.
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 148 * 128 * sm_mhz * 1e6
+    mean_ms = {k: statistics.mean(v) for k, v in per_phase.items()}
+    enc_ms = sum(mean_ms[k] for k in ("stage1", "group_linear_c", "stage2", "group_linear_tokens"))
+    enc_flops = points * ENC_FLOP_PER_POINT + B * N_GROUP * ENC_FLOP_PER_GROUP
+    group_bytes = B * (N_POINTS * 12 + N_GROUP * GROUP_SIZE * 12 + N_GROUP * 12)
+    roofline_all = {
+        "fps": {"bound": "sm_issue", "ms": mean_ms["fps"], "unit": "lane-instr/s",
+                "achieved": B * FPS_LANE_INSTR_PER_CLOUD / (mean_ms["fps"] * 1e-3), "peak": issue_peak},
+        "knn_group": {"bound": "sm_issue", "ms": mean_ms["knn_group"], "unit": "lane-instr/s",
+                      "achieved": B * KNN_LANE_INSTR_PER_CLOUD / (mean_ms["knn_group"] * 1e-3), "peak": issue_peak,
+                      "hbm_frac": group_bytes / (mean_ms["knn_group"] * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "spatial_index": {"bound": "latency", "ms": mean_ms["spatial_index"]},
+        "encoder_total": {"bound": "tensor", "ms": enc_ms, "unit": "TFLOP/s",
+                          "achieved": enc_flops / (enc_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"]},
+    }
+    for v in roofline_all.values():
+        if "peak" in v:
+            v["frac"] = v["achieved"] / v["peak"]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -291,7 +325,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": B * N_GROUP * (384 + 3) * 4, "ms_per_step": ms_e2e / args.steps,
                 "checksum": checksum},
         # spatial index build, fps, knn_search, stage1, group_linear, stage2, group_linear
-        "gpu_launches": 7 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": 7 * args.steps, "roofline": roofline, "roofline_all": roofline_all, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 

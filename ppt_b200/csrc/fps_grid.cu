@@ -165,8 +165,8 @@ int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int6
   static int warps = 0;
   if (!warps) {  // tuning knob; the default is what measured best on B200
     const char* e = getenv("PPT_FPS_GRID_WARPS");
-    warps = e ? atoi(e) : 32;
-    if (warps != 8 && warps != 16 && warps != 32) warps = 32;
+    warps = e ? atoi(e) : 16;
+    if (warps != 8 && warps != 16 && warps != 32) warps = 16;
   }
   if (warps == 8) return launch_fps_grid<8>(xyz, start, index, idx_out, centers_out, B, N, G, st);
   if (warps == 16) return launch_fps_grid<16>(xyz, start, index, idx_out, centers_out, B, N, G, st);
