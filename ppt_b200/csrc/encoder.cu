@@ -32,8 +32,7 @@ namespace {
 
 using namespace tc05;
 
-constexpr int ENC_THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps
-constexpr int EPI_THREADS = 256;
+// stage kernels: producer warp, MMA warp, EPW epilogue warps (8, or 16 where the epilogue side is the bottleneck)
 constexpr int LIN_THREADS = 192;      // group_linear: producer, MMA, 4 epilogue warps
 constexpr int LIN_EPI = 128;
 constexpr uint32_t IMG = 16384;       // one operand image: 128 rows x 64 K x 2 B
@@ -116,8 +115,8 @@ __device__ __forceinline__ void store_relu8(unsigned char* base, uint32_t off, u
 // ======================================================================================
 // stage kernels
 // ======================================================================================
-template <uint32_t FMT, int SPLIT, int NT, int STAGE>
-__global__ void __launch_bounds__(ENC_THREADS, 1)
+template <uint32_t FMT, int SPLIT, int NT, int STAGE, int EPW>
+__global__ void __launch_bounds__((EPW + 2) * 32, 1)
 encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
                      const float* __restrict__ cbuf,          // stage 2: [groups_pad, 512]
                      unsigned char* __restrict__ out_img,     // stage 1: g images, stage 2: t images
@@ -132,8 +131,10 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   constexpr uint32_t H3_BYTES = STAGE == 2 ? (NT / 64) * MNBLK : 0u;  // one split part, MN-major
   constexpr uint32_t STAGE_BYTES = SPLIT * IMG;
   constexpr int TCOLS = 2 * NT;
-  constexpr int CPW = NT / 2;                        // accumulator columns per epilogue thread
+  constexpr int EPI_THREADS = EPW * 32;
+  constexpr int CPW = NT / (EPW / 4);                // accumulator columns per epilogue thread
   constexpr int GH = CPW / 32;                       // groups per epilogue thread
+  static_assert(EPW % 4 == 0 && CPW >= 32, "each TMEM lane quadrant needs EPW/4 warps of >= 32 columns");
 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* h1buf = smem;                                   // [NH1][SPLIT][2][NT x 128 B]
@@ -237,10 +238,10 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
-    const int e = tid - 64;                 // 0..255
+    // ===================== epilogue warps (2 .. EPW+1) =====================
+    const int e = tid - 64;                 // 0 .. EPI_THREADS-1
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;       // which half of the accumulator columns
+    const int half = (warp - 2) >> 2;       // which slice (CPW columns) of the accumulator
     const int m = quad * 32 + lane;         // output-channel row inside a 128-row unit
     const int col0 = half * CPW;
     const float* bias_b4 = reinterpret_cast<const float*>(blob + L.b4());
@@ -560,8 +561,10 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
                 float* tokens_out, long long groups, int phases, cudaStream_t st) {
   const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
-  auto k1 = encoder_stage_kernel<FMT, SPLIT, NT, 1>;
-  auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2>;
+  // stage 1 is bound by its epilogue side (layer-1 build + max): 16 epilogue warps where 32 columns each fit
+  constexpr int EPW1 = NT >= 128 ? 16 : 8, EPW2 = 8;
+  auto k1 = encoder_stage_kernel<FMT, SPLIT, NT, 1, EPW1>;
+  auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
   auto kb = group_linear_kernel<FMT, SPLIT, 4>;
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
   constexpr size_t s1 = stage_smem_bytes<SPLIT, NT, 1>(), s2 = stage_smem_bytes<SPLIT, NT, 2>(),
@@ -584,11 +587,11 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   const float* scales = reinterpret_cast<const float*>(blob + L.scales());
   // Rows of the last operand-image tile beyond `groups` are never written; they only feed accumulator
   // columns that are never stored.
-  if (phases & 1) k1<<<grid_t, ENC_THREADS, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
+  if (phases & 1) k1<<<grid_t, (EPW1 + 2) * 32, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
                                         scales + 1, cbuf, groups, tiles128);
-  if (phases & 4) k2<<<grid_t, ENC_THREADS, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
+  if (phases & 4) k2<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
   if ((phases & 8) && tokens_out)
     kd<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(),
                                         reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,
