@@ -25,6 +25,8 @@
 // L2 with 1-D bulk async copies into a ring (full/empty mbarriers); warp 1 issues
 // tcgen05.mma into two alternating TMEM accumulators; warps 2-9 build h1, drain the
 // accumulators (tcgen05.ld), apply bias/ReLU/max and write the next operand.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -53,7 +55,8 @@ struct BlobLayout {
   __host__ __device__ uint32_t W32() const { return W3A() + 16 * split * IMG; }  // 4 x 2
   __host__ __device__ uint32_t W4() const { return W32() + 8 * split * IMG; }    // 2 x 8
   __host__ __device__ uint32_t WR() const { return W4() + 16 * split * IMG; }    // 3 x 4
-  __host__ __device__ uint32_t total() const { return WR() + 12 * split * IMG; }
+  __host__ __device__ uint32_t W1T() const { return WR() + 12 * split * IMG; }   // layer-1 image (1, unsplit)
+  __host__ __device__ uint32_t total() const { return W1T() + IMG; }
 };
 
 struct Ring {  // position in a ring of mbarrier-guarded stages
@@ -395,6 +398,237 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 }
 
 // ======================================================================================
+// stage 1 with layer 1 on the tensor core as well
+// ======================================================================================
+// Same result as encoder_stage_kernel<STAGE 1>, but h1 = relu(W1'x + b1') is ONE K=16 tcgen05.mma per
+// tile instead of 1500 FFMA + 500 LDS per tile on the CUDA cores (which bounded that kernel): the blob's
+// W1T image holds [W_hi | W_hi | W_lo | b_hi | b_lo] per channel along K and the epilogue warps write
+// [x_hi | x_lo | x_hi | 1 | 1] per point (encoder_pack.layer1_image), so the fp32 accumulator equals the
+// fp32 product up to the dropped W_lo.x_lo term.  The accumulator (channels = lanes, points = columns) is
+// drained by channel-owning threads, so h1 becomes an MN-major operand like h3.
+//
+// Software pipeline per CTA (tile index n): the MMA warp issues L1(n+1) BEFORE the two W2 units of tile n,
+// and the epilogue warps convert L1(n+1) while those units run:
+//   MMA      : L1(n+1) | unit0(n) unit1(n)
+//   epilogue : convert(n+1) -> h1[(n+1)%2] | max-epilogue unit0(n), unit1(n) | point rows X(n+2)
+template <uint32_t FMT, int SPLIT, int NT, int EPW>
+__global__ void __launch_bounds__((EPW + 2) * 32, 1)
+encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
+                         unsigned char* __restrict__ out_img, long long num_groups, int num_tiles) {
+  constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
+  constexpr int GPT = NT / 32;
+  constexpr int EPI_THREADS = EPW * 32;
+  constexpr int CPW = NT / (EPW / 4);
+  constexpr int GH = CPW / 32;
+  static_assert(EPW % 4 == 0 && CPW >= 32, "each TMEM lane quadrant needs EPW/4 warps of >= 32 columns");
+  constexpr uint32_t XBYTES = NT * 128u;                       // one point-row operand: NT rows x 128 B (32 B used)
+  constexpr uint32_t H1BLK = 16384u;                           // MN-major h1: 16 K-atoms x 1 KB per 64 points
+  constexpr uint32_t H1_BYTES = (NT / 64) * H1BLK;             // one split part of one buffer
+  constexpr uint32_t H1_BUF = SPLIT * H1_BYTES;
+  constexpr uint32_t STAGE_BYTES = SPLIT * IMG;
+  constexpr int TCOLS = NT >= 128 ? 512 : 256;                 // two unit accumulators + the layer-1 accumulator
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* w1img = smem;                                   // [16 KB]
+  unsigned char* xbuf = w1img + IMG;                             // [2][XBYTES]
+  unsigned char* h1buf = xbuf + 2 * XBYTES;                      // [2][SPLIT][H1_BYTES]
+  unsigned char* ring = h1buf + 2 * H1_BUF;                      // [NSTAGE][SPLIT][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_BYTES);
+  uint64_t* full = bars;                   // [NSTAGE]
+  uint64_t* empty = full + NSTAGE;         // [NSTAGE]
+  uint64_t* acc_full = empty + NSTAGE;     // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint64_t* h1_ready = acc_empty + 2;      // [2]
+  uint64_t* x_ready = h1_ready + 2;        // [2]
+  uint64_t* l1_full = x_ready + 2;         // [1]
+  uint64_t* l1_empty = l1_full + 1;        // [1]
+  uint64_t* w1_full = l1_empty + 1;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w1_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BlobLayout L{(uint32_t)SPLIT};
+  const float* sc = reinterpret_cast<const float*>(blob + L.scales());
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&h1_ready[i], EPI_THREADS); mbar_init(&x_ready[i], EPI_THREADS); }
+    mbar_init(l1_full, 1);
+    mbar_init(l1_empty, EPI_THREADS);
+    mbar_init(w1_full, 1);
+    mbar_fence_init();
+  }
+  // the unused 96 bytes of every point row must be finite zeros (they sit in K slots the MMA never reads,
+  // but keep the buffer defined); done once
+  for (int i = tid; i < (int)(2 * XBYTES / 16); i += (EPW + 2) * 32)
+    reinterpret_cast<uint4*>(xbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t l1_tmem = tbase + 2u * NT;
+
+  if (warp == 0) {
+    // ===================== producer: the layer-1 image once, then the W2 ring =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w1_full, IMG);
+      bulk_g2s(w1img, blob + L.W1T(), IMG, w1_full);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int c = 0; c < 4; ++c, ++it) {  // unit u = c / 2, K chunk kc = c % 2: images are consecutive
+          const uint32_t s = it % NSTAGE;
+          mbar_wait_relaxed(&empty[s], ((it / NSTAGE) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          bulk_g2s(ring + s * STAGE_BYTES, blob + L.W2() + (size_t)c * STAGE_BYTES, STAGE_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: converged warp, one elected lane issues =====================
+    const uint32_t idesc_l1 = make_idesc(FMT, 128, NT, 0), idesc_mn = make_idesc(FMT, 128, NT, 1);
+    constexpr uint32_t HI = sdesc_hi(1024u);
+    const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u);
+    const uint32_t w1_lo = sdesc_lo(smem_u32(w1img), 16u), x_lo0 = sdesc_lo(smem_u32(xbuf), 16u);
+    const uint32_t h1_lo0 = sdesc_lo(smem_u32(h1buf), H1BLK);
+    auto issue_l1 = [&](uint32_t n) {  // layer 1 of tile index n: one K=16 slice
+      mbar_wait(&x_ready[n & 1u], (n >> 1) & 1u);
+      mbar_wait(l1_empty, (n & 1u) ^ 1u);  // the n-th use waits for the drain of use n-1
+      fence_after_sync();
+      umma_f16_elect(l1_tmem, sdesc_join(w1_lo, HI), sdesc_join(x_lo0 + (n & 1u) * (XBYTES >> 4), HI), idesc_l1, 0u);
+      umma_commit_elect(l1_full);
+    };
+    mbar_wait(w1_full, 0);
+    uint32_t it = 0, n = 0;
+    if ((int)blockIdx.x < num_tiles) issue_l1(0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      if (tile + (int)gridDim.x < num_tiles) issue_l1(n + 1);
+      mbar_wait(&h1_ready[n & 1u], (n >> 1) & 1u);
+      const uint32_t h1_lo = h1_lo0 + (n & 1u) * (H1_BUF >> 4);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        mbar_wait(&acc_empty[u], (n & 1u) ^ 1u);
+        fence_after_sync();
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE;
+          mbar_wait(&full[s], (it / NSTAGE) & 1u);
+          fence_after_sync();
+          issue_k64<SPLIT, true>(tbase + (uint32_t)(u * NT), a_lo0 + s * (STAGE_BYTES >> 4),
+                                 h1_lo + (uint32_t)kc * 512u, H1_BYTES >> 4, idesc_mn, kc == 0);
+          umma_commit_elect(&empty[s]);
+        }
+        umma_commit_elect(&acc_full[u]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int e = tid - 64;
+    const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;      // channel
+    const int col0 = part * CPW;
+    const float inv_p1 = __ldg(sc + 0), grp_scale = __ldg(sc + 6);
+
+    float nx = 0.f, ny = 0.f, nz = 0.f;  // this thread's point for the NEXT build_x (threads e < NT)
+    auto fetch_point = [&](int tile) {
+      nx = ny = nz = 0.f;
+      const long long gp = (long long)tile * NT + e;
+      if (e < NT && tile < num_tiles && gp < num_groups * 32) {
+        const float* src = nbhd + gp * 3;
+        nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
+      }
+    };
+    // point rows of tile index n: [x_hi y_hi z_hi | x_lo y_lo z_lo | x_hi y_hi z_hi | 1 | 1 | 0 ...]
+    auto build_x = [&](uint32_t n, int tile_after) {
+      if (e < NT) {
+        const uint32_t hxy = pack2<FMT, false>(nx, ny), hz1 = pack2<FMT, false>(nz, 1.0f);
+        const float2 fxy = unpack2<FMT>(hxy), fz = unpack2<FMT>(hz1);
+        const uint32_t lxy = pack2<FMT, false>(nx - fxy.x, ny - fxy.y), lz = pack2<FMT, false>(nz - fz.x, 0.f);
+        const uint32_t hx = hxy & 0xffffu, hy = hxy >> 16, hz = hz1 & 0xffffu, one = hz1 >> 16;
+        const uint32_t lx = lxy & 0xffffu, ly = lxy >> 16, lzz = lz & 0xffffu;
+        // k: 0 xh 1 yh | 2 zh 3 xl | 4 yl 5 zl | 6 xh 7 yh || 8 zh 9 one | 10 one 11 0 | 0 | 0
+        const uint4 p0 = make_uint4(hx | (hy << 16), hz | (lx << 16), ly | (lzz << 16), hx | (hy << 16));
+        const uint4 p1 = make_uint4(hz | (one << 16), one, 0u, 0u);
+        unsigned char* row = xbuf + (n & 1u) * XBYTES + (uint32_t)e * 128u;
+        *reinterpret_cast<uint4*>(row + ((0u ^ (uint32_t)(e & 7)) << 4)) = p0;
+        *reinterpret_cast<uint4*>(row + ((1u ^ (uint32_t)(e & 7)) << 4)) = p1;
+      }
+      fetch_point(tile_after);
+      fence_proxy_async_smem();
+      mbar_arrive(&x_ready[n & 1u]);
+    };
+    // layer-1 accumulator of tile index n -> relu -> h1[n % 2] (MN-major: this thread's channel is the K row)
+    auto convert = [&](uint32_t n) {
+      mbar_wait(l1_full, n & 1u);
+      fence_after_sync();
+      unsigned char* dst = h1buf + (n & 1u) * H1_BUF;
+      const uint32_t krow = (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u, sw = (uint32_t)(m & 7);
+      const uint32_t t_addr = l1_tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
+#pragma unroll
+      for (int jj = 0; jj < GH; ++jj) {
+        float v[32];
+        tmem_ld32(t_addr + jj * 32, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pt = col0 + jj * 32 + q * 8;
+          const uint32_t off = (uint32_t)(pt >> 6) * H1BLK + krow + ((((uint32_t)(pt & 63) >> 3) ^ sw) << 4);
+          store_relu8<FMT, SPLIT>(dst, off, H1_BYTES, v + q * 8);
+        }
+      }
+      fence_proxy_async_smem();
+      fence_before_sync();
+      mbar_arrive(&h1_ready[n & 1u]);
+      mbar_arrive(l1_empty);
+    };
+
+    const int t0 = blockIdx.x, stride = gridDim.x;
+    if (t0 < num_tiles) {
+      fetch_point(t0);
+      build_x(0, t0 + stride);
+      if (t0 + stride < num_tiles) build_x(1, t0 + 2 * stride);
+      convert(0);
+    }
+    uint32_t n = 0;
+    for (int tile = t0; tile < num_tiles; tile += stride, ++n) {
+      if (tile + stride < num_tiles) convert(n + 1);
+      const long long g0 = (long long)tile * GPT + part * GH;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        mbar_wait(&acc_full[u], n & 1u);
+        fence_after_sync();
+        const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(u * NT + col0);
+        const int ch = u * 128 + m;
+#pragma unroll
+        for (int jj = 0; jj < GH; ++jj) {
+          float v[32];
+          tmem_ld32(t_addr + jj * 32, v);
+          float mx = v[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+          mx *= inv_p1;
+          const long long g = g0 + jj;
+          if (g < num_groups) {
+            const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * (SPLIT * IMG);
+            store_operand<FMT, SPLIT>(out_img + img, sw128_kmajor_off((int)(g & 127), ch & 63), IMG, mx * grp_scale);
+          }
+        }
+        fence_before_sync();
+        mbar_arrive(&acc_empty[u]);
+      }
+      // X(n) was consumed by L1(n), complete before convert(n): its slot is free for tile index n+2
+      if (tile + 2 * stride < num_tiles) build_x(n + 2, tile + 3 * stride);
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TCOLS>(tbase);
+}
+
+// ======================================================================================
 // group_linear: out[g][o] = sum_k W[o][k] * act[g][k] + bias[o], act given as operand images
 // ======================================================================================
 template <uint32_t FMT, int SPLIT, int NUNITS>
@@ -526,6 +760,11 @@ constexpr size_t stage_smem_bytes() {
   return (size_t)(STAGE == 1 ? 2 : 1) * SPLIT * (2u * NT * 128u) + (STAGE == 2 ? (size_t)SPLIT * (NT / 64) * MNBLK : 0) +
          (size_t)NSTAGE * SPLIT * IMG + 256 + 2048;
 }
+template <int SPLIT, int NT>
+constexpr size_t stage1_tc_smem_bytes() {
+  constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
+  return (size_t)IMG + 2 * (size_t)NT * 128 + 2 * (size_t)SPLIT * (NT / 64) * 16384 + (size_t)NSTAGE * SPLIT * IMG + 256;
+}
 template <int SPLIT>
 constexpr size_t linear_smem_bytes() {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
@@ -564,6 +803,14 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   // stage 1 is bound by its epilogue side (layer-1 build + max): 16 epilogue warps where 32 columns each fit
   constexpr int EPW1 = NT >= 128 ? 16 : 8, EPW2 = 8;
   auto k1 = encoder_stage_kernel<FMT, SPLIT, NT, 1, EPW1>;
+  auto k1tc = encoder_stage1_tc_kernel<FMT, SPLIT, NT, 8>;
+  constexpr size_t s1tc = stage1_tc_smem_bytes<SPLIT, NT>();
+  static_assert(s1tc <= 232448, "shared memory budget (227 KB per CTA)");
+  static int use_tc = -1;  // tuning knob: PPT_STAGE1_TC=0 selects the CUDA-core layer-1 variant
+  if (use_tc < 0) {
+    const char* ev = getenv("PPT_STAGE1_TC");
+    use_tc = ev ? (atoi(ev) != 0) : 1;
+  }
   auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
   auto kb = group_linear_kernel<FMT, SPLIT, 4>;
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
@@ -573,6 +820,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   static bool configured = false;
   if (!configured) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1tc));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
@@ -587,7 +835,12 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   const float* scales = reinterpret_cast<const float*>(blob + L.scales());
   // Rows of the last operand-image tile beyond `groups` are never written; they only feed accumulator
   // columns that are never stored.
-  if (phases & 1) k1<<<grid_t, (EPW1 + 2) * 32, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
+  if (phases & 1) {
+    if (use_tc)
+      k1tc<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles);
+    else
+      k1<<<grid_t, (EPW1 + 2) * 32, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
+  }
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
                                         scales + 1, cbuf, groups, tiles128);

@@ -26,7 +26,8 @@ Blob layout (bytes), mirrored by csrc/encoder.cu (EncoderBlob):
     [0, 8192)            fp32 section: W1' rows {w0,w1,w2,b} [128][4], bias_c [512], b4 [256], bias_tok [384],
                          scales [8] = 1/(weight scale * operand scale) of the five GEMMs, point-activation
                          scale, group-operand scale, 0   (all 1.0 outside the fp32-parity mode)
-    then W2 (2 units x 2 chunks), W3A (4 x 4), W32 (4 x 2), W4 (2 x 8), WR (3 x 4) operand images.
+    then W2 (2 units x 2 chunks), W3A (4 x 4), W32 (4 x 2), W4 (2 x 8), WR (3 x 4) operand images,
+    then W1T: the layer-1 image of layer1_image() (one 16 KB image in every mode).
 """
 import torch
 
@@ -58,7 +59,26 @@ def weight_scale(w):
 
 def packed_bytes(mode):
     n = sum((r // 128) * (c // 64) for _, r, c in SECTIONS)
-    return F32_SECTION_BYTES + n * split_of(mode) * IMAGE_BYTES
+    return F32_SECTION_BYTES + n * split_of(mode) * IMAGE_BYTES + IMAGE_BYTES  # + the layer-1 image (W1T)
+
+
+def layer1_image(w1, dtype):
+    """Layer 1 (K = 3 plus bias) as ONE tensor-core K=16 slice.  Weights and coordinates are both
+    split into hi + lo operand parts laid out along K, so a single MMA evaluates
+        W_hi.x_hi + W_hi.x_lo + W_lo.x_hi + b_hi + b_lo      (fp32 accumulate)
+    i.e. the fp32 product up to the dropped W_lo.x_lo term.  Row = channel, K slots:
+        0-2 W_hi | 3-5 W_hi | 6-8 W_lo | 9 b_hi | 10 b_lo | 11-63 zero
+    (the kernel writes the matching point rows: x_hi | x_lo | x_hi | 1 | 1 | 0)."""
+    w1 = w1.to(torch.float32)
+    hi = w1.to(dtype)
+    lo = (w1 - hi.to(torch.float32)).to(dtype)
+    k = torch.zeros(128, 64, dtype=torch.float32)
+    k[:, 0:3] = hi[:, :3].float()
+    k[:, 3:6] = hi[:, :3].float()
+    k[:, 6:9] = lo[:, :3].float()
+    k[:, 9] = hi[:, 3].float()
+    k[:, 10] = lo[:, 3].float()
+    return pack_kmajor(k, dtype, 1)  # every entry is exactly representable: no second rounding
 
 
 def pack_kmajor(w, dtype, split=1):
@@ -127,6 +147,7 @@ def pack_encoder(sd, mode):
     head = torch.zeros(F32_SECTION_BYTES, dtype=torch.uint8)
     head[: f32.numel() * 4] = f32.view(torch.uint8)
     parts = [head] + [pack_kmajor((f[name] * ws[name]).to(torch.float32), dtype, split) for name, _, _ in SECTIONS]
+    parts.append(layer1_image(f["W1"] * act, dtype))
     blob = torch.cat(parts)
     assert blob.numel() == packed_bytes(mode), (blob.numel(), packed_bytes(mode))
     return blob
