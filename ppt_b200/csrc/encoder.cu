@@ -432,11 +432,9 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
   unsigned char* w1img = smem;                                   // [16 KB]
   unsigned char* xbuf = w1img + IMG;                             // [2][XBYTES]
   unsigned char* h1buf = xbuf + 2 * XBYTES;                      // [2][SPLIT][H1_BYTES]
-  unsigned char* ring = h1buf + 2 * H1_BUF;                      // [NSTAGE][SPLIT][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_BYTES);
-  uint64_t* full = bars;                   // [NSTAGE]
-  uint64_t* empty = full + NSTAGE;         // [NSTAGE]
-  uint64_t* acc_full = empty + NSTAGE;     // [2]
+  unsigned char* w2img = h1buf + 2 * H1_BUF;                     // [4][SPLIT][16 KB]: all of W2, resident
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w2img + 4 * STAGE_BYTES);
+  uint64_t* acc_full = bars;               // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint64_t* h1_ready = acc_empty + 2;      // [2]
   uint64_t* x_ready = h1_ready + 2;        // [2]
@@ -451,7 +449,6 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_THREADS); }
     for (int i = 0; i < 2; ++i) { mbar_init(&h1_ready[i], EPI_THREADS); mbar_init(&x_ready[i], EPI_THREADS); }
     mbar_init(l1_full, 1);
@@ -472,25 +469,20 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
   const uint32_t l1_tmem = tbase + 2u * NT;
 
   if (warp == 0) {
-    // ===================== producer: the layer-1 image once, then the W2 ring =====================
+    // ===================== producer: every weight of this kernel, once =====================
+    // W2 is 4 images (64 KB): it stays resident, so nothing is streamed per tile (a 4-stage ring
+    // cannot cover the ~1600-cycle latency of a bulk copy at this kernel's consumption rate).
     if (lane == 0) {
-      mbar_arrive_expect_tx(w1_full, IMG);
+      mbar_arrive_expect_tx(w1_full, IMG + 4 * STAGE_BYTES);
       bulk_g2s(w1img, blob + L.W1T(), IMG, w1_full);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < 4; ++c, ++it) {  // unit u = c / 2, K chunk kc = c % 2: images are consecutive
-          const uint32_t s = it % NSTAGE;
-          mbar_wait_relaxed(&empty[s], ((it / NSTAGE) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          bulk_g2s(ring + s * STAGE_BYTES, blob + L.W2() + (size_t)c * STAGE_BYTES, STAGE_BYTES, &full[s]);
-        }
-      }
+      for (int c = 0; c < 4; ++c)  // unit u = c / 2, K chunk kc = c % 2: images are consecutive in the blob
+        bulk_g2s(w2img + c * STAGE_BYTES, blob + L.W2() + (size_t)c * STAGE_BYTES, STAGE_BYTES, w1_full);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: converged warp, one elected lane issues =====================
     const uint32_t idesc_l1 = make_idesc(FMT, 128, NT, 0), idesc_mn = make_idesc(FMT, 128, NT, 1);
     constexpr uint32_t HI = sdesc_hi(1024u);
-    const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u);
+    const uint32_t a_lo0 = sdesc_lo(smem_u32(w2img), 16u);
     const uint32_t w1_lo = sdesc_lo(smem_u32(w1img), 16u), x_lo0 = sdesc_lo(smem_u32(xbuf), 16u);
     const uint32_t h1_lo0 = sdesc_lo(smem_u32(h1buf), H1BLK);
     auto issue_l1 = [&](uint32_t n) {  // layer 1 of tile index n: one K=16 slice
@@ -501,7 +493,7 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
       umma_commit_elect(l1_full);
     };
     mbar_wait(w1_full, 0);
-    uint32_t it = 0, n = 0;
+    uint32_t n = 0;
     if ((int)blockIdx.x < num_tiles) issue_l1(0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
       if (tile + (int)gridDim.x < num_tiles) issue_l1(n + 1);
@@ -512,14 +504,9 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
         mbar_wait(&acc_empty[u], (n & 1u) ^ 1u);
         fence_after_sync();
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc, ++it) {
-          const uint32_t s = it % NSTAGE;
-          mbar_wait(&full[s], (it / NSTAGE) & 1u);
-          fence_after_sync();
-          issue_k64<SPLIT, true>(tbase + (uint32_t)(u * NT), a_lo0 + s * (STAGE_BYTES >> 4),
+        for (int kc = 0; kc < 2; ++kc)
+          issue_k64<SPLIT, true>(tbase + (uint32_t)(u * NT), a_lo0 + (uint32_t)(u * 2 + kc) * (STAGE_BYTES >> 4),
                                  h1_lo + (uint32_t)kc * 512u, H1_BYTES >> 4, idesc_mn, kc == 0);
-          umma_commit_elect(&empty[s]);
-        }
         umma_commit_elect(&acc_full[u]);
       }
     }
@@ -763,7 +750,8 @@ constexpr size_t stage_smem_bytes() {
 template <int SPLIT, int NT>
 constexpr size_t stage1_tc_smem_bytes() {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
-  return (size_t)IMG + 2 * (size_t)NT * 128 + 2 * (size_t)SPLIT * (NT / 64) * 16384 + (size_t)NSTAGE * SPLIT * IMG + 256;
+  (void)NSTAGE;
+  return (size_t)IMG + 2 * (size_t)NT * 128 + 2 * (size_t)SPLIT * (NT / 64) * 16384 + (size_t)4 * SPLIT * IMG + 256;
 }
 template <int SPLIT>
 constexpr size_t linear_smem_bytes() {

@@ -185,67 +185,68 @@ knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ wo
 }
 
 // ---------------------------------------------------------------------------------------------
-struct TopList {  // lane i holds the i-th smallest (d, idx); tau = entry k-1 (warp-uniform)
-  float d;
-  int i;
-  float tau_d;
-  int tau_i;
+// (distance, original index) as ONE 64-bit key whose unsigned order is the lexicographic order: the
+// high word is the distance with its bits flipped into unsigned order (negative distances exist, F3;
+// -0 is canonicalised to +0 first), the low word the index.  A compare-exchange is then a 64-bit
+// compare and a select instead of two float compares, an int compare and predicate logic.
+__device__ __forceinline__ unsigned long long make_key(float d, int idx) {
+  const unsigned b = __float_as_uint(d + 0.0f);
+  const unsigned f = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+  return ((unsigned long long)f << 32) | (unsigned)idx;
+}
+__device__ __forceinline__ float key_dist(unsigned long long key) {
+  const unsigned f = (unsigned)(key >> 32);
+  return __uint_as_float(f ^ ((f >> 31) ? 0x80000000u : 0xffffffffu));
+}
+constexpr unsigned long long KEY_INF = 0xff8000007fffffffull;  // (+inf, INT_MAX)
+
+struct TopList {  // lane i holds the i-th smallest key; tau = entry k-1 (warp-uniform)
+  unsigned long long key;
+  unsigned long long tau;
 };
 
-__device__ __forceinline__ bool pair_less(float da, int ia, float db, int ib) {
-  return da < db || (da == db && ia < ib);
-}
-
 // One compare-exchange stage of a bitonic network across the warp: partner = lane ^ j.
-__device__ __forceinline__ void bitonic_stage(float& d, int& i, int j, bool want_min, int lane) {
-  const float od = __shfl_xor_sync(PPT_FULL_MASK, d, j);
-  const int oi = __shfl_xor_sync(PPT_FULL_MASK, i, j);
-  const bool other_less = pair_less(od, oi, d, i);
-  if (other_less == want_min) { d = od; i = oi; }
+__device__ __forceinline__ void bitonic_stage(unsigned long long& key, int j, bool want_min) {
+  const unsigned long long o = __shfl_xor_sync(PPT_FULL_MASK, key, j);
+  if ((o < key) == want_min) key = o;
 }
-// Full ascending sort of one (d, idx) pair per lane: 15 stages.
-__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane) {
+// Full ascending sort of one key per lane: 15 stages.
+__device__ __forceinline__ void bitonic_sort32(unsigned long long& key, int lane) {
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1)
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1)
-      bitonic_stage(d, i, j, ((lane & j) == 0) == ((lane & k) == 0), lane);
+    for (int j = k >> 1; j > 0; j >>= 1) bitonic_stage(key, j, ((lane & j) == 0) == ((lane & k) == 0));
 }
-// list := the 32 smallest of (list U row), ascending.  Both inputs one pair per lane; the row need not be sorted.
-__device__ __forceinline__ void merge_row(TopList& t, float d, int i, int k, int lane) {
-  bitonic_sort32(d, i, lane);
-  const float rd = __shfl_sync(PPT_FULL_MASK, d, 31 - lane);  // descending copy of the row
-  const int ri = __shfl_sync(PPT_FULL_MASK, i, 31 - lane);
-  if (pair_less(rd, ri, t.d, t.i)) { t.d = rd; t.i = ri; }      // element-wise min: a bitonic sequence
+// list := the 32 smallest of (list U row), ascending.  Both inputs one key per lane; the row need not be sorted.
+__device__ __forceinline__ void merge_row(TopList& t, unsigned long long key, int k, int lane) {
+  bitonic_sort32(key, lane);
+  const unsigned long long r = __shfl_sync(PPT_FULL_MASK, key, 31 - lane);  // descending copy of the row
+  if (r < t.key) t.key = r;                                                  // element-wise min: a bitonic sequence
 #pragma unroll
-  for (int j = 16; j > 0; j >>= 1) bitonic_stage(t.d, t.i, j, (lane & j) == 0, lane);
-  t.tau_d = __shfl_sync(PPT_FULL_MASK, t.d, k - 1);
-  t.tau_i = __shfl_sync(PPT_FULL_MASK, t.i, k - 1);
+  for (int j = 16; j > 0; j >>= 1) bitonic_stage(t.key, j, (lane & j) == 0);
+  t.tau = __shfl_sync(PPT_FULL_MASK, t.key, k - 1);
 }
 
 __device__ __forceinline__ void scan_row(TopList& t, const float4* __restrict__ pts, const int* __restrict__ sidx,
                                          int row, float qx, float qy, float qz, float qn, int k, int lane) {
   const float4 p = pts[row * 32 + lane];
-  const int pi = sidx[row * 32 + lane];
-  const float d = ppt_pair_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
-  unsigned bal = __ballot_sync(PPT_FULL_MASK, pair_less(d, pi, t.tau_d, t.tau_i));
+  const unsigned long long key =
+      make_key(ppt_pair_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w), sidx[row * 32 + lane]);
+  unsigned bal = __ballot_sync(PPT_FULL_MASK, key < t.tau);
   if (__popc(bal) >= MERGE_MIN) {  // many candidates (seed rows, loose tau): one sort + merge
-    merge_row(t, d, pi, k, lane);
+    merge_row(t, key, k, lane);
     return;
   }
   while (bal) {
     const int src = __ffs(bal) - 1;
     bal &= bal - 1;
-    const float cd = __shfl_sync(PPT_FULL_MASK, d, src);
-    const int ci = __shfl_sync(PPT_FULL_MASK, pi, src);
-    if (!pair_less(cd, ci, t.tau_d, t.tau_i)) continue;  // tau tightened since the vote (warp-uniform)
-    const int pos = __popc(__ballot_sync(PPT_FULL_MASK, pair_less(t.d, t.i, cd, ci)));
-    const float ud = __shfl_up_sync(PPT_FULL_MASK, t.d, 1);
-    const int ui = __shfl_up_sync(PPT_FULL_MASK, t.i, 1);
-    if (lane == pos) { t.d = cd; t.i = ci; }
-    else if (lane > pos) { t.d = ud; t.i = ui; }
-    t.tau_d = __shfl_sync(PPT_FULL_MASK, t.d, k - 1);
-    t.tau_i = __shfl_sync(PPT_FULL_MASK, t.i, k - 1);
+    const unsigned long long c = __shfl_sync(PPT_FULL_MASK, key, src);
+    if (!(c < t.tau)) continue;  // tau tightened since the vote (warp-uniform)
+    const int pos = __popc(__ballot_sync(PPT_FULL_MASK, t.key < c));
+    const unsigned long long up = __shfl_up_sync(PPT_FULL_MASK, t.key, 1);
+    if (lane == pos) t.key = c;
+    else if (lane > pos) t.key = up;
+    t.tau = __shfl_sync(PPT_FULL_MASK, t.key, k - 1);
   }
 }
 
@@ -286,7 +287,7 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
     const float qx = qp[0], qy = qp[1], qz = qp[2];
     const float qn = ppt_sqnorm3(qx, qy, qz);
     TopList t;
-    t.d = inf; t.i = 0x7fffffff; t.tau_d = inf; t.tau_i = 0x7fffffff;
+    t.key = KEY_INF; t.tau = KEY_INF;
 
     // seed: the rows around the query's own cell
     const int r0 = min(rows - 1, __ldg(cell_start + cell_of(qx, qy, qz, hdr.lo, hdr.inv)) >> 5);
@@ -306,23 +307,26 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
         slack = 2e-6f * (qn + bx.npmax);
       }
       // conservative: keep the row unless lb > tau + 2e-6 (|q|^2 + max|p|^2 + |tau|)
-      unsigned bal = __ballot_sync(PPT_FULL_MASK, !(lb > t.tau_d + slack + 2e-6f * fabsf(t.tau_d)));
+      float tau_d = key_dist(t.tau);
+      unsigned bal = __ballot_sync(PPT_FULL_MASK, !(lb > tau_d + slack + 2e-6f * fabsf(tau_d)));
       while (bal) {
         const int src = __ffs(bal) - 1;
         bal &= bal - 1;
         const float lbr = __shfl_sync(PPT_FULL_MASK, lb, src);
         const float slr = __shfl_sync(PPT_FULL_MASK, slack, src);
-        if (lbr > t.tau_d + slr + 2e-6f * fabsf(t.tau_d)) continue;  // tau tightened meanwhile
+        tau_d = key_dist(t.tau);
+        if (lbr > tau_d + slr + 2e-6f * fabsf(tau_d)) continue;  // tau tightened meanwhile
         scan_row(t, pts, sidx, rb + src, qx, qy, qz, qn, k, lane);
       }
     }
 
     if (lane < k) {
       const size_t o = ((size_t)b * S + q) * k + lane;
-      if (idx_out) idx_out[o] = (int64_t)t.i;
-      if (dist_out) dist_out[o] = t.d;
+      const int ti = (int)(unsigned)(t.key & 0xffffffffull);
+      if (idx_out) idx_out[o] = (int64_t)ti;
+      if (dist_out) dist_out[o] = key_dist(t.key);
       if (GROUP) {
-        const float* p = cloud + (size_t)t.i * 3;
+        const float* p = cloud + (size_t)ti * 3;
         nb_out[o * 3 + 0] = __fsub_rn(p[0], qx);
         nb_out[o * 3 + 1] = __fsub_rn(p[1], qy);
         nb_out[o * 3 + 2] = __fsub_rn(p[2], qz);
