@@ -410,7 +410,7 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 // Software pipeline per CTA (tile index n): the MMA warp issues L1(n+1) BEFORE the two W2 units of tile n,
 // and the epilogue warps convert L1(n+1) while those units run:
 //   MMA      : L1(n+1) | unit0(n) unit1(n)
-//   epilogue : convert(n+1) -> h1[(n+1)%2] | max-epilogue unit0(n), unit1(n) | point rows X(n+2)
+//   epilogue : convert(n+1) -> h1[(n+1)%2] | point rows X(n+2) | max-epilogue unit0(n), unit1(n)
 template <uint32_t FMT, int SPLIT, int NT, int EPW>
 __global__ void __launch_bounds__((EPW + 2) * 32, 1)
 encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
@@ -581,6 +581,9 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
     uint32_t n = 0;
     for (int tile = t0; tile < num_tiles; tile += stride, ++n) {
       if (tile + stride < num_tiles) convert(n + 1);
+      // X(n) was consumed by L1(n), complete before convert(n): its slot is free for tile index n+2.
+      // Built BEFORE the unit epilogues: L1(n+2) is the first thing the MMA warp issues next iteration.
+      if (tile + 2 * stride < num_tiles) build_x(n + 2, tile + 3 * stride);
       const long long g0 = (long long)tile * GPT + part * GH;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -605,8 +608,6 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
         fence_before_sync();
         mbar_arrive(&acc_empty[u]);
       }
-      // X(n) was consumed by L1(n), complete before convert(n): its slot is free for tile index n+2
-      if (tile + 2 * stride < num_tiles) build_x(n + 2, tile + 3 * stride);
     }
   }
 
@@ -749,8 +750,6 @@ constexpr size_t stage_smem_bytes() {
 }
 template <int SPLIT, int NT>
 constexpr size_t stage1_tc_smem_bytes() {
-  constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
-  (void)NSTAGE;
   return (size_t)IMG + 2 * (size_t)NT * 128 + 2 * (size_t)SPLIT * (NT / 64) * 16384 + (size_t)4 * SPLIT * IMG + 256;
 }
 template <int SPLIT>

@@ -255,3 +255,44 @@ def test_rejects_cpu_tensors_and_bad_sizes(ops):
         ops.knn(33, torch.zeros(1, 64, 3).cuda(), torch.zeros(1, 2, 3).cuda())
     with pytest.raises(RuntimeError):
         ops.fps(torch.zeros(1, 70000, 3).cuda(), 4, torch.zeros(1, dtype=torch.int64).cuda())
+
+
+def test_ssg_grouping_at_cfg3_size_against_reference_digests(ops, golden):
+    """BASELINE configs[2]: 32 clouds x 1024 pts, FPS 512/128, ball query r=0.2/0.4, nsample 32/64."""
+    f = golden("sa_ssg_cfg3")
+    B, N, seed = int(f["B"]), int(f["N"]), int(f["seed"])
+    xyz_h = cloud("S", B, N, seed)
+    assert digest(xyz_h) == str(f["xyz_sha"])
+    xyz = xyz_h.cuda()
+    z = torch.zeros(B, dtype=torch.int64, device="cuda")
+    f1, c1 = ops.fps(xyz, 512, z, return_centers=True)
+    assert digest(f1) == str(f["fps1_sha"])
+    b1 = ops.ball_query(0.2, 32, xyz, c1)
+    assert digest(b1) == str(f["ball1_sha"])
+    assert digest(ops.group_concat(xyz, c1, None, b1)) == str(f["grp1_sha"])
+    f2, c2 = ops.fps(c1, 128, z, return_centers=True)
+    assert digest(f2) == str(f["fps2_sha"])
+    b2 = ops.ball_query(0.4, 64, c1, c2)
+    assert digest(b2) == str(f["ball2_sha"])
+    feats = torch.randn(B, 512, 128, generator=torch.Generator().manual_seed(seed + 100))
+    assert digest(feats) == str(f["feats_sha"])
+    assert digest(ops.group_concat(c1, c2, feats.cuda(), b2, xyz_first=True)) == str(f["grp2_sha"])
+
+
+def test_msg_and_feature_propagation_at_cfg4_size_against_reference_digests(ops, golden):
+    """BASELINE configs[3]: 2048-pt clouds, MSG ball queries and three_nn / three_interpolate with D = 384."""
+    f = golden("msg_fp_cfg4")
+    B, N, D, seed = int(f["B"]), int(f["N"]), int(f["D"]), int(f["seed"])
+    xyz_h = cloud("S", B, N, seed)
+    assert digest(xyz_h) == str(f["xyz_sha"])
+    xyz = xyz_h.cuda()
+    f1, c1 = ops.fps(xyz, 512, torch.zeros(B, dtype=torch.int64, device="cuda"), return_centers=True)
+    assert digest(f1) == str(f["fps1_sha"])
+    for r, k in ((0.1, 16), (0.2, 32), (0.4, 128)):
+        assert digest(ops.ball_query(r, k, xyz, c1)) == str(f["ball_%g_%d_sha" % (r, k)])
+    feats = torch.randn(B, 512, D, generator=torch.Generator().manual_seed(seed + 100))
+    assert digest(feats) == str(f["feats_sha"])
+    assert len(f["nn_tie_rows"]) == 0
+    d, i = ops.three_nn(xyz, c1)
+    assert digest(d) == str(f["nn_dist_sha"]) and digest(i) == str(f["nn_idx_sha"])
+    assert digest(ops.three_interpolate(feats.cuda(), i, d)) == str(f["interp_sha"])
