@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppt_b200.so")
+LIB_PATH = os.environ.get("PPT_B200_LIB") or os.path.join(_HERE, "libppt_b200.so")  # override: A/B builds
 ABI_VERSION = 1
 
 _c = ctypes

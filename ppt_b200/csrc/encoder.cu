@@ -38,6 +38,10 @@ using namespace tc05;
 constexpr int LIN_THREADS = 192;      // group_linear: producer, MMA, 4 epilogue warps
 constexpr int LIN_EPI = 128;
 constexpr uint32_t IMG = 16384;       // one operand image: 128 rows x 64 K x 2 B
+#ifndef PPT_RING_PIECES
+#define PPT_RING_PIECES 1
+#endif
+constexpr int RING_PIECES = PPT_RING_PIECES;  // bulk copies per ring stage in the stage-2 producer
 constexpr uint32_t MNBLK = 65536;     // MN-major h3: bytes between 64-point blocks (64 K-atoms x 1 KB)
 
 // ---- packed weight blob (ppt_b200/encoder_pack.py) -----------------------------------
@@ -192,8 +196,12 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
             const uint32_t s = r.stage<NSTAGE>();
             mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
             mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-            bulk_g2s(ring + s * STAGE_BYTES, blob + sec + (size_t)(blk * nkc + kc) * STAGE_BYTES, STAGE_BYTES,
-                     &full[s]);
+            // PIECES concurrent copies per stage (same barrier, same bytes): tuning knob for the copy latency
+            const unsigned char* src = blob + sec + (size_t)(blk * nkc + kc) * STAGE_BYTES;
+#pragma unroll
+            for (int pc = 0; pc < RING_PIECES; ++pc)
+              bulk_g2s(ring + s * STAGE_BYTES + pc * (STAGE_BYTES / RING_PIECES), src + pc * (STAGE_BYTES / RING_PIECES),
+                       STAGE_BYTES / RING_PIECES, &full[s]);
             ++r.it;
           }
         }
