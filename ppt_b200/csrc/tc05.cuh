@@ -7,6 +7,10 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#ifndef PPT_PRODUCER_SLEEP_NS
+#define PPT_PRODUCER_SLEEP_NS 64
+#endif
+
 namespace tc05 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -51,8 +55,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
-    if (++spins > (1u << 24)) __trap();
+#if PPT_PRODUCER_SLEEP_NS > 0
+    __nanosleep(PPT_PRODUCER_SLEEP_NS);
+#endif
+    if (++spins > (1u << 26)) __trap();
   }
 }
 
