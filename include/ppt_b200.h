@@ -150,6 +150,10 @@ int ppt_encoder_forward_phases(const float *neighborhood, const void *packed, vo
  *   a [128,K] f32, b [N,K] f32 -> d [128,N] f32 = a * b^T with operands rounded to `mode`'s type. */
 int ppt_selftest_umma(const float *a, const float *b, float *d, int N, int K, int mode, void *stream);
 
+/* The same through a CTA pair (tcgen05 cta_group::2, cluster of two CTAs):
+ *   a [256,K] f32, b [N,K] f32 -> d [256,N] f32.  N in {64,128,192,256}, mode bits 0-2 as above. */
+int ppt_selftest_umma_pair(const float *a, const float *b, float *d, int N, int K, int mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

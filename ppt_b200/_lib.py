@@ -30,6 +30,7 @@ SIGNATURES = {
     "ppt_encoder_forward": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p]),
     "ppt_encoder_forward_phases": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p]),
     "ppt_selftest_umma": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "ppt_selftest_umma_pair": (_i, [_p, _p, _p, _i, _i, _i, _p]),
 }
 
 _lib = None

@@ -284,3 +284,15 @@ def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, 
                 e1.record()
                 phase_events.append((name, e0, e1))
     return (tokens, feats) if return_features else tokens
+
+
+def selftest_umma_pair(a, b, mode=ENC_FP16, b_mn_major=False):
+    """D[256,N] = A[256,K] @ B[N,K]^T on a CTA pair (tcgen05 cta_group::2)."""
+    _need_cuda(a, b)
+    a, b = _f32(a), _f32(b)
+    N, K = b.shape
+    d = torch.empty((256, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().ppt_selftest_umma_pair(_ptr(a), _ptr(b), _ptr(d), N, K, mode | (4 if b_mn_major else 0),
+                                                      _stream(a)), "ppt_selftest_umma_pair")
+    return d
