@@ -625,6 +625,380 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
 }
 
 // ======================================================================================
+// stage 2 on CTA pairs (tcgen05 cta_group::2)
+// ======================================================================================
+// The single-CTA stage 2 re-reads 4 KB of weights and 4 KB of activations from shared memory for every
+// M128 x N128 x K16 instruction (64 tensor cycles) and streams 384 KB of weights per 128-point tile from L2.
+// Here two CTAs of a cluster work on a pair-tile of 256 points with M = 256 instructions, and the operand
+// roles are swapped with respect to the single-CTA kernel -- activations are A (points = M = accumulator
+// lanes), weights are B (channels = N = accumulator columns):
+//   * CTA r owns points [128 r, 128 r + 128) of the tile: its rows of every A operand (h1, h3) and of every
+//     accumulator.  An epilogue thread owns one point and writes that point's row of h3, K-major, into its
+//     own CTA's shared memory: no activation crosses between the CTAs (a first version with channels on the
+//     lanes pushed half of h3 through DSMEM and ran at half the speed);
+//   * CTA r streams only its half of the channels of every weight block (its half of B; the hardware shares
+//     it with the peer): half the ring traffic per CTA, half the L2 traffic per point;
+//   * the max over a group's 32 points is a reduction over the 32 lanes of a warp (CREDUX.MAX);
+//   * hand-offs that involve both CTAs (operands ready, accumulators drained, ring stage filled) go through
+//     mbarriers of the leader CTA (remote arrivals from the peer).
+// Tensor memory: columns [0, 256) the W4 h3 accumulator (256 channels), [256, 384) and [384, 512) two
+// accumulators for the 128-channel units of W32 h1.  Per tile the leader issues, in this fixed order,
+//     P0 P1 G0 G1 P2 G2 G3 P3 G4 G5 G6 G7
+// (Pv = W32 unit v: N = 128, K = 128; Gc = W4 K-chunk c: N = 256, K = 64; 512 tensor cycles each), one ring stage
+// per item.  Gc needs h3 channels [64 c, 64 c + 64) = half the epilogue of unit c / 2, so the tensor pipe
+// always has two or more items to run while the epilogue warps turn an accumulator into h3.  The same order
+// lets h3 live in four chunk slots instead of eight (chunk c + 4 is written by the epilogue of unit c / 2 + 2,
+// whose instructions are issued after Gc: by the time that accumulator is full, Gc has finished reading), and
+// the 64 KB this frees make the weight ring six stages deep -- deep enough to cover L2 latency plus the
+// hop through the peer.
+// Warp roles per CTA: 0 weight producer, 1 issuer of the P items (leader) / ring-stage forwarder (peer),
+// 2-9 epilogue, 10 issuer of the G items (leader only).
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// Item i of the per-tile schedule: 0..3 = W32 unit v, 4..11 = 4 + W4 chunk c.
+__host__ __device__ constexpr int pair_sched(int i) {
+  constexpr int code[12] = {0, 1, 4, 5, 2, 6, 7, 3, 8, 9, 10, 11};
+  return code[i];
+}
+
+template <uint32_t FMT>
+__global__ void __launch_bounds__(352, 1)
+encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
+                           const float* __restrict__ cbuf, unsigned char* __restrict__ out_img,
+                           float* __restrict__ features_out, long long num_groups, int num_ptiles) {
+  constexpr int NSTAGE = 6, EPW = 8, NTC = 128;      // NTC: points per CTA per pair-tile
+  constexpr uint32_t H1_BYTES = 2u * NTC * 128u;     // K-major: 2 chunks x [128 points x 64 channels]
+  constexpr uint32_t H3_BYTES = 4u * IMG;            // K-major [128 points x 64 channels] chunks: chunk c in slot c % 4
+  constexpr int TCOLS = 512;
+  constexpr uint32_t ACC_G3 = 0, ACC_P2 = 256;       // tensor-memory columns
+  constexpr int ITEMS = 12;                          // ring stages per tile and CTA
+  static_assert(ITEMS % NSTAGE == 0 && (ITEMS / NSTAGE) % 2 == 0, "static ring schedule");
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* h1buf = smem;
+  unsigned char* h3buf = h1buf + H1_BYTES;
+  unsigned char* ring = h3buf + H3_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * IMG);
+  uint64_t* full = bars;                    // [6] own ring stage landed
+  uint64_t* empty = full + NSTAGE;          // [6] stage consumed (commit, multicast to both CTAs)
+  uint64_t* full_peer = empty + NSTAGE;     // [6] leader only: the peer's stage landed
+  uint64_t* p2_full = full_peer + NSTAGE;   // [2] W32 accumulator complete (commit, multicast)
+  uint64_t* g3_full = p2_full + 2;          // [1] W4 accumulator complete (commit, multicast)
+  uint64_t* max_done = g3_full + 1;         // [1] leader only: the W4 accumulator was drained by both CTAs
+  uint64_t* h1_ready = max_done + 1;        // [1] leader only: h1 of both CTAs written
+  uint64_t* h3_ready = h1_ready + 1;        // [8] leader only: h3 chunk c written (and its accumulator half read)
+  uint64_t* g_done = h3_ready + 8;          // [4] the W4 chunk in h3 slot s was consumed (commit, multicast)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_done + 4);
+  float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 512);
+  float* c_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512 + 2048);  // [8 warps][256]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const BlobLayout L{1u};
+  const float* sc = reinterpret_cast<const float*>(blob + L.scales());
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&full_peer[s], 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(&p2_full[i], 1);
+    mbar_init(g3_full, 1);
+    mbar_init(max_done, 2 * EPW);
+    mbar_init(h1_ready, 2 * EPW);
+    for (int i = 0; i < 8; ++i) mbar_init(&h3_ready[i], EPW);  // 4 warps (one column half) of each CTA
+    for (int i = 0; i < 4; ++i) mbar_init(&g_done[i], 1);
+    mbar_fence_init();
+  }
+  if (tid < 128) {
+    float4 w = __ldg(reinterpret_cast<const float4*>(blob + L.w1()) + tid);
+    const float s = __ldg(sc + 5);
+    w.x *= s; w.y *= s; w.z *= s; w.w *= s;
+    w1s[tid] = w;
+  }
+  if (warp == 1) tmem_alloc_pair<TCOLS>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // barrier inits of both CTAs are visible before any remote arrive
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  if (tbase != 0) __trap();  // 512 columns = the whole tensor memory of the SM
+
+  if (warp == 0) {
+    // ===================== weight producer: this CTA's half of every weight block =====================
+    if (lane == 0) {
+      uint32_t tpar = 0;
+      for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+          const int code = pair_sched(i);
+          const int st = i % NSTAGE;
+          const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
+          mbar_wait_relaxed(&empty[st], sph ^ 1u);
+          mbar_arrive_expect_tx(&full[st], IMG);
+          if (code < 4) {
+            // W32 unit v = code, both K chunks: rows [64 rank, 64 rank + 64) of each 128-row image (8 KB, contiguous)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              bulk_g2s(ring + st * IMG + k * (IMG / 2), blob + L.W32() + (uint32_t)(code * 2 + k) * IMG + rank * (IMG / 2),
+                       IMG / 2, &full[st]);
+          } else {
+            // W4 chunk c = code - 4: channels [128 rank, 128 rank + 128)
+            bulk_g2s(ring + st * IMG, blob + L.W4() + (rank * 8u + (uint32_t)(code - 4)) * IMG, IMG, &full[st]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer: tell the leader when a ring stage has landed here =====================
+    for (int tile = pair; tile < num_ptiles; tile += npairs) {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        mbar_wait(&full[i % NSTAGE], (uint32_t)(i / NSTAGE) & 1u);
+        if (lane == 0) mbar_arrive_peer(&full_peer[i % NSTAGE], 0);
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== leader, warp 1: issues the W32 h1 units (P items) =====================
+    // Two warps issue the tensor instructions of a tile (this one the P items, warp 10 the G items): the
+    // instruction stream around each tcgen05.mma (descriptor moves into uniform registers, elect, commit) costs
+    // about as many cycles as the instruction runs, so a single issuing warp caps the tensor pipe near 60 %.
+    // Fully unrolled per tile: every item has a compile-time ring stage and phase.
+    constexpr uint32_t idesc_p = make_idesc(FMT, 256, 128, 0);
+    constexpr uint32_t HI = sdesc_hi(1024u);
+    const uint32_t w_lo0 = sdesc_lo(smem_u32(ring), 16u);
+    const uint32_t h1_lo = sdesc_lo(smem_u32(h1buf), 16u);
+    uint32_t tpar = 0;  // parity of the tile counter
+    for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
+      mbar_wait(h1_ready, tpar);
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int code = pair_sched(i);
+        if (code >= 4) continue;
+        const int v = code;
+        const int st = i % NSTAGE;
+        const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
+        const uint32_t w_lo = w_lo0 + (uint32_t)st * (IMG >> 4);
+        // the accumulator of unit v was last read by the epilogue of unit v - 2 (this tile: chunks 2v-4, 2v-3) or
+        // of unit v + 2 of the previous tile (chunks 2v+4, 2v+5)
+        const int c0 = v >= 2 ? 2 * v - 4 : 2 * v + 4;
+        const uint32_t dpar = v >= 2 ? tpar : tpar ^ 1u;
+        mbar_wait(&h3_ready[c0], dpar);
+        mbar_wait(&h3_ready[c0 + 1], dpar);
+        mbar_wait(&full[st], sph);
+        mbar_wait(&full_peer[st], sph);
+        fence_after_sync();
+        const uint32_t d_tmem = ACC_P2 + (uint32_t)(v & 1) * 128u;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16)
+            umma_f16_pair_elect(d_tmem, sdesc_join(h1_lo + (uint32_t)kk * ((NTC * 128u) >> 4) + (uint32_t)k16 * 2u, HI),
+                                sdesc_join(w_lo + (uint32_t)kk * (IMG >> 5) + (uint32_t)k16 * 2u, HI), idesc_p,
+                                (kk == 0 && k16 == 0) ? 0u : 1u);
+        umma_commit_pair_elect(&empty[st], 3);
+        umma_commit_pair_elect(&p2_full[v & 1], 3);
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== leader, warp 10: issues the W4 h3 chunks (G items); idle in the peer =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc_g = make_idesc(FMT, 256, 256, 0);
+      constexpr uint32_t HI = sdesc_hi(1024u);
+      const uint32_t w_lo0 = sdesc_lo(smem_u32(ring), 16u);
+      const uint32_t h3_lo = sdesc_lo(smem_u32(h3buf), 16u);
+      uint32_t tpar = 0;
+      for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+          const int code = pair_sched(i);
+          if (code < 4) continue;
+          const int c = code - 4;
+          const int st = i % NSTAGE;
+          const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
+          const uint32_t w_lo = w_lo0 + (uint32_t)st * (IMG >> 4);
+          if (c == 0) mbar_wait(max_done, tpar ^ 1u);  // the W4 accumulator of the previous tile is in registers
+          mbar_wait(&h3_ready[c], tpar);
+          mbar_wait(&full[st], sph);
+          mbar_wait(&full_peer[st], sph);
+          fence_after_sync();
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16)
+            umma_f16_pair_elect(ACC_G3, sdesc_join(h3_lo + (uint32_t)(c & 3) * (IMG >> 4) + (uint32_t)k16 * 2u, HI),
+                                sdesc_join(w_lo + (uint32_t)k16 * 2u, HI), idesc_g, (c == 0 && k16 == 0) ? 0u : 1u);
+          umma_commit_pair_elect(&empty[st], 3);
+          umma_commit_pair_elect(&g_done[c & 3], 3);  // h3 slot c % 4 may be overwritten
+          if (c == 7) umma_commit_pair_elect(g3_full, 3);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9) of both CTAs =====================
+    const int e = tid - 64;
+    const int quad = warp & 3;               // accumulator lanes [32 quad, 32 quad + 32) = group `quad` of this CTA
+    const int part = (warp - 2) >> 2;        // column half of every accumulator
+    const int prow = quad * 32 + lane;       // this thread's point (row of h3)
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const float* bias_b4 = reinterpret_cast<const float*>(blob + L.b4());
+    const float inv_g3 = __ldg(sc + 3), act_scale = __ldg(sc + 5), grp_scale = __ldg(sc + 6);
+    const float inv_p2s = __ldg(sc + 2) * act_scale;
+
+    auto arrive_leader = [&](uint64_t* bar) {  // one arrival per warp, after every lane has fenced its writes
+      __syncwarp();
+      if (lane == 0) mbar_arrive_peer(bar, 0);
+    };
+
+    // h1 of this CTA's 128 points (CUDA cores, K = 3), K-major
+    const int p = e % NTC, ch0 = (e / NTC) * 64;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    auto fetch_point = [&](int tile) {
+      nx = ny = nz = 0.f;
+      const long long gp = (long long)tile * 256 + (long long)rank * NTC + p;
+      if (tile < num_ptiles && gp < num_groups * 32) {
+        const float* src = nbhd + gp * 3;
+        nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
+      }
+    };
+    auto build_h1 = [&](int tile_after) {
+      const float x = nx, y = ny, z = nz;
+      fetch_point(tile_after);
+#pragma unroll 4
+      for (int c8 = 0; c8 < 64; c8 += 8) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 w = w1s[ch0 + c8 + t];
+          v[t] = fmaf(w.z, z, fmaf(w.y, y, fmaf(w.x, x, w.w)));
+        }
+        const int ch = ch0 + c8;
+        store_relu8<FMT, 1>(h1buf, (uint32_t)(ch >> 6) * (NTC * 128u) + sw128_kmajor_off(p, ch & 63), 0u, v);
+      }
+      fence_proxy_async_smem();
+      arrive_leader(h1_ready);
+    };
+
+    // c[group][ch] for the channels this warp handles (unit v: 128 v + 64 part + [0, 64)), staged per tile in a
+    // warp-private kilobyte of shared memory: c_w[64 v + j]
+    float* c_w = c_s + (warp - 2) * 256;
+    float4 cpre[2];
+    auto fetch_c = [&](int tile) {
+      const long long g = (long long)tile * 8 + (long long)rank * 4 + quad;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int f = 4 * (lane + 32 * h);  // position in c_w
+        cpre[h] = (tile < num_ptiles && g < num_groups)
+                      ? __ldg(reinterpret_cast<const float4*>(cbuf + g * 512 + (f >> 6) * 128 + part * 64 + (f & 63)))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto stage_c = [&]() {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        reinterpret_cast<float4*>(c_w)[lane + 32 * h] = make_float4(cpre[h].x * act_scale, cpre[h].y * act_scale,
+                                                                    cpre[h].z * act_scale, cpre[h].w * act_scale);
+      __syncwarp();
+    };
+
+    if (pair < num_ptiles) {
+      fetch_point(pair);
+      fetch_c(pair);
+      build_h1(pair + npairs);
+      stage_c();
+    }
+
+    uint32_t tpar = 0;
+    for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
+      const long long g = (long long)tile * 8 + (long long)rank * 4 + quad;  // this warp's group
+      const bool g_ok = g < num_groups;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        // h3[point][ch] = relu(acc + c[group][ch]) for ch = 128 v + 64 part + [0, 64) = K chunk 2 v + part of W4 h3
+        mbar_wait(&p2_full[v & 1], (uint32_t)(v >> 1) & 1u);  // each accumulator completes twice per tile
+        fence_after_sync();
+        const uint32_t t_addr = lane_base + ACC_P2 + (uint32_t)(v & 1) * 128u + (uint32_t)part * 64u;
+        uint32_t r0[32], r1[32];
+        tmem_ld32_async(t_addr, r0);
+        tmem_ld32_async(t_addr + 32, r1);
+        tmem_wait_ld();
+        const uint32_t img = (uint32_t)((2 * v + part) & 3) * IMG;
+        // the slot still holds chunk 2v+part-4 (this tile) or 2v+part+4 (previous tile) until its G item is complete;
+        // each slot's barrier completes twice per tile
+        mbar_wait(&g_done[(2 * v + part) & 3], v < 2 ? 1u : 0u);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 cv = reinterpret_cast<const float4*>(c_w + v * 64 + jj * 32)[i];  // broadcast
+            x[4 * i + 0] = fmaf(__uint_as_float(jj ? r1[4 * i + 0] : r0[4 * i + 0]), inv_p2s, cv.x);
+            x[4 * i + 1] = fmaf(__uint_as_float(jj ? r1[4 * i + 1] : r0[4 * i + 1]), inv_p2s, cv.y);
+            x[4 * i + 2] = fmaf(__uint_as_float(jj ? r1[4 * i + 2] : r0[4 * i + 2]), inv_p2s, cv.z);
+            x[4 * i + 3] = fmaf(__uint_as_float(jj ? r1[4 * i + 3] : r0[4 * i + 3]), inv_p2s, cv.w);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            store_relu8<FMT, 1>(h3buf, img + sw128_kmajor_off(prow, jj * 32 + q4 * 8), 0u, x + q4 * 8);
+        }
+        fence_proxy_async_smem();
+        fence_before_sync();
+        arrive_leader(&h3_ready[2 * v + part]);
+        if (v == 3) {
+          // unit 3's accumulator was full: every W32 h1 instruction of this tile is complete, h1 is free
+          const int next = tile + npairs;
+          fetch_c(next);
+          if (next < num_ptiles) build_h1(next + npairs);
+          stage_c();
+        }
+      }
+
+      // per-group max of W4 h3: channels 128 part + [0, 128), max over the warp's 32 lanes (points)
+      mbar_wait(g3_full, tpar);
+      fence_after_sync();
+#pragma unroll 1
+      for (int jj = 0; jj < 4; jj += 2) {
+        uint32_t r0[32], r1[32];
+        const uint32_t t_addr = lane_base + ACC_G3 + (uint32_t)part * 128u + (uint32_t)jj * 32u;
+        tmem_ld32_async(t_addr, r0);
+        tmem_ld32_async(t_addr + 32, r1);
+        tmem_wait_ld();
+        if (jj == 2) {  // the accumulator is in registers: hand it back before reducing
+          fence_before_sync();
+          arrive_leader(max_done);
+        }
+        float mx0 = 0.f, mx1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float a = warp_max_f32(__uint_as_float(r0[i]));
+          const float b = warp_max_f32(__uint_as_float(r1[i]));
+          if (lane == i) { mx0 = a; mx1 = b; }
+        }
+        if (g_ok) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float mx = (h ? mx1 : mx0) * inv_g3;
+            const int ch = part * 128 + (jj + h) * 32 + lane;
+            const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * IMG;
+            store_operand<FMT, 1>(out_img + img, sw128_kmajor_off((int)(g & 127), ch & 63), IMG, mx * grp_scale);
+            if (features_out) features_out[g * 256 + ch] = mx + __ldg(bias_b4 + ch);
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may exit (or free tensor memory) while the other can still reach it
+  if (warp == 1) tmem_dealloc_pair<TCOLS>(tbase);
+}
+
+// ======================================================================================
 // group_linear: out[g][o] = sum_k W[o][k] * act[g][k] + bias[o], act given as operand images
 // ======================================================================================
 template <uint32_t FMT, int SPLIT, int NUNITS>
@@ -806,6 +1180,16 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     const char* ev = getenv("PPT_STAGE1_TC");
     use_tc = ev ? (atoi(ev) != 0) : 1;
   }
+  // PPT_STAGE2_PAIR=1 selects the CTA-pair (cta_group::2) stage 2.  It is bit-compatible with the single-CTA
+  // kernel's tolerance and parity-tested, but as of round 1 it is ~8 % slower (0.635 ms against 0.585 ms on the
+  // 128-cloud step: every P -> epilogue -> G hand-off crosses the pair and the tile pipeline is not yet deep
+  // enough to hide those hops), so the single-CTA kernel stays the default.
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* ev = getenv("PPT_STAGE2_PAIR");
+    use_pair = ev ? (atoi(ev) != 0) : 0;
+  }
+  auto k2p = encoder_stage2_pair_kernel<FMT>;
   auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
   auto kb = group_linear_kernel<FMT, SPLIT, 4>;
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
@@ -817,6 +1201,8 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1tc));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2p, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)stage_smem_bytes<1, 128, 2>()));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     configured = true;
@@ -839,7 +1225,30 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
                                         scales + 1, cbuf, groups, tiles128);
-  if (phases & 4) k2<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
+  if (phases & 4) {
+    if (SPLIT == 1 && use_pair) {
+      const int ptiles = (int)((points + 255) / 256);
+      const int npairs = ptiles < sms / 2 ? ptiles : sms / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * npairs);
+      cfg.blockDim = dim3(352);
+      cfg.dynamicSmemBytes = stage_smem_bytes<1, 128, 2>();
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const unsigned char* blob_c = blob;
+      unsigned char* timg = ws + W.t_img;
+      PPT_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, k2p, nbhd, blob_c, (const float*)cbuf, timg, features_out, groups,
+                                            ptiles));
+    } else {
+      k2<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
+    }
+  }
   if ((phases & 8) && tokens_out)
     kd<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(),
                                         reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,

@@ -110,6 +110,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load without the wait, so that several loads are in flight before one tmem_wait_ld().
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- UMMA descriptors ---------------------------------------------------------------
 // Operand formats of tcgen05.mma.kind::f16 (instruction descriptor bits [7,10) / [10,13)).
 constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1;
@@ -220,7 +235,53 @@ __device__ __forceinline__ void umma_commit_pair_elect(uint64_t* bar, uint16_t c
       "h"(cta_mask)
       : "memory");
 }
+// Wait with cluster-scope acquire: the arrivals may come from the other CTA of the pair.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();
+  } while (!ok);
+}
+// Generic-proxy writes (local or to the peer CTA's shared memory) -> visible to the async proxy everywhere.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Address of `local_smem_addr` in CTA `rank`'s shared memory (shared::cluster window).
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
 // Arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope).
+// Wait of a converged warp whose loop branch is warp-uniform (vote): ptxas then treats the code after the wait
+// as convergent and keeps loop counters, barrier addresses and MMA descriptors in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+// Arrival on the barrier at the same offset in CTA `rank` with the default (CTA-scope release) semantics:
+// the cheap form -- no MEMBAR.GPU / ERRBAR -- for hand-offs whose payload is shared memory that the
+// arriving thread has already made visible to the async proxy of its own SM (fence.proxy.async.shared::cta)
+// or tensor memory it has finished reading (tcgen05.wait::ld + tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mbar_arrive_peer(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"

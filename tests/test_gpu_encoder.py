@@ -16,10 +16,10 @@ CHILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_encoder_child
 TOL = {0: 1e-3, 1: 8e-3, 2: 1e-5}
 
 
-def run_child(case, mode):
+def run_child(case, mode, env=None):
     try:
         out = subprocess.run([sys.executable, CHILD, str(case), str(mode)], capture_output=True, text=True,
-                             timeout=300)
+                             timeout=300, env=dict(os.environ, **(env or {})))
     except subprocess.TimeoutExpired:
         pytest.fail("encoder child hung (killed after 300 s)")
     assert out.returncode == 0, out.stderr[-3000:]
@@ -30,6 +30,17 @@ def run_child(case, mode):
 @pytest.mark.parametrize("case", ["golden", "4", "1", "131", "1500", "16384"])
 def test_encoder_tokens(case, mode):
     r = run_child(case, mode)
+    assert r["finite"] and r["repeatable"], r
+    for key in ("tokens", "features"):
+        assert r[key]["max"] <= TOL[mode], (key, r)
+        assert r[key]["rms"] <= TOL[mode], (key, r)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", ["golden", "1", "7", "131", "1500", "16384"])
+def test_encoder_tokens_cta_pair_stage2(case, mode):
+    """The experimental cta_group::2 stage 2 (PPT_STAGE2_PAIR=1): same tolerances, ragged tails included."""
+    r = run_child(case, mode, env={"PPT_STAGE2_PAIR": "1"})
     assert r["finite"] and r["repeatable"], r
     for key in ("tokens", "features"):
         assert r[key]["max"] <= TOL[mode], (key, r)
