@@ -244,6 +244,33 @@ def run_ours(args):
     for name, a, b in phase_events:
         per_phase.setdefault(name, []).append(a.elapsed_time(b))
 
+    # ---- widened row f2: the same step with the cls rows and pos_embed(center), i.e. the
+    # (x, pos) arguments of self.blocks (point_encoder.py:241-249); not part of `value` ----
+    tok.load_front_end_state(torch_port.make_front_end_state())
+    pos_blob = tok._pos_blob(dev)
+    for i in range(3):
+        tok.forward_assembled(resident[i % ROTATE])
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    for i in range(args.steps):
+        tok.forward_assembled(resident[i % ROTATE])
+    f1.record()
+    barrier()
+    ms_assembled = max_over_ranks(f0.elapsed_time(f1))
+    centers = [torch.rand(B, N_GROUP, 3, device=dev) * 2 - 1 for _ in range(3)]
+    mode_id = ops.ENC_MODES[args.precision]
+    pos_ms = []
+    for i in range(3 + args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.tokenizer_forward(None, centers[i % 3], None, pos_blob, mode=mode_id, want_x=False)
+        b.record()
+        if i >= 3:
+            pos_ms.append((a, b))
+    torch.cuda.synchronize()
+    pos_ms = statistics.mean(a.elapsed_time(b) for a, b in pos_ms)
+
     # ---- timed region 2: end to end through the public API with pinned host buffers ----
     # HostPipeline: H2D of the clouds, the kernels and D2H of tokens + centres on three streams,
     # two slots in flight; every step's inputs start in pinned host memory and its results end there.
@@ -309,6 +336,16 @@ def run_ours(args):
         if "peak" in v:
             v["frac"] = v["achieved"] / v["peak"]
 
+    pos_bytes = B * (N_GROUP * 12 + (N_GROUP + 1) * 384 * 4)
+    widened = {"f2_token_assembly": {
+        "what": "x = cat(cls_token, tokens), pos = cat(cls_pos, pos_embed(center)) [B, 513, 384] each; tokens stored "
+                "straight into x, pos_embed 128->384 on tcgen05",
+        "value": clouds_total / (ms_assembled * 1e-3), "unit": UNIT, "ms_per_step": ms_assembled / args.steps,
+        "pos_path": {"kernels": "pos_hidden_kernel + group_linear<K=128>", "bound": "hbm", "ms": pos_ms,
+                     "achieved": pos_bytes / (pos_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": pos_bytes / (pos_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "bytes_per_launch": pos_bytes}}}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
@@ -328,7 +365,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": B * N_GROUP * (384 + 3) * 4, "ms_per_step": ms_e2e / args.steps,
                 "checksum": checksum},
         # spatial index build, fps, knn_search, stage1, group_linear, stage2, group_linear
-        "gpu_launches": 7 * args.steps, "roofline": roofline, "roofline_all": roofline_all, "cpu_baseline": cpu,
+        "gpu_launches": 7 * args.steps, "roofline": roofline, "roofline_all": roofline_all, "widened": widened, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 

@@ -145,6 +145,23 @@ int ppt_encoder_forward_phases(const float *neighborhood, const void *packed, vo
                                float *features_out, float *tokens_out, int64_t num_groups, int mode,
                                int phases, void *stream);
 
+/* ---- pos_embed + token assembly (the step right after the tokenizer) ----------
+ * PointTransformer.forward, models/pointbert/point_encoder.py:239-247:
+ *     x   = cat(cls_token, reduce_dim(encoder(neighborhood)))         [clouds, G+1, 384]
+ *     pos = cat(cls_pos,   pos_embed(center))                         [clouds, G+1, 384]
+ * with pos_embed = Linear(3,128) -> GELU (erf) -> Linear(128,384) (point_encoder.py:138-142).  The
+ * tokens are stored straight into rows 1..G of x_out (no separate tokens tensor, no concatenation
+ * pass), the 128 -> 384 layer runs on the tensor cores like reduce_dim.
+ *   posembed_packed: ppt_b200/encoder_pack.py:pack_pos_embed (opaque), ppt_posembed_packed_bytes(mode) bytes;
+ *   workspace: ppt_tokenizer_workspace_bytes(num_groups, mode) bytes;
+ *   center [num_groups, 3] f32; num_groups = clouds * groups_per_cloud, groups_per_cloud >= 32;
+ *   x_out may be NULL (only pos is computed; neighborhood / encoder_packed are then unused). */
+int64_t ppt_posembed_packed_bytes(int mode);
+int64_t ppt_tokenizer_workspace_bytes(int64_t num_groups, int mode);
+int ppt_tokenizer_forward(const float *neighborhood, const float *center, const void *encoder_packed,
+                          const void *posembed_packed, void *workspace, float *x_out, float *pos_out,
+                          int64_t num_groups, int groups_per_cloud, int mode, void *stream);
+
 /* Self-test of the tcgen05 building blocks (one 128 x N x K GEMM through the
  * same smem layouts, descriptors and epilogue the Encoder uses).
  *   a [128,K] f32, b [N,K] f32 -> d [128,N] f32 = a * b^T with operands rounded to `mode`'s type. */

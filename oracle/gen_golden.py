@@ -166,8 +166,45 @@ def gen_encoder(ns):
     print("encoder tokens", tuple(tok.shape), "absmax", float(tok.abs().max()))
 
 
+def gen_front_end(ns):
+    """The unmodified reference PointTransformer (models/pointbert/point_encoder.py:111-256) up to the call of
+    self.blocks: a forward pre-hook records the (x, pos) it is given (:241-249).  depth 1 keeps the unused
+    transformer small; group_divider / encoder / reduce_dim / cls rows / pos_embed are the real modules."""
+    import importlib
+    import types
+    pe = importlib.import_module("models.pointbert.point_encoder")
+    cfg = types.SimpleNamespace(trans_dim=384, depth=1, drop_path_rate=0.1, cls_dim=40, num_heads=6, group_size=32,
+                                num_group=64, encoder_dims=256)
+    model = pe.PointTransformer(cfg, args=types.SimpleNamespace()).eval()
+    sd = torch_port.make_encoder_state()
+    front = torch_port.make_front_end_state()
+    missing = model.encoder.load_state_dict({k: v for k, v in sd.items() if k in torch_port.ENCODER_KEYS}, strict=False)
+    assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing
+    model.reduce_dim.load_state_dict({"weight": sd["reduce_dim.weight"], "bias": sd["reduce_dim.bias"]})
+    with torch.no_grad():
+        model.cls_token.copy_(front["cls_token"])
+        model.cls_pos.copy_(front["cls_pos"])
+    model.pos_embed.load_state_dict({k[len("pos_embed."):]: v for k, v in front.items() if k.startswith("pos_embed.")})
+    seen = {}
+    model.blocks.register_forward_pre_hook(lambda m, a: seen.update(x=a[0].clone(), pos=a[1].clone()))
+    xyz = cloud("U", 3, 1024, 4343)
+    with refimport.fixed_fps_start(0), torch.no_grad():
+        model(xyz)
+        nb, center = model.group_divider(xyz)
+    # the restatement agrees with the reference on the same tokens
+    x2, pos2 = torch_port.assemble_forward(front, seen["x"][:, 1:], center)
+    assert torch.equal(x2, seen["x"]) and (pos2 - seen["pos"]).abs().max() <= 1e-6 * seen["pos"].abs().max()
+    np.savez_compressed(os.path.join(OUT, "front_end_small.npz"), xyz=xyz.numpy(), neighborhood=nb.numpy(),
+                        center=center.numpy(), x=seen["x"].numpy(), pos=seen["pos"].numpy(),
+                        torch_version=torch.__version__)
+    print("front end x", tuple(seen["x"].shape), "pos absmax", float(seen["pos"].abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "front_end":  # regenerate only the newest fixture
+        gen_front_end(refimport.load())
+        return
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     ns = refimport.load()
     gen_sqdist(ns)
@@ -182,6 +219,7 @@ def main():
     gen_msg_fp(ns, "msg_fp_small", 1, 2048, 1238, 16, full=True)
     gen_msg_fp(ns, "msg_fp_cfg4", 8, 2048, 1238, 384, full=False)
     gen_encoder(ns)
+    gen_front_end(ns)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("fixtures total bytes", tot)
 

@@ -154,3 +154,27 @@ def encoder_forward(sd, point_groups, eps=1e-5):
 def tokens_forward(sd, point_groups):
     """Encoder then reduce_dim (models/pointbert/point_encoder.py:239): (B,G,n,3) -> (B,G,384)."""
     return F.linear(encoder_forward(sd, point_groups), sd["reduce_dim.weight"], sd["reduce_dim.bias"])
+
+
+# ---- pos_embed + token assembly (models/pointbert/point_encoder.py:135-142, 241-247) --------------------
+FRONT_KEYS = ("cls_token", "cls_pos", "pos_embed.0.weight", "pos_embed.0.bias", "pos_embed.2.weight", "pos_embed.2.bias")
+
+
+def make_front_end_state(seed=1):
+    """Seeded random-init cls_token / cls_pos / pos_embed with the reference's shapes (trans_dim 384)."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s, scale=1.0: (torch.rand(*s, generator=g) * 2 - 1) * scale
+    return {"cls_token": r(1, 1, 384, scale=0.5), "cls_pos": torch.randn(1, 1, 384, generator=g),
+            "pos_embed.0.weight": r(128, 3, scale=3 ** -0.5), "pos_embed.0.bias": r(128, scale=3 ** -0.5),
+            "pos_embed.2.weight": r(384, 128, scale=128 ** -0.5), "pos_embed.2.bias": r(384, scale=128 ** -0.5)}
+
+
+def assemble_forward(front, tokens, center):
+    """x = cat(cls_token, tokens), pos = cat(cls_pos, pos_embed(center)) -- point_encoder.py:241-247 restated."""
+    B = tokens.shape[0]
+    h = torch.nn.functional.linear(center, front["pos_embed.0.weight"], front["pos_embed.0.bias"])
+    h = torch.nn.functional.gelu(h)  # nn.GELU() default: exact erf form
+    p = torch.nn.functional.linear(h, front["pos_embed.2.weight"], front["pos_embed.2.bias"])
+    x = torch.cat((front["cls_token"].expand(B, -1, -1), tokens), dim=1)
+    pos = torch.cat((front["cls_pos"].expand(B, -1, -1), p), dim=1)
+    return x, pos

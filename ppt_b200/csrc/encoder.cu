@@ -999,18 +999,21 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
 }
 
 // ======================================================================================
-// group_linear: out[g][o] = sum_k W[o][k] * act[g][k] + bias[o], act given as operand images
+// group_linear: out[row(g)][o] = sum_k W[o][k] * act[g][k] + bias[o], act given as operand images
+// (K = 64 KCH).  row(g) = g, or -- rows_per_cloud = G > 0, the token-assembly layout of
+// models/pointbert/point_encoder.py:245-246 -- g + g / G + 1: every cloud's G rows follow one row that
+// belongs to the cls token.  G >= 32 so that a run of 32 consecutive groups crosses at most one cloud boundary.
 // ======================================================================================
-template <uint32_t FMT, int SPLIT, int NUNITS>
+template <uint32_t FMT, int SPLIT, int NUNITS, int KCH = 4>
 __global__ void __launch_bounds__(LIN_THREADS, 1)
 group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned char* __restrict__ wsec,
                     const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ out,
-                    long long num_groups, int num_tiles) {
+                    long long num_groups, int num_tiles, int rows_per_cloud) {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int NT = 128;                      // groups per tile (MMA N)
   constexpr int NOUT = NUNITS * 128;
   constexpr uint32_t STAGE_BYTES = SPLIT * IMG;
-  constexpr uint32_t B_BYTES = 4u * SPLIT * IMG;  // [kc][split][16 KB]
+  constexpr uint32_t B_BYTES = (uint32_t)KCH * SPLIT * IMG;  // [kc][split][16 KB]
   constexpr int TCOLS = 2 * NT;
 
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -1047,15 +1050,15 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         mbar_wait_relaxed(b_empty, (tile_it & 1u) ^ 1u);
         mbar_arrive_expect_tx(b_full, B_BYTES);
-        for (int kc = 0; kc < 4; ++kc)
-          bulk_g2s(bbuf + kc * STAGE_BYTES, act_img + ((size_t)tile * 4 + kc) * STAGE_BYTES, STAGE_BYTES, b_full);
+        for (int kc = 0; kc < KCH; ++kc)
+          bulk_g2s(bbuf + kc * STAGE_BYTES, act_img + ((size_t)tile * KCH + kc) * STAGE_BYTES, STAGE_BYTES, b_full);
 #pragma unroll 1
         for (int u = 0; u < NUNITS; ++u)
-          for (int kc = 0; kc < 4; ++kc) {
+          for (int kc = 0; kc < KCH; ++kc) {
             const uint32_t s = r.stage<NSTAGE>();
             mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
             mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-            bulk_g2s(ring + s * STAGE_BYTES, wsec + (size_t)(u * 4 + kc) * STAGE_BYTES, STAGE_BYTES, &full[s]);
+            bulk_g2s(ring + s * STAGE_BYTES, wsec + (size_t)(u * KCH + kc) * STAGE_BYTES, STAGE_BYTES, &full[s]);
             ++r.it;
           }
       }
@@ -1073,7 +1076,7 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
           mbar_wait(&acc_empty[buf], ((unit_it >> 1) & 1u) ^ 1u);
           fence_after_sync();
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc, ++it) {
+          for (int kc = 0; kc < KCH; ++kc, ++it) {
             const uint32_t s = it % NSTAGE;
             mbar_wait(&full[s], (it / NSTAGE) & 1u);
             fence_after_sync();
@@ -1106,9 +1109,16 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
           float v[32];
           tmem_ld32(t_addr + j * 32, v);
           const long long g0 = (long long)tile * NT + j * 32;
+          long long row0 = g0;
+          int wrap = 32;  // first i of this run that belongs to the next cloud
+          if (rows_per_cloud > 0) {
+            const long long q = g0 / rows_per_cloud;
+            row0 = g0 + q + 1;
+            wrap = (int)((q + 1) * rows_per_cloud - g0);
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (g0 + i < num_groups) out[(g0 + i) * NOUT + o] = fmaf(v[i], inv_scale, bo);
+            if (g0 + i < num_groups) out[(row0 + i + (i >= wrap ? 1 : 0)) * NOUT + o] = fmaf(v[i], inv_scale, bo);
         }
         fence_before_sync();
         mbar_arrive(&acc_empty[buf]);
@@ -1119,6 +1129,78 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TCOLS>(tbase);
+}
+
+// ======================================================================================
+// pos_embed layer 1 + cls rows (models/pointbert/point_encoder.py:138-142, 241-247)
+// ======================================================================================
+// pos = Linear(128, 384)(GELU(Linear(3, 128)(center))).  The 3 -> 128 layer and the exact (erf) GELU run here
+// in fp32 on CUDA cores, one thread per centre, and are written straight into the K-major operand images
+// that group_linear<KCH = 2> multiplies with the packed 128 -> 384 weight; that kernel stores into rows
+// 1..G of each cloud of pos_out.  Row 0 of each cloud (cls_token in x, cls_pos in pos) is written here.
+// Blob: fp32 section {W1 rows {w0,w1,w2,b} [128][4] | b2 [384] | cls_token [384] | cls_pos [384] | scales [4] =
+// 1/(weight scale * hidden scale), hidden scale, 0, 0} in 8192 bytes, then W2 images [3 units][2 chunks][split].
+struct PosBlobLayout {
+  __host__ __device__ static constexpr uint32_t w1() { return 0; }
+  __host__ __device__ static constexpr uint32_t b2() { return 2048; }
+  __host__ __device__ static constexpr uint32_t cls_token() { return 3584; }
+  __host__ __device__ static constexpr uint32_t cls_pos() { return 5120; }
+  __host__ __device__ static constexpr uint32_t scales() { return 6656; }
+  __host__ __device__ static constexpr uint32_t W2() { return 8192; }
+  __host__ __device__ static constexpr uint32_t total(uint32_t split) { return 8192 + 3 * 2 * split * IMG; }
+};
+
+template <uint32_t FMT, int SPLIT>
+__global__ void __launch_bounds__(128)
+pos_hidden_kernel(const float* __restrict__ center, const unsigned char* __restrict__ pblob,
+                  unsigned char* __restrict__ h_img, float* __restrict__ x_out, float* __restrict__ pos_out,
+                  long long num_groups, int rows_per_cloud) {
+  __shared__ float4 w1s[128];
+  const int tid = threadIdx.x;
+  const float hscale = __ldg(reinterpret_cast<const float*>(pblob + PosBlobLayout::scales()) + 1);
+  w1s[tid] = __ldg(reinterpret_cast<const float4*>(pblob + PosBlobLayout::w1()) + tid);
+  __syncthreads();
+  const long long tiles = (num_groups + 127) / 128;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long g = tile * 128 + tid;
+    if (g < num_groups) {
+      const float x = __ldg(center + g * 3), y = __ldg(center + g * 3 + 1), z = __ldg(center + g * 3 + 2);
+      unsigned char* img = h_img + (size_t)tile * 2 * SPLIT * IMG;
+#pragma unroll 2
+      for (int c8 = 0; c8 < 128; c8 += 8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 w = w1s[c8 + 2 * t + h];
+            const float a = fmaf(w.z, z, fmaf(w.y, y, fmaf(w.x, x, w.w)));
+            v[h] = 0.5f * a * (1.f + erff(a * 0.70710678118654752440f)) * hscale;  // nn.GELU() (erf form)
+          }
+          hi[t] = pack2<FMT, false>(v[0], v[1]);
+          if (SPLIT == 2) {
+            const float2 r = unpack2<FMT>(hi[t]);
+            lo[t] = pack2<FMT, false>(v[0] - r.x, v[1] - r.y);
+          }
+        }
+        unsigned char* dst = img + (size_t)(c8 >> 6) * SPLIT * IMG + sw128_kmajor_off(tid, c8 & 63);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (SPLIT == 2) *reinterpret_cast<uint4*>(dst + IMG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  // row 0 of every cloud
+  const long long clouds = num_groups / rows_per_cloud;
+  const float* cls_token = reinterpret_cast<const float*>(pblob + PosBlobLayout::cls_token());
+  const float* cls_pos = reinterpret_cast<const float*>(pblob + PosBlobLayout::cls_pos());
+  for (long long i = (long long)blockIdx.x * 128 + tid; i < clouds * 384; i += (long long)gridDim.x * 128) {
+    const long long b = i / 384;
+    const int o = (int)(i - b * 384);
+    const long long dst = b * (rows_per_cloud + 1) * 384 + o;
+    if (x_out) x_out[dst] = __ldg(cls_token + o);
+    pos_out[dst] = __ldg(cls_pos + o);
+  }
 }
 
 // ======================================================================================
@@ -1152,7 +1234,7 @@ int num_sms() {
 }
 
 struct Workspace {
-  size_t g_img, c_buf, t_img, total;
+  size_t g_img, c_buf, t_img, total, h_img, total_tokenizer;
   Workspace(long long groups, int split) {
     const size_t tiles128 = (size_t)((groups + 127) / 128);
     const size_t img = tiles128 * 4 * (size_t)split * IMG;
@@ -1160,13 +1242,15 @@ struct Workspace {
     t_img = img;
     c_buf = 2 * img;
     total = c_buf + tiles128 * 128 * 512 * sizeof(float);
+    h_img = total;  // pos_embed hidden layer, K = 128: 2 chunks per 128-centre tile (ppt_tokenizer_forward only)
+    total_tokenizer = h_img + tiles128 * 2 * (size_t)split * IMG;
   }
 };
 
 // phases: bit 0 stage1, bit 1 group_linear(c), bit 2 stage2, bit 3 group_linear(tokens)
 template <uint32_t FMT, int SPLIT, int NT>
 int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws, float* features_out,
-                float* tokens_out, long long groups, int phases, cudaStream_t st) {
+                float* tokens_out, long long groups, int phases, cudaStream_t st, int rows_per_cloud = 0) {
   const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
   // stage 1 is bound by its epilogue side (layer-1 build + max): 16 epilogue warps where 32 columns each fit
@@ -1224,7 +1308,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   }
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
-                                        scales + 1, cbuf, groups, tiles128);
+                                        scales + 1, cbuf, groups, tiles128, 0);
   if (phases & 4) {
     if (SPLIT == 1 && use_pair) {
       const int ptiles = (int)((points + 255) / 256);
@@ -1252,8 +1336,35 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   if ((phases & 8) && tokens_out)
     kd<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(),
                                         reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,
-                                        groups, tiles128);
+                                        groups, tiles128, rows_per_cloud);
   return ppt_launch_status();
+}
+
+// Encoder + reduce_dim into rows 1..G of x_out, pos_embed(center) into rows 1..G of pos_out, cls rows.
+template <uint32_t FMT, int SPLIT, int NT>
+int run_tokenizer(const float* nbhd, const float* center, const unsigned char* blob, const unsigned char* pblob,
+                  unsigned char* ws, float* x_out, float* pos_out, long long groups, int rows_per_cloud,
+                  cudaStream_t st) {
+  const Workspace W(groups, SPLIT);
+  auto kp = group_linear_kernel<FMT, SPLIT, 3, 2>;
+  constexpr size_t sl = linear_smem_bytes<SPLIT>();
+  static bool configured = false;
+  if (!configured) {
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
+    configured = true;
+  }
+  const int tiles128 = (int)((groups + 127) / 128);
+  const int sms = num_sms();
+  const int grid_g = tiles128 < sms ? tiles128 : sms;
+  // pos path first: it only depends on the centres, and its hidden images do not alias the encoder's workspace
+  pos_hidden_kernel<FMT, SPLIT><<<tiles128 < 4 * sms ? tiles128 : 4 * sms, 128, 0, st>>>(
+      center, pblob, ws + W.h_img, x_out, pos_out, groups, rows_per_cloud);
+  kp<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.h_img, pblob + PosBlobLayout::W2(),
+                                      reinterpret_cast<const float*>(pblob + PosBlobLayout::b2()),
+                                      reinterpret_cast<const float*>(pblob + PosBlobLayout::scales()), pos_out, groups,
+                                      tiles128, rows_per_cloud);
+  if (!x_out) return ppt_launch_status();
+  return run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, x_out, groups, 15, st, rows_per_cloud);
 }
 
 }  // namespace
@@ -1297,4 +1408,44 @@ extern "C" PPT_EXPORT int ppt_encoder_forward(const float* neighborhood, const v
                                               void* stream) {
   return ppt_encoder_forward_phases(neighborhood, packed, workspace, features_out, tokens_out, num_groups, mode, 15,
                                     stream);
+}
+
+extern "C" PPT_EXPORT int64_t ppt_posembed_packed_bytes(int mode) {
+  if (mode < PPT_ENC_FP16 || mode > PPT_ENC_FP16X3) return PPT_EINVAL;
+  return (int64_t)PosBlobLayout::total(mode == PPT_ENC_FP16X3 ? 2u : 1u);
+}
+
+extern "C" PPT_EXPORT int64_t ppt_tokenizer_workspace_bytes(int64_t num_groups, int mode) {
+  if (mode < PPT_ENC_FP16 || mode > PPT_ENC_FP16X3 || num_groups < 1) return PPT_EINVAL;
+  return (int64_t)Workspace(num_groups, mode == PPT_ENC_FP16X3 ? 2 : 1).total_tokenizer;
+}
+
+extern "C" PPT_EXPORT int ppt_tokenizer_forward(const float* neighborhood, const float* center,
+                                                const void* encoder_packed, const void* posembed_packed,
+                                                void* workspace, float* x_out, float* pos_out, int64_t num_groups,
+                                                int groups_per_cloud, int mode, void* stream) {
+  if (!center || !posembed_packed || !workspace || !pos_out || num_groups < 1) return PPT_EINVAL;
+  if (x_out && (!neighborhood || !encoder_packed)) return PPT_EINVAL;
+  if (groups_per_cloud < 32 || num_groups % groups_per_cloud != 0) return PPT_EINVAL;
+  if (num_groups > (1ll << 31) / 32) return PPT_ERANGE;
+  if ((reinterpret_cast<uintptr_t>(posembed_packed) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
+      (reinterpret_cast<uintptr_t>(encoder_packed) & 15))
+    return PPT_EINVAL;
+  const unsigned char* blob = static_cast<const unsigned char*>(encoder_packed);
+  const unsigned char* pblob = static_cast<const unsigned char*>(posembed_packed);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case PPT_ENC_FP16:
+      return run_tokenizer<tc05::FMT_F16, 1, 128>(neighborhood, center, blob, pblob, ws, x_out, pos_out, num_groups,
+                                                  groups_per_cloud, st);
+    case PPT_ENC_BF16:
+      return run_tokenizer<tc05::FMT_BF16, 1, 128>(neighborhood, center, blob, pblob, ws, x_out, pos_out, num_groups,
+                                                   groups_per_cloud, st);
+    case PPT_ENC_FP16X3:
+      return run_tokenizer<tc05::FMT_F16, 2, 64>(neighborhood, center, blob, pblob, ws, x_out, pos_out, num_groups,
+                                                 groups_per_cloud, st);
+    default:
+      return PPT_EINVAL;
+  }
 }

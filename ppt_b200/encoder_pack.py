@@ -151,3 +151,38 @@ def pack_encoder(sd, mode):
     blob = torch.cat(parts)
     assert blob.numel() == packed_bytes(mode), (blob.numel(), packed_bytes(mode))
     return blob
+
+
+# ---- pos_embed + cls rows (models/pointbert/point_encoder.py:135-142) ----------------------------------
+POS_F32_SECTION_BYTES = 8192
+POS_HIDDEN_SCALE = 64.0   # fp32-parity mode: GELU outputs as fp16 hi/lo operands
+
+
+def pos_packed_bytes(mode):
+    return POS_F32_SECTION_BYTES + 3 * 2 * split_of(mode) * IMAGE_BYTES
+
+
+def pack_pos_embed(pos_embed_sd, cls_token, cls_pos, mode):
+    """pos_embed = Sequential(Linear(3,128), GELU, Linear(128,384)) state dict (keys 0.weight, 0.bias, 2.weight,
+    2.bias), cls_token / cls_pos [1,1,384] -> uint8 CPU blob for ppt_tokenizer_forward.
+
+    fp32 section: W1 rows {w0,w1,w2,b1} [128][4] | b2 [384] | cls_token [384] | cls_pos [384] |
+    scales {1/(weight scale * hidden scale), hidden scale, 0, 0}; then the 128 -> 384 weight as
+    [3 units][2 chunks][split] K-major operand images (pack_kmajor)."""
+    d = {k: v.detach().to(torch.float64).cpu() for k, v in pos_embed_sd.items()}
+    w1, b1, w2, b2 = d["0.weight"], d["0.bias"], d["2.weight"], d["2.bias"]
+    if tuple(w1.shape) != (128, 3) or tuple(w2.shape) != (384, 128):
+        raise ValueError("kernels are specialised for pos_embed 3 -> 128 -> 384 (point_encoder.py:138-142)")
+    dtype, split = operand_dtype(mode), split_of(mode)
+    wscale = weight_scale(w2) if mode == ENC_FP16X3 else 1.0
+    hscale = POS_HIDDEN_SCALE if mode == ENC_FP16X3 else 1.0
+    scales = torch.tensor([1.0 / (wscale * hscale), hscale, 0.0, 0.0], dtype=torch.float64)
+    f32 = torch.cat([torch.cat([w1, b1[:, None]], dim=1).reshape(-1), b2,
+                     cls_token.detach().to(torch.float64).cpu().reshape(-1),
+                     cls_pos.detach().to(torch.float64).cpu().reshape(-1), scales]).to(torch.float32)
+    assert f32.numel() == 512 + 3 * 384 + 4
+    head = torch.zeros(POS_F32_SECTION_BYTES, dtype=torch.uint8)
+    head[: f32.numel() * 4] = f32.view(torch.uint8)
+    blob = torch.cat([head, pack_kmajor((w2 * wscale).to(torch.float32), dtype, split)])
+    assert blob.numel() == pos_packed_bytes(mode)
+    return blob

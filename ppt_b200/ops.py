@@ -286,6 +286,44 @@ def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, 
     return (tokens, feats) if return_features else tokens
 
 
+def tokenizer_forward(neighborhood, center, enc_packed, pos_packed, mode=ENC_FP16, want_x=True):
+    """The tokenizer's tail in one call (models/pointbert/point_encoder.py:239-247):
+
+        x   = cat(cls_token, reduce_dim(encoder(neighborhood)), dim=1)     [B, G+1, 384]
+        pos = cat(cls_pos,   pos_embed(center),                 dim=1)     [B, G+1, 384]
+
+    neighborhood [B, G, 32, 3], center [B, G, 3] fp32 CUDA; `enc_packed` / `pos_packed` are the blobs of
+    encoder_pack.pack_encoder / pack_pos_embed for `mode`.  want_x=False computes only pos."""
+    _need_cuda(center, pos_packed)
+    ct = _f32(center)
+    if ct.dim() != 3 or ct.shape[-1] != 3:
+        raise ValueError("center must be [B, G, 3]")
+    B, G = int(ct.shape[0]), int(ct.shape[1])
+    if G < 32:
+        raise ValueError("token assembly needs num_group >= 32")
+    lib = _lib.load()
+    if pos_packed.dtype != torch.uint8 or pos_packed.numel() != lib.ppt_posembed_packed_bytes(mode):
+        raise ValueError("packed pos_embed blob does not match mode %d" % mode)
+    nb = None
+    if want_x:
+        _need_cuda(neighborhood, enc_packed)
+        nb = _f32(neighborhood)
+        if tuple(nb.shape) != (B, G, 32, 3):
+            raise ValueError("neighborhood must be [B, G, 32, 3] matching center")
+        if enc_packed.dtype != torch.uint8 or enc_packed.numel() != lib.ppt_encoder_packed_bytes(mode):
+            raise ValueError("packed weight blob does not match mode %d" % mode)
+    x = torch.empty((B, G + 1, 384), dtype=torch.float32, device=ct.device) if want_x else None
+    pos = torch.empty((B, G + 1, 384), dtype=torch.float32, device=ct.device)
+    if B == 0:
+        return x, pos
+    ws = _workspace((ct.device, "encoder"), lib.ppt_tokenizer_workspace_bytes(B * G, mode))
+    with torch.cuda.device(ct.device):
+        _lib.check(lib.ppt_tokenizer_forward(_ptr(nb), _ptr(ct), _ptr(enc_packed) if want_x else None, _ptr(pos_packed),
+                                             _ptr(ws), _ptr(x), _ptr(pos), B * G, G, mode, _stream(ct)),
+                   "ppt_tokenizer_forward")
+    return x, pos
+
+
 def selftest_umma_pair(a, b, mode=ENC_FP16, b_mn_major=False):
     """D[256,N] = A[256,K] @ B[N,K]^T on a CTA pair (tcgen05 cta_group::2)."""
     _need_cuda(a, b)

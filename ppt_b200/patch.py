@@ -33,6 +33,7 @@ _FUNCTIONS = {
         "square_distance": pointbert.square_distance, "query_ball_point": pointnet2.query_ball_point,
         "sample_and_group": pointnet2.sample_and_group,
     },
+    "models.pointbert.point_encoder": {},  # PointTransformer.forward (class patch below)
     "models.pointmlp.pointMLP": {
         "farthest_point_sample": pointbert.farthest_point_sample, "index_points": pointbert.index_points,
         "knn_point": pointbert.knn_point, "square_distance": pointbert.square_distance,
@@ -89,6 +90,49 @@ def _encoder_forward(self, point_groups):
     return ops.encoder_forward(point_groups, self._ppt_blob, mode=mode, return_features=True, want_tokens=False)[1]
 
 
+def point_transformer_front_end(model, pts):
+    """Lines 236-247 of PointTransformer.forward (models/pointbert/point_encoder.py) on the reference's own module
+    instance: returns the (x, pos) that `model.blocks(x, pos)` consumes.  Grouping, Encoder, reduce_dim, the
+    cls rows and pos_embed run as one kernel pipeline (ops.tokenizer_forward); the packed weights are rebuilt
+    when any of the parameters involved changes."""
+    neighborhood, center = model.group_divider(pts)
+    mode = ops.ENC_MODES[getattr(model, "ppt_precision", "fp16")]
+    enc_t = list(model.encoder.parameters()) + list(model.encoder.buffers()) + list(model.reduce_dim.parameters())
+    pos_t = [model.cls_token, model.cls_pos] + list(model.pos_embed.parameters())
+    key = (mode, str(pts.device)) + tuple((t.data_ptr(), t._version) for t in enc_t + pos_t)
+    if getattr(model, "_ppt_front_key", None) != key:
+        sd = dict(model.encoder.state_dict())
+        sd["reduce_dim.weight"], sd["reduce_dim.bias"] = model.reduce_dim.weight, model.reduce_dim.bias
+        blobs = (encoder_pack.pack_encoder(sd, mode).to(pts.device),
+                 encoder_pack.pack_pos_embed(model.pos_embed.state_dict(), model.cls_token, model.cls_pos, mode)
+                 .to(pts.device))
+        object.__setattr__(model, "_ppt_front_blobs", blobs)
+        object.__setattr__(model, "_ppt_front_key", key)
+    enc_blob, pos_blob = model._ppt_front_blobs
+    return ops.tokenizer_forward(neighborhood, center, enc_blob, pos_blob, mode=mode)
+
+
+def _front_end_fusable(model, pts):
+    enc = model.encoder
+    # forward only: fine under no_grad, or when everything involved is frozen (PPT: models/ULIP_models.py:505)
+    involved = list(enc.parameters()) + list(model.reduce_dim.parameters()) + list(model.pos_embed.parameters()) + \
+        [model.cls_token, model.cls_pos]
+    frozen = not torch.is_grad_enabled() or not (pts.requires_grad or any(p.requires_grad for p in involved))
+    return (pts.is_cuda and not enc.training and frozen and model.group_size == 32
+            and model.num_group >= 32 and getattr(enc, "encoder_channel", 0) == 256
+            and tuple(model.reduce_dim.weight.shape) == (384, 256) and tuple(model.pos_embed[0].weight.shape) == (128, 3))
+
+
+def _point_transformer_forward(self, pts, _original):
+    """PointTransformer.forward, models/pointbert/point_encoder.py:234-256: fused front end, then the
+    reference's own transformer blocks, norm and [cls, max] readout."""
+    if not _front_end_fusable(self, pts):
+        return _original(self, pts)
+    x, pos = point_transformer_front_end(self, pts)
+    x = self.norm(self.blocks(x, pos, task="cls"))
+    return torch.cat([x[:, 0], x[:, 1:].max(1)[0]], dim=-1)
+
+
 def _fp_forward(self, xyz1, xyz2, points1, points2):
     return pointnet2.PointNetFeaturePropagation.forward(self, xyz1, xyz2, points1, points2)
 
@@ -121,6 +165,13 @@ def patch_reference(modules=None):
 
             _set(mod.Group, "forward", group_fwd)
             _set(mod.Encoder, "forward", enc_fwd)
+        if modname == "models.pointbert.point_encoder" and hasattr(mod, "PointTransformer"):
+            orig_pt = mod.PointTransformer.forward
+
+            def pt_fwd(self, pts, _o=orig_pt):
+                return _point_transformer_forward(self, pts, _o)
+
+            _set(mod.PointTransformer, "forward", pt_fwd)
         if modname in ("models.pointnet2.pointnet2_utils", "models.pointbert.pointnet2_utils"):
             cls = getattr(mod, "PointNetFeaturePropagation", None)
             if cls is not None:

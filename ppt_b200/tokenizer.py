@@ -4,14 +4,15 @@
                  --mini-PointNet (tcgen05)--> features [B,G,256] --reduce_dim--> tokens [B,G,384]
 
 which is group_divider + encoder + reduce_dim of PointTransformer.forward
-(models/pointbert/point_encoder.py:236-239).  Clouds are independent, so multi-GPU is a
+(models/pointbert/point_encoder.py:236-239).  `forward_assembled` adds the next step (:241-247): the cls
+token row, pos_embed(center) and the cls_pos row, i.e. the two tensors `self.blocks(x, pos)` consumes.  Clouds are independent, so multi-GPU is a
 contiguous batch shard per rank with no collective in the loop (SURVEY.md section 8e);
 `gather_tokens` is the one validation-time all-gather.
 """
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import encoder_pack, ops
 from .pointbert import Encoder, _as_start, _draw_start
 
 
@@ -22,7 +23,13 @@ class PointTokenizer(nn.Module):
         self.encoder = Encoder(encoder_dims, precision=precision)
         self.reduce_dim = nn.Linear(encoder_dims, trans_dim)
         self.encoder.attach_reduce_dim(self.reduce_dim)
+        # same names and shapes as PointTransformer's (models/pointbert/point_encoder.py:135-142)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, trans_dim))
+        self.cls_pos = nn.Parameter(torch.randn(1, 1, trans_dim))
+        self.pos_embed = nn.Sequential(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, trans_dim))
         self.start_idx = None
+        self._pos_packed = None
+        self._pos_key = None
 
     def load_reference_state(self, sd):
         """Accepts the torch_port / reference naming: first_conv.*, second_conv.*, reduce_dim.*"""
@@ -31,6 +38,35 @@ class PointTokenizer(nn.Module):
         self.reduce_dim.load_state_dict({"weight": sd["reduce_dim.weight"], "bias": sd["reduce_dim.bias"]})
         self.encoder._packed = None
         return self
+
+    def load_front_end_state(self, module):
+        """Copies cls_token, cls_pos and pos_embed from a reference PointTransformer (or its state dict)."""
+        sd = module if isinstance(module, dict) else module.state_dict()
+        with torch.no_grad():
+            self.cls_token.copy_(sd["cls_token"])
+            self.cls_pos.copy_(sd["cls_pos"])
+        self.pos_embed.load_state_dict({k[len("pos_embed."):]: v for k, v in sd.items() if k.startswith("pos_embed.")})
+        self._pos_packed = None
+        return self
+
+    def _pos_blob(self, device):
+        mode = ops.ENC_MODES[self.encoder.precision]
+        tensors = [self.cls_token, self.cls_pos] + list(self.pos_embed.parameters())
+        key = (mode, str(device)) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._pos_packed is None or self._pos_key != key:
+            self._pos_packed = encoder_pack.pack_pos_embed(self.pos_embed.state_dict(), self.cls_token, self.cls_pos,
+                                                           mode).to(device)
+            self._pos_key = key
+        return self._pos_packed
+
+    @torch.no_grad()
+    def forward_assembled(self, xyz):
+        """xyz [B,N,3] (CUDA) -> x [B,G+1,384], pos [B,G+1,384], center [B,G,3]: the arguments of
+        `self.blocks(x, pos)` in PointTransformer.forward (models/pointbert/point_encoder.py:241-249)."""
+        neighborhood, center = self.group(xyz)
+        blob, mode = self.encoder._blob(xyz.device)
+        x, pos = ops.tokenizer_forward(neighborhood, center, blob, self._pos_blob(xyz.device), mode=mode)
+        return x, pos, center
 
     def group(self, xyz):
         start = _draw_start(xyz) if self.start_idx is None else _as_start(self.start_idx, xyz)

@@ -216,3 +216,62 @@ def test_patch_reference_diverts_cuda_tensors_on_a_stand_in_tree():
                 sys.modules.pop(n, None)
             else:
                 sys.modules[n] = m
+
+
+def test_point_transformer_forward_with_fused_front_end_on_a_stand_in():
+    """PointTransformer.forward (models/pointbert/point_encoder.py:234-256) with the fused front end, on a stand-in
+    that has the reference's attribute names; the unfused body is lines 236-256 written with torch ops."""
+    from ppt_b200 import patch, pointbert
+
+    class Blocks(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(384, 384)
+
+        def forward(self, x, pos, task="cls"):
+            return self.lin(x + pos)
+
+    class PointTransformer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.group_size, self.num_group = 32, 64
+            self.group_divider = pointbert.Group(num_group=64, group_size=32)
+            self.group_divider.start_idx = 0
+            self.encoder = pointbert.Encoder(256)
+            self.reduce_dim = torch.nn.Linear(256, 384)
+            self.cls_token = torch.nn.Parameter(torch.randn(1, 1, 384) * 0.1)
+            self.cls_pos = torch.nn.Parameter(torch.randn(1, 1, 384))
+            self.pos_embed = torch.nn.Sequential(torch.nn.Linear(3, 128), torch.nn.GELU(), torch.nn.Linear(128, 384))
+            self.blocks, self.norm = Blocks(), torch.nn.LayerNorm(384)
+
+    def reference_body(self, pts):
+        neighborhood, center = self.group_divider(pts)
+        tokens = self.reduce_dim(self.encoder._forward_torch(neighborhood))
+        x = torch.cat((self.cls_token.expand(tokens.size(0), -1, -1), tokens), dim=1)
+        pos = torch.cat((self.cls_pos.expand(tokens.size(0), -1, -1), self.pos_embed(center)), dim=1)
+        x = self.norm(self.blocks(x, pos, task="cls"))
+        return torch.cat([x[:, 0], x[:, 1:].max(1)[0]], dim=-1)
+
+    torch.manual_seed(3)
+    model = PointTransformer()
+    sd = torch_port.make_encoder_state()
+    model.encoder.load_state_dict({k: v for k, v in sd.items() if k in torch_port.ENCODER_KEYS}, strict=False)
+    model = model.cuda().eval()
+    xyz = cloud("U", 3, 2048, 9).cuda()
+    calls = []
+    with torch.no_grad():
+        want = reference_body(model, xyz)
+        got = patch._point_transformer_forward(model, xyz, lambda s, p: calls.append(1) or reference_body(s, p))
+        assert not calls, "the fused path must run for CUDA eval input"
+        assert float((got - want).abs().max() / want.abs().max()) < 2e-3
+        x, pos = patch.point_transformer_front_end(model, xyz)
+        assert x.shape == (3, 65, 384) and torch.equal(x[:, 0], model.cls_token.expand(3, -1, -1)[:, 0])
+        assert torch.equal(pos[:, 0], model.cls_pos.expand(3, -1, -1)[:, 0])
+        with torch.no_grad():
+            model.cls_pos.add_(1.0)   # a parameter update must invalidate the packed blob
+        _, pos2 = patch.point_transformer_front_end(model, xyz)
+        assert torch.allclose(pos2[:, 0], pos[:, 0] + 1.0)
+    model.encoder.train()
+    with torch.no_grad():
+        patch._point_transformer_forward(model, xyz, lambda s, p: calls.append(1) or want)
+    assert calls == [1], "train-mode BatchNorm keeps the reference body"

@@ -23,6 +23,9 @@ def test_library_exports_every_declared_symbol():
     assert lib.ppt_abi_version() == _lib.ABI_VERSION
     assert b"invalid" in lib.ppt_strerror(-1)
     assert lib.ppt_encoder_packed_bytes(0) == 925696 + 16384
+    assert lib.ppt_posembed_packed_bytes(0) == 8192 + 6 * 16384
+    assert lib.ppt_posembed_packed_bytes(2) == 8192 + 12 * 16384
+    assert lib.ppt_tokenizer_workspace_bytes(128, 0) == lib.ppt_encoder_workspace_bytes(128, 0) + 2 * 16384
     nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (\w+)", nm))
     assert declared <= exported
@@ -160,6 +163,36 @@ def test_patch_reference_keeps_cpu_behaviour_and_is_reversible():
         with refimport.fixed_fps_start(0):
             after = ns.dvae.Group(16, 8)(xyz)  # CPU tensors still take the reference's own code
         assert torch.equal(before[0], after[0]) and torch.equal(before[1], after[1])
+        # PointTransformer.forward is patched too and leaves CPU inputs to the reference's own body
+        import importlib
+        import types
+        pe = importlib.import_module("models.pointbert.point_encoder")
+        assert "PointTransformer.forward" in names
+        cfg = types.SimpleNamespace(trans_dim=384, depth=1, drop_path_rate=0.0, cls_dim=40, num_heads=6,
+                                    group_size=32, num_group=32, encoder_dims=256)
+        model = pe.PointTransformer(cfg, args=types.SimpleNamespace()).eval()
+        with refimport.fixed_fps_start(0), torch.no_grad():
+            patched = model(xyz)
+            original = pe.PointTransformer.forward.__defaults__[0](model, xyz)
+        assert patched.shape == (1, 768) and torch.equal(patched, original)
     finally:
         patch.unpatch_reference()
     assert not hasattr(ns.dvae.knn_point, "__ppt_b200_original__")
+
+
+def test_pos_embed_packing_matches_abi_sizes():
+    from ppt_b200 import _lib, encoder_pack as ep
+    from oracle import torch_port
+    front = torch_port.make_front_end_state()
+    pe = {k[len("pos_embed."):]: v for k, v in front.items() if k.startswith("pos_embed.")}
+    lib = _lib.load()
+    for mode in (0, 1, 2):
+        blob = ep.pack_pos_embed(pe, front["cls_token"], front["cls_pos"], mode)
+        assert blob.numel() == ep.pos_packed_bytes(mode) == lib.ppt_posembed_packed_bytes(mode)
+        head = blob[:8192].view(torch.float32)
+        assert torch.equal(head[512 + 384:512 + 768], front["cls_token"].reshape(-1))   # copied verbatim
+        assert torch.equal(head[512 + 768:512 + 1152], front["cls_pos"].reshape(-1))
+        assert float(head[512 + 1152]) * float(head[512 + 1153]) > 0                     # the two scales
+    with pytest.raises(ValueError):
+        ep.pack_pos_embed({"0.weight": torch.zeros(64, 3), "0.bias": torch.zeros(64), "2.weight": torch.zeros(384, 64),
+                           "2.bias": torch.zeros(384)}, front["cls_token"], front["cls_pos"], 0)

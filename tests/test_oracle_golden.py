@@ -154,3 +154,18 @@ def test_encoder_port_matches_reference_tokens(golden):
     for got, ref in ((feat, f["features"]), (tok, f["tokens"])):
         rel = np.abs(got - ref).max() / np.abs(ref).max()
         assert rel <= 1e-6, rel
+
+
+def test_token_assembly_port_matches_reference_point_transformer(golden):
+    """x / pos handed to self.blocks by the unmodified PointTransformer (point_encoder.py:241-249)."""
+    f = golden("front_end_small")
+    sd, front = torch_port.make_encoder_state(), torch_port.make_front_end_state()
+    with torch.no_grad():
+        nb, center = torch.from_numpy(f["neighborhood"]), torch.from_numpy(f["center"])
+        B, G = center.shape[:2]
+        tok = torch_port.tokens_forward(sd, nb)
+        x, pos = torch_port.assemble_forward(front, tok, center)
+    assert x.shape == (B, G + 1, 384) and pos.shape == (B, G + 1, 384)
+    for got, ref in ((x.numpy(), f["x"]), (pos.numpy(), f["pos"])):
+        assert np.abs(got - ref).max() / np.abs(ref).max() <= 1e-6
+    assert np.array_equal(x[:, 0].numpy(), f["x"][:, 0]) and np.array_equal(pos[:, 0].numpy(), f["pos"][:, 0])
