@@ -1004,7 +1004,7 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
 // models/pointbert/point_encoder.py:245-246 -- g + g / G + 1: every cloud's G rows follow one row that
 // belongs to the cls token.  G >= 32 so that a run of 32 consecutive groups crosses at most one cloud boundary.
 // ======================================================================================
-template <uint32_t FMT, int SPLIT, int NUNITS, int KCH = 4>
+template <uint32_t FMT, int SPLIT, int NUNITS, int KCH = 4, bool ASSEMBLE = false>
 __global__ void __launch_bounds__(LIN_THREADS, 1)
 group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned char* __restrict__ wsec,
                     const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ out,
@@ -1109,16 +1109,21 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
           float v[32];
           tmem_ld32(t_addr + j * 32, v);
           const long long g0 = (long long)tile * NT + j * 32;
-          long long row0 = g0;
-          int wrap = 32;  // first i of this run that belongs to the next cloud
-          if (rows_per_cloud > 0) {
-            const long long q = g0 / rows_per_cloud;
-            row0 = g0 + q + 1;
-            wrap = (int)((q + 1) * rows_per_cloud - g0);
-          }
+          if (!ASSEMBLE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (g0 + i < num_groups) out[(row0 + i + (i >= wrap ? 1 : 0)) * NOUT + o] = fmaf(v[i], inv_scale, bo);
+            for (int i = 0; i < 32; ++i)
+              if (g0 + i < num_groups) out[(g0 + i) * NOUT + o] = fmaf(v[i], inv_scale, bo);
+          } else {
+            const long long q = g0 / rows_per_cloud;
+            const int wrap = (int)((q + 1) * rows_per_cloud - g0);  // first i that belongs to the next cloud
+            const long long left = num_groups - g0;
+            const int limit = left < 32 ? (int)left : 32;
+            float* p0 = out + (g0 + q + 1) * NOUT + o;  // rows of this cloud
+            float* p1 = p0 + NOUT;                      // rows of the next one: skip its cls row
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < limit) (i < wrap ? p0 : p1)[i * NOUT] = fmaf(v[i], inv_scale, bo);
+          }
         }
         fence_before_sync();
         mbar_arrive(&acc_empty[buf]);
@@ -1151,23 +1156,24 @@ struct PosBlobLayout {
 };
 
 template <uint32_t FMT, int SPLIT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 pos_hidden_kernel(const float* __restrict__ center, const unsigned char* __restrict__ pblob,
                   unsigned char* __restrict__ h_img, float* __restrict__ x_out, float* __restrict__ pos_out,
                   long long num_groups, int rows_per_cloud) {
+  // 512 threads per 128-centre tile: thread = (centre row, quarter of the 128 hidden channels)
   __shared__ float4 w1s[128];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, row = tid & 127, quarter = tid >> 7;
   const float hscale = __ldg(reinterpret_cast<const float*>(pblob + PosBlobLayout::scales()) + 1);
-  w1s[tid] = __ldg(reinterpret_cast<const float4*>(pblob + PosBlobLayout::w1()) + tid);
+  if (tid < 128) w1s[tid] = __ldg(reinterpret_cast<const float4*>(pblob + PosBlobLayout::w1()) + tid);
   __syncthreads();
   const long long tiles = (num_groups + 127) / 128;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long g = tile * 128 + tid;
+    const long long g = tile * 128 + row;
     if (g < num_groups) {
       const float x = __ldg(center + g * 3), y = __ldg(center + g * 3 + 1), z = __ldg(center + g * 3 + 2);
       unsigned char* img = h_img + (size_t)tile * 2 * SPLIT * IMG;
 #pragma unroll 2
-      for (int c8 = 0; c8 < 128; c8 += 8) {
+      for (int c8 = quarter * 32; c8 < quarter * 32 + 32; c8 += 8) {
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -1184,7 +1190,7 @@ pos_hidden_kernel(const float* __restrict__ center, const unsigned char* __restr
             lo[t] = pack2<FMT, false>(v[0] - r.x, v[1] - r.y);
           }
         }
-        unsigned char* dst = img + (size_t)(c8 >> 6) * SPLIT * IMG + sw128_kmajor_off(tid, c8 & 63);
+        unsigned char* dst = img + (size_t)(c8 >> 6) * SPLIT * IMG + sw128_kmajor_off(row, c8 & 63);
         *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if (SPLIT == 2) *reinterpret_cast<uint4*>(dst + IMG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
@@ -1194,7 +1200,7 @@ pos_hidden_kernel(const float* __restrict__ center, const unsigned char* __restr
   const long long clouds = num_groups / rows_per_cloud;
   const float* cls_token = reinterpret_cast<const float*>(pblob + PosBlobLayout::cls_token());
   const float* cls_pos = reinterpret_cast<const float*>(pblob + PosBlobLayout::cls_pos());
-  for (long long i = (long long)blockIdx.x * 128 + tid; i < clouds * 384; i += (long long)gridDim.x * 128) {
+  for (long long i = (long long)blockIdx.x * 512 + tid; i < clouds * 384; i += (long long)gridDim.x * 512) {
     const long long b = i / 384;
     const int o = (int)(i - b * 384);
     const long long dst = b * (rows_per_cloud + 1) * 384 + o;
@@ -1277,6 +1283,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
   auto kb = group_linear_kernel<FMT, SPLIT, 4>;
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
+  auto kda = group_linear_kernel<FMT, SPLIT, 3, 4, true>;
   constexpr size_t s1 = stage_smem_bytes<SPLIT, NT, 1>(), s2 = stage_smem_bytes<SPLIT, NT, 2>(),
                    sl = linear_smem_bytes<SPLIT>();
   static_assert(s2 <= 232448 && s1 <= 232448 && sl <= 232448, "shared memory budget (227 KB per CTA)");
@@ -1289,6 +1296,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
                                             (int)stage_smem_bytes<1, 128, 2>()));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kda, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     configured = true;
   }
   const long long points = groups * 32;
@@ -1334,9 +1342,9 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     }
   }
   if ((phases & 8) && tokens_out)
-    kd<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.t_img, blob + L.WR(),
-                                        reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,
-                                        groups, tiles128, rows_per_cloud);
+    (rows_per_cloud > 0 ? kda : kd)<<<grid_g, LIN_THREADS, sl, st>>>(
+        ws + W.t_img, blob + L.WR(), reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,
+        groups, tiles128, rows_per_cloud);
   return ppt_launch_status();
 }
 
@@ -1346,7 +1354,7 @@ int run_tokenizer(const float* nbhd, const float* center, const unsigned char* b
                   unsigned char* ws, float* x_out, float* pos_out, long long groups, int rows_per_cloud,
                   cudaStream_t st) {
   const Workspace W(groups, SPLIT);
-  auto kp = group_linear_kernel<FMT, SPLIT, 3, 2>;
+  auto kp = group_linear_kernel<FMT, SPLIT, 3, 2, true>;
   constexpr size_t sl = linear_smem_bytes<SPLIT>();
   static bool configured = false;
   if (!configured) {
@@ -1357,7 +1365,7 @@ int run_tokenizer(const float* nbhd, const float* center, const unsigned char* b
   const int sms = num_sms();
   const int grid_g = tiles128 < sms ? tiles128 : sms;
   // pos path first: it only depends on the centres, and its hidden images do not alias the encoder's workspace
-  pos_hidden_kernel<FMT, SPLIT><<<tiles128 < 4 * sms ? tiles128 : 4 * sms, 128, 0, st>>>(
+  pos_hidden_kernel<FMT, SPLIT><<<tiles128 < 4 * sms ? tiles128 : 4 * sms, 512, 0, st>>>(
       center, pblob, ws + W.h_img, x_out, pos_out, groups, rows_per_cloud);
   kp<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.h_img, pblob + PosBlobLayout::W2(),
                                       reinterpret_cast<const float*>(pblob + PosBlobLayout::b2()),
