@@ -145,6 +145,31 @@ int ppt_encoder_forward_phases(const float *neighborhood, const void *packed, vo
                                float *features_out, float *tokens_out, int64_t num_groups, int mode,
                                int phases, void *stream);
 
+/* ---- Encoder.forward under model.train(): batch-statistics BatchNorm --------
+ * PPT trains with model.train() (main_cls.py:169), which puts the FROZEN Encoder's two BatchNorm1d layers
+ * (models/pointbert/dvae.py:190,196) in batch-statistics mode: they normalise with the mean / biased variance
+ * of the current batch and update their running statistics (momentum, unbiased variance, num_batches_tracked).
+ * Forward only (the Encoder's parameters take no gradient in PPT, models/ULIP_models.py:505).
+ *   packed_train: MUTABLE device copy of the blob packed with both BatchNorms as identities
+ *                 (ppt_b200/encoder_pack.py:pack_encoder_train); sections that depend on the batch are rewritten;
+ *   bn: device pointers into the module's own tensors (fp32 contiguous; num_batches_tracked int64 or NULL);
+ *       running_mean / running_var / num_batches_tracked are updated in place, in stream order;
+ *   workspace: ppt_encoder_train_workspace_bytes(num_groups, mode) bytes. */
+typedef struct {
+  const float *conv1_weight, *conv1_bias;       /* first_conv.0: [128,3(,1)], [128] */
+  const float *bn1_weight, *bn1_bias;           /* first_conv.1 */
+  float *bn1_running_mean, *bn1_running_var;    /* [128] */
+  int64_t *bn1_num_batches_tracked;
+  const float *bn2_weight, *bn2_bias;           /* second_conv.1 */
+  float *bn2_running_mean, *bn2_running_var;    /* [512] */
+  int64_t *bn2_num_batches_tracked;
+  float momentum, eps;                          /* 0.1, 1e-5 in the reference */
+} ppt_encoder_bn_t;
+int64_t ppt_encoder_train_workspace_bytes(int64_t num_groups, int mode);
+int ppt_encoder_forward_train(const float *neighborhood, void *packed_train, const ppt_encoder_bn_t *bn,
+                              void *workspace, float *features_out, float *tokens_out, int64_t num_groups,
+                              int mode, void *stream);
+
 /* ---- pos_embed + token assembly (the step right after the tokenizer) ----------
  * PointTransformer.forward, models/pointbert/point_encoder.py:239-247:
  *     x   = cat(cls_token, reduce_dim(encoder(neighborhood)))         [clouds, G+1, 384]

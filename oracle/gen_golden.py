@@ -166,6 +166,34 @@ def gen_encoder(ns):
     print("encoder tokens", tuple(tok.shape), "absmax", float(tok.abs().max()))
 
 
+def gen_encoder_train(ns):
+    """Reference Encoder under .train() (dvae.py:184-215; main_cls.py:169 puts the frozen module in this mode):
+    features, reduce_dim tokens and the running statistics after ONE forward, seeded weights."""
+    sd = torch_port.make_encoder_state()
+    enc = ns.dvae.Encoder(256).train()
+    missing = enc.load_state_dict({k: v for k, v in sd.items() if k in torch_port.ENCODER_KEYS}, strict=False)
+    assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing
+    reduce_dim = torch.nn.Linear(256, 384)
+    reduce_dim.load_state_dict({"weight": sd["reduce_dim.weight"], "bias": sd["reduce_dim.bias"]})
+    xyz = cloud("U", 3, 1024, 4444)
+    with refimport.fixed_fps_start(0):
+        nb, _ = ns.dvae.Group(50, 32)(xyz)   # 150 groups: a ragged last tile
+    with torch.no_grad():
+        feat = enc(nb)
+        tok = reduce_dim(feat)
+    after = {k: v.clone() for k, v in enc.state_dict().items() if "running_" in k or "num_batches" in k}
+    port_feat, port_stats = torch_port.encoder_forward_train(sd, nb)
+    assert (port_feat - feat).abs().max() <= 1e-6 * feat.abs().max()
+    for k, v in port_stats.items():
+        assert (v - after[k]).abs().max() <= 1e-6 * after[k].abs().max(), k
+    rec = {"neighborhood": nb.numpy(), "features": feat.numpy(), "tokens": tok.numpy(),
+           "torch_version": torch.__version__}
+    for k, v in after.items():
+        rec["after." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "encoder_train_small.npz"), **rec)
+    print("encoder train-mode features", tuple(feat.shape), "absmax", float(feat.abs().max()))
+
+
 def gen_front_end(ns):
     """The unmodified reference PointTransformer (models/pointbert/point_encoder.py:111-256) up to the call of
     self.blocks: a forward pre-hook records the (x, pos) it is given (:241-249).  depth 1 keeps the unused
@@ -202,8 +230,8 @@ def gen_front_end(ns):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] == "front_end":  # regenerate only the newest fixture
-        gen_front_end(refimport.load())
+    if len(sys.argv) > 1:  # regenerate one fixture only: front_end | encoder_train
+        {"front_end": gen_front_end, "encoder_train": gen_encoder_train}[sys.argv[1]](refimport.load())
         return
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     ns = refimport.load()
@@ -220,6 +248,7 @@ def main():
     gen_msg_fp(ns, "msg_fp_cfg4", 8, 2048, 1238, 384, full=False)
     gen_encoder(ns)
     gen_front_end(ns)
+    gen_encoder_train(ns)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("fixtures total bytes", tot)
 

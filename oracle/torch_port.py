@@ -178,3 +178,23 @@ def assemble_forward(front, tokens, center):
     x = torch.cat((front["cls_token"].expand(B, -1, -1), tokens), dim=1)
     pos = torch.cat((front["cls_pos"].expand(B, -1, -1), p), dim=1)
     return x, pos
+
+
+# ---- Encoder under model.train(): batch-statistics BatchNorm (dvae.py:190,196; main_cls.py:169; F9) ---------
+def encoder_forward_train(sd, neighborhood, momentum=0.1, eps=1e-5):
+    """dvae.py:201-215 with both BatchNorm1d layers in training mode.  Returns (features [B,G,256], updated
+    running statistics as a dict) without modifying `sd`."""
+    F = torch.nn.functional
+    bs, g, n, _ = neighborhood.shape
+    new = {k: sd[k].clone() for k in sd if "running_" in k}
+    x = neighborhood.reshape(bs * g, n, 3).transpose(2, 1)
+    y = F.conv1d(x, sd["first_conv.0.weight"], sd["first_conv.0.bias"])
+    y = F.batch_norm(y, new["first_conv.1.running_mean"], new["first_conv.1.running_var"], sd["first_conv.1.weight"],
+                     sd["first_conv.1.bias"], True, momentum, eps)
+    f = F.conv1d(F.relu(y), sd["first_conv.3.weight"], sd["first_conv.3.bias"])
+    glob = torch.max(f, dim=2, keepdim=True)[0]
+    y = F.conv1d(torch.cat([glob.expand(-1, -1, n), f], dim=1), sd["second_conv.0.weight"], sd["second_conv.0.bias"])
+    y = F.batch_norm(y, new["second_conv.1.running_mean"], new["second_conv.1.running_var"], sd["second_conv.1.weight"],
+                     sd["second_conv.1.bias"], True, momentum, eps)
+    f = F.conv1d(F.relu(y), sd["second_conv.3.weight"], sd["second_conv.3.bias"])
+    return torch.max(f, dim=2)[0].reshape(bs, g, -1), new

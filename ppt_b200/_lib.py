@@ -9,6 +9,18 @@ ABI_VERSION = 1
 _c = ctypes
 _p, _i, _f, _i64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64
 
+
+
+class EncoderBn(_c.Structure):
+    """ppt_encoder_bn_t (include/ppt_b200.h): device pointers into the Encoder's BatchNorm / conv tensors."""
+    _fields_ = [("conv1_weight", _p), ("conv1_bias", _p),
+                ("bn1_weight", _p), ("bn1_bias", _p), ("bn1_running_mean", _p), ("bn1_running_var", _p),
+                ("bn1_num_batches_tracked", _p),
+                ("bn2_weight", _p), ("bn2_bias", _p), ("bn2_running_mean", _p), ("bn2_running_var", _p),
+                ("bn2_num_batches_tracked", _p),
+                ("momentum", _f), ("eps", _f)]
+
+
 # name -> (restype, argtypes); must list every function declared in include/ppt_b200.h
 SIGNATURES = {
     "ppt_abi_version": (_i, []),
@@ -29,6 +41,8 @@ SIGNATURES = {
     "ppt_encoder_workspace_bytes": (_i64, [_i64, _i]),
     "ppt_encoder_forward": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p]),
     "ppt_encoder_forward_phases": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p]),
+    "ppt_encoder_train_workspace_bytes": (_i64, [_i64, _i]),
+    "ppt_encoder_forward_train": (_i, [_p, _p, _c.POINTER(EncoderBn), _p, _p, _p, _i64, _i, _p]),
     "ppt_posembed_packed_bytes": (_i64, [_i]),
     "ppt_tokenizer_workspace_bytes": (_i64, [_i64, _i]),
     "ppt_tokenizer_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),

@@ -122,16 +122,28 @@ __device__ __forceinline__ void store_relu8(unsigned char* base, uint32_t off, u
 // ======================================================================================
 // stage kernels
 // ======================================================================================
-template <uint32_t FMT, int SPLIT, int NT, int STAGE, int EPW>
+// BN (stage 2 only; train-mode BatchNorm of second_conv.1, DESIGN.md "train mode"):
+//   BN_EVAL   the blob's W32 / c carry the folded running statistics (the inference path);
+//   BN_STATS  first pass of a training step: only the four W32 h1 units run, and instead of writing h3 the
+//             epilogue accumulates sum and sum of squares per channel of y = W32 h1 + c (raw, un-normalised
+//             weights) into bn_stats[0..511] / [512..1023] (fp64 atomics, one per channel, half and CTA);
+//   BN_APPLY  second pass: h3 = relu(s[ch] * y + t[ch]) with s = bn_vec[ch], t = bn_vec[512 + ch] from the
+//             batch statistics -- folded into the per-unit accumulator scale and the prefetched c values, so
+//             the inner loop is the same single FFMA per element as BN_EVAL.
+constexpr int BN_EVAL = 0, BN_STATS = 1, BN_APPLY = 2;
+
+template <uint32_t FMT, int SPLIT, int NT, int STAGE, int EPW, int BN = BN_EVAL>
 __global__ void __launch_bounds__((EPW + 2) * 32, 1)
 encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
                      const float* __restrict__ cbuf,          // stage 2: [groups_pad, 512]
                      unsigned char* __restrict__ out_img,     // stage 1: g images, stage 2: t images
                      float* __restrict__ features_out,        // stage 2, nullable: [groups, 256]
-                     long long num_groups, int num_tiles) {
+                     long long num_groups, int num_tiles,
+                     double* __restrict__ bn_stats = nullptr, const float* __restrict__ bn_vec = nullptr) {
+  static_assert(BN == BN_EVAL || STAGE == 2, "batch statistics belong to stage 2");
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int GPT = NT / 32;                       // groups per tile
-  constexpr int NUNITS = STAGE == 1 ? 2 : 6;
+  constexpr int NUNITS = STAGE == 1 ? 2 : (BN == BN_STATS ? 4 : 6);
   constexpr int NH1 = STAGE == 1 ? 2 : 1;            // h1 buffers (stage 1 builds one tile ahead)
   constexpr uint32_t H1_BYTES = 2u * NT * 128u;      // one split part of one buffer: 2 K-chunks, K-major
   constexpr uint32_t H1_BUF = SPLIT * H1_BYTES;
@@ -259,6 +271,14 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
     const float inv_p1 = __ldg(sc + 0), inv_g3 = __ldg(sc + 3);
     const float act_scale = __ldg(sc + 5), grp_scale = __ldg(sc + 6);
     const float inv_p2s = __ldg(sc + 2) * act_scale;  // accumulator -> scaled activation, one FFMA per element
+    // per-unit accumulator scale and shift of this thread's channels (BN_APPLY: batch-statistics BatchNorm)
+    float u_scale[4], u_shift[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      u_scale[u] = BN == BN_APPLY ? __ldg(bn_vec + u * 128 + m) : 1.f;
+      u_shift[u] = BN == BN_APPLY ? __ldg(bn_vec + 512 + u * 128 + m) : 0.f;
+    }
+    double st_sum[4] = {0.0, 0.0, 0.0, 0.0}, st_sq[4] = {0.0, 0.0, 0.0, 0.0};  // BN_STATS
 
     // This thread's point of a tile, fetched one build ahead: the load comes from HBM (the neighbourhoods
     // are read here for the first time) and would otherwise stall the first FFMA of every build.
@@ -304,7 +324,8 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 #pragma unroll
         for (int jj = 0; jj < GH; ++jj) {
           const long long g = (long long)tile * GPT + half * GH + jj;
-          cnext[u][jj] = g < num_groups ? __ldg(cbuf + g * 512 + u * 128 + m) * act_scale : 0.f;
+          const float cv = g < num_groups ? __ldg(cbuf + g * 512 + u * 128 + m) : 0.f;
+          cnext[u][jj] = (BN == BN_APPLY ? fmaf(cv, u_scale[u], u_shift[u]) : cv) * act_scale;
         }
     };
 
@@ -333,9 +354,35 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
         fence_after_sync();
         const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * NT + col0);
 
-        if (relu_unit) {
+        if (relu_unit && BN == BN_STATS) {
+          // y = acc + c over this thread's channel and valid points: fp32 sums per 32-point group, fp64 across
+          const float inv_true = __ldg(sc + 2);
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < GH; ++jj) {
+            float v[32];
+            tmem_ld32(t_addr + jj * 32, v);
+            if (g0 + jj < num_groups) {
+              const float cv = ccur[u < 4 ? u : 0][jj] / act_scale;  // act_scale is a power of two
+              float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float y = fmaf(v[i], inv_true, cv);
+                a1 += y;
+                a2 = fmaf(y, y, a2);
+              }
+              s1 += a1;
+              s2 += a2;
+            }
+          }
+          st_sum[u < 4 ? u : 0] += (double)s1;
+          st_sq[u < 4 ? u : 0] += (double)s2;
+          fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+        } else if (relu_unit) {
           // h3[p][ch] = relu(acc + c[group][ch]); ch = u*128 + m is this thread's K index (MN-major B).
           const int ch = u * 128 + m;
+          const float a_unit = BN == BN_APPLY ? inv_p2s * u_scale[u < 4 ? u : 0] : inv_p2s;
           const uint32_t krow = (uint32_t)(ch >> 3) * 1024u + (uint32_t)(ch & 7) * 128u;
           const uint32_t sw = (uint32_t)(ch & 7);
 #pragma unroll
@@ -344,7 +391,7 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
             tmem_ld32(t_addr + jj * 32, v);
             const float cv = ccur[u < 4 ? u : 0][jj];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], inv_p2s, cv);
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], a_unit, cv);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int n = col0 + jj * 32 + q * 8;
@@ -396,6 +443,13 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
       if (STAGE == 1) {
         const int next2 = tile + 2 * gridDim.x;
         if (next2 < num_tiles) build_h1(next2, tile_it & 1u, next2 + gridDim.x);
+      }
+    }
+    if (BN == BN_STATS) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        atomicAdd(bn_stats + u * 128 + m, st_sum[u]);
+        atomicAdd(bn_stats + 512 + u * 128 + m, st_sq[u]);
       }
     }
   }
@@ -1210,6 +1264,106 @@ pos_hidden_kernel(const float* __restrict__ center, const unsigned char* __restr
 }
 
 // ======================================================================================
+// train-mode BatchNorm (models/pointbert/dvae.py:190,196 under model.train(), main_cls.py:169)
+// ======================================================================================
+// first_conv.1 normalises y = W x + b (3 -> 128), which is affine in the coordinates: its batch mean and biased
+// variance follow exactly from the mean and covariance of the points, mean_y = W mu + b, var_y = W Sigma W^T.
+// bn_moments_kernel reduces the nine first and second moments in fp64; bn_fold1_kernel folds the batch
+// statistics into W1' (fp32 rows for stage 2 and the K = 16 layer-1 operand image for stage 1, the layout of
+// encoder_pack.layer1_image) inside the caller's mutable blob and applies the momentum update to the
+// running statistics.  second_conv.1 sits behind a ReLU, so its statistics need a pass over the data
+// (encoder_stage_kernel<BN_STATS>); bn_fold2_kernel turns the sums into per-channel scale / shift.
+__global__ void __launch_bounds__(256)
+bn_moments_kernel(const float* __restrict__ nbhd, long long npoints, double* __restrict__ mom) {
+  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npoints; i += (long long)gridDim.x * blockDim.x) {
+    const double x = __ldg(nbhd + i * 3), y = __ldg(nbhd + i * 3 + 1), z = __ldg(nbhd + i * 3 + 2);
+    a[0] += x; a[1] += y; a[2] += z;
+    a[3] += x * x; a[4] += x * y; a[5] += x * z; a[6] += y * y; a[7] += y * z; a[8] += z * z;
+  }
+  __shared__ double part[8][9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double v = a[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double v = 0;
+    for (int w = 0; w < 8; ++w) v += part[w][threadIdx.x];
+    atomicAdd(mom + threadIdx.x, v);
+  }
+}
+
+struct BnDevice {  // device pointers of the two BatchNorm1d modules and the convolution in front of the first
+  const float *conv1_w, *conv1_b;
+  const float *bn1_w, *bn1_b;
+  float *bn1_rm, *bn1_rv;
+  long long* bn1_nbt;
+  const float *bn2_w, *bn2_b;
+  float *bn2_rm, *bn2_rv;
+  long long* bn2_nbt;
+  float momentum, eps;
+};
+
+template <uint32_t FMT>
+__global__ void __launch_bounds__(128)
+bn_fold1_kernel(BnDevice bn, const double* __restrict__ mom, long long npoints, unsigned char* __restrict__ blob,
+                uint32_t split) {
+  const BlobLayout L{split};
+  const int ch = threadIdx.x;
+  const double n = (double)npoints;
+  const double mx = mom[0] / n, my = mom[1] / n, mz = mom[2] / n;
+  const double cxx = mom[3] / n - mx * mx, cxy = mom[4] / n - mx * my, cxz = mom[5] / n - mx * mz;
+  const double cyy = mom[6] / n - my * my, cyz = mom[7] / n - my * mz, czz = mom[8] / n - mz * mz;
+  const double w0 = bn.conv1_w[ch * 3], w1 = bn.conv1_w[ch * 3 + 1], w2 = bn.conv1_w[ch * 3 + 2], b = bn.conv1_b[ch];
+  const double mean = w0 * mx + w1 * my + w2 * mz + b;
+  double var = w0 * w0 * cxx + w1 * w1 * cyy + w2 * w2 * czz + 2.0 * (w0 * w1 * cxy + w0 * w2 * cxz + w1 * w2 * cyz);
+  var = var < 0.0 ? 0.0 : var;
+  const double s = (double)bn.bn1_w[ch] / sqrt(var + (double)bn.eps);
+  const float f[4] = {(float)(w0 * s), (float)(w1 * s), (float)(w2 * s), (float)((b - mean) * s + (double)bn.bn1_b[ch])};
+  reinterpret_cast<float4*>(blob + L.w1())[ch] = make_float4(f[0], f[1], f[2], f[3]);
+  // layer-1 operand image, row = channel: [W_hi(3) | W_hi(3) | W_lo(3) | b_hi | b_lo | 0 ...] of act_scale * W1'
+  const float act = reinterpret_cast<const float*>(blob + L.scales())[5];
+  uint16_t hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = f[k] * act;
+    hi[k] = to_operand<FMT>(v);
+    lo[k] = to_operand<FMT>(v - from_operand<FMT>(hi[k]));
+  }
+  unsigned char* img = blob + L.W1T();
+  auto put = [&](int k, uint16_t v) { *reinterpret_cast<uint16_t*>(img + sw128_kmajor_off(ch, k)) = v; };
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { put(k, hi[k]); put(3 + k, hi[k]); put(6 + k, lo[k]); }
+  put(9, hi[3]);
+  put(10, lo[3]);
+  // running statistics: momentum update with the unbiased variance (torch.nn.BatchNorm1d)
+  const double unbiased = npoints > 1 ? var * n / (n - 1.0) : var;
+  bn.bn1_rm[ch] = (float)((1.0 - bn.momentum) * (double)bn.bn1_rm[ch] + (double)bn.momentum * mean);
+  bn.bn1_rv[ch] = (float)((1.0 - bn.momentum) * (double)bn.bn1_rv[ch] + (double)bn.momentum * unbiased);
+  if (ch == 0 && bn.bn1_nbt) *bn.bn1_nbt += 1;
+}
+
+__global__ void __launch_bounds__(512)
+bn_fold2_kernel(BnDevice bn, const double* __restrict__ stats, long long npoints, float* __restrict__ bn_vec) {
+  const int ch = threadIdx.x;
+  const double n = (double)npoints;
+  const double mean = stats[ch] / n;
+  double var = stats[512 + ch] / n - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const double s = (double)bn.bn2_w[ch] / sqrt(var + (double)bn.eps);
+  bn_vec[ch] = (float)s;
+  bn_vec[512 + ch] = (float)((double)bn.bn2_b[ch] - mean * s);
+  const double unbiased = npoints > 1 ? var * n / (n - 1.0) : var;
+  bn.bn2_rm[ch] = (float)((1.0 - bn.momentum) * (double)bn.bn2_rm[ch] + (double)bn.momentum * mean);
+  bn.bn2_rv[ch] = (float)((1.0 - bn.momentum) * (double)bn.bn2_rv[ch] + (double)bn.momentum * unbiased);
+  if (ch == 0 && bn.bn2_nbt) *bn.bn2_nbt += 1;
+}
+
+// ======================================================================================
 // host side
 // ======================================================================================
 template <int SPLIT, int NT, int STAGE>
@@ -1250,7 +1404,13 @@ struct Workspace {
     total = c_buf + tiles128 * 128 * 512 * sizeof(float);
     h_img = total;  // pos_embed hidden layer, K = 128: 2 chunks per 128-centre tile (ppt_tokenizer_forward only)
     total_tokenizer = h_img + tiles128 * 2 * (size_t)split * IMG;
+    // train mode: 16 doubles of point moments, 1024 doubles of channel sums, 1024 floats of scale / shift
+    bn_mom = total_tokenizer;
+    bn_stats = bn_mom + 16 * sizeof(double);
+    bn_vec = bn_stats + 1024 * sizeof(double);
+    total_train = bn_vec + 1024 * sizeof(float);
   }
+  size_t bn_mom, bn_stats, bn_vec, total_train;
 };
 
 // phases: bit 0 stage1, bit 1 group_linear(c), bit 2 stage2, bit 3 group_linear(tokens)
@@ -1312,7 +1472,8 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     if (use_tc)
       k1tc<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles);
     else
-      k1<<<grid_t, (EPW1 + 2) * 32, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles);
+      k1<<<grid_t, (EPW1 + 2) * 32, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles, nullptr,
+                                              nullptr);
   }
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
@@ -1338,7 +1499,8 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
       PPT_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, k2p, nbhd, blob_c, (const float*)cbuf, timg, features_out, groups,
                                             ptiles));
     } else {
-      k2<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
+      k2<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr,
+                                              nullptr);
     }
   }
   if ((phases & 8) && tokens_out)
@@ -1373,6 +1535,42 @@ int run_tokenizer(const float* nbhd, const float* center, const unsigned char* b
                                       tiles128, rows_per_cloud);
   if (!x_out) return ppt_launch_status();
   return run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, x_out, groups, 15, st, rows_per_cloud);
+}
+
+// Encoder.forward under model.train(): batch-statistics BatchNorm, forward only.  `blob` is the caller's MUTABLE
+// copy packed with both BatchNorms as identities (raw convolution weights); its W1' sections are rewritten here.
+template <uint32_t FMT, int SPLIT, int NT>
+int run_encoder_train(const float* nbhd, unsigned char* blob, const BnDevice& bn, unsigned char* ws,
+                      float* features_out, float* tokens_out, long long groups, cudaStream_t st) {
+  const Workspace W(groups, SPLIT);
+  auto k2s = encoder_stage_kernel<FMT, SPLIT, NT, 2, 8, BN_STATS>;
+  auto k2a = encoder_stage_kernel<FMT, SPLIT, NT, 2, 8, BN_APPLY>;
+  constexpr size_t s2 = stage_smem_bytes<SPLIT, NT, 2>();
+  static bool configured = false;
+  if (!configured) {
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    configured = true;
+  }
+  const long long points = groups * 32;
+  const int tiles = (int)((points + NT - 1) / NT);
+  const int sms = num_sms();
+  const int grid_t = tiles < sms ? tiles : sms;
+  double* mom = reinterpret_cast<double*>(ws + W.bn_mom);
+  double* stats = reinterpret_cast<double*>(ws + W.bn_stats);
+  float* bn_vec = reinterpret_cast<float*>(ws + W.bn_vec);
+  float* cbuf = reinterpret_cast<float*>(ws + W.c_buf);
+  PPT_RETURN_IF_CUDA(cudaMemsetAsync(mom, 0, (16 + 1024) * sizeof(double), st));
+  const long long want = (points + 255) / 256;
+  bn_moments_kernel<<<(int)(want < 4 * sms ? want : 4 * sms), 256, 0, st>>>(nbhd, points, mom);
+  bn_fold1_kernel<FMT><<<1, 128, 0, st>>>(bn, mom, points, blob, (uint32_t)SPLIT);
+  int rc = run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, nullptr, groups, 3, st);  // stage 1, c (raw weights)
+  if (rc) return rc;
+  k2s<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, nullptr, nullptr, groups, tiles, stats, nullptr);
+  bn_fold2_kernel<<<1, 512, 0, st>>>(bn, stats, points, bn_vec);
+  k2a<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr, bn_vec);
+  if (tokens_out) return run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, tokens_out, groups, 8, st);
+  return ppt_launch_status();
 }
 
 }  // namespace
@@ -1453,6 +1651,45 @@ extern "C" PPT_EXPORT int ppt_tokenizer_forward(const float* neighborhood, const
     case PPT_ENC_FP16X3:
       return run_tokenizer<tc05::FMT_F16, 2, 64>(neighborhood, center, blob, pblob, ws, x_out, pos_out, num_groups,
                                                  groups_per_cloud, st);
+    default:
+      return PPT_EINVAL;
+  }
+}
+
+extern "C" PPT_EXPORT int64_t ppt_encoder_train_workspace_bytes(int64_t num_groups, int mode) {
+  if (mode < PPT_ENC_FP16 || mode > PPT_ENC_FP16X3 || num_groups < 1) return PPT_EINVAL;
+  return (int64_t)Workspace(num_groups, mode == PPT_ENC_FP16X3 ? 2 : 1).total_train;
+}
+
+extern "C" PPT_EXPORT int ppt_encoder_forward_train(const float* neighborhood, void* packed_train,
+                                                    const ppt_encoder_bn_t* bn, void* workspace, float* features_out,
+                                                    float* tokens_out, int64_t num_groups, int mode, void* stream) {
+  if (!neighborhood || !packed_train || !bn || !workspace || (!tokens_out && !features_out) || num_groups < 1)
+    return PPT_EINVAL;
+  if (!bn->conv1_weight || !bn->conv1_bias || !bn->bn1_weight || !bn->bn1_bias || !bn->bn1_running_mean ||
+      !bn->bn1_running_var || !bn->bn2_weight || !bn->bn2_bias || !bn->bn2_running_mean || !bn->bn2_running_var)
+    return PPT_EINVAL;
+  if (!(bn->momentum >= 0.f && bn->momentum <= 1.f) || !(bn->eps > 0.f)) return PPT_EINVAL;
+  if (num_groups > (1ll << 31) / 32) return PPT_ERANGE;
+  if ((reinterpret_cast<uintptr_t>(packed_train) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return PPT_EINVAL;
+  BnDevice d;
+  d.conv1_w = bn->conv1_weight; d.conv1_b = bn->conv1_bias;
+  d.bn1_w = bn->bn1_weight; d.bn1_b = bn->bn1_bias; d.bn1_rm = bn->bn1_running_mean; d.bn1_rv = bn->bn1_running_var;
+  d.bn1_nbt = reinterpret_cast<long long*>(bn->bn1_num_batches_tracked);
+  d.bn2_w = bn->bn2_weight; d.bn2_b = bn->bn2_bias; d.bn2_rm = bn->bn2_running_mean; d.bn2_rv = bn->bn2_running_var;
+  d.bn2_nbt = reinterpret_cast<long long*>(bn->bn2_num_batches_tracked);
+  d.momentum = bn->momentum; d.eps = bn->eps;
+  unsigned char* blob = static_cast<unsigned char*>(packed_train);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case PPT_ENC_FP16:
+      return run_encoder_train<tc05::FMT_F16, 1, 128>(neighborhood, blob, d, ws, features_out, tokens_out, num_groups, st);
+    case PPT_ENC_BF16:
+      return run_encoder_train<tc05::FMT_BF16, 1, 128>(neighborhood, blob, d, ws, features_out, tokens_out, num_groups, st);
+    case PPT_ENC_FP16X3:
+      return run_encoder_train<tc05::FMT_F16, 2, 64>(neighborhood, blob, d, ws, features_out, tokens_out, num_groups, st);
     default:
       return PPT_EINVAL;
   }

@@ -186,3 +186,19 @@ def pack_pos_embed(pos_embed_sd, cls_token, cls_pos, mode):
     blob = torch.cat([head, pack_kmajor((w2 * wscale).to(torch.float32), dtype, split)])
     assert blob.numel() == pos_packed_bytes(mode)
     return blob
+
+
+# ---- train-mode BatchNorm (models/pointbert/dvae.py:190,196 under model.train()) -------------
+def pack_encoder_train(sd, mode):
+    """The blob ppt_encoder_forward_train works on: both BatchNorms packed as identities, i.e. the raw
+    convolution weights.  The kernels fold the statistics of the current batch themselves (first_conv.1 into the
+    W1' sections of this blob, which is why the device copy must be the caller's own mutable one; second_conv.1
+    as per-channel scale / shift applied to the accumulators)."""
+    ident = dict(sd)
+    for conv, c in (("first_conv.1", 128), ("second_conv.1", 512)):
+        ref = sd[conv + ".weight"]
+        ident[conv + ".weight"] = torch.ones(c, dtype=ref.dtype)
+        ident[conv + ".bias"] = torch.zeros(c, dtype=ref.dtype)
+        ident[conv + ".running_mean"] = torch.zeros(c, dtype=ref.dtype)
+        ident[conv + ".running_var"] = torch.full((c,), 1.0 - 1e-5, dtype=torch.float64)  # fold(): var + eps == 1
+    return pack_encoder(ident, mode)

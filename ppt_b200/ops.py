@@ -286,6 +286,49 @@ def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, 
     return (tokens, feats) if return_features else tokens
 
 
+def encoder_forward_train(neighborhood, packed_train, bn, mode=ENC_FP16, return_features=False, want_tokens=True):
+    """Encoder.forward under model.train() (batch-statistics BatchNorm, forward only).
+
+    `packed_train`: the caller's own uint8 CUDA copy of encoder_pack.pack_encoder_train(state_dict, mode) -- it is
+    written to.  `bn`: dict of the module's CUDA tensors conv1_weight, conv1_bias, bn{1,2}_{weight,bias,
+    running_mean,running_var,num_batches_tracked} plus floats momentum, eps; the running statistics and counters
+    are updated in place like torch.nn.BatchNorm1d does."""
+    _need_cuda(neighborhood, packed_train)
+    nb = _f32(neighborhood)
+    if nb.dim() < 3 or nb.shape[-1] != 3 or nb.shape[-2] != 32:
+        raise ValueError("neighborhood must be [..., 32, 3]")
+    lead = tuple(nb.shape[:-2])
+    groups = 1
+    for d in lead:
+        groups *= d
+    lib = _lib.load()
+    if packed_train.dtype != torch.uint8 or packed_train.numel() != lib.ppt_encoder_packed_bytes(mode):
+        raise ValueError("packed weight blob does not match mode %d" % mode)
+    if groups == 0 or not (want_tokens or return_features):
+        raise ValueError("nothing to compute")
+    st = _lib.EncoderBn()
+    for name, _ in _lib.EncoderBn._fields_:
+        v = bn[name]
+        if name in ("momentum", "eps"):
+            setattr(st, name, float(v))
+            continue
+        if v is None and name.endswith("num_batches_tracked"):
+            setattr(st, name, None)
+            continue
+        want = torch.int64 if name.endswith("num_batches_tracked") else torch.float32
+        if not (v.is_cuda and v.dtype == want and v.is_contiguous()):
+            raise ValueError("bn[%r] must be a contiguous CUDA %s tensor" % (name, want))
+        setattr(st, name, v.data_ptr())
+    tokens = torch.empty(lead + (384,), dtype=torch.float32, device=nb.device) if want_tokens else None
+    feats = torch.empty(lead + (256,), dtype=torch.float32, device=nb.device) if return_features else None
+    ws = _workspace((nb.device, "encoder"), lib.ppt_encoder_train_workspace_bytes(groups, mode))
+    import ctypes
+    with torch.cuda.device(nb.device):
+        _lib.check(lib.ppt_encoder_forward_train(_ptr(nb), _ptr(packed_train), ctypes.byref(st), _ptr(ws), _ptr(feats),
+                                                 _ptr(tokens), groups, mode, _stream(nb)), "ppt_encoder_forward_train")
+    return (tokens, feats) if return_features else tokens
+
+
 def tokenizer_forward(neighborhood, center, enc_packed, pos_packed, mode=ENC_FP16, want_x=True):
     """The tokenizer's tail in one call (models/pointbert/point_encoder.py:239-247):
 

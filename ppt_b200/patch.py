@@ -80,11 +80,10 @@ def _encoder_forward(self, point_groups):
     """Encoder.forward (eval), models/pointbert/dvae.py:201-215, on the reference's own module instance."""
     mode = ops.ENC_MODES[getattr(self, "ppt_precision", "fp16")]
     tensors = list(self.parameters()) + list(self.buffers())
-    key = (mode, str(point_groups.device)) + tuple((t.data_ptr(), t._version) for t in tensors)
+    key = (mode, str(point_groups.device), getattr(self, "_bn_epoch", 0)) + \
+        tuple((t.data_ptr(), t._version) for t in tensors)
     if getattr(self, "_ppt_key", None) != key:
-        sd = dict(self.state_dict())
-        ref = sd["first_conv.0.weight"]
-        sd["reduce_dim.weight"], sd["reduce_dim.bias"] = ref.new_zeros((384, 256)), ref.new_zeros((384,))
+        sd = _encoder_state_zero_reduce(self)
         object.__setattr__(self, "_ppt_blob", encoder_pack.pack_encoder(sd, mode).to(point_groups.device))
         object.__setattr__(self, "_ppt_key", key)
     return ops.encoder_forward(point_groups, self._ppt_blob, mode=mode, return_features=True, want_tokens=False)[1]
@@ -99,7 +98,8 @@ def point_transformer_front_end(model, pts):
     mode = ops.ENC_MODES[getattr(model, "ppt_precision", "fp16")]
     enc_t = list(model.encoder.parameters()) + list(model.encoder.buffers()) + list(model.reduce_dim.parameters())
     pos_t = [model.cls_token, model.cls_pos] + list(model.pos_embed.parameters())
-    key = (mode, str(pts.device)) + tuple((t.data_ptr(), t._version) for t in enc_t + pos_t)
+    key = (mode, str(pts.device), getattr(model.encoder, "_bn_epoch", 0)) + \
+        tuple((t.data_ptr(), t._version) for t in enc_t + pos_t)
     if getattr(model, "_ppt_front_key", None) != key:
         sd = dict(model.encoder.state_dict())
         sd["reduce_dim.weight"], sd["reduce_dim.bias"] = model.reduce_dim.weight, model.reduce_dim.bias
@@ -133,6 +133,19 @@ def _point_transformer_forward(self, pts, _original):
     return torch.cat([x[:, 0], x[:, 1:].max(1)[0]], dim=-1)
 
 
+def _encoder_state_zero_reduce(self):
+    sd = dict(self.state_dict())
+    ref = sd["first_conv.0.weight"]
+    sd["reduce_dim.weight"], sd["reduce_dim.bias"] = ref.new_zeros((384, 256)), ref.new_zeros((384,))
+    return sd
+
+
+def _encoder_forward_train(self, point_groups):
+    """Encoder.forward under model.train() (main_cls.py:169): batch-statistics BatchNorm, fused, forward only."""
+    mode = ops.ENC_MODES[getattr(self, "ppt_precision", "fp16")]
+    return pointbert.train_forward(self, point_groups, lambda: _encoder_state_zero_reduce(self), mode, want_tokens=False)
+
+
 def _fp_forward(self, xyz1, xyz2, points1, points2):
     return pointnet2.PointNetFeaturePropagation.forward(self, xyz1, xyz2, points1, points2)
 
@@ -160,6 +173,8 @@ def patch_reference(modules=None):
                 return _group_forward(self, xyz) if xyz.is_cuda else _o(self, xyz)
 
             def enc_fwd(self, pg, _o=orig_e):
+                if pg.is_cuda and self.training and pointbert.train_forward_fusable(self, pg):
+                    return _encoder_forward_train(self, pg)
                 fused = pg.is_cuda and not self.training and pg.shape[2] == 32 and self.encoder_channel == 256
                 return _encoder_forward(self, pg) if fused else _o(self, pg)
 

@@ -68,13 +68,49 @@ class Group(nn.Module):
         return neighborhood, center
 
 
+def train_forward_fusable(module, point_groups, reduce_dim=None):
+    """The fused batch-statistics path is forward only: usable when no tensor involved needs a gradient."""
+    bn1, bn2 = module.first_conv[1], module.second_conv[1]
+    params = list(module.parameters()) + (list(reduce_dim.parameters()) if reduce_dim is not None else [])
+    needs_grad = torch.is_grad_enabled() and (point_groups.requires_grad or any(p.requires_grad for p in params))
+    return (point_groups.is_cuda and not needs_grad and point_groups.dim() == 4 and point_groups.shape[2] == 32
+            and module.encoder_channel == 256 and point_groups.shape[0] * point_groups.shape[1] * 32 > 1
+            and all(isinstance(b, nn.BatchNorm1d) and b.track_running_stats and b.momentum is not None and b.affine
+                    for b in (bn1, bn2)) and bn1.eps == bn2.eps and bn1.momentum == bn2.momentum)
+
+
+def train_forward(module, point_groups, state_for_pack, mode, want_tokens):
+    """Encoder.forward (models/pointbert/dvae.py:201-215) with its BatchNorms in batch-statistics mode, on any
+    module with the reference's layout (first_conv / second_conv Sequentials).  Returns tokens [B,G,384]
+    (reduce_dim fused) or the Encoder's own features [B,G,256]."""
+    conv1, bn1, bn2 = module.first_conv[0], module.first_conv[1], module.second_conv[1]
+    static = [p for n, p in module.named_parameters() if not n.startswith(("first_conv.1.", "second_conv.1."))]
+    key = (mode, str(point_groups.device)) + tuple((t.data_ptr(), t._version) for t in static)
+    if getattr(module, "_ppt_train_key", None) != key:
+        blob = encoder_pack.pack_encoder_train(state_for_pack(), mode).to(point_groups.device)
+        object.__setattr__(module, "_ppt_train_blob", blob)
+        object.__setattr__(module, "_ppt_train_key", key)
+    bn = {"conv1_weight": conv1.weight, "conv1_bias": conv1.bias,
+          "bn1_weight": bn1.weight, "bn1_bias": bn1.bias, "bn1_running_mean": bn1.running_mean,
+          "bn1_running_var": bn1.running_var, "bn1_num_batches_tracked": bn1.num_batches_tracked,
+          "bn2_weight": bn2.weight, "bn2_bias": bn2.bias, "bn2_running_mean": bn2.running_mean,
+          "bn2_running_var": bn2.running_var, "bn2_num_batches_tracked": bn2.num_batches_tracked,
+          "momentum": bn1.momentum, "eps": bn1.eps}
+    out = ops.encoder_forward_train(point_groups, module._ppt_train_blob, bn, mode=mode, return_features=not want_tokens,
+                                    want_tokens=want_tokens)
+    object.__setattr__(module, "_bn_epoch", getattr(module, "_bn_epoch", 0) + 1)  # eval blobs are stale now
+    return out if want_tokens else out[1]
+
+
 class Encoder(nn.Module):
     """models/pointbert/dvae.py:184-215 -- same sub-module / state_dict names, so the ULIP
     checkpoints keep loading (models/ULIP_models.py:487-507).
 
     eval(): BatchNorm is folded and the whole stack runs in the tcgen05 kernels.
     train(): the reference puts the frozen Encoder's BatchNorm in batch-statistics mode
-    (main_cls.py:169); that path runs the module's own torch layers on the GPU.
+    (main_cls.py:169).  When nothing needs a gradient (PPT freezes the Encoder,
+    models/ULIP_models.py:505) that runs fused too (ops.encoder_forward_train: batch statistics, running-stat
+    momentum update in place); otherwise the module's own torch layers run on the GPU.
     """
 
     def __init__(self, encoder_channel, precision="fp16"):
@@ -112,11 +148,15 @@ class Encoder(nn.Module):
         tensors = list(self.parameters()) + list(self.buffers())
         if self._reduce_dim is not None:
             tensors += [self._reduce_dim.weight, self._reduce_dim.bias]
-        key = (mode, str(device)) + tuple((t.data_ptr(), t._version) for t in tensors)
+        # _bn_epoch: the fused train path updates the running statistics from a kernel (no version bump)
+        key = (mode, str(device), getattr(self, "_bn_epoch", 0)) + tuple((t.data_ptr(), t._version) for t in tensors)
         if self._packed is None or self._packed_key != key:
             self._packed = encoder_pack.pack_encoder(self._state_for_pack(), mode).to(device)
             self._packed_key = key
         return self._packed, mode
+
+    def _train_fusable(self, point_groups):
+        return train_forward_fusable(self, point_groups, self._reduce_dim)
 
     def _forward_torch(self, point_groups):
         bs, g, n, _ = point_groups.shape
@@ -130,6 +170,9 @@ class Encoder(nn.Module):
         if self._reduce_dim is None:
             raise RuntimeError("attach_reduce_dim() first")
         if self.training:
+            if self._train_fusable(point_groups):
+                return train_forward(self, point_groups, self._state_for_pack, ops.ENC_MODES[self.precision],
+                                     want_tokens=True)
             return self._reduce_dim(self._forward_torch(point_groups))
         blob, mode = self._blob(point_groups.device)
         return ops.encoder_forward(point_groups, blob, mode=mode)
@@ -138,6 +181,9 @@ class Encoder(nn.Module):
     def forward(self, point_groups):
         """point_groups [B,G,N,3] -> feature_global [B,G,C]."""
         if self.training:
+            if self._train_fusable(point_groups):
+                return train_forward(self, point_groups, self._state_for_pack, ops.ENC_MODES[self.precision],
+                                     want_tokens=False)
             return self._forward_torch(point_groups)
         if point_groups.shape[2] != 32 or self.encoder_channel != 256:
             raise RuntimeError("fused Encoder is specialised for 32-point groups and encoder_dims=256 "

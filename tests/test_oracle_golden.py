@@ -169,3 +169,16 @@ def test_token_assembly_port_matches_reference_point_transformer(golden):
     for got, ref in ((x.numpy(), f["x"]), (pos.numpy(), f["pos"])):
         assert np.abs(got - ref).max() / np.abs(ref).max() <= 1e-6
     assert np.array_equal(x[:, 0].numpy(), f["x"][:, 0]) and np.array_equal(pos[:, 0].numpy(), f["pos"][:, 0])
+
+
+def test_train_mode_encoder_port_matches_reference(golden):
+    """Reference Encoder under .train(): batch-statistics BatchNorm and its running-stat update (F9)."""
+    f = golden("encoder_train_small")
+    sd = torch_port.make_encoder_state()
+    with torch.no_grad():
+        feat, stats = torch_port.encoder_forward_train(sd, torch.from_numpy(f["neighborhood"]))
+    assert np.abs(feat.numpy() - f["features"]).max() / np.abs(f["features"]).max() <= 1e-6
+    for k, v in stats.items():
+        ref = f["after." + k]
+        assert np.abs(v.numpy() - ref).max() <= 1e-6 * np.abs(ref).max(), k
+    assert int(f["after.first_conv.1.num_batches_tracked"]) == 1
