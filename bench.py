@@ -271,6 +271,22 @@ def run_ours(args):
     torch.cuda.synchronize()
     pos_ms = statistics.mean(a.elapsed_time(b) for a, b in pos_ms)
 
+    # ---- widened row f3: the same tokenizer step with the Encoder's BatchNorms in batch-statistics mode
+    # (model.train(), main_cls.py:169): two more passes (point moments; W32 h1 statistics) and the running-stat
+    # update; not part of `value` ----
+    tok.encoder.train()
+    for i in range(3):
+        tok(resident[i % ROTATE])
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0e.record()
+    for i in range(args.steps):
+        tok(resident[i % ROTATE])
+    t1e.record()
+    barrier()
+    ms_train = max_over_ranks(t0e.elapsed_time(t1e))
+    tok.encoder.eval()
+
     # ---- timed region 2: end to end through the public API with pinned host buffers ----
     # HostPipeline: H2D of the clouds, the kernels and D2H of tokens + centres on three streams,
     # two slots in flight; every step's inputs start in pinned host memory and its results end there.
@@ -345,6 +361,12 @@ def run_ours(args):
                      "achieved": pos_bytes / (pos_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": pos_bytes / (pos_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "bytes_per_launch": pos_bytes}}}
+
+    widened["f3_train_mode_batchnorm"] = {
+        "what": "Group + Encoder with batch-statistics BatchNorm (forward only, running stats updated in place) + "
+                "reduce_dim; adds bn_moments, bn_fold1, stage-2 statistics pass (the four W32 h1 units), bn_fold2",
+        "value": clouds_total / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / args.steps,
+        "extra_ms_over_eval": (ms_train - ms_total) / args.steps}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
