@@ -196,6 +196,11 @@ int ppt_selftest_umma(const float *a, const float *b, float *d, int N, int K, in
  *   a [256,K] f32, b [N,K] f32 -> d [256,N] f32.  N in {64,128,192,256}, mode bits 0-2 as above. */
 int ppt_selftest_umma_pair(const float *a, const float *b, float *d, int N, int K, int mode, void *stream);
 
+/* Measurement aid (bench.py): one device thread records (globaltimer ns, clock64 cycles) pairs every
+ * period_ns into out [samples][2] int64, on `stream` -- run it on a side stream next to the kernels under
+ * test to see the SM clock inside them (DESIGN.md "clocks under load"). */
+int ppt_clock_probe(void *out, int samples, int64_t period_ns, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@
 // L2 with 1-D bulk async copies into a ring (full/empty mbarriers); warp 1 issues
 // tcgen05.mma into two alternating TMEM accumulators; warps 2-9 build h1, drain the
 // accumulators (tcgen05.ld), apply bias/ReLU/max and write the next operand.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -692,19 +693,25 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
 //     lanes pushed half of h3 through DSMEM and ran at half the speed);
 //   * CTA r streams only its half of the channels of every weight block (its half of B; the hardware shares
 //     it with the peer): half the ring traffic per CTA, half the L2 traffic per point;
-//   * the max over a group's 32 points is a reduction over the 32 lanes of a warp (CREDUX.MAX);
+//   * only the last layer (W4 h3, whose output is max-pooled, not fed to another layer) goes back to weights = A:
+//     K-major rows of h3 serve as either operand, and with channels on the lanes the max over a group's 32
+//     points is a max over a thread's registers (a first version reduced over lanes with CREDUX.MAX and spent
+//     2800 cycles per tile on it);
 //   * hand-offs that involve both CTAs (operands ready, accumulators drained, ring stage filled) go through
 //     mbarriers of the leader CTA (remote arrivals from the peer).
 // Tensor memory: columns [0, 256) the W4 h3 accumulator (256 channels), [256, 384) and [384, 512) two
-// accumulators for the 128-channel units of W32 h1.  Per tile the leader issues, in this fixed order,
-//     P0 P1 G0 G1 P2 G2 G3 P3 G4 G5 G6 G7
-// (Pv = W32 unit v: N = 128, K = 128; Gc = W4 K-chunk c: N = 256, K = 64; 512 tensor cycles each), one ring stage
-// per item.  Gc needs h3 channels [64 c, 64 c + 64) = half the epilogue of unit c / 2, so the tensor pipe
-// always has two or more items to run while the epilogue warps turn an accumulator into h3.  The same order
-// lets h3 live in four chunk slots instead of eight (chunk c + 4 is written by the epilogue of unit c / 2 + 2,
-// whose instructions are issued after Gc: by the time that accumulator is full, Gc has finished reading), and
-// the 64 KB this frees make the weight ring six stages deep -- deep enough to cover L2 latency plus the
-// hop through the peer.
+// accumulators for the 128-channel units of W32 h1.  Per iteration the leader issues, in this fixed order,
+//     P0  G4' G5'  P1  G6' G7'  P2  G0 G1  P3  G2 G3
+// (Pv = W32 unit v of the current tile: N = 128, K = 128; Gc = W4 K-chunk c: N = 256, K = 64, primed = of the
+// PREVIOUS tile; 512 tensor cycles each), one ring stage per item.  Every hand-off through the epilogue warps
+// (accumulator -> h3 -> next instruction, a chain of ~2000 cycles of barrier wake-ups, tcgen05.ld, conversion,
+// proxy fence and a possibly remote arrive) is given five or six items of slack: Gc follows unit c / 2 by
+// six items, unit v + 2 reuses unit v's accumulator five items later.  h3 lives in four chunk slots (chunk c in
+// slot c % 4; g_done[slot] says when its reader has finished), and the weight ring is six stages deep --
+// enough to cover L2 latency plus the hop through the peer.  The first iteration has no primed items and one
+// extra iteration after the last tile has only primed ones; absent items still take their ring stage (the
+// producer arrives without a copy, the issuer commits without instructions) so that stage indices and phases
+// stay compile-time constants.
 // Warp roles per CTA: 0 weight producer, 1 issuer of the P items (leader) / ring-stage forwarder (peer),
 // 2-9 epilogue, 10 issuer of the G items (leader only).
 __device__ __forceinline__ float warp_max_f32(float v) {
@@ -713,9 +720,10 @@ __device__ __forceinline__ float warp_max_f32(float v) {
   return r;
 }
 
-// Item i of the per-tile schedule: 0..3 = W32 unit v, 4..11 = 4 + W4 chunk c.
+// Item i of the per-iteration schedule: 0..3 = W32 unit v (current tile), 4 + c = W4 chunk c (c >= 4: of the
+// previous tile).
 __host__ __device__ constexpr int pair_sched(int i) {
-  constexpr int code[12] = {0, 1, 4, 5, 2, 6, 7, 3, 8, 9, 10, 11};
+  constexpr int code[12] = {0, 8, 9, 1, 10, 11, 2, 4, 5, 3, 6, 7};
   return code[i];
 }
 
@@ -723,7 +731,16 @@ template <uint32_t FMT>
 __global__ void __launch_bounds__(352, 1)
 encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
                            const float* __restrict__ cbuf, unsigned char* __restrict__ out_img,
-                           float* __restrict__ features_out, long long num_groups, int num_ptiles) {
+                           float* __restrict__ features_out, long long num_groups, int num_ptiles,
+                           long long* __restrict__ trace) {
+  // Debug timeline (PPT_PAIR_TRACE): clock64 of the leader CTA of pair 0 at the events of iterations < 32,
+  // trace[it * 64 + slot]; slots 0-11 item issued (after commit), 12-23 item's waits satisfied, 32-35 unit v
+  // accumulator seen full by epilogue warp 2, 36-39 unit v h3 handed over, 40 group max accumulator seen full,
+  // 41 group max handed back, 42 h1 built.
+#define PAIR_TRACE(it_, slot_)                                                                    \
+  do {                                                                                            \
+    if (trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it_) < 32) trace[(it_) * 64 + (slot_)] = clock64(); \
+  } while (0)
   constexpr int NSTAGE = 6, EPW = 8, NTC = 128;      // NTC: points per CTA per pair-tile
   constexpr uint32_t H1_BYTES = 2u * NTC * 128u;     // K-major: 2 chunks x [128 points x 64 channels]
   constexpr uint32_t H3_BYTES = 4u * IMG;            // K-major [128 points x 64 channels] chunks: chunk c in slot c % 4
@@ -732,6 +749,14 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
   constexpr int ITEMS = 12;                          // ring stages per tile and CTA
   static_assert(ITEMS % NSTAGE == 0 && (ITEMS / NSTAGE) % 2 == 0, "static ring schedule");
 
+  if (trace && threadIdx.x == 0 && (blockIdx.x & 1) == 0) {
+    trace[32 * 64 + (blockIdx.x >> 1) * 2] = clock64();
+    if (blockIdx.x == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      trace[32 * 64 + 200] = (long long)ns;
+    }
+  }
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* h1buf = smem;
   unsigned char* h3buf = h1buf + H1_BYTES;
@@ -780,27 +805,31 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   if (tbase != 0) __trap();  // 512 columns = the whole tensor memory of the SM
+  const int ntiles = pair < num_ptiles ? (num_ptiles - pair + npairs - 1) / npairs : 0;  // tiles of this pair
 
   if (warp == 0) {
     // ===================== weight producer: this CTA's half of every weight block =====================
     if (lane == 0) {
-      uint32_t tpar = 0;
-      for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
+      for (int it = 0; it <= ntiles; ++it) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
           const int code = pair_sched(i);
           const int st = i % NSTAGE;
           const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
+          const bool present = code >= 8 ? it >= 1 : it < ntiles;
           mbar_wait_relaxed(&empty[st], sph ^ 1u);
-          mbar_arrive_expect_tx(&full[st], IMG);
-          if (code < 4) {
+          if (!present) {
+            mbar_arrive(&full[st]);  // the stage is taken without a copy
+          } else if (code < 4) {
             // W32 unit v = code, both K chunks: rows [64 rank, 64 rank + 64) of each 128-row image (8 KB, contiguous)
+            mbar_arrive_expect_tx(&full[st], IMG);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
               bulk_g2s(ring + st * IMG + k * (IMG / 2), blob + L.W32() + (uint32_t)(code * 2 + k) * IMG + rank * (IMG / 2),
                        IMG / 2, &full[st]);
           } else {
             // W4 chunk c = code - 4: channels [128 rank, 128 rank + 128)
+            mbar_arrive_expect_tx(&full[st], IMG);
             bulk_g2s(ring + st * IMG, blob + L.W4() + (rank * 8u + (uint32_t)(code - 4)) * IMG, IMG, &full[st]);
           }
         }
@@ -809,7 +838,7 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
     __syncwarp();
   } else if (warp == 1 && rank != 0) {
     // ===================== peer: tell the leader when a ring stage has landed here =====================
-    for (int tile = pair; tile < num_ptiles; tile += npairs) {
+    for (int it = 0; it <= ntiles; ++it) {
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         mbar_wait(&full[i % NSTAGE], (uint32_t)(i / NSTAGE) & 1u);
@@ -819,17 +848,18 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
     }
   } else if (warp == 1) {
     // ===================== leader, warp 1: issues the W32 h1 units (P items) =====================
-    // Two warps issue the tensor instructions of a tile (this one the P items, warp 10 the G items): the
-    // instruction stream around each tcgen05.mma (descriptor moves into uniform registers, elect, commit) costs
-    // about as many cycles as the instruction runs, so a single issuing warp caps the tensor pipe near 60 %.
-    // Fully unrolled per tile: every item has a compile-time ring stage and phase.
+    // Two warps issue the tensor instructions (this one the P items, warp 10 the G items): the instruction
+    // stream around each tcgen05.mma (descriptor moves into uniform registers, elect, commit) costs about as
+    // many cycles as the instruction runs, so a single issuing warp caps the tensor pipe near 60 %.
+    // Fully unrolled per iteration: every item has a compile-time ring stage and phase.
     constexpr uint32_t idesc_p = make_idesc(FMT, 256, 128, 0);
     constexpr uint32_t HI = sdesc_hi(1024u);
     const uint32_t w_lo0 = sdesc_lo(smem_u32(ring), 16u);
     const uint32_t h1_lo = sdesc_lo(smem_u32(h1buf), 16u);
     uint32_t tpar = 0;  // parity of the tile counter
-    for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
-      mbar_wait(h1_ready, tpar);
+    for (int it = 0; it <= ntiles; ++it, tpar ^= 1u) {
+      const bool cur = it < ntiles;
+      if (cur) mbar_wait(h1_ready, tpar);
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         const int code = pair_sched(i);
@@ -838,25 +868,31 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
         const int st = i % NSTAGE;
         const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
         const uint32_t w_lo = w_lo0 + (uint32_t)st * (IMG >> 4);
-        // the accumulator of unit v was last read by the epilogue of unit v - 2 (this tile: chunks 2v-4, 2v-3) or
-        // of unit v + 2 of the previous tile (chunks 2v+4, 2v+5)
-        const int c0 = v >= 2 ? 2 * v - 4 : 2 * v + 4;
-        const uint32_t dpar = v >= 2 ? tpar : tpar ^ 1u;
-        mbar_wait(&h3_ready[c0], dpar);
-        mbar_wait(&h3_ready[c0 + 1], dpar);
+        if (cur) {
+          // the accumulator of unit v was last read by the epilogue of unit v - 2 (this tile: chunks 2v-4, 2v-3)
+          // or of unit v + 2 of the previous tile (chunks 2v+4, 2v+5)
+          const int c0 = v >= 2 ? 2 * v - 4 : 2 * v + 4;
+          const uint32_t dpar = v >= 2 ? tpar : tpar ^ 1u;
+          mbar_wait(&h3_ready[c0], dpar);
+          mbar_wait(&h3_ready[c0 + 1], dpar);
+        }
         mbar_wait(&full[st], sph);
         mbar_wait(&full_peer[st], sph);
         fence_after_sync();
-        const uint32_t d_tmem = ACC_P2 + (uint32_t)(v & 1) * 128u;
+        PAIR_TRACE(it, 12 + i);
+        if (cur) {
+          const uint32_t d_tmem = ACC_P2 + (uint32_t)(v & 1) * 128u;
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
+          for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16)
-            umma_f16_pair_elect(d_tmem, sdesc_join(h1_lo + (uint32_t)kk * ((NTC * 128u) >> 4) + (uint32_t)k16 * 2u, HI),
-                                sdesc_join(w_lo + (uint32_t)kk * (IMG >> 5) + (uint32_t)k16 * 2u, HI), idesc_p,
-                                (kk == 0 && k16 == 0) ? 0u : 1u);
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_f16_pair_elect(d_tmem, sdesc_join(h1_lo + (uint32_t)kk * ((NTC * 128u) >> 4) + (uint32_t)k16 * 2u, HI),
+                                  sdesc_join(w_lo + (uint32_t)kk * (IMG >> 5) + (uint32_t)k16 * 2u, HI), idesc_p,
+                                  (kk == 0 && k16 == 0) ? 0u : 1u);
+        }
         umma_commit_pair_elect(&empty[st], 3);
-        umma_commit_pair_elect(&p2_full[v & 1], 3);
+        if (cur) umma_commit_pair_elect(&p2_full[v & 1], 3);
+        PAIR_TRACE(it, i);
       }
     }
   } else if (warp == 10) {
@@ -867,7 +903,7 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
       const uint32_t w_lo0 = sdesc_lo(smem_u32(ring), 16u);
       const uint32_t h3_lo = sdesc_lo(smem_u32(h3buf), 16u);
       uint32_t tpar = 0;
-      for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
+      for (int it = 0; it <= ntiles; ++it, tpar ^= 1u) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
           const int code = pair_sched(i);
@@ -876,18 +912,31 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
           const int st = i % NSTAGE;
           const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
           const uint32_t w_lo = w_lo0 + (uint32_t)st * (IMG >> 4);
-          if (c == 0) mbar_wait(max_done, tpar ^ 1u);  // the W4 accumulator of the previous tile is in registers
-          mbar_wait(&h3_ready[c], tpar);
+          const bool present = c >= 4 ? it >= 1 : it < ntiles;
+          const uint32_t par = c >= 4 ? tpar ^ 1u : tpar;  // parity of the tile this chunk belongs to
+          if (present) {
+            if (c == 0) mbar_wait(max_done, tpar ^ 1u);  // the W4 accumulator of the previous tile is in registers
+            mbar_wait(&h3_ready[c], par);
+          }
           mbar_wait(&full[st], sph);
           mbar_wait(&full_peer[st], sph);
           fence_after_sync();
+          PAIR_TRACE(it, 12 + i);
+          if (present) {
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16)
-            umma_f16_pair_elect(ACC_G3, sdesc_join(h3_lo + (uint32_t)(c & 3) * (IMG >> 4) + (uint32_t)k16 * 2u, HI),
-                                sdesc_join(w_lo + (uint32_t)k16 * 2u, HI), idesc_g, (c == 0 && k16 == 0) ? 0u : 1u);
+            for (int k16 = 0; k16 < 4; ++k16)
+              // operand roles swapped back for this layer: A = W4 (channels on the lanes), B = h3 (points on the
+              // columns; K-major rows of h3 serve as either operand), so the group max is a max over registers
+              umma_f16_pair_elect(ACC_G3, sdesc_join(w_lo + (uint32_t)k16 * 2u, HI),
+                                  sdesc_join(h3_lo + (uint32_t)(c & 3) * (IMG >> 4) + (uint32_t)k16 * 2u, HI), idesc_g,
+                                  (c == 0 && k16 == 0) ? 0u : 1u);
+          }
           umma_commit_pair_elect(&empty[st], 3);
-          umma_commit_pair_elect(&g_done[c & 3], 3);  // h3 slot c % 4 may be overwritten
-          if (c == 7) umma_commit_pair_elect(g3_full, 3);
+          if (present) {
+            umma_commit_pair_elect(&g_done[c & 3], 3);  // h3 slot c % 4 may be overwritten
+            if (c == 7) umma_commit_pair_elect(g3_full, 3);
+          }
+          PAIR_TRACE(it, i);
         }
       }
     }
@@ -907,32 +956,47 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
       if (lane == 0) mbar_arrive_peer(bar, 0);
     };
 
-    // h1 of this CTA's 128 points (CUDA cores, K = 3), K-major
-    const int p = e % NTC, ch0 = (e / NTC) * 64;
-    float nx = 0.f, ny = 0.f, nz = 0.f;
+    // h1 of this CTA's 128 points (CUDA cores, K = 3), K-major.  Warp w computes channels [16 w, 16 w + 16) -- its 16
+    // weight rows are read from shared memory once (broadcast) and stay in registers -- for the four points
+    // lane, lane + 32, lane + 64, lane + 96 of every lane: 4 independent FFMA chains per weight instead of one
+    // shared-memory load per 3 FFMAs (which left these 8 warps latency-bound: 1800 cycles per tile).
+    const int hw = warp - 2;  // 0..7
+    float px[4], py[4], pz[4];
     auto fetch_point = [&](int tile) {
-      nx = ny = nz = 0.f;
-      const long long gp = (long long)tile * 256 + (long long)rank * NTC + p;
-      if (tile < num_ptiles && gp < num_groups * 32) {
-        const float* src = nbhd + gp * 3;
-        nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        px[j] = py[j] = pz[j] = 0.f;
+        const long long gp = (long long)tile * 256 + (long long)rank * NTC + lane + 32 * j;
+        if (tile < num_ptiles && gp < num_groups * 32) {
+          const float* src = nbhd + gp * 3;
+          px[j] = __ldg(src); py[j] = __ldg(src + 1); pz[j] = __ldg(src + 2);
+        }
       }
     };
+    int trace_it = 99;
     auto build_h1 = [&](int tile_after) {
-      const float x = nx, y = ny, z = nz;
-      fetch_point(tile_after);
-#pragma unroll 4
-      for (int c8 = 0; c8 < 64; c8 += 8) {
-        float v[8];
+      float x[4], y[4], z[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 w = w1s[ch0 + c8 + t];
-          v[t] = fmaf(w.z, z, fmaf(w.y, y, fmaf(w.x, x, w.w)));
+      for (int j = 0; j < 4; ++j) { x[j] = px[j]; y[j] = py[j]; z[j] = pz[j]; }
+      fetch_point(tile_after);
+      if (warp == 2) PAIR_TRACE(trace_it, 43);
+#pragma unroll
+      for (int c8 = 0; c8 < 16; c8 += 8) {
+        float4 w[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[t] = w1s[hw * 16 + c8 + t];
+        const int ch = hw * 16 + c8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = fmaf(w[t].z, z[j], fmaf(w[t].y, y[j], fmaf(w[t].x, x[j], w[t].w)));
+          store_relu8<FMT, 1>(h1buf, (uint32_t)(ch >> 6) * (NTC * 128u) + sw128_kmajor_off(lane + 32 * j, ch & 63), 0u, v);
         }
-        const int ch = ch0 + c8;
-        store_relu8<FMT, 1>(h1buf, (uint32_t)(ch >> 6) * (NTC * 128u) + sw128_kmajor_off(p, ch & 63), 0u, v);
       }
+      if (warp == 2) PAIR_TRACE(trace_it, 44);
       fence_proxy_async_smem();
+      if (warp == 2) PAIR_TRACE(trace_it, 45);
       arrive_leader(h1_ready);
     };
 
@@ -958,60 +1022,50 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
       __syncwarp();
     };
 
-    if (pair < num_ptiles) {
+    if (ntiles > 0) {
       fetch_point(pair);
       fetch_c(pair);
       build_h1(pair + npairs);
       stage_c();
     }
 
-    uint32_t tpar = 0;
-    for (int tile = pair; tile < num_ptiles; tile += npairs, tpar ^= 1u) {
-      const long long g = (long long)tile * 8 + (long long)rank * 4 + quad;  // this warp's group
-      const bool g_ok = g < num_groups;
+    // one relu unit: h3[point][ch] = relu(acc + c[group][ch]) for ch = 128 v + 64 part + [0, 64) = chunk 2 v + part
+    auto relu_unit = [&](int v) {
+      const uint32_t t_addr = lane_base + ACC_P2 + (uint32_t)(v & 1) * 128u + (uint32_t)part * 64u;
+      uint32_t r0[32], r1[32];
+      tmem_ld32_async(t_addr, r0);
+      tmem_ld32_async(t_addr + 32, r1);
+      tmem_wait_ld();
+      const uint32_t img = (uint32_t)((2 * v + part) & 3) * IMG;
+      // the slot still holds chunk 2v+part-4 (this tile) or 2v+part+4 (previous tile) until its G item is complete;
+      // each slot's barrier completes twice per tile
+      mbar_wait(&g_done[(2 * v + part) & 3], v < 2 ? 1u : 0u);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        // h3[point][ch] = relu(acc + c[group][ch]) for ch = 128 v + 64 part + [0, 64) = K chunk 2 v + part of W4 h3
-        mbar_wait(&p2_full[v & 1], (uint32_t)(v >> 1) & 1u);  // each accumulator completes twice per tile
-        fence_after_sync();
-        const uint32_t t_addr = lane_base + ACC_P2 + (uint32_t)(v & 1) * 128u + (uint32_t)part * 64u;
-        uint32_t r0[32], r1[32];
-        tmem_ld32_async(t_addr, r0);
-        tmem_ld32_async(t_addr + 32, r1);
-        tmem_wait_ld();
-        const uint32_t img = (uint32_t)((2 * v + part) & 3) * IMG;
-        // the slot still holds chunk 2v+part-4 (this tile) or 2v+part+4 (previous tile) until its G item is complete;
-        // each slot's barrier completes twice per tile
-        mbar_wait(&g_done[(2 * v + part) & 3], v < 2 ? 1u : 0u);
+      for (int jj = 0; jj < 2; ++jj) {
+        float x[32];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 cv = reinterpret_cast<const float4*>(c_w + v * 64 + jj * 32)[i];  // broadcast
-            x[4 * i + 0] = fmaf(__uint_as_float(jj ? r1[4 * i + 0] : r0[4 * i + 0]), inv_p2s, cv.x);
-            x[4 * i + 1] = fmaf(__uint_as_float(jj ? r1[4 * i + 1] : r0[4 * i + 1]), inv_p2s, cv.y);
-            x[4 * i + 2] = fmaf(__uint_as_float(jj ? r1[4 * i + 2] : r0[4 * i + 2]), inv_p2s, cv.z);
-            x[4 * i + 3] = fmaf(__uint_as_float(jj ? r1[4 * i + 3] : r0[4 * i + 3]), inv_p2s, cv.w);
-          }
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            store_relu8<FMT, 1>(h3buf, img + sw128_kmajor_off(prow, jj * 32 + q4 * 8), 0u, x + q4 * 8);
+        for (int i = 0; i < 8; ++i) {
+          const float4 cv = reinterpret_cast<const float4*>(c_w + v * 64 + jj * 32)[i];  // broadcast
+          x[4 * i + 0] = fmaf(__uint_as_float(jj ? r1[4 * i + 0] : r0[4 * i + 0]), inv_p2s, cv.x);
+          x[4 * i + 1] = fmaf(__uint_as_float(jj ? r1[4 * i + 1] : r0[4 * i + 1]), inv_p2s, cv.y);
+          x[4 * i + 2] = fmaf(__uint_as_float(jj ? r1[4 * i + 2] : r0[4 * i + 2]), inv_p2s, cv.z);
+          x[4 * i + 3] = fmaf(__uint_as_float(jj ? r1[4 * i + 3] : r0[4 * i + 3]), inv_p2s, cv.w);
         }
-        fence_proxy_async_smem();
-        fence_before_sync();
-        arrive_leader(&h3_ready[2 * v + part]);
-        if (v == 3) {
-          // unit 3's accumulator was full: every W32 h1 instruction of this tile is complete, h1 is free
-          const int next = tile + npairs;
-          fetch_c(next);
-          if (next < num_ptiles) build_h1(next + npairs);
-          stage_c();
-        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          store_relu8<FMT, 1>(h3buf, img + sw128_kmajor_off(prow, jj * 32 + q4 * 8), 0u, x + q4 * 8);
       }
+      fence_proxy_async_smem();
+      fence_before_sync();
+      arrive_leader(&h3_ready[2 * v + part]);
+    };
 
-      // per-group max of W4 h3: channels 128 part + [0, 128), max over the warp's 32 lanes (points)
-      mbar_wait(g3_full, tpar);
+    // per-group max of W4 h3 of tile `tile`.  This accumulator has channels on the lanes (CTA r: 128 r + lane) and
+    // the pair-tile's 256 points on the columns (32 columns = one group), so the max is over a thread's registers.
+    auto max_unit = [&](int tile, uint32_t par) {
+      const int ch = (int)rank * 128 + quad * 32 + lane;
+      const float b4v = __ldg(bias_b4 + ch);
+      mbar_wait(g3_full, par);
       fence_after_sync();
 #pragma unroll 1
       for (int jj = 0; jj < 4; jj += 2) {
@@ -1024,23 +1078,52 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
           fence_before_sync();
           arrive_leader(max_done);
         }
-        float mx0 = 0.f, mx1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float a = warp_max_f32(__uint_as_float(r0[i]));
-          const float b = warp_max_f32(__uint_as_float(r1[i]));
-          if (lane == i) { mx0 = a; mx1 = b; }
-        }
-        if (g_ok) {
+        for (int h = 0; h < 2; ++h) {
+          float mx = __uint_as_float(h ? r1[0] : r0[0]);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float mx = (h ? mx1 : mx0) * inv_g3;
-            const int ch = part * 128 + (jj + h) * 32 + lane;
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(h ? r1[i] : r0[i]));
+          mx *= inv_g3;
+          const long long g = (long long)tile * 8 + part * 4 + jj + h;
+          if (g < num_groups) {
             const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * IMG;
             store_operand<FMT, 1>(out_img + img, sw128_kmajor_off((int)(g & 127), ch & 63), IMG, mx * grp_scale);
-            if (features_out) features_out[g * 256 + ch] = mx + __ldg(bias_b4 + ch);
+            if (features_out) features_out[g * 256 + ch] = mx + b4v;
           }
         }
+      }
+    };
+
+    // Program order per iteration: unit 0 of the current tile, the group max of the previous tile (its last chunk
+    // G7' is issued between P1 and P2; G0 needs the accumulator back and unit 2 needs G0 / G1 complete before it may
+    // overwrite their h3 slots), units 1 and 2, then -- as soon as unit 3's accumulator is full, i.e. every W32 h1
+    // instruction of the tile is complete -- h1 of the next tile, then unit 3.  Measured with PPT_PAIR_TRACE: the
+    // iteration period (8.4 k cycles against 6.1 k of tensor work) is the dependency cycle through these eight
+    // warps; the max placed after unit 1 instead lengthens it (8.7 k).
+    uint32_t tpar = 0;
+    for (int it = 0; it <= ntiles; ++it, tpar ^= 1u) {
+      const int tile = pair + it * npairs;
+      const bool cur = it < ntiles;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (v == 1 && it >= 1) {
+          max_unit(tile - npairs, tpar ^ 1u);
+          if (warp == 2) PAIR_TRACE(it, 41);
+        }
+        if (!cur) continue;
+        mbar_wait(&p2_full[v & 1], (uint32_t)(v >> 1) & 1u);  // each accumulator completes twice per tile
+        fence_after_sync();
+        if (warp == 2) PAIR_TRACE(it, 32 + v);
+        if (v == 3) {
+          const int next = tile + npairs;
+          trace_it = it;
+          fetch_c(next);
+          if (next < num_ptiles) build_h1(next + npairs);
+        }
+        if (warp == 2 && v == 3) PAIR_TRACE(it, 42);
+        relu_unit(v);
+        if (warp == 2) PAIR_TRACE(it, 36 + v);
+        if (v == 3) stage_c();  // after the last read of this tile's c values
       }
     }
   }
@@ -1050,6 +1133,14 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
   __syncthreads();
   cluster_sync_all();  // neither CTA may exit (or free tensor memory) while the other can still reach it
   if (warp == 1) tmem_dealloc_pair<TCOLS>(tbase);
+  if (trace && threadIdx.x == 0 && (blockIdx.x & 1) == 0) {
+    trace[32 * 64 + (blockIdx.x >> 1) * 2 + 1] = clock64();
+    if (blockIdx.x == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      trace[32 * 64 + 201] = (long long)ns;
+    }
+  }
 }
 
 // ======================================================================================
@@ -1496,8 +1587,35 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
       cfg.numAttrs = 1;
       const unsigned char* blob_c = blob;
       unsigned char* timg = ws + W.t_img;
+      // PPT_PAIR_TRACE=1: a 16 KB device buffer receives the timeline of pair 0 (see the kernel); it is printed
+      // to stderr (with a synchronisation) -- debugging only
+      static long long* trace = nullptr;
+      static int want_trace = -1;
+      if (want_trace < 0) {
+        const char* ev = getenv("PPT_PAIR_TRACE");
+        want_trace = ev ? atoi(ev) : 0;
+        if (want_trace) {
+          cudaMalloc(&trace, (32 * 64 + 256) * sizeof(long long));
+          cudaMemset(trace, 0, (32 * 64 + 256) * sizeof(long long));
+        }
+      }
       PPT_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, k2p, nbhd, blob_c, (const float*)cbuf, timg, features_out, groups,
-                                            ptiles));
+                                            ptiles, trace));
+      if (want_trace > 0 && trace) {
+        --want_trace;  // print the first `want_trace` launches
+        cudaStreamSynchronize(st);
+        static long long host[32 * 64 + 256];
+        cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "PAIRSPAN");  // per leader CTA: kernel-entry to kernel-exit cycles on its SM
+        for (int k = 0; k < 74; ++k) fprintf(stderr, " %lld", host[32 * 64 + 2 * k + 1] - host[32 * 64 + 2 * k]);
+        fprintf(stderr, "\nPAIRCLOCK pair0 %lld cycles in %lld ns\n", host[32 * 64 + 1] - host[32 * 64],
+                host[32 * 64 + 201] - host[32 * 64 + 200]);
+        for (int it = 0; it < 32; ++it) {
+          fprintf(stderr, "PAIRTRACE %d", it);
+          for (int k = 0; k < 46; ++k) fprintf(stderr, " %lld", host[it * 64 + k] ? host[it * 64 + k] - host[12] : 0ll);
+          fprintf(stderr, "\n");
+        }
+      }
     } else {
       k2<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr,
                                               nullptr);

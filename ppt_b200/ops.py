@@ -377,3 +377,31 @@ def selftest_umma_pair(a, b, mode=ENC_FP16, b_mn_major=False):
         _lib.check(_lib.load().ppt_selftest_umma_pair(_ptr(a), _ptr(b), _ptr(d), N, K, mode | (4 if b_mn_major else 0),
                                                       _stream(a)), "ppt_selftest_umma_pair")
     return d
+
+
+class ClockProbe:
+    """SM clock seen INSIDE kernels: a one-thread kernel on a side stream samples (globaltimer, clock64) every
+    `period_us`; mhz() after the work of interest has been synchronised.  Measurement aid for bench.py."""
+
+    def __init__(self, device, duration_ms=50.0, period_us=20.0):
+        self.samples = max(2, int(duration_ms * 1e3 / period_us))
+        self.buf = torch.zeros((self.samples, 2), dtype=torch.int64, device=device)
+        self.stream = torch.cuda.Stream(device)
+        self.period_ns = int(period_us * 1e3)
+
+    def start(self):
+        with torch.cuda.device(self.buf.device):
+            _lib.check(_lib.load().ppt_clock_probe(_ptr(self.buf), self.samples, self.period_ns,
+                                                   self.stream.cuda_stream), "ppt_clock_probe")
+        return self
+
+    def mhz(self):
+        """-> (mean MHz, min MHz over 10-sample windows, number of samples) over the probe's lifetime."""
+        self.stream.synchronize()
+        b = self.buf.cpu()
+        b = b[b[:, 0] > 0]
+        if b.shape[0] < 12:
+            return None
+        mean = float(b[-1, 1] - b[0, 1]) / float(b[-1, 0] - b[0, 0]) * 1e3
+        win = (b[10:, 1] - b[:-10, 1]).double() / (b[10:, 0] - b[:-10, 0]).double() * 1e3
+        return mean, float(win.min()), float(win.max()), int(b.shape[0])
