@@ -231,6 +231,7 @@ def run_ours(args):
     phase_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # nvidia-smi samples every 200 ms; the SM clock inside the sub-millisecond kernels is measured on the device
     t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
@@ -238,6 +239,12 @@ def run_ours(args):
     e1.record()
     barrier()
     t_wall1 = time.time()
+    # untimed repeat of the same steps with the measurement build of stage 2 (CTA 0 accumulates globaltimer ns and
+    # clock64 cycles of every launch): the SM clock inside the dominant kernel
+    with ops.Stage2ClockTrace(dev) as clock_trace:
+        for i in range(args.steps):
+            step(i)
+        barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     per_phase = {}
@@ -246,46 +253,48 @@ def run_ours(args):
 
     # ---- widened row f2: the same step with the cls rows and pos_embed(center), i.e. the
     # (x, pos) arguments of self.blocks (point_encoder.py:241-249); not part of `value` ----
-    tok.load_front_end_state(torch_port.make_front_end_state())
-    pos_blob = tok._pos_blob(dev)
-    for i in range(3):
-        tok.forward_assembled(resident[i % ROTATE])
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    f0.record()
-    for i in range(args.steps):
-        tok.forward_assembled(resident[i % ROTATE])
-    f1.record()
-    barrier()
-    ms_assembled = max_over_ranks(f0.elapsed_time(f1))
-    centers = [torch.rand(B, N_GROUP, 3, device=dev) * 2 - 1 for _ in range(3)]
-    mode_id = ops.ENC_MODES[args.precision]
-    pos_ms = []
-    for i in range(3 + args.steps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.tokenizer_forward(None, centers[i % 3], None, pos_blob, mode=mode_id, want_x=False)
-        b.record()
-        if i >= 3:
-            pos_ms.append((a, b))
-    torch.cuda.synchronize()
-    pos_ms = statistics.mean(a.elapsed_time(b) for a, b in pos_ms)
+    ms_assembled = pos_ms = ms_train = None
+    if not args.no_widened:
+        tok.load_front_end_state(torch_port.make_front_end_state())
+        pos_blob = tok._pos_blob(dev)
+        for i in range(3):
+            tok.forward_assembled(resident[i % ROTATE])
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record()
+        for i in range(args.steps):
+            tok.forward_assembled(resident[i % ROTATE])
+        f1.record()
+        barrier()
+        ms_assembled = max_over_ranks(f0.elapsed_time(f1))
+        centers = [torch.rand(B, N_GROUP, 3, device=dev) * 2 - 1 for _ in range(3)]
+        mode_id = ops.ENC_MODES[args.precision]
+        pos_ev = []
+        for i in range(3 + args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.tokenizer_forward(None, centers[i % 3], None, pos_blob, mode=mode_id, want_x=False)
+            b.record()
+            if i >= 3:
+                pos_ev.append((a, b))
+        torch.cuda.synchronize()
+        pos_ms = statistics.mean(a.elapsed_time(b) for a, b in pos_ev)
 
-    # ---- widened row f3: the same tokenizer step with the Encoder's BatchNorms in batch-statistics mode
-    # (model.train(), main_cls.py:169): two more passes (point moments; W32 h1 statistics) and the running-stat
-    # update; not part of `value` ----
-    tok.encoder.train()
-    for i in range(3):
-        tok(resident[i % ROTATE])
-    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0e.record()
-    for i in range(args.steps):
-        tok(resident[i % ROTATE])
-    t1e.record()
-    barrier()
-    ms_train = max_over_ranks(t0e.elapsed_time(t1e))
-    tok.encoder.eval()
+        # ---- widened row f3: the same tokenizer step with the Encoder's BatchNorms in batch-statistics mode
+        # (model.train(), main_cls.py:169): two more passes (point moments; W32 h1 statistics) and the
+        # running-stat update; not part of `value` ----
+        tok.encoder.train()
+        for i in range(3):
+            tok(resident[i % ROTATE])
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0e.record()
+        for i in range(args.steps):
+            tok(resident[i % ROTATE])
+        t1e.record()
+        barrier()
+        ms_train = max_over_ranks(t0e.elapsed_time(t1e))
+        tok.encoder.eval()
 
     # ---- timed region 2: end to end through the public API with pinned host buffers ----
     # HostPipeline: H2D of the clouds, the kernels and D2H of tokens + centres on three streams,
@@ -313,6 +322,11 @@ def run_ours(args):
     if rank != 0:
         return
 
+    if clocks is not None and clock_trace.mhz is not None:
+        clocks["sm_mhz_inside_stage2"] = round(clock_trace.mhz, 1)
+        clocks["sm_mhz_inside_stage2_how"] = ("untimed repeat of the timed steps with the measurement build of stage 2: CTA 0 of "
+                                              "every launch sums clock64 cycles and globaltimer ns; nvidia-smi's 200 ms "
+                                              "samples miss the dip")
     peaks = load_peaks()
     clouds_total = B * world * args.steps
     value = clouds_total / (ms_total * 1e-3)
@@ -352,21 +366,23 @@ def run_ours(args):
         if "peak" in v:
             v["frac"] = v["achieved"] / v["peak"]
 
-    pos_bytes = B * (N_GROUP * 12 + (N_GROUP + 1) * 384 * 4)
-    widened = {"f2_token_assembly": {
-        "what": "x = cat(cls_token, tokens), pos = cat(cls_pos, pos_embed(center)) [B, 513, 384] each; tokens stored "
-                "straight into x, pos_embed 128->384 on tcgen05",
-        "value": clouds_total / (ms_assembled * 1e-3), "unit": UNIT, "ms_per_step": ms_assembled / args.steps,
-        "pos_path": {"kernels": "pos_hidden_kernel + group_linear<K=128>", "bound": "hbm", "ms": pos_ms,
-                     "achieved": pos_bytes / (pos_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": pos_bytes / (pos_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "bytes_per_launch": pos_bytes}}}
+    widened = None
+    if ms_assembled is not None:
+        pos_bytes = B * (N_GROUP * 12 + (N_GROUP + 1) * 384 * 4)
+        widened = {"f2_token_assembly": {
+            "what": "x = cat(cls_token, tokens), pos = cat(cls_pos, pos_embed(center)) [B, 513, 384] each; tokens stored "
+                    "straight into x, pos_embed 128->384 on tcgen05",
+            "value": clouds_total / (ms_assembled * 1e-3), "unit": UNIT, "ms_per_step": ms_assembled / args.steps,
+            "pos_path": {"kernels": "pos_hidden_kernel + group_linear<K=128>", "bound": "hbm", "ms": pos_ms,
+                         "achieved": pos_bytes / (pos_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": pos_bytes / (pos_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "bytes_per_launch": pos_bytes}}}
 
-    widened["f3_train_mode_batchnorm"] = {
-        "what": "Group + Encoder with batch-statistics BatchNorm (forward only, running stats updated in place) + "
-                "reduce_dim; adds bn_moments, bn_fold1, stage-2 statistics pass (the four W32 h1 units), bn_fold2",
-        "value": clouds_total / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / args.steps,
-        "extra_ms_over_eval": (ms_train - ms_total) / args.steps}
+        widened["f3_train_mode_batchnorm"] = {
+            "what": "Group + Encoder with batch-statistics BatchNorm (forward only, running stats updated in place) + "
+                    "reduce_dim; adds bn_moments, bn_fold1, stage-2 statistics pass (the four W32 h1 units), bn_fold2",
+            "value": clouds_total / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / args.steps,
+            "extra_ms_over_eval": (ms_train - ms_total) / args.steps}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -400,6 +416,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-widened", action="store_true",
+                    help="skip the extra timed loops of the widened rows (f2 token assembly, f3 train mode): "
+                         "profiling runs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -201,6 +201,11 @@ int ppt_selftest_umma_pair(const float *a, const float *b, float *d, int N, int 
  * test to see the SM clock inside them (DESIGN.md "clocks under load"). */
 int ppt_clock_probe(void *out, int samples, int64_t period_ns, void *stream);
 
+/* Measurement aid without any perturbation: while `acc` (device int64[2], zeroed by the caller) is set, CTA 0 of
+ * every Encoder stage-2 launch adds its lifetime in nanoseconds (globaltimer) to acc[0] and in SM cycles (clock64)
+ * to acc[1]; acc[1] / acc[0] is the SM clock in GHz inside that kernel.  NULL switches it off (the default). */
+int ppt_set_clock_trace(void *acc);
+
 #ifdef __cplusplus
 }
 #endif

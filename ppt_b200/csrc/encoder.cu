@@ -133,15 +133,19 @@ __device__ __forceinline__ void store_relu8(unsigned char* base, uint32_t off, u
 //             the inner loop is the same single FFMA per element as BN_EVAL.
 constexpr int BN_EVAL = 0, BN_STATS = 1, BN_APPLY = 2;
 
-template <uint32_t FMT, int SPLIT, int NT, int STAGE, int EPW, int BN = BN_EVAL>
+// CLK: measurement build of the same kernel (ppt_set_clock_trace).  A separate instantiation because even these few
+// instructions at kernel entry / exit changed ptxas's schedule of the MMA-issue loop and cost 7 % (0.59 -> 0.63 ms).
+template <uint32_t FMT, int SPLIT, int NT, int STAGE, int EPW, int BN = BN_EVAL, bool CLK = false>
 __global__ void __launch_bounds__((EPW + 2) * 32, 1)
 encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
                      const float* __restrict__ cbuf,          // stage 2: [groups_pad, 512]
                      unsigned char* __restrict__ out_img,     // stage 1: g images, stage 2: t images
                      float* __restrict__ features_out,        // stage 2, nullable: [groups, 256]
                      long long num_groups, int num_tiles,
-                     double* __restrict__ bn_stats = nullptr, const float* __restrict__ bn_vec = nullptr) {
+                     double* __restrict__ bn_stats = nullptr, const float* __restrict__ bn_vec = nullptr,
+                     long long* __restrict__ clock_acc = nullptr) {
   static_assert(BN == BN_EVAL || STAGE == 2, "batch statistics belong to stage 2");
+
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int GPT = NT / 32;                       // groups per tile
   constexpr int NUNITS = STAGE == 1 ? 2 : (BN == BN_STATS ? 4 : 6);
@@ -169,10 +173,19 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   uint64_t* h3_ready = h1_ready + 2;       // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h3_ready + 4);
   float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [128]
+  long long* clk0 = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(bars) + 192);  // [2], see below
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BlobLayout L{(uint32_t)SPLIT};
   const float* sc = reinterpret_cast<const float*>(blob + L.scales());
+  // measurement aid (ppt_set_clock_trace): CTA 0 adds its lifetime in ns and in SM cycles to clock_acc[0..1];
+  // the start values wait in shared memory so that no register stays live across the kernel
+  if (CLK && clock_acc && blockIdx.x == 0 && tid == 0) {
+    long long ns0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    clk0[0] = ns0;
+    clk0[1] = clock64();
+  }
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
@@ -458,6 +471,12 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TCOLS>(tbase);
+  if (CLK && clock_acc && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+    atomicAdd(reinterpret_cast<unsigned long long*>(clock_acc), (unsigned long long)(ns1 - clk0[0]));
+    atomicAdd(reinterpret_cast<unsigned long long*>(clock_acc) + 1, (unsigned long long)(clock64() - clk0[1]));
+  }
 }
 
 // ======================================================================================
@@ -1473,6 +1492,8 @@ constexpr size_t linear_smem_bytes() {
   return (size_t)4 * SPLIT * IMG + (size_t)NSTAGE * SPLIT * IMG + 256;
 }
 
+long long* g_clock_trace = nullptr;  // ppt_set_clock_trace
+
 int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -1532,6 +1553,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   }
   auto k2p = encoder_stage2_pair_kernel<FMT>;
   auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
+  auto k2clk = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2, BN_EVAL, true>;
   auto kb = group_linear_kernel<FMT, SPLIT, 4>;
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
   auto kda = group_linear_kernel<FMT, SPLIT, 3, 4, true>;
@@ -1543,6 +1565,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1tc));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2clk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2p, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)stage_smem_bytes<1, 128, 2>()));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
@@ -1564,7 +1587,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
       k1tc<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles);
     else
       k1<<<grid_t, (EPW1 + 2) * 32, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles, nullptr,
-                                              nullptr);
+                                              nullptr, nullptr);
   }
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
@@ -1617,8 +1640,8 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
         }
       }
     } else {
-      k2<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr,
-                                              nullptr);
+      (g_clock_trace ? k2clk : k2)<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out,
+                                                                        groups, tiles, nullptr, nullptr, g_clock_trace);
     }
   }
   if ((phases & 8) && tokens_out)
@@ -1684,9 +1707,10 @@ int run_encoder_train(const float* nbhd, unsigned char* blob, const BnDevice& bn
   bn_fold1_kernel<FMT><<<1, 128, 0, st>>>(bn, mom, points, blob, (uint32_t)SPLIT);
   int rc = run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, nullptr, groups, 3, st);  // stage 1, c (raw weights)
   if (rc) return rc;
-  k2s<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, nullptr, nullptr, groups, tiles, stats, nullptr);
+  k2s<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, nullptr, nullptr, groups, tiles, stats, nullptr, nullptr);
   bn_fold2_kernel<<<1, 512, 0, st>>>(bn, stats, points, bn_vec);
-  k2a<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr, bn_vec);
+  k2a<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr, bn_vec,
+                                        nullptr);
   if (tokens_out) return run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, tokens_out, groups, 8, st);
   return ppt_launch_status();
 }
@@ -1811,4 +1835,9 @@ extern "C" PPT_EXPORT int ppt_encoder_forward_train(const float* neighborhood, v
     default:
       return PPT_EINVAL;
   }
+}
+
+extern "C" PPT_EXPORT int ppt_set_clock_trace(void* acc) {
+  g_clock_trace = static_cast<long long*>(acc);
+  return 0;
 }

@@ -379,9 +379,32 @@ def selftest_umma_pair(a, b, mode=ENC_FP16, b_mn_major=False):
     return d
 
 
+class Stage2ClockTrace:
+    """SM clock inside the Encoder's stage-2 kernel, without perturbing it: CTA 0 of every launch adds its lifetime
+    in ns and in SM cycles to a device accumulator (ppt_set_clock_trace).  Use as a context manager; .mhz after."""
+
+    def __init__(self, device):
+        self.acc = torch.zeros(2, dtype=torch.int64, device=device)
+        self.mhz = None
+
+    def __enter__(self):
+        _lib.check(_lib.load().ppt_set_clock_trace(_ptr(self.acc)), "ppt_set_clock_trace")
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().ppt_set_clock_trace(None)
+        torch.cuda.synchronize(self.acc.device)
+        ns, cyc = (int(v) for v in self.acc.cpu())
+        self.mhz = cyc / ns * 1e3 if ns > 0 else None
+        return False
+
+
 class ClockProbe:
     """SM clock seen INSIDE kernels: a one-thread kernel on a side stream samples (globaltimer, clock64) every
-    `period_us`; mhz() after the work of interest has been synchronised.  Measurement aid for bench.py."""
+    `period_us`; mhz() after the work of interest has been synchronised.  CAUTION: the probe's CTA holds the 1 KB of
+    reserved shared memory that a 227 KB CTA needs, so on its SM the Encoder stage kernels cannot be resident and
+    run their last CTA as a second wave (about 1.7x slower): use it for clocks (tools/kernel_clocks.py), never
+    inside a timed region -- bench.py uses Stage2ClockTrace instead."""
 
     def __init__(self, device, duration_ms=50.0, period_us=20.0):
         self.samples = max(2, int(duration_ms * 1e3 / period_us))
