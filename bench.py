@@ -296,6 +296,47 @@ def run_ours(args):
         ms_train = max_over_ranks(t0e.elapsed_time(t1e))
         tok.encoder.eval()
 
+        # ---- widened row f4: DGCNN edge features at the part-seg shapes (512 queries <- 256 keys, C = 384, k = 4,
+        # point_encoder.py:409-411) and the data loader's FPS (data/dataset_3d.py:40-61; 10000 -> 1024) ----
+        gB, gC, gNq, gNk, gk = 32, 384, 512, 256, 4
+        gq, gkf = torch.randn(gB, gC, gNq, device=dev), torch.randn(gB, gC, gNk, device=dev)
+        gidx = torch.randint(0, gNk, (gB, gNq, gk), device=dev)
+        gf_ev = []
+        for i in range(3 + args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.graph_feature(gq, gkf, gidx)
+            b.record()
+            if i >= 3:
+                gf_ev.append((a, b))
+        torch.cuda.synchronize()
+        gf_ms = statistics.mean(a.elapsed_time(b) for a, b in gf_ev)
+        gf_bytes = 4 * (gB * 2 * gC * gNq * gk + gB * gC * (gNq + gNk)) + 8 * gB * gNq * gk
+        from ppt_b200 import data as ppt_data
+        import numpy as _np
+        lp = _np.random.RandomState(0).uniform(-1, 1, size=(10000, 3)).astype(_np.float32)
+        ppt_data.farthest_point_sample_indices(lp, 1024, start=0)
+        t0l = time.perf_counter()
+        for _ in range(5):
+            ppt_data.farthest_point_sample_indices(lp, 1024, start=0)
+        loader_ms = (time.perf_counter() - t0l) / 5 * 1e3
+        lb = _np.stack([lp] * 32)
+        ppt_data.farthest_point_sample_batch(lb, 1024, [0] * 32)
+        t0l = time.perf_counter()
+        ppt_data.farthest_point_sample_batch(lb, 1024, [0] * 32)
+        loader_batch_ms = (time.perf_counter() - t0l) * 1e3 / 32
+        loader_cpu_ms = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu as oracle_cpu
+            t0l = time.perf_counter()
+            oracle_cpu.loader_fps_indices(lp, 1024, 0)
+            loader_cpu_ms = (time.perf_counter() - t0l) * 1e3
+        f4 = {"graph_feature": {"shape": "B=32, C=384, 512 queries <- 256 keys, k=4", "bound": "hbm", "ms": gf_ms,
+                                "achieved": gf_bytes / (gf_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                "bytes_per_launch": gf_bytes},
+              "loader_fps_10000_to_1024": {"ms_per_cloud_single_call": loader_ms, "ms_per_cloud_batched_32": loader_batch_ms,
+                                           "reference_numpy_ms_per_cloud": loader_cpu_ms}}
+
     # ---- timed region 2: end to end through the public API with pinned host buffers ----
     # HostPipeline: H2D of the clouds, the kernels and D2H of tokens + centres on three streams,
     # two slots in flight; every step's inputs start in pinned host memory and its results end there.
@@ -383,6 +424,11 @@ def run_ours(args):
                     "reduce_dim; adds bn_moments, bn_fold1, stage-2 statistics pass (the four W32 h1 units), bn_fold2",
             "value": clouds_total / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / args.steps,
             "extra_ms_over_eval": (ms_train - ms_total) / args.steps}
+
+    if widened is not None:
+        f4["graph_feature"]["peak"] = peaks["hbm_gbs"]
+        f4["graph_feature"]["frac"] = f4["graph_feature"]["achieved"] / peaks["hbm_gbs"]
+        widened["f4_part_seg_and_loader"] = f4
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

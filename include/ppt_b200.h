@@ -120,6 +120,18 @@ int ppt_three_interpolate(const float *feats, const int64_t *idx, const float *d
 int ppt_three_interpolate_grad(const float *grad_out, const int64_t *idx, const float *dist,
                                float *grad_feats, int B, int N, int S, int D, void *stream);
 
+/* DGCNN_Propagation.get_graph_feature behind its kNN (models/pointbert/pointnet2_utils.py:392-442, the part-seg
+ * head, point_encoder.py:409-411):
+ *   out[b, c, q, j] = x_k[b, c, idx[b,q,j]] - x_q[b, c, q]   (c < C),   out[b, C + c, q, j] = x_q[b, c, q].
+ * x_q [B,C,Nq], x_k [B,C,Nk] f32 channel-first, idx [B,Nq,k] int64 in [0,Nk) -> out [B,2C,Nq,k] f32.  Bit-exact. */
+int ppt_graph_feature(const float *x_q, const float *x_k, const int64_t *idx, float *out,
+                      int B, int C, int Nq, int Nk, int k, void *stream);
+
+/* Its gradient w.r.t. x_q [B,C,Nq] (written) and x_k [B,C,Nk] (accumulated with atomics into a buffer the
+ * caller has zero-filled); grad_out [B,2C,Nq,k]. */
+int ppt_graph_feature_grad(const float *grad_out, const int64_t *idx, float *grad_xq, float *grad_xk,
+                           int B, int C, int Nq, int Nk, int k, void *stream);
+
 /* ---- mini-PointNet patch Encoder + reduce_dim (tcgen05) ---------------------
  * Encoder.forward in eval mode, models/pointbert/dvae.py:201-215, followed by
  * reduce_dim, models/pointbert/point_encoder.py:133,239.

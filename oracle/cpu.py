@@ -149,3 +149,21 @@ def group_forward(xyz, num_group, group_size, start=0):
                             fidx.ctypes.data_as(_i64p), kidx.ctypes.data_as(_i64p),
                             B, N, num_group, group_size)
     return nb, ctr, fidx, kidx
+
+
+def loader_fps_indices(point, npoint, start):
+    """data/dataset_3d.py:40-61 restated (numpy, same statements) with the start index as an argument instead of the
+    np.random.randint draw; returns the index array (the reference returns point[indices])."""
+    N = point.shape[0]
+    xyz = point[:, :3]
+    centroids = np.zeros((npoint,))
+    distance = np.ones((N,)) * 1e10
+    farthest = int(start)
+    for i in range(npoint):
+        centroids[i] = farthest
+        centroid = xyz[farthest, :]
+        dist = np.sum((xyz - centroid) ** 2, -1)
+        mask = dist < distance
+        distance[mask] = dist[mask]
+        farthest = np.argmax(distance, -1)
+    return centroids.astype(np.int64)

@@ -194,6 +194,62 @@ def gen_encoder_train(ns):
     print("encoder train-mode features", tuple(feat.shape), "absmax", float(feat.abs().max()))
 
 
+def gen_graph_feature(ns):
+    """DGCNN_Propagation.get_graph_feature of the unmodified reference (pointnet2_utils.py:392-442), k = 4:
+    the cross-level call (queries 128, keys 64) in full and the part-seg point counts (512 <- 256; C = 96 to keep the fixture small) as digests."""
+    from oracle.inputs import digest
+    dg = ns.pb_pn2.DGCNN_Propagation(k=4)
+    g = torch.Generator().manual_seed(4545)
+    rec = {}
+    for tag, (B, C, Nq, Nk), full in (("small", (2, 24, 128, 64), True), ("partseg", (2, 96, 512, 256), False)):
+        coor_k = cloud("S", B, Nk, 4545 + Nk).permute(0, 2, 1).contiguous()
+        coor_q = cloud("S", B, Nq, 4546 + Nq).permute(0, 2, 1).contiguous()
+        x_q, x_k = torch.randn(B, C, Nq, generator=g), torch.randn(B, C, Nk, generator=g)
+        with torch.no_grad():
+            feat = dg.get_graph_feature(coor_q, x_q, coor_k, x_k)
+        port, idx = torch_port.graph_feature(coor_q, x_q, coor_k, x_k, 4)
+        # neighbour order inside the k is unspecified in the reference (topk sorted=False): compare per-(q) sets
+        assert torch.equal(feat.sort(-1)[0], port.sort(-1)[0])
+        rec.update({tag + ".coor_q": coor_q.numpy(), tag + ".coor_k": coor_k.numpy(), tag + ".x_q": x_q.numpy(),
+                    tag + ".x_k": x_k.numpy()})
+        if full:
+            rec[tag + ".feature_sorted"] = feat.sort(-1)[0].numpy()
+            rec[tag + ".idx_sorted"] = idx.sort(-1)[0].numpy()
+        else:
+            rec[tag + ".feature_sorted_sha"] = digest(feat.sort(-1)[0])
+        # self-graph call of the second layer (keys = queries)
+        with torch.no_grad():
+            feat2 = dg.get_graph_feature(coor_q, x_q, coor_q, x_q)
+        rec[tag + ".self_feature_sorted_sha"] = digest(feat2.sort(-1)[0])
+    np.savez_compressed(os.path.join(OUT, "graph_feature.npz"), **rec)
+    print("graph_feature fixtures", sorted(rec))
+
+
+def gen_loader_fps(ns):
+    """The data loader's numpy FPS (data/dataset_3d.py:40-61).  The module itself cannot be imported (F12), so the
+    function's own source text is executed; np.random.seed pins its np.random.randint draw."""
+    import re
+    src = open(os.path.join(refimport.REFERENCE_ROOT, "data", "dataset_3d.py")).read()
+    m = re.search(r"^def farthest_point_sample\(point, npoint\):.*?^    return point\n", src, re.S | re.M)
+    scope = {"np": np}
+    exec(m.group(0), scope)  # noqa: S102 -- the reference's function, unmodified
+    from oracle import cpu
+    rec = {}
+    for tag, (N, D, npoint, seed) in (("a", (3000, 6, 256, 7)), ("b", (10000, 3, 1024, 8))):
+        rng = np.random.RandomState(seed)
+        point = rng.uniform(-1, 1, size=(N, D)).astype(np.float32)
+        np.random.seed(seed)
+        start = np.random.randint(0, N)
+        np.random.seed(seed)
+        ref = scope["farthest_point_sample"](point, npoint)
+        idx = cpu.loader_fps_indices(point, npoint, start)
+        assert np.array_equal(point[idx], ref)
+        rec.update({tag + ".point": point, tag + ".npoint": npoint, tag + ".seed": seed, tag + ".start": start,
+                    tag + ".indices": idx})
+    np.savez_compressed(os.path.join(OUT, "loader_fps.npz"), **rec)
+    print("loader fps fixtures", {k: (v.shape if hasattr(v, "shape") else v) for k, v in rec.items()})
+
+
 def gen_front_end(ns):
     """The unmodified reference PointTransformer (models/pointbert/point_encoder.py:111-256) up to the call of
     self.blocks: a forward pre-hook records the (x, pos) it is given (:241-249).  depth 1 keeps the unused
@@ -231,7 +287,8 @@ def gen_front_end(ns):
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1:  # regenerate one fixture only: front_end | encoder_train
-        {"front_end": gen_front_end, "encoder_train": gen_encoder_train}[sys.argv[1]](refimport.load())
+        {"front_end": gen_front_end, "encoder_train": gen_encoder_train, "graph_feature": gen_graph_feature,
+         "loader_fps": gen_loader_fps}[sys.argv[1]](refimport.load())
         return
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     ns = refimport.load()
@@ -249,6 +306,8 @@ def main():
     gen_encoder(ns)
     gen_front_end(ns)
     gen_encoder_train(ns)
+    gen_graph_feature(ns)
+    gen_loader_fps(ns)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("fixtures total bytes", tot)
 

@@ -198,3 +198,13 @@ def encoder_forward_train(sd, neighborhood, momentum=0.1, eps=1e-5):
                      sd["second_conv.1.bias"], True, momentum, eps)
     f = F.conv1d(F.relu(y), sd["second_conv.3.weight"], sd["second_conv.3.bias"])
     return torch.max(f, dim=2)[0].reshape(bs, g, -1), new
+
+
+# ---- DGCNN_Propagation.get_graph_feature (models/pointbert/pointnet2_utils.py:392-442) ---------------------
+def graph_feature(coor_q, x_q, coor_k, x_k, k):
+    """Restated with explicit indexing: cat(x_k[b, :, idx] - x_q, x_q) -> [B, 2C, Nq, k]; returns (feature, idx)."""
+    idx = knn_indices(k, coor_k.permute(0, 2, 1), coor_q.permute(0, 2, 1))          # [B, Nq, k]
+    B, C, Nq = x_q.shape
+    nb = torch.gather(x_k.unsqueeze(2).expand(B, C, Nq, x_k.shape[2]), 3, idx.unsqueeze(1).expand(B, C, Nq, k))
+    xq = x_q.unsqueeze(-1).expand(-1, -1, -1, k)
+    return torch.cat((nb - xq, xq), dim=1), idx

@@ -25,6 +25,7 @@ PER_FILE = {
     "ball_query.cu": ["-fmad=false"],
     "gather.cu": ["-fmad=false"],
     "interp.cu": ["-fmad=false"],
+    "graph_feature.cu": ["-fmad=false"],
 }
 
 

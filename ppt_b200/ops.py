@@ -211,6 +211,54 @@ def three_interpolate(feats, idx, dist):
     return _interp_fwd(feats, idx, dist)
 
 
+def _graph_feature_fwd(x_q, x_k, idx):
+    B, C, Nq = x_q.shape
+    Nk, k = x_k.shape[2], idx.shape[2]
+    out = torch.empty((B, 2 * C, Nq, k), dtype=torch.float32, device=x_q.device)
+    if out.numel():
+        with torch.cuda.device(x_q.device):
+            _lib.check(_lib.load().ppt_graph_feature(_ptr(x_q), _ptr(x_k), _ptr(idx), _ptr(out), B, C, Nq, Nk, k,
+                                                     _stream(x_q)), "ppt_graph_feature")
+    return out
+
+
+class _GraphFeature(torch.autograd.Function):
+    """The part-seg head trains through the edge features (DGCNN_Propagation, point_encoder.py:409-411)."""
+
+    @staticmethod
+    def forward(ctx, x_q, x_k, idx):
+        ctx.save_for_backward(idx)
+        ctx.Nk = x_k.shape[2]
+        return _graph_feature_fwd(x_q, x_k, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grad_out = _f32(grad_out)
+        B, C2, Nq, k = grad_out.shape
+        C = C2 // 2
+        grad_xq = torch.empty((B, C, Nq), dtype=torch.float32, device=grad_out.device)
+        grad_xk = torch.zeros((B, C, ctx.Nk), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _lib.check(_lib.load().ppt_graph_feature_grad(_ptr(grad_out), _ptr(idx), _ptr(grad_xq), _ptr(grad_xk), B, C,
+                                                          Nq, ctx.Nk, k, _stream(grad_out)), "ppt_graph_feature_grad")
+        return grad_xq, grad_xk, None
+
+
+def graph_feature(x_q, x_k, idx):
+    """Edge features of DGCNN_Propagation.get_graph_feature (models/pointbert/pointnet2_utils.py:418-442):
+    x_q [B,C,Nq], x_k [B,C,Nk] channel-first, idx [B,Nq,k] int64 (neighbours of each query among the keys)
+    -> [B, 2C, Nq, k] = cat(x_k[idx] - x_q, x_q).  Differentiable w.r.t. x_q and x_k."""
+    _need_cuda(x_q, x_k, idx)
+    x_q, x_k, idx = _f32(x_q), _f32(x_k), _i64(idx)
+    if x_q.dim() != 3 or x_k.dim() != 3 or idx.dim() != 3 or x_q.shape[:2] != x_k.shape[:2] or \
+            idx.shape[:2] != (x_q.shape[0], x_q.shape[2]):
+        raise ValueError("graph_feature: x_q [B,C,Nq], x_k [B,C,Nk], idx [B,Nq,k]")
+    if torch.is_grad_enabled() and (x_q.requires_grad or x_k.requires_grad):
+        return _GraphFeature.apply(x_q, x_k, idx)
+    return _graph_feature_fwd(x_q, x_k, idx)
+
+
 def selftest_umma(a, b, mode=ENC_FP16, b_mn_major=False, a_packed=None):
     """D[128,N] = A[128,K] @ B[N,K]^T through the Encoder's tcgen05 building blocks."""
     _need_cuda(a, b)

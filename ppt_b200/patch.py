@@ -198,6 +198,16 @@ def patch_reference(modules=None):
                     return _o(self, xyz1, xyz2, points1, points2)
 
                 _set(cls, "forward", fp_fwd)
+            dg = getattr(mod, "DGCNN_Propagation", None)
+            if dg is not None:
+                orig_gf = dg.get_graph_feature
+
+                def graph_fwd(self, coor_q, x_q, coor_k, x_k, _o=orig_gf):
+                    if x_q.is_cuda:
+                        return pointnet2.get_graph_feature(coor_q, x_q, coor_k, x_k, self.k)
+                    return _o(self, coor_q, x_q, coor_k, x_k)
+
+                _set(dg, "get_graph_feature", graph_fwd)
             msg = getattr(mod, "PointNetSetAbstractionMsg", None)
             if msg is not None:
                 orig_m = msg.forward

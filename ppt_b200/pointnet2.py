@@ -162,3 +162,12 @@ class PointNetFeaturePropagation(nn.Module):
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             new_points = F.relu(bn(conv(new_points)))
         return new_points
+
+
+def get_graph_feature(coor_q, x_q, coor_k, x_k, k):
+    """DGCNN_Propagation.get_graph_feature (models/pointbert/pointnet2_utils.py:392-442): kNN of every query
+    among the keys (k = 4 in the part-seg head, point_encoder.py:303-304), then the edge features
+    cat(x_k[idx] - x_q, x_q) -> [B, 2C, Nq, k].  coor_* [B,3,N*], x_* [B,C,N*] channel-first."""
+    with torch.no_grad():
+        idx = ops.knn(k, coor_k.permute(0, 2, 1).contiguous(), coor_q.permute(0, 2, 1).contiguous())
+    return ops.graph_feature(x_q, x_k, idx)

@@ -1,5 +1,6 @@
 """The reference-facing layer (ppt_b200.pointbert / pointnet2 / patch / tokenizer) on the GPU:
 same signatures and results as the reference's functions and modules."""
+import os
 import sys
 import types
 
@@ -275,3 +276,55 @@ def test_point_transformer_forward_with_fused_front_end_on_a_stand_in():
     with torch.no_grad():
         patch._point_transformer_forward(model, xyz, lambda s, p: calls.append(1) or want)
     assert calls == [1], "train-mode BatchNorm keeps the reference body"
+
+
+def test_graph_feature_matches_reference_fixture_and_gradients():
+    """DGCNN_Propagation.get_graph_feature (pointnet2_utils.py:392-442, row f4): forward bit-exact against the
+    fixture recorded from the unmodified reference; backward against autograd through the torch restatement."""
+    from oracle.inputs import digest
+    from ppt_b200 import ops, pointnet2
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_feature.npz"))
+    for tag in ("small", "partseg"):
+        coor_q, x_q, coor_k, x_k = (torch.from_numpy(f[tag + "." + n]).cuda() for n in ("coor_q", "x_q", "coor_k", "x_k"))
+        feat = pointnet2.get_graph_feature(coor_q, x_q, coor_k, x_k, 4)
+        assert feat.shape == (x_q.shape[0], 2 * x_q.shape[1], x_q.shape[2], 4) and feat.is_contiguous()
+        if tag == "small":
+            assert np.array_equal(feat.sort(-1)[0].cpu().numpy(), f["small.feature_sorted"])
+        else:
+            assert digest(feat.sort(-1)[0]) == str(f["partseg.feature_sorted_sha"])
+        self_feat = pointnet2.get_graph_feature(coor_q, x_q, coor_q, x_q, 4)
+        assert digest(self_feat.sort(-1)[0]) == str(f[tag + ".self_feature_sorted_sha"])
+    # same neighbour order as the (distance, index)-ordered kNN kernel: elementwise equal to the restatement on its idx
+    coor_q, x_q, coor_k, x_k = (torch.from_numpy(f["small." + n]) for n in ("coor_q", "x_q", "coor_k", "x_k"))
+    idx = ops.knn(4, coor_k.permute(0, 2, 1).contiguous().cuda(), coor_q.permute(0, 2, 1).contiguous().cuda())
+    xq, xk = x_q.clone().cuda().requires_grad_(True), x_k.clone().cuda().requires_grad_(True)
+    out = ops.graph_feature(xq, xk, idx)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    rq, rk = x_q.clone().requires_grad_(True), x_k.clone().requires_grad_(True)
+    B, C, Nq = rq.shape
+    ic = idx.cpu()
+    nb = torch.gather(rk.unsqueeze(2).expand(B, C, Nq, rk.shape[2]), 3, ic.unsqueeze(1).expand(B, C, Nq, 4))
+    ref = torch.cat((nb - rq.unsqueeze(-1), rq.unsqueeze(-1).expand(-1, -1, -1, 4)), dim=1)
+    assert torch.equal(out.detach().cpu(), ref.detach())
+    (ref * w.cpu()).sum().backward()
+    assert torch.allclose(xq.grad.cpu(), rq.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(xk.grad.cpu(), rk.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_loader_fps_drop_in_matches_reference_fixture():
+    """ppt_b200.data.farthest_point_sample == data/dataset_3d.py:40-61 (row f4), including the numpy RNG draw."""
+    from ppt_b200 import data
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loader_fps.npz"))
+    for tag in ("a", "b"):
+        point, npoint, seed = f[tag + ".point"], int(f[tag + ".npoint"]), int(f[tag + ".seed"])
+        np.random.seed(seed)
+        got = data.farthest_point_sample(point, npoint)             # draws np.random.randint(0, N) like the reference
+        assert got.dtype == np.float32 and np.array_equal(got, point[f[tag + ".indices"]])
+        idx = data.farthest_point_sample_indices(point, npoint, start=int(f[tag + ".start"]))
+        assert np.array_equal(idx, f[tag + ".indices"])
+    both = np.stack([f["a.point"][:3000, :3], f["b.point"][:3000, :3]])
+    bidx = data.farthest_point_sample_batch(both, 64, [int(f["a.start"]), 5])
+    assert np.array_equal(bidx[0], f["a.indices"][:64])
+    with pytest.raises(TypeError):
+        data.farthest_point_sample(f["a.point"].astype(np.float64), 8)

@@ -182,3 +182,31 @@ def test_train_mode_encoder_port_matches_reference(golden):
         ref = f["after." + k]
         assert np.abs(v.numpy() - ref).max() <= 1e-6 * np.abs(ref).max(), k
     assert int(f["after.first_conv.1.num_batches_tracked"]) == 1
+
+
+def test_graph_feature_port_matches_reference(golden):
+    """DGCNN_Propagation.get_graph_feature (row f4): neighbour order inside k is unspecified -> per-row sorted."""
+    from oracle.inputs import digest
+    f = golden("graph_feature")
+    for tag in ("small", "partseg"):
+        args = [torch.from_numpy(f[tag + "." + n]) for n in ("coor_q", "x_q", "coor_k", "x_k")]
+        feat, idx = torch_port.graph_feature(*args, 4)
+        if tag == "small":
+            assert np.array_equal(feat.sort(-1)[0].numpy(), f["small.feature_sorted"])
+            assert np.array_equal(idx.sort(-1)[0].numpy(), f["small.idx_sorted"])
+        else:
+            assert digest(feat.sort(-1)[0]) == str(f["partseg.feature_sorted_sha"])
+        self_feat, _ = torch_port.graph_feature(args[0], args[1], args[0], args[1], 4)
+        assert digest(self_feat.sort(-1)[0]) == str(f[tag + ".self_feature_sorted_sha"])
+
+
+def test_loader_fps_port_matches_reference(golden):
+    """data/dataset_3d.py:40-61 (row f4): the fixture was recorded by executing the reference function's own source."""
+    f = golden("loader_fps")
+    for tag in ("a", "b"):
+        idx = cpu.loader_fps_indices(f[tag + ".point"], int(f[tag + ".npoint"]), int(f[tag + ".start"]))
+        assert np.array_equal(idx, f[tag + ".indices"])
+        # and the C oracle's FPS (the kernels' checker) agrees with it: one semantics for all FPS copies (F13)
+        xyz = np.ascontiguousarray(f[tag + ".point"][None, :, :3])
+        c_idx = cpu.farthest_point_sample(xyz, int(f[tag + ".npoint"]), np.array([int(f[tag + ".start"])]))
+        assert np.array_equal(np.asarray(c_idx)[0], f[tag + ".indices"])
