@@ -27,6 +27,27 @@ graph_feature_kernel(const float* __restrict__ x_q, const float* __restrict__ x_
   out[((long long)b * 2 * C + C + c) * per_c + r] = xq;
 }
 
+// k == 4 (the part-seg head, point_encoder.py:303-304): one thread per (b, c, q), 16-byte loads of the four
+// indices' int64 pairs and 16-byte stores of both output halves.
+__global__ void __launch_bounds__(256)
+graph_feature_k4_kernel(const float* __restrict__ x_q, const float* __restrict__ x_k, const int64_t* __restrict__ idx,
+                        float* __restrict__ out, int C, int Nq, int Nk, long long total /* B*C*Nq */) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const long long bc = e / Nq;
+  const int q = (int)(e - bc * Nq);
+  const int b = (int)(bc / C), c = (int)(bc - (long long)b * C);
+  const longlong2* ip = reinterpret_cast<const longlong2*>(idx + ((long long)b * Nq + q) * 4);
+  const longlong2 i01 = __ldg(ip), i23 = __ldg(ip + 1);
+  const float xq = __ldg(x_q + e);
+  const float* row = x_k + bc * Nk;
+  const float4 d = make_float4(__fsub_rn(__ldg(row + i01.x), xq), __fsub_rn(__ldg(row + i01.y), xq),
+                               __fsub_rn(__ldg(row + i23.x), xq), __fsub_rn(__ldg(row + i23.y), xq));
+  const long long per_c = (long long)Nq * 4;
+  *reinterpret_cast<float4*>(out + ((long long)b * 2 * C + c) * per_c + (long long)q * 4) = d;
+  *reinterpret_cast<float4*>(out + ((long long)b * 2 * C + C + c) * per_c + (long long)q * 4) = make_float4(xq, xq, xq, xq);
+}
+
 // grad_xq[b,c,q] = sum_j (g[b,C+c,q,j] - g[b,c,q,j]);  grad_xk[b,c,idx[b,q,j]] += g[b,c,q,j]  (zero-filled by the caller)
 __global__ void __launch_bounds__(256)
 graph_feature_grad_kernel(const float* __restrict__ gout, const int64_t* __restrict__ idx, float* __restrict__ grad_xq,
@@ -56,6 +77,12 @@ extern "C" PPT_EXPORT int ppt_graph_feature(const float* x_q, const float* x_k, 
   if (!x_q || !x_k || !idx || !out || B < 1 || C < 1 || Nq < 1 || Nk < 1 || k < 1) return PPT_EINVAL;
   const long long total = (long long)B * C * Nq * k;
   if ((total + 255) / 256 > 0x7fffffffll) return PPT_ERANGE;
+  if (k == 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(idx) & 15) == 0) {
+    const long long t4 = total / 4;
+    graph_feature_k4_kernel<<<(unsigned)((t4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_q, x_k, idx, out, C, Nq,
+                                                                                           Nk, t4);
+    return ppt_launch_status();
+  }
   graph_feature_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_q, x_k, idx, out, C, Nq, Nk,
                                                                                          k, total);
   return ppt_launch_status();
