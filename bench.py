@@ -331,6 +331,43 @@ def run_ours(args):
             t0l = time.perf_counter()
             oracle_cpu.loader_fps_indices(lp, 1024, 0)
             loader_cpu_ms = (time.perf_counter() - t0l) * 1e3
+        # ---- widened row f1: set-abstraction level 2 of Pointnet2_Ssg at cfg 3 sizes (32 clouds, 512 points with
+        # 128-d features -> 128 centres, ball (0.4, 64), MLP 131 -> 128 -> 128 -> 256): fused tensor-core path vs the
+        # module's own Conv2d/BatchNorm2d stack (cuDNN fp32) on the same kernels' geometry ----
+        from ppt_b200 import pointnet2 as ppt_pn2
+        sa2 = ppt_pn2.PointNetSetAbstraction(128, 0.4, 64, 131, [128, 128, 256], False).to(dev).eval()
+        sa2.load_state_dict({k: v.to(dev) for k, v in torch_port.make_sa_state(131, [128, 128, 256], 11).items()},
+                            strict=False)
+        sa2.start_idx = 0
+        pn = torch.randn(32, 512, 3, device=dev)
+        sx = (pn / pn.norm(dim=-1, keepdim=True)).permute(0, 2, 1).contiguous()
+        sf = torch.randn(32, 128, 512, device=dev)
+
+        def time_sa(fused):
+            real = ops.sa_mlp_supported
+            if not fused:
+                ops.sa_mlp_supported = lambda *a: False
+            try:
+                with torch.no_grad():
+                    for _ in range(3):
+                        sa2(sx, sf)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(args.steps):
+                        sa2(sx, sf)
+                    b.record()
+                    torch.cuda.synchronize()
+            finally:
+                ops.sa_mlp_supported = real
+            return a.elapsed_time(b) / args.steps
+
+        sa_fused_ms, sa_torch_ms = time_sa(True), time_sa(False)
+        sa_flops = 2.0 * 32 * 128 * 64 * (131 * 128 + 128 * 128 + 128 * 256)
+        f1 = {"what": "PointNetSetAbstraction(128, 0.4, 64, 131, [128,128,256]) forward, 32 clouds x 512 points, eval: FPS + "
+                      "ball query + (gather -> fp16 operand images -> 3 tcgen05 layers -> max-pool) vs the same geometry "
+                      "+ ppt_group_concat + the module's Conv2d/BN2d/ReLU stack",
+              "fused_ms": sa_fused_ms, "torch_layers_ms": sa_torch_ms, "mlp_flops": sa_flops}
+
         f4 = {"graph_feature": {"shape": "B=32, C=384, 512 queries <- 256 keys, k=4", "bound": "hbm", "ms": gf_ms,
                                 "achieved": gf_bytes / (gf_ms * 1e-3) / 1e9, "unit": "GB/s",
                                 "bytes_per_launch": gf_bytes},
@@ -429,6 +466,7 @@ def run_ours(args):
         f4["graph_feature"]["peak"] = peaks["hbm_gbs"]
         f4["graph_feature"]["frac"] = f4["graph_feature"]["achieved"] / peaks["hbm_gbs"]
         widened["f4_part_seg_and_loader"] = f4
+        widened["f1_sa_shared_mlp"] = f1
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -132,6 +132,23 @@ int ppt_graph_feature(const float *x_q, const float *x_k, const int64_t *idx, fl
 int ppt_graph_feature_grad(const float *grad_out, const int64_t *idx, float *grad_xq, float *grad_xk,
                            int B, int C, int Nq, int Nk, int k, void *stream);
 
+/* ---- PointNet++ set-abstraction shared MLP + max-pool (tcgen05) --------------
+ * PointNetSetAbstraction[Msg].forward behind the grouping, eval mode (models/pointnet2/pointnet2_utils.py:196-201,
+ * 256-261): 3 x (Conv2d 1x1 + BatchNorm2d + ReLU) over [xyz - centre, features] of every (group, sample), then max
+ * over the nsample samples.  The gather / centre / concat is fused into the build of the first layer's operand
+ * images; activations between layers are fp16 operand images in `workspace`.
+ *   xyz [B,N,3], feats [B,N,D] (channel-last; NULL iff D == 0), new_xyz [B,S,3] (zeros for group_all),
+ *   idx [B,S,nsample] int64 (ppt_ball_query; arange for group_all), nsample in {16,32,64,128};
+ *   packed: ppt_b200/encoder_pack.py:pack_sa_mlp (BatchNorm folded, layer-1 columns in [features, xyz] order),
+ *   ppt_sa_mlp_packed_bytes(D + 3, c1, c2, c3) bytes (PPT_ERANGE if a layer has more than 512 input channels);
+ *   workspace: ppt_sa_mlp_workspace_bytes(B*S*nsample, D + 3, c1, c2, c3) bytes;
+ *   out [B, c3, S] f32 (channel-first, as the module returns it).  mode: PPT_ENC_FP16 or PPT_ENC_BF16. */
+int64_t ppt_sa_mlp_packed_bytes(int c0, int c1, int c2, int c3);
+int64_t ppt_sa_mlp_workspace_bytes(int64_t num_columns, int c0, int c1, int c2, int c3);
+int ppt_sa_mlp_forward(const float *xyz, const float *feats, const float *new_xyz, const int64_t *idx,
+                       const void *packed, void *workspace, float *out, int B, int N, int S, int nsample, int D,
+                       int c1, int c2, int c3, int mode, void *stream);
+
 /* ---- mini-PointNet patch Encoder + reduce_dim (tcgen05) ---------------------
  * Encoder.forward in eval mode, models/pointbert/dvae.py:201-215, followed by
  * reduce_dim, models/pointbert/point_encoder.py:133,239.

@@ -250,6 +250,41 @@ def gen_loader_fps(ns):
     print("loader fps fixtures", {k: (v.shape if hasattr(v, "shape") else v) for k, v in rec.items()})
 
 
+def gen_sa_mlp(ns):
+    """The unmodified reference PointNetSetAbstraction / ...Msg in eval mode with seeded weights (three-layer
+    shared MLPs as in models/pointnet2/pointnet2.py:11-13, 45-47): outputs for the fused tensor-core path (row f1)."""
+    rec = {}
+    # SSG level 2: 131 -> 128 -> 128 -> 256, ball (0.4, 64); 512 points with 128-d features, 128 centres
+    xyz = cloud("S", 1, 512, 4646)
+    feats = torch.randn(1, 512, 128, generator=torch.Generator().manual_seed(4646))
+    sa = ns.pn2.PointNetSetAbstraction(128, 0.4, 64, 128 + 3, [128, 128, 256], False).eval()
+    sa.load_state_dict(torch_port.make_sa_state(131, [128, 128, 256], 11), strict=False)
+    with refimport.fixed_fps_start(0), torch.no_grad():
+        nx, out = sa(xyz.permute(0, 2, 1), feats.permute(0, 2, 1))
+    rec.update({"ssg2.xyz": xyz.numpy(), "ssg2.feats": feats.numpy(), "ssg2.new_xyz": nx.numpy(), "ssg2.out": out.numpy()})
+    # SSG level 3 (group_all): 259 -> 256 -> 512 -> 1024 over 128 points
+    xyz3 = cloud("S", 2, 128, 4647)
+    feats3 = torch.randn(2, 128, 256, generator=torch.Generator().manual_seed(4647))
+    sa3 = ns.pn2.PointNetSetAbstraction(None, None, None, 256 + 3, [256, 512, 1024], True).eval()
+    sa3.load_state_dict(torch_port.make_sa_state(259, [256, 512, 1024], 12), strict=False)
+    with torch.no_grad():
+        _, out3 = sa3(xyz3.permute(0, 2, 1), feats3.permute(0, 2, 1))
+    rec.update({"ssg3.xyz": xyz3.numpy(), "ssg3.feats": feats3.numpy(), "ssg3.out": out3.numpy()})
+    # MSG level 1: xyz only, three radii / nsample 16, 32, 128, widths of pointnet2.py:45
+    xyzm = cloud("S", 2, 1024, 4648)
+    widths = [[32, 32, 64], [64, 64, 128], [64, 96, 128]]
+    msg = ns.pn2.PointNetSetAbstractionMsg(128, [0.1, 0.2, 0.4], [16, 32, 128], 0, widths).eval()
+    sd = {}
+    for j, w in enumerate(widths):
+        sd.update(torch_port.make_sa_state(3, w, 20 + j, "conv_blocks.%d." % j, "bn_blocks.%d." % j))
+    msg.load_state_dict(sd, strict=False)
+    with refimport.fixed_fps_start(0), torch.no_grad():
+        _, outm = msg(xyzm.permute(0, 2, 1), None)
+    rec.update({"msg1.xyz": xyzm.numpy(), "msg1.out": outm.numpy()})
+    np.savez_compressed(os.path.join(OUT, "sa_mlp.npz"), **rec)
+    print("sa_mlp fixtures", {k: v.shape for k, v in rec.items()})
+
+
 def gen_front_end(ns):
     """The unmodified reference PointTransformer (models/pointbert/point_encoder.py:111-256) up to the call of
     self.blocks: a forward pre-hook records the (x, pos) it is given (:241-249).  depth 1 keeps the unused
@@ -288,7 +323,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1:  # regenerate one fixture only: front_end | encoder_train
         {"front_end": gen_front_end, "encoder_train": gen_encoder_train, "graph_feature": gen_graph_feature,
-         "loader_fps": gen_loader_fps}[sys.argv[1]](refimport.load())
+         "loader_fps": gen_loader_fps, "sa_mlp": gen_sa_mlp}[sys.argv[1]](refimport.load())
         return
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     ns = refimport.load()
@@ -308,6 +343,7 @@ def main():
     gen_encoder_train(ns)
     gen_graph_feature(ns)
     gen_loader_fps(ns)
+    gen_sa_mlp(ns)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("fixtures total bytes", tot)
 

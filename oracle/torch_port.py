@@ -208,3 +208,33 @@ def graph_feature(coor_q, x_q, coor_k, x_k, k):
     nb = torch.gather(x_k.unsqueeze(2).expand(B, C, Nq, x_k.shape[2]), 3, idx.unsqueeze(1).expand(B, C, Nq, k))
     xq = x_q.unsqueeze(-1).expand(-1, -1, -1, k)
     return torch.cat((nb - xq, xq), dim=1), idx
+
+
+# ---- PointNet++ set-abstraction shared MLP (models/pointnet2/pointnet2_utils.py:161-266) ----------------------
+def make_sa_state(in_channel, mlp, seed, conv_prefix="mlp_convs.", bn_prefix="mlp_bns."):
+    """Seeded weights for one Conv2d(1x1)+BatchNorm2d stack with the reference's parameter names, including
+    non-trivial running statistics (fresh modules have mean 0 / var 1, which would hide folding mistakes)."""
+    g = torch.Generator().manual_seed(seed)
+    sd, last = {}, in_channel
+    for i, out in enumerate(mlp):
+        bound = last ** -0.5
+        sd["%s%d.weight" % (conv_prefix, i)] = (torch.rand(out, last, 1, 1, generator=g) * 2 - 1) * bound
+        sd["%s%d.bias" % (conv_prefix, i)] = (torch.rand(out, generator=g) * 2 - 1) * bound
+        sd["%s%d.weight" % (bn_prefix, i)] = torch.rand(out, generator=g) + 0.5
+        sd["%s%d.bias" % (bn_prefix, i)] = torch.randn(out, generator=g) * 0.1
+        sd["%s%d.running_mean" % (bn_prefix, i)] = torch.randn(out, generator=g) * 0.1
+        sd["%s%d.running_var" % (bn_prefix, i)] = torch.rand(out, generator=g) + 0.5
+        last = out
+    return sd
+
+
+def sa_mlp_max(grouped, sd, n_layers, conv_prefix="mlp_convs.", bn_prefix="mlp_bns.", eps=1e-5):
+    """grouped [B, S, K, C0] -> 3 x relu(bn_eval(conv1x1)) -> max over K -> [B, C3, S]  (:196-201 restated)."""
+    F = torch.nn.functional
+    x = grouped.permute(0, 3, 2, 1)
+    for i in range(n_layers):
+        x = F.conv2d(x, sd["%s%d.weight" % (conv_prefix, i)], sd["%s%d.bias" % (conv_prefix, i)])
+        x = F.batch_norm(x, sd["%s%d.running_mean" % (bn_prefix, i)], sd["%s%d.running_var" % (bn_prefix, i)],
+                         sd["%s%d.weight" % (bn_prefix, i)], sd["%s%d.bias" % (bn_prefix, i)], False, 0.1, eps)
+        x = F.relu(x)
+    return torch.max(x, 2)[0]

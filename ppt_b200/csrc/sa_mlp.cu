@@ -1,0 +1,317 @@
+// PointNet++ set-abstraction shared MLP + max-pool on tcgen05, sm_100a.
+//
+// Reference: PointNetSetAbstraction / PointNetSetAbstractionMsg.forward after the grouping,
+// models/pointnet2/pointnet2_utils.py:196-201, 256-261 (eval mode):
+//     new_points [B, C0, nsample, S]  ->  3 x (Conv2d 1x1 + BatchNorm2d + ReLU)  ->  max over nsample  ->  [B, C3, S]
+// Here (BatchNorm folded on the host, ppt_b200/encoder_pack.py:pack_sa_mlp):
+//   sa_gather_image_kernel     the ball-query gather + centre subtraction + concat writes the fp16 K-major operand
+//                              images of layer 1 directly: the fp32 [B, S, nsample, C0] tensor never exists;
+//   pointwise_linear_kernel    one layer = relu(W' act + b') on the tensor core, tile = 128 (group, sample) columns,
+//                              weights streamed through a 4 x 16 KB mbarrier ring (the group_linear pipeline of
+//                              encoder.cu); layers 1, 2 store their output as the next layer's operand images
+//                              (fp16, half the bytes of the reference's fp32 activations), the last layer max-pools
+//                              over each group's nsample accumulator columns in registers and stores [B, C3, S].
+// Activations between layers round-trip through HBM (as fp16): this is the tensor-core version of the module, not
+// yet the single-kernel fusion -- the layers are HBM-bound, see DESIGN.md section 9.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace {
+
+using namespace tc05;
+
+constexpr uint32_t IMG = 16384;   // one operand image: 128 rows x 64 K x 2 bytes, K-major, 128-byte swizzle
+constexpr int SA_THREADS = 192;   // producer, MMA issuer, 4 epilogue warps
+constexpr int SA_EPI = 128;
+constexpr int SA_NSTAGE = 4;
+constexpr int SA_MAX_KC = 8;      // <= 512 input channels per layer
+
+// ---- grouping -> layer-1 operand images ---------------------------------------------------------------
+// Column = one (b, s, j) neighbour; channel order [features (D) | xyz - centre (3) | zero padding] (the weight
+// columns are permuted to match on the host, so the SSG [xyz, feats] and MSG [feats, xyz] orders share it).
+template <uint32_t FMT>
+__global__ void __launch_bounds__(256)
+sa_gather_image_kernel(const float* __restrict__ xyz, const float* __restrict__ feats,
+                       const float* __restrict__ new_xyz, const int64_t* __restrict__ idx,
+                       unsigned char* __restrict__ img, int N, int S, int ns, int D, int KC, long long total) {
+  const int r = threadIdx.x & 127, hh = threadIdx.x >> 7;
+  const long long tiles = (total + 127) / 128;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long col = tile * 128 + r;
+    const bool ok = col < total;
+    long long n = 0;
+    int b = 0;
+    float cx = 0.f, cy = 0.f, cz = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+    if (ok) {
+      const long long g = col / ns;  // b * S + s
+      b = (int)(g / S);
+      n = __ldg(idx + col);
+      n = n < 0 ? 0 : (n >= N ? N - 1 : n);  // ball query never returns its "nothing in range" sentinel for centres of the cloud
+      const float* c = new_xyz + g * 3;
+      const float* p = xyz + ((long long)b * N + n) * 3;
+      cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
+      px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+    }
+    const float rel[3] = {__fsub_rn(px, cx), __fsub_rn(py, cy), __fsub_rn(pz, cz)};
+    const float* frow = feats ? feats + ((long long)b * N + n) * D : nullptr;
+    unsigned char* base = img + (size_t)tile * KC * IMG;
+    for (int c8 = hh * 8; c8 < KC * 64; c8 += 16) {
+      float v[8];
+      if (ok && frow && c8 + 8 <= D && (D & 3) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(frow + c8));
+        const float4 e = __ldg(reinterpret_cast<const float4*>(frow + c8 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = e.x; v[5] = e.y; v[6] = e.z; v[7] = e.w;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int c = c8 + t;
+          v[t] = !ok ? 0.f : (c < D ? __ldg(frow + c) : (c < D + 3 ? rel[c - D] : 0.f));
+        }
+      }
+      uint4 w;
+      w.x = pack2<FMT, false>(v[0], v[1]); w.y = pack2<FMT, false>(v[2], v[3]);
+      w.z = pack2<FMT, false>(v[4], v[5]); w.w = pack2<FMT, false>(v[6], v[7]);
+      *reinterpret_cast<uint4*>(base + (size_t)(c8 >> 6) * IMG + sw128_kmajor_off(r, c8 & 63)) = w;
+    }
+  }
+}
+
+// ---- one layer ---------------------------------------------------------------------------------------------
+// out = relu(W act + bias); act as operand images [tile][KC][16 KB]; W as images [U][KC][16 KB] (rows padded to
+// 128 U with zeros, K padded to 64 KC).  POOL = false: store as the next layer's images [tile][2 U][16 KB];
+// POOL = true: max over each group's `ns` columns (ns in {16, 32, 64, 128}), out [B, c_out, S] fp32.
+template <uint32_t FMT, bool POOL>
+__global__ void __launch_bounds__(SA_THREADS, 1)
+pointwise_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned char* __restrict__ wimg,
+                        const float* __restrict__ bias, unsigned char* __restrict__ out_img, float* __restrict__ out,
+                        int KC, int U, int c_out, int ns, int S, long long num_groups, long long total_cols,
+                        int num_tiles) {
+  constexpr int NT = 128;
+  constexpr int TCOLS = 2 * NT;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* bbuf = smem;                         // [KC][16 KB] activations of the tile
+  unsigned char* ring = bbuf + (size_t)KC * IMG;      // [SA_NSTAGE][16 KB] weights
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + SA_NSTAGE * IMG);
+  uint64_t* full = bars;
+  uint64_t* empty = full + SA_NSTAGE;
+  uint64_t* acc_full = empty + SA_NSTAGE;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* b_full = acc_empty + 2;
+  uint64_t* b_empty = b_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < SA_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], SA_EPI); }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, tile_it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        mbar_wait_relaxed(b_empty, (tile_it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(b_full, (uint32_t)KC * IMG);
+        for (int kc = 0; kc < KC; ++kc)
+          bulk_g2s(bbuf + (size_t)kc * IMG, act_img + ((size_t)tile * KC + kc) * IMG, IMG, b_full);
+        for (int u = 0; u < U; ++u)
+          for (int kc = 0; kc < KC; ++kc, ++it) {
+            const uint32_t s = it % SA_NSTAGE;
+            mbar_wait_relaxed(&empty[s], ((it / SA_NSTAGE) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&full[s], IMG);
+            bulk_g2s(ring + s * IMG, wimg + ((size_t)u * KC + kc) * IMG, IMG, &full[s]);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(FMT, 128, NT, 0);
+    constexpr uint32_t HI = sdesc_hi(1024u);
+    const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u), b_lo0 = sdesc_lo(smem_u32(bbuf), 16u);
+    uint32_t it = 0, tile_it = 0, unit_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      mbar_wait(b_full, tile_it & 1u);
+      for (int u = 0; u < U; ++u, ++unit_it) {
+        const uint32_t buf = unit_it & 1u;
+        mbar_wait(&acc_empty[buf], ((unit_it >> 1) & 1u) ^ 1u);
+        fence_after_sync();
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const uint32_t s = it % SA_NSTAGE;
+          mbar_wait(&full[s], (it / SA_NSTAGE) & 1u);
+          fence_after_sync();
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16)
+            umma_f16_elect(tbase + buf * NT, sdesc_join(a_lo0 + s * (IMG >> 4) + (uint32_t)k16 * 2u, HI),
+                           sdesc_join(b_lo0 + (uint32_t)kc * (IMG >> 4) + (uint32_t)k16 * 2u, HI), idesc,
+                           (kc == 0 && k16 == 0) ? 0u : 1u);
+          umma_commit_elect(&empty[s]);
+        }
+        umma_commit_elect(&acc_full[buf]);
+        if (u == U - 1) umma_commit_elect(b_empty);  // every MMA that reads this tile's activations is complete
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    uint32_t unit_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int u = 0; u < U; ++u, ++unit_it) {
+        const uint32_t buf = unit_it & 1u;
+        const int o = u * 128 + m;
+        const float bo = __ldg(bias + o);
+        mbar_wait(&acc_full[buf], (unit_it >> 1) & 1u);
+        fence_after_sync();
+        const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + buf * NT;
+        float run = 0.f;  // POOL: running max of the current group (values are >= 0 after the ReLU)
+#pragma unroll 1
+        for (int j = 0; j < NT / 32; ++j) {
+          float v[32];
+          tmem_ld32(t_addr + j * 32, v);
+          const long long col0 = (long long)tile * NT + j * 32;
+          if (!POOL) {
+            unsigned char* dst = out_img + ((size_t)tile * (2 * U) + (size_t)(o >> 6)) * IMG;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              *reinterpret_cast<uint16_t*>(dst + sw128_kmajor_off(j * 32 + i, o & 63)) =
+                  to_operand<FMT>(fmaxf(v[i] + bo, 0.f));
+          } else {
+            // relu(max(x) + b) == max(relu(x + b)): pool first, one bias add per group
+            if (ns == 16) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float mx = v[16 * h];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[16 * h + i]);
+                const long long g = (col0 + 16 * h) / 16;
+                if (g < num_groups && o < c_out) out[((g / S) * c_out + o) * S + g % S] = fmaxf(mx + bo, 0.f);
+              }
+            } else {
+              float mx = v[0];
+#pragma unroll
+              for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+              const int per = ns / 32;  // 32-column chunks per group: 1, 2 or 4
+              run = (j % per) == 0 ? mx : fmaxf(run, mx);
+              if ((j % per) == per - 1) {
+                const long long g = col0 / ns;
+                if (g < num_groups && o < c_out) out[((g / S) * c_out + o) * S + g % S] = fmaxf(run + bo, 0.f);
+              }
+            }
+          }
+        }
+        fence_before_sync();
+        mbar_arrive(&acc_empty[buf]);
+      }
+    }
+    (void)total_cols;
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TCOLS>(tbase);
+}
+
+int num_sms_sa() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+struct SaDims {
+  int kc0, u1, u2, u3;  // K chunks of the input, 128-row units of the three layers
+  __host__ SaDims(int c0, int c1, int c2, int c3)
+      : kc0((c0 + 63) / 64), u1((c1 + 127) / 128), u2((c2 + 127) / 128), u3((c3 + 127) / 128) {}
+  // blob: fp32 biases [128 (u1 + u2 + u3)] padded to 1 KB, then W1 [u1][kc0], W2 [u2][2 u1], W3 [u3][2 u2] images
+  size_t bias_bytes() const { return (((size_t)(u1 + u2 + u3) * 128 * 4) + 1023) & ~(size_t)1023; }
+  size_t w1() const { return bias_bytes(); }
+  size_t w2() const { return w1() + (size_t)u1 * kc0 * IMG; }
+  size_t w3() const { return w2() + (size_t)u2 * 2 * u1 * IMG; }
+  size_t total() const { return w3() + (size_t)u3 * 2 * u2 * IMG; }
+  bool ok() const { return kc0 <= SA_MAX_KC && 2 * u1 <= SA_MAX_KC && 2 * u2 <= SA_MAX_KC && u3 <= 8; }
+  // workspace: the three activation image sets
+  size_t ws0(long long tiles) const { (void)tiles; return 0; }
+  size_t ws1(long long tiles) const { return (size_t)tiles * kc0 * IMG; }
+  size_t ws2(long long tiles) const { return ws1(tiles) + (size_t)tiles * 2 * u1 * IMG; }
+  size_t ws_total(long long tiles) const { return ws2(tiles) + (size_t)tiles * 2 * u2 * IMG; }
+};
+
+template <uint32_t FMT>
+int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
+               const unsigned char* blob, unsigned char* ws, float* out, int B, int N, int S, int ns, int D,
+               const SaDims& d, int c3, cudaStream_t st) {
+  const long long groups = (long long)B * S, total = groups * ns;
+  const long long tiles_ll = (total + 127) / 128;
+  if (tiles_ll > 0x7fffffffll) return PPT_ERANGE;
+  const int tiles = (int)tiles_ll;
+  auto kl = pointwise_linear_kernel<FMT, false>;
+  auto kp = pointwise_linear_kernel<FMT, true>;
+  const size_t smem_max = (size_t)SA_MAX_KC * IMG + SA_NSTAGE * IMG + 256;
+  static bool configured = false;
+  if (!configured) {
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    configured = true;
+  }
+  const int sms = num_sms_sa();
+  const int grid = tiles < sms ? tiles : sms;
+  const float* bias = reinterpret_cast<const float*>(blob);
+  sa_gather_image_kernel<FMT><<<tiles < 8 * sms ? tiles : 8 * sms, 256, 0, st>>>(xyz, feats, new_xyz, idx, ws + d.ws0(tiles),
+                                                                               N, S, ns, D, d.kc0, total);
+  auto smem = [](int kc) { return (size_t)kc * IMG + SA_NSTAGE * IMG + 256; };
+  kl<<<grid, SA_THREADS, smem(d.kc0), st>>>(ws + d.ws0(tiles), blob + d.w1(), bias, ws + d.ws1(tiles), nullptr, d.kc0,
+                                            d.u1, 0, ns, S, groups, total, tiles);
+  kl<<<grid, SA_THREADS, smem(2 * d.u1), st>>>(ws + d.ws1(tiles), blob + d.w2(), bias + d.u1 * 128, ws + d.ws2(tiles),
+                                               nullptr, 2 * d.u1, d.u2, 0, ns, S, groups, total, tiles);
+  kp<<<grid, SA_THREADS, smem(2 * d.u2), st>>>(ws + d.ws2(tiles), blob + d.w3(), bias + (d.u1 + d.u2) * 128, nullptr,
+                                               out, 2 * d.u2, d.u3, c3, ns, S, groups, total, tiles);
+  return ppt_launch_status();
+}
+
+}  // namespace
+
+extern "C" PPT_EXPORT int64_t ppt_sa_mlp_packed_bytes(int c0, int c1, int c2, int c3) {
+  if (c0 < 1 || c1 < 1 || c2 < 1 || c3 < 1) return PPT_EINVAL;
+  const SaDims d(c0, c1, c2, c3);
+  return d.ok() ? (int64_t)d.total() : PPT_ERANGE;
+}
+
+extern "C" PPT_EXPORT int64_t ppt_sa_mlp_workspace_bytes(int64_t num_columns, int c0, int c1, int c2, int c3) {
+  if (num_columns < 1 || c0 < 1 || c1 < 1 || c2 < 1 || c3 < 1) return PPT_EINVAL;
+  const SaDims d(c0, c1, c2, c3);
+  return d.ok() ? (int64_t)d.ws_total((num_columns + 127) / 128) : PPT_ERANGE;
+}
+
+extern "C" PPT_EXPORT int ppt_sa_mlp_forward(const float* xyz, const float* feats, const float* new_xyz,
+                                             const int64_t* idx, const void* packed, void* workspace, float* out,
+                                             int B, int N, int S, int nsample, int D, int c1, int c2, int c3, int mode,
+                                             void* stream) {
+  if (!xyz || !new_xyz || !idx || !packed || !workspace || !out || B < 1 || N < 1 || S < 1 || D < 0) return PPT_EINVAL;
+  if (D > 0 && !feats) return PPT_EINVAL;
+  if (nsample != 16 && nsample != 32 && nsample != 64 && nsample != 128) return PPT_ERANGE;
+  if ((reinterpret_cast<uintptr_t>(packed) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PPT_EINVAL;
+  const SaDims d(D + 3, c1, c2, c3);
+  if (c1 < 1 || c2 < 1 || c3 < 1 || !d.ok()) return PPT_ERANGE;
+  const unsigned char* blob = static_cast<const unsigned char*>(packed);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  if (mode == PPT_ENC_FP16)
+    return run_sa_mlp<tc05::FMT_F16>(xyz, D > 0 ? feats : nullptr, new_xyz, idx, blob, ws, out, B, N, S, nsample, D, d, c3,
+                                     (cudaStream_t)stream);
+  if (mode == PPT_ENC_BF16)
+    return run_sa_mlp<tc05::FMT_BF16>(xyz, D > 0 ? feats : nullptr, new_xyz, idx, blob, ws, out, B, N, S, nsample, D, d,
+                                      c3, (cudaStream_t)stream);
+  return PPT_EINVAL;
+}

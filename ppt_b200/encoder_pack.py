@@ -202,3 +202,51 @@ def pack_encoder_train(sd, mode):
         ident[conv + ".running_mean"] = torch.zeros(c, dtype=ref.dtype)
         ident[conv + ".running_var"] = torch.full((c,), 1.0 - 1e-5, dtype=torch.float64)  # fold(): var + eps == 1
     return pack_encoder(ident, mode)
+
+
+# ---- PointNet++ set-abstraction shared MLP (models/pointnet2/pointnet2_utils.py:166-172, 213-226) ---------------
+def fold_conv_bn(conv_w, conv_b, bn_w, bn_b, bn_mean, bn_var, eps):
+    """Conv (1x1) followed by eval-mode BatchNorm as one affine map: W' [Cout, Cin], b' [Cout] (fp64)."""
+    w = conv_w.detach().to(torch.float64).cpu().reshape(conv_w.shape[0], -1)
+    s = bn_w.detach().to(torch.float64).cpu() / torch.sqrt(bn_var.detach().to(torch.float64).cpu() + eps)
+    b = conv_b.detach().to(torch.float64).cpu() if conv_b is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    return w * s[:, None], (b - bn_mean.detach().to(torch.float64).cpu()) * s + bn_b.detach().to(torch.float64).cpu()
+
+
+def sa_mlp_packed_bytes(c0, c1, c2, c3):
+    kc0, u1, u2, u3 = (c0 + 63) // 64, (c1 + 127) // 128, (c2 + 127) // 128, (c3 + 127) // 128
+    bias = ((u1 + u2 + u3) * 128 * 4 + 1023) // 1024 * 1024
+    return bias + (u1 * kc0 + u2 * 2 * u1 + u3 * 2 * u2) * IMAGE_BYTES
+
+
+def pack_sa_mlp(convs, bns, xyz_first, mode):
+    """Three Conv2d(1x1) + BatchNorm2d pairs (eval mode) -> uint8 CPU blob for ppt_sa_mlp_forward.
+    xyz_first: the module concatenates [xyz, features] (PointNetSetAbstraction, sample_and_group) rather than
+    [features, xyz] (PointNetSetAbstractionMsg); the kernel's order is [features, xyz], so layer 1's columns move."""
+    if len(convs) != 3 or mode not in (ENC_FP16, ENC_BF16):
+        raise ValueError("fused SA MLP: exactly three layers, fp16 or bf16 operands")
+    dtype = operand_dtype(mode)
+    folded = [fold_conv_bn(c.weight, c.bias, b.weight, b.bias, b.running_mean, b.running_var, b.eps)
+              for c, b in zip(convs, bns)]
+    w1 = folded[0][0]
+    if xyz_first:
+        w1 = torch.cat([w1[:, 3:], w1[:, :3]], dim=1)
+    ws = [w1, folded[1][0], folded[2][0]]
+    c0, c1, c2, c3 = w1.shape[1], w1.shape[0], ws[1].shape[0], ws[2].shape[0]
+    if ws[1].shape[1] != c1 or ws[2].shape[1] != c2:
+        raise ValueError("layer shapes do not chain")
+    u = [(c + 127) // 128 for c in (c1, c2, c3)]
+    kin = [(c0 + 63) // 64 * 64, 2 * u[0] * 64, 2 * u[1] * 64]
+    bias = torch.zeros(sum(u) * 128, dtype=torch.float32)
+    parts, off = [], 0
+    for l in range(3):
+        wp = torch.zeros(u[l] * 128, kin[l], dtype=torch.float32)
+        wp[: ws[l].shape[0], : ws[l].shape[1]] = ws[l].to(torch.float32)
+        parts.append(pack_kmajor(wp, dtype, 1))
+        bias[off: off + ws[l].shape[0]] = folded[l][1].to(torch.float32)
+        off += u[l] * 128
+    head = torch.zeros((bias.numel() * 4 + 1023) // 1024 * 1024, dtype=torch.uint8)
+    head[: bias.numel() * 4] = bias.view(torch.uint8)
+    blob = torch.cat([head] + parts)
+    assert blob.numel() == sa_mlp_packed_bytes(c0, c1, c2, c3), (blob.numel(), sa_mlp_packed_bytes(c0, c1, c2, c3))
+    return blob, (c0, c1, c2, c3)

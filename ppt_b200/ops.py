@@ -259,6 +259,37 @@ def graph_feature(x_q, x_k, idx):
     return _graph_feature_fwd(x_q, x_k, idx)
 
 
+def sa_mlp_supported(c0, c1, c2, c3, nsample):
+    """Whether ppt_sa_mlp_forward covers this layer stack (<= 512 input channels per layer, nsample 16/32/64/128)."""
+    return nsample in (16, 32, 64, 128) and _lib.load().ppt_sa_mlp_packed_bytes(c0, c1, c2, c3) > 0
+
+
+def sa_mlp_forward(xyz, feats, new_xyz, idx, packed, dims, mode=ENC_FP16):
+    """Grouping gather + 3 x (Conv 1x1 + BN + ReLU) + max over nsample of a PointNet++ set-abstraction level
+    (models/pointnet2/pointnet2_utils.py:196-201, 256-261; eval mode).  xyz [B,N,3], feats [B,N,D] or None,
+    new_xyz [B,S,3], idx [B,S,nsample] int64; `packed`, `dims` from encoder_pack.pack_sa_mlp -> [B, c3, S]."""
+    _need_cuda(xyz, new_xyz, idx, packed)
+    xyz, new_xyz, idx = _f32(xyz), _f32(new_xyz), _i64(idx)
+    B, N, _ = xyz.shape
+    S, ns = idx.shape[1], idx.shape[2]
+    c0, c1, c2, c3 = dims
+    D = c0 - 3
+    if D > 0:
+        feats = _f32(feats)
+        if tuple(feats.shape) != (B, N, D):
+            raise ValueError("feats must be [B, N, %d]" % D)
+    lib = _lib.load()
+    if packed.dtype != torch.uint8 or packed.numel() != lib.ppt_sa_mlp_packed_bytes(c0, c1, c2, c3):
+        raise ValueError("packed SA-MLP blob does not match its dims")
+    out = torch.empty((B, c3, S), dtype=torch.float32, device=xyz.device)
+    ws = _workspace((xyz.device, "sa_mlp"), lib.ppt_sa_mlp_workspace_bytes(B * S * ns, c0, c1, c2, c3))
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.ppt_sa_mlp_forward(_ptr(xyz), _ptr(feats) if D > 0 else None, _ptr(new_xyz), _ptr(idx), _ptr(packed),
+                                          _ptr(ws), _ptr(out), B, N, S, ns, D, c1, c2, c3, mode, _stream(xyz)),
+                   "ppt_sa_mlp_forward")
+    return out
+
+
 def selftest_umma(a, b, mode=ENC_FP16, b_mn_major=False, a_packed=None):
     """D[128,N] = A[128,K] @ B[N,K]^T through the Encoder's tcgen05 building blocks."""
     _need_cuda(a, b)

@@ -208,6 +208,18 @@ def patch_reference(modules=None):
                     return _o(self, coor_q, x_q, coor_k, x_k)
 
                 _set(dg, "get_graph_feature", graph_fwd)
+            ssg = getattr(mod, "PointNetSetAbstraction", None)
+            if ssg is not None:
+                orig_s = ssg.forward
+
+                def ssg_fwd(self, xyz, points, _o=orig_s):
+                    if xyz.is_cuda:
+                        if not hasattr(self, "start_idx"):
+                            self.start_idx = None
+                        return pointnet2.PointNetSetAbstraction.forward(self, xyz, points)  # fused shared MLP in eval
+                    return _o(self, xyz, points)
+
+                _set(ssg, "forward", ssg_fwd)
             msg = getattr(mod, "PointNetSetAbstractionMsg", None)
             if msg is not None:
                 orig_m = msg.forward

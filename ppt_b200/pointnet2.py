@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import encoder_pack, ops
 from .pointbert import _as_start, index_points, knn_point, square_distance  # noqa: F401  (same functions)
 
 
@@ -52,6 +52,33 @@ def sample_and_group_all(xyz, points):
     return new_xyz, grouped_xyz
 
 
+def _fused_mlp_max(owner, key, xyz, points, new_xyz, idx, convs, bns, xyz_first):
+    """The shared MLP + max-pool of a set-abstraction level on the tensor cores (ops.sa_mlp_forward), gather fused.
+    Returns None when the fused path does not apply (train-mode BatchNorm, gradients needed, unsupported widths):
+    the caller then runs the reference's own layer stack."""
+    if owner.training or len(convs) != 3 or not xyz.is_cuda:
+        return None
+    params = [p for m in list(convs) + list(bns) for p in m.parameters()]
+    if torch.is_grad_enabled() and (xyz.requires_grad or (points is not None and points.requires_grad)
+                                    or any(p.requires_grad for p in params)):
+        return None
+    c0 = 3 + (0 if points is None else points.shape[-1])
+    widths = [c.out_channels for c in convs]
+    if convs[0].in_channels != c0 or not ops.sa_mlp_supported(c0, *widths, idx.shape[2]):
+        return None
+    mode = ops.ENC_MODES[getattr(owner, "ppt_precision", "fp16")]
+    if mode not in (ops.ENC_FP16, ops.ENC_BF16):
+        return None
+    tensors = params + [b for m in bns for b in m.buffers()]
+    ckey = (mode, str(xyz.device)) + tuple((t.data_ptr(), t._version) for t in tensors)
+    cache = owner.__dict__.setdefault("_ppt_sa_cache", {})
+    if key not in cache or cache[key][0] != ckey:
+        blob, dims = encoder_pack.pack_sa_mlp(convs, bns, xyz_first, mode)
+        cache[key] = (ckey, blob.to(xyz.device), dims)
+    _, blob, dims = cache[key]
+    return ops.sa_mlp_forward(xyz, points, new_xyz, idx, blob, dims, mode=mode)
+
+
 def _shared_mlp_max(new_points, convs, bns):
     # [B, S, K, C] -> [B, C, K, S] -> Conv2d/BN/ReLU stack -> max over K  (:196-201)
     x = new_points.permute(0, 3, 2, 1)
@@ -82,12 +109,20 @@ class PointNetSetAbstraction(nn.Module):
         xyz = xyz.permute(0, 2, 1).contiguous()
         if points is not None:
             points = points.permute(0, 2, 1).contiguous()
+        # eval mode: FPS / ball query, then gather + shared MLP + max-pool as one tensor-core pipeline (row f1)
         if self.group_all:
-            new_xyz, new_points = sample_and_group_all(xyz, points)
+            new_xyz = torch.zeros(xyz.shape[0], 1, 3, device=xyz.device)
+            idx = torch.arange(xyz.shape[1], device=xyz.device).view(1, 1, -1).expand(xyz.shape[0], 1, -1).contiguous()
         else:
-            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points,
-                                                   start_idx=self.start_idx)
-        new_points = _shared_mlp_max(new_points, self.mlp_convs, self.mlp_bns)
+            new_xyz = ops.gather(xyz, farthest_point_sample(xyz, self.npoint, self.start_idx))
+            idx = ops.ball_query(self.radius, self.nsample, xyz, new_xyz)
+        new_points = _fused_mlp_max(self, 0, xyz, points, new_xyz, idx, self.mlp_convs, self.mlp_bns, xyz_first=True)
+        if new_points is None:
+            if self.group_all:
+                new_xyz, grouped = sample_and_group_all(xyz, points)
+            else:
+                grouped = ops.group_concat(xyz, new_xyz, points, idx, xyz_first=True)
+            new_points = _shared_mlp_max(grouped, self.mlp_convs, self.mlp_bns)
         if self.remove_last:
             return new_points
         return new_xyz.permute(0, 2, 1), new_points
@@ -121,8 +156,12 @@ class PointNetSetAbstractionMsg(nn.Module):
         outs = []
         for i, radius in enumerate(self.radius_list):
             idx = ops.ball_query(radius, self.nsample_list[i], xyz, new_xyz)
-            grouped = ops.group_concat(xyz, new_xyz, points, idx, xyz_first=False)
-            outs.append(_shared_mlp_max(grouped, self.conv_blocks[i], self.bn_blocks[i]))
+            out = _fused_mlp_max(self, i, xyz, points, new_xyz, idx, self.conv_blocks[i], self.bn_blocks[i],
+                                 xyz_first=False)
+            if out is None:
+                grouped = ops.group_concat(xyz, new_xyz, points, idx, xyz_first=False)
+                out = _shared_mlp_max(grouped, self.conv_blocks[i], self.bn_blocks[i])
+            outs.append(out)
         return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=1)
 
 

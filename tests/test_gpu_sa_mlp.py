@@ -1,0 +1,31 @@
+"""Set-abstraction shared MLP + max-pool on the tensor cores: the modules of
+ppt_b200.pointnet2 in eval mode against outputs recorded from the unmodified reference modules
+(models/pointnet2/pointnet2_utils.py:161-266) with the same seeded weights.  Child process: a pipeline bug can at
+worst kill the child."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CHILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_sa_mlp_child.py")
+TOL = {"fp16": 2e-3, "bf16": 1.5e-2}  # three chained layers with 16-bit operands, norm-relative
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", ["ssg2", "ssg3", "msg1"])
+def test_sa_mlp_modules(case, precision):
+    try:
+        out = subprocess.run([sys.executable, CHILD, case, precision], capture_output=True, text=True, timeout=300)
+    except subprocess.TimeoutExpired:
+        pytest.fail("sa_mlp child hung (killed after 300 s)")
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["fused"], "the tensor-core path must have run"
+    assert r["finite"] and r["geometry_equal"], r
+    assert r["max"] <= TOL[precision] and r["rms"] <= TOL[precision], r
+    assert r["unfused_max"] <= 1e-4, r          # the torch layer stack on the same kernels' geometry
+    assert r["train_mode_unfused"], r

@@ -210,3 +210,21 @@ def test_loader_fps_port_matches_reference(golden):
         xyz = np.ascontiguousarray(f[tag + ".point"][None, :, :3])
         c_idx = cpu.farthest_point_sample(xyz, int(f[tag + ".npoint"]), np.array([int(f[tag + ".start"])]))
         assert np.array_equal(np.asarray(c_idx)[0], f[tag + ".indices"])
+
+
+def test_sa_mlp_port_matches_reference(golden):
+    """Set-abstraction shared MLP + max-pool (row f1) of the unmodified reference modules in eval mode."""
+    f = golden("sa_mlp")
+    # SSG level 2 through the oracle's geometry + the restated layer stack
+    xyz, feats = f["ssg2.xyz"], f["ssg2.feats"]
+    fi = cpu.farthest_point_sample(xyz, 128, 0)
+    c = cpu.index_points(xyz, fi)
+    b = cpu.query_ball_point(0.4, 64, xyz, c)
+    grouped = np.concatenate([cpu.group_center(xyz, b, c), cpu.index_points(feats, b)], -1)
+    out = torch_port.sa_mlp_max(torch.from_numpy(grouped), torch_port.make_sa_state(131, [128, 128, 256], 11), 3)
+    assert np.array_equal(np.transpose(c, (0, 2, 1)), f["ssg2.new_xyz"])
+    assert np.abs(out.numpy() - f["ssg2.out"]).max() <= 1e-5 * np.abs(f["ssg2.out"]).max()
+    # group_all
+    g3 = np.concatenate([f["ssg3.xyz"], f["ssg3.feats"]], -1)[:, None]
+    out3 = torch_port.sa_mlp_max(torch.from_numpy(g3), torch_port.make_sa_state(259, [256, 512, 1024], 12), 3)
+    assert np.abs(out3.numpy() - f["ssg3.out"]).max() <= 1e-5 * np.abs(f["ssg3.out"]).max()
