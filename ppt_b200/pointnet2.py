@@ -1,10 +1,11 @@
 """Drop-in counterparts of models/pointnet2/pointnet2_utils.py (and the copy in
 models/pointbert/pointnet2_utils.py) of the reference tree.
 
-The geometry (FPS, ball query, grouping, three_nn / three_interpolate) runs in the sm_100a
-kernels; the shared MLPs of the set-abstraction / feature-propagation modules stay the
-module's own Conv/BatchNorm layers (SURVEY.md section 8f lists fusing them as the next
-step), so state dicts and outputs keep the reference's layout: channel-first in, channel-first out.
+The geometry (FPS, ball query, grouping, three_nn / three_interpolate, DGCNN edge features) runs in the
+sm_100a kernels.  The shared MLP + max-pool of the set-abstraction modules runs on the tensor cores in eval mode
+(ops.sa_mlp_forward) and falls back to the module's own Conv/BatchNorm layers in train
+mode or when a gradient is needed; the feature-propagation MLPs stay torch layers.  State dicts and outputs keep
+the reference's layout: channel-first in, channel-first out.
 """
 import torch
 import torch.nn as nn
