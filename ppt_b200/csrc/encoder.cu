@@ -332,9 +332,8 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 
     float cnext[4][GH];
     auto load_c = [&](int tile) {
-      if (STAGE != 2) return;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < (STAGE == 2 ? 4 : 0); ++u)
 #pragma unroll
         for (int jj = 0; jj < GH; ++jj) {
           const long long g = (long long)tile * GPT + half * GH + jj;
@@ -497,7 +496,6 @@ template <uint32_t FMT, int SPLIT, int NT, int EPW>
 __global__ void __launch_bounds__((EPW + 2) * 32, 1)
 encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
                          unsigned char* __restrict__ out_img, long long num_groups, int num_tiles) {
-  constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int GPT = NT / 32;
   constexpr int EPI_THREADS = EPW * 32;
   constexpr int CPW = NT / (EPW / 4);
@@ -733,12 +731,6 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
 // stay compile-time constants.
 // Warp roles per CTA: 0 weight producer, 1 issuer of the P items (leader) / ring-stage forwarder (peer),
 // 2-9 epilogue, 10 issuer of the G items (leader only).
-__device__ __forceinline__ float warp_max_f32(float v) {
-  float r;
-  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-  return r;
-}
-
 // Item i of the per-iteration schedule: 0..3 = W32 unit v (current tile), 4 + c = W4 chunk c (c >= 4: of the
 // previous tile).
 __host__ __device__ constexpr int pair_sched(int i) {
@@ -961,7 +953,6 @@ encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* 
     }
   } else {
     // ===================== epilogue warps (2..9) of both CTAs =====================
-    const int e = tid - 64;
     const int quad = warp & 3;               // accumulator lanes [32 quad, 32 quad + 32) = group `quad` of this CTA
     const int part = (warp - 2) >> 2;        // column half of every accumulator
     const int prow = quad * 32 + lane;       // this thread's point (row of h3)
