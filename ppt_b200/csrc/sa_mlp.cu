@@ -220,6 +220,234 @@ pointwise_linear_kernel(const unsigned char* __restrict__ act_img, const unsigne
   if (warp == 1) tmem_dealloc<TCOLS>(tbase);
 }
 
+// ---- the three layers in ONE kernel: activations never leave shared memory ---------------------------------
+// Tile = 128 (group, sample) columns.  Per tile: the 8 epilogue warps gather [features | xyz - centre] into the
+// K-major input operand (region X); layer 1 -> ReLU -> MN-major operand in region Y; layer 2 -> ReLU -> MN-major
+// operand in region X (the input is dead by then: every layer-1 instruction has completed once its accumulators
+// were drained); layer 3 -> max over each group's columns -> out.  Weights = A operand (channels on the TMEM lanes,
+// so bias, ReLU and the pooling are per-thread), streamed through an mbarrier ring of `nstage` x 16 KB; two
+// alternating 128-column accumulators.  Layers of one tile run back to back (no cross-tile overlap yet).
+// Shared memory: X = max(16 KB kc0, 32 KB u2), Y = 32 KB u1, ring, barriers -- run_sa_mlp picks this kernel when that
+// fits (all PointNet++ levels of models/pointnet2/pointnet2.py except MSG level 3's 643 input channels).
+constexpr int SAF_THREADS = 320;  // producer, MMA issuer, 8 epilogue warps
+constexpr int SAF_EPI = 256;
+
+template <uint32_t FMT>
+__global__ void __launch_bounds__(SAF_THREADS, 1)
+sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, const float* __restrict__ new_xyz,
+                const int64_t* __restrict__ idx, const unsigned char* __restrict__ blob, float* __restrict__ out,
+                int N, int S, int ns, int D, int kc0, int u1, int u2, int u3, int c3, int nstage, uint32_t x_bytes,
+                uint32_t w1_off, uint32_t w2_off, uint32_t w3_off, long long num_groups, long long total, int num_tiles) {
+  constexpr int NT = 128;
+  constexpr int TCOLS = 2 * NT;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* xbuf = smem;                               // input (K-major) / layer-2 output (MN-major)
+  unsigned char* ybuf = xbuf + x_bytes;                     // layer-1 output (MN-major), 32 KB u1
+  unsigned char* ring = ybuf + (size_t)u1 * 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * IMG);
+  uint64_t* full = bars;                // [4]
+  uint64_t* empty = full + 4;           // [4]
+  uint64_t* acc_full = empty + 4;       // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint64_t* in_ready = acc_empty + 2;   // [1] gathered input written
+  uint64_t* act_ready = in_ready + 1;   // [2] layer 1 / layer 2 output written (all units)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], SAF_EPI); }
+    mbar_init(in_ready, SAF_EPI);
+    mbar_init(&act_ready[0], (uint32_t)(SAF_EPI * u1));
+    mbar_init(&act_ready[1], (uint32_t)(SAF_EPI * u2));
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const int units[3] = {u1, u2, u3};
+  const int chunks[3] = {kc0, 2 * u1, 2 * u2};
+  const uint32_t woff[3] = {w1_off, w2_off, w3_off};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int l = 0; l < 3; ++l)
+          for (int u = 0; u < units[l]; ++u)
+            for (int kc = 0; kc < chunks[l]; ++kc, ++it) {
+              const uint32_t s = it % (uint32_t)nstage;
+              mbar_wait_relaxed(&empty[s], ((it / (uint32_t)nstage) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&full[s], IMG);
+              bulk_g2s(ring + s * IMG, blob + woff[l] + ((size_t)u * chunks[l] + kc) * IMG, IMG, &full[s]);
+            }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_k = make_idesc(FMT, 128, NT, 0), idesc_mn = make_idesc(FMT, 128, NT, 1);
+    constexpr uint32_t HI = sdesc_hi(1024u);
+    const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u);
+    const uint32_t b_lo[3] = {sdesc_lo(smem_u32(xbuf), 16u), sdesc_lo(smem_u32(ybuf), (uint32_t)u1 * 16384u),
+                              sdesc_lo(smem_u32(xbuf), (uint32_t)u2 * 16384u)};
+    uint32_t it = 0, tile_it = 0, unit_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      for (int l = 0; l < 3; ++l) {
+        mbar_wait(l == 0 ? in_ready : &act_ready[l - 1], tile_it & 1u);
+        fence_after_sync();
+        for (int u = 0; u < units[l]; ++u, ++unit_it) {
+          const uint32_t buf = unit_it & 1u;
+          mbar_wait(&acc_empty[buf], ((unit_it >> 1) & 1u) ^ 1u);
+          fence_after_sync();
+          for (int kc = 0; kc < chunks[l]; ++kc, ++it) {
+            const uint32_t s = it % (uint32_t)nstage;
+            mbar_wait(&full[s], (it / (uint32_t)nstage) & 1u);
+            fence_after_sync();
+            // K-major input: chunk = one 16 KB image, +32 B per K=16 slice; MN-major activations: chunk = 8 K-atoms of
+            // 1 KB, +2 KB per K=16 slice (tc05.cuh: make_sdesc)
+            const uint32_t bk = l == 0 ? b_lo[0] + (uint32_t)kc * (IMG >> 4) : b_lo[l] + (uint32_t)kc * 512u;
+            const uint32_t bstep = l == 0 ? 2u : 128u;
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_f16_elect(tbase + buf * NT, sdesc_join(a_lo0 + s * (IMG >> 4) + (uint32_t)k16 * 2u, HI),
+                             sdesc_join(bk + (uint32_t)k16 * bstep, HI), l == 0 ? idesc_k : idesc_mn,
+                             (kc == 0 && k16 == 0) ? 0u : 1u);
+            umma_commit_elect(&empty[s]);
+          }
+          umma_commit_elect(&acc_full[buf]);
+        }
+      }
+    }
+  } else {
+    const int e = tid - 64;
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;      // channel row inside a 128-row unit
+    const int col0 = half * 64;          // this thread's 64 accumulator columns
+    const int r = e & 127, hh = e >> 7;  // gather: column r, chunk parity hh
+    const float* biasv = reinterpret_cast<const float*>(blob);
+    uint32_t unit_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // ---- gather: [features (D) | xyz - centre (3) | 0] of column r into the K-major input operand ----
+      {
+        const long long col = (long long)tile * NT + r;
+        const bool ok = col < total;
+        long long n = 0;
+        int b = 0;
+        float cx = 0.f, cy = 0.f, cz = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+        if (ok) {
+          const long long g = col / ns;
+          b = (int)(g / S);
+          n = __ldg(idx + col);
+          n = n < 0 ? 0 : (n >= N ? N - 1 : n);
+          const float* c = new_xyz + g * 3;
+          const float* p = xyz + ((long long)b * N + n) * 3;
+          cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
+          px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+        }
+        const float rel[3] = {__fsub_rn(px, cx), __fsub_rn(py, cy), __fsub_rn(pz, cz)};
+        const float* frow = feats ? feats + ((long long)b * N + n) * D : nullptr;
+        for (int c8 = hh * 8; c8 < kc0 * 64; c8 += 16) {
+          float v[8];
+          if (ok && frow && c8 + 8 <= D && (D & 3) == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(frow + c8));
+            const float4 f = __ldg(reinterpret_cast<const float4*>(frow + c8 + 4));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int c = c8 + t;
+              v[t] = !ok ? 0.f : (c < D ? __ldg(frow + c) : (c < D + 3 ? rel[c - D] : 0.f));
+            }
+          }
+          uint4 w;
+          w.x = pack2<FMT, false>(v[0], v[1]); w.y = pack2<FMT, false>(v[2], v[3]);
+          w.z = pack2<FMT, false>(v[4], v[5]); w.w = pack2<FMT, false>(v[6], v[7]);
+          *reinterpret_cast<uint4*>(xbuf + (size_t)(c8 >> 6) * IMG + sw128_kmajor_off(r, c8 & 63)) = w;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(in_ready);
+      }
+      int boff = 0;
+      for (int l = 0; l < 3; ++l) {
+        unsigned char* dst = l == 0 ? ybuf : xbuf;
+        const uint32_t mnblk = (uint32_t)units[l] * 16384u;  // bytes between 64-column blocks of this layer's output
+        for (int u = 0; u < units[l]; ++u, ++unit_it) {
+          const uint32_t buf = unit_it & 1u;
+          const int ch = u * 128 + m;
+          const float bo = __ldg(biasv + boff + ch);
+          mbar_wait(&acc_full[buf], (unit_it >> 1) & 1u);
+          fence_after_sync();
+          const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + buf * NT + (uint32_t)col0;
+          if (l < 2) {
+            const uint32_t krow = (uint32_t)(ch >> 3) * 1024u + (uint32_t)(ch & 7) * 128u, sw = (uint32_t)(ch & 7);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              float v[32];
+              tmem_ld32(t_addr + jj * 32, v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int n = col0 + jj * 32 + q * 8;
+                const uint32_t off = (uint32_t)(n >> 6) * mnblk + krow + ((((uint32_t)(n & 63) >> 3) ^ sw) << 4);
+                const float* w = v + q * 8;
+                *reinterpret_cast<uint4*>(dst + off) =
+                    make_uint4(pack2<FMT, true>(w[0] + bo, w[1] + bo), pack2<FMT, true>(w[2] + bo, w[3] + bo),
+                               pack2<FMT, true>(w[4] + bo, w[5] + bo), pack2<FMT, true>(w[6] + bo, w[7] + bo));
+              }
+            }
+            fence_proxy_async_smem();
+            fence_before_sync();
+            mbar_arrive(&acc_empty[buf]);
+            mbar_arrive(&act_ready[l]);
+          } else {
+            // relu(max(x) + b) == max(relu(x + b)): pool first, one bias add per group
+            float run = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              float v[32];
+              tmem_ld32(t_addr + jj * 32, v);
+              const long long cbase = (long long)tile * NT + col0 + jj * 32;
+              if (ns == 16) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  float mx = v[16 * h];
+#pragma unroll
+                  for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[16 * h + i]);
+                  const long long g = (cbase + 16 * h) / 16;
+                  if (g < num_groups && ch < c3) out[((g / S) * c3 + ch) * S + g % S] = fmaxf(mx + bo, 0.f);
+                }
+              } else {
+                float mx = v[0];
+#pragma unroll
+                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+                const long long g = cbase / ns;
+                if (ns == 32) {
+                  if (g < num_groups && ch < c3) out[((g / S) * c3 + ch) * S + g % S] = fmaxf(mx + bo, 0.f);
+                } else {
+                  run = jj == 0 ? mx : fmaxf(run, mx);
+                  if (jj == 1 && g < num_groups && ch < c3) {
+                    const float y = fmaxf(run + bo, 0.f);
+                    float* o = out + ((g / S) * c3 + ch) * S + g % S;
+                    if (ns == 64) *o = y;
+                    else atomicMax(reinterpret_cast<int*>(o), __float_as_int(y));  // ns == 128: two halves; y >= 0, out zeroed
+                  }
+                }
+              }
+            }
+            fence_before_sync();
+            mbar_arrive(&acc_empty[buf]);
+          }
+        }
+        boff += units[l] * 128;
+      }
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TCOLS>(tbase);
+}
+
 int num_sms_sa() {
   static int sms = 0;
   if (!sms) {
@@ -269,6 +497,31 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
   const int sms = num_sms_sa();
   const int grid = tiles < sms ? tiles : sms;
   const float* bias = reinterpret_cast<const float*>(blob);
+  // single-kernel path: activations stay in shared memory (PPT_SA_FUSED=0 forces the per-layer kernels)
+  static int use_fused = -1;
+  if (use_fused < 0) {
+    const char* ev = getenv("PPT_SA_FUSED");
+    use_fused = ev ? (atoi(ev) != 0) : 1;
+  }
+  const size_t x_bytes = (size_t)d.kc0 * IMG > (size_t)d.u2 * 32768 ? (size_t)d.kc0 * IMG : (size_t)d.u2 * 32768;
+  const size_t fixed = x_bytes + (size_t)d.u1 * 32768 + 256;
+  int nstage = 0;
+  for (int n = 4; n >= 2 && !nstage; --n)
+    if (fixed + (size_t)n * IMG <= 232448) nstage = n;
+  if (use_fused && nstage) {
+    auto kf = sa_fused_kernel<FMT>;
+    static bool fused_configured = false;
+    if (!fused_configured) {
+      PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      fused_configured = true;
+    }
+    if (ns == 128) PPT_RETURN_IF_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * c3 * sizeof(float), st));
+    kf<<<grid, SAF_THREADS, fixed + (size_t)nstage * IMG, st>>>(xyz, feats, new_xyz, idx, blob, out, N, S, ns, D, d.kc0,
+                                                              d.u1, d.u2, d.u3, c3, nstage, (uint32_t)x_bytes,
+                                                              (uint32_t)d.w1(), (uint32_t)d.w2(), (uint32_t)d.w3(),
+                                                              groups, total, tiles);
+    return ppt_launch_status();
+  }
   sa_gather_image_kernel<FMT><<<tiles < 8 * sms ? tiles : 8 * sms, 256, 0, st>>>(xyz, feats, new_xyz, idx, ws + d.ws0(tiles),
                                                                                N, S, ns, D, d.kc0, total);
   auto smem = [](int kc) { return (size_t)kc * IMG + SA_NSTAGE * IMG + 256; };
