@@ -226,7 +226,8 @@ pointwise_linear_kernel(const unsigned char* __restrict__ act_img, const unsigne
 // operand in region X (the input is dead by then: every layer-1 instruction has completed once its accumulators
 // were drained); layer 3 -> max over each group's columns -> out.  Weights = A operand (channels on the TMEM lanes,
 // so bias, ReLU and the pooling are per-thread), streamed through an mbarrier ring of `nstage` x 16 KB; two
-// alternating 128-column accumulators.  Layers of one tile run back to back (no cross-tile overlap yet).
+// alternating 128-column accumulators.  Layers of one tile run back to back (no cross-tile overlap yet: a variant
+// with 4 epilogue warps and two resident CTAs per SM measured slower, 179 us against 134 us on SSG level 2).
 // Shared memory: X = max(16 KB kc0, 32 KB u2), Y = 32 KB u1, ring, barriers -- run_sa_mlp picks this kernel when that
 // fits (all PointNet++ levels of models/pointnet2/pointnet2.py except MSG level 3's 643 input channels).
 constexpr int SAF_THREADS = 320;  // producer, MMA issuer, 8 epilogue warps
@@ -347,23 +348,34 @@ sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, 
         }
         const float rel[3] = {__fsub_rn(px, cx), __fsub_rn(py, cy), __fsub_rn(pz, cz)};
         const float* frow = feats ? feats + ((long long)b * N + n) * D : nullptr;
-        for (int c8 = hh * 8; c8 < kc0 * 64; c8 += 16) {
-          float v[8];
-          if (ok && frow && c8 + 8 <= D && (D & 3) == 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(frow + c8));
-            const float4 f = __ldg(reinterpret_cast<const float4*>(frow + c8 + 4));
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
-          } else {
+        // four chunks per pass: all eight 16-byte loads of a pass are issued before the first conversion, so the
+        // (L2-latency-bound) gather keeps 128 bytes per thread in flight instead of 32
+        for (int c0 = hh * 8; c0 < kc0 * 64; c0 += 64) {
+          float4 ld[4][2];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int c = c8 + t;
-              v[t] = !ok ? 0.f : (c < D ? __ldg(frow + c) : (c < D + 3 ? rel[c - D] : 0.f));
-            }
+          for (int k = 0; k < 4; ++k) {
+            const int c8 = c0 + 16 * k;
+            const bool vec = ok && frow && c8 + 8 <= D && (D & 3) == 0;
+            ld[k][0] = vec ? __ldg(reinterpret_cast<const float4*>(frow + c8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ld[k][1] = vec ? __ldg(reinterpret_cast<const float4*>(frow + c8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          uint4 w;
-          w.x = pack2<FMT, false>(v[0], v[1]); w.y = pack2<FMT, false>(v[2], v[3]);
-          w.z = pack2<FMT, false>(v[4], v[5]); w.w = pack2<FMT, false>(v[6], v[7]);
-          *reinterpret_cast<uint4*>(xbuf + (size_t)(c8 >> 6) * IMG + sw128_kmajor_off(r, c8 & 63)) = w;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c8 = c0 + 16 * k;
+            if (c8 >= kc0 * 64) break;
+            float v[8] = {ld[k][0].x, ld[k][0].y, ld[k][0].z, ld[k][0].w, ld[k][1].x, ld[k][1].y, ld[k][1].z, ld[k][1].w};
+            if (ok && !(frow && c8 + 8 <= D && (D & 3) == 0)) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const int c = c8 + t;
+                v[t] = c < D ? __ldg(frow + c) : (c < D + 3 ? rel[c - D] : 0.f);
+              }
+            }
+            uint4 w;
+            w.x = pack2<FMT, false>(v[0], v[1]); w.y = pack2<FMT, false>(v[2], v[3]);
+            w.z = pack2<FMT, false>(v[4], v[5]); w.w = pack2<FMT, false>(v[6], v[7]);
+            *reinterpret_cast<uint4*>(xbuf + (size_t)(c8 >> 6) * IMG + sw128_kmajor_off(r, c8 & 63)) = w;
+          }
         }
         fence_proxy_async_smem();
         mbar_arrive(in_ready);
