@@ -4,15 +4,14 @@
 // models/pointnet2/pointnet2_utils.py:196-201, 256-261 (eval mode):
 //     new_points [B, C0, nsample, S]  ->  3 x (Conv2d 1x1 + BatchNorm2d + ReLU)  ->  max over nsample  ->  [B, C3, S]
 // Here (BatchNorm folded on the host, ppt_b200/encoder_pack.py:pack_sa_mlp):
-//   sa_gather_image_kernel     the ball-query gather + centre subtraction + concat writes the fp16 K-major operand
-//                              images of layer 1 directly: the fp32 [B, S, nsample, C0] tensor never exists;
-//   pointwise_linear_kernel    one layer = relu(W' act + b') on the tensor core, tile = 128 (group, sample) columns,
-//                              weights streamed through a 4 x 16 KB mbarrier ring (the group_linear pipeline of
-//                              encoder.cu); layers 1, 2 store their output as the next layer's operand images
-//                              (fp16, half the bytes of the reference's fp32 activations), the last layer max-pools
-//                              over each group's nsample accumulator columns in registers and stores [B, C3, S].
-// Activations between layers round-trip through HBM (as fp16): this is the tensor-core version of the module, not
-// yet the single-kernel fusion -- the layers are HBM-bound, see DESIGN.md section 9.
+//   sa_fused_kernel            the default: gather + centre subtraction + concat -> three tensor-core layers -> max
+//                              over nsample in ONE kernel per 128-column tile, activations resident in shared memory;
+//   sa_gather_image_kernel,    the first version and the fallback when the activation regions do not fit
+//   pointwise_linear_kernel    (PPT_SA_FUSED=0 selects it): the gather writes the fp16 K-major operand images of
+//                              layer 1 to HBM, then one kernel per layer = relu(W' act + b') on the tensor core (the
+//                              group_linear pipeline of encoder.cu); layers 1, 2 store the next layer's operand images,
+//                              the last one max-pools over each group's accumulator columns and stores [B, C3, S].
+// In both, the fp32 [B, S, nsample, C0] tensor of sample_and_group never exists.  DESIGN.md section 9.
 #include <stdlib.h>
 
 #include "common.cuh"
