@@ -237,13 +237,15 @@ __global__ void __launch_bounds__(SAF_THREADS, 1)
 sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, const float* __restrict__ new_xyz,
                 const int64_t* __restrict__ idx, const unsigned char* __restrict__ blob, float* __restrict__ out,
                 int N, int S, int ns, int D, int kc0, int u1, int u2, int u3, int c3, int nstage, uint32_t x_bytes,
+                uint32_t z_off /* 0: layer-2 output aliases the input; else its own region (gather prefetch) */,
                 uint32_t w1_off, uint32_t w2_off, uint32_t w3_off, long long num_groups, long long total, int num_tiles) {
   constexpr int NT = 128;
   constexpr int TCOLS = 2 * NT;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* xbuf = smem;                               // input (K-major) / layer-2 output (MN-major)
   unsigned char* ybuf = xbuf + x_bytes;                     // layer-1 output (MN-major), 32 KB u1
-  unsigned char* ring = ybuf + (size_t)u1 * 32768;
+  unsigned char* zbuf = z_off ? smem + z_off : xbuf;        // layer-2 output (MN-major)
+  unsigned char* ring = (z_off ? zbuf + (size_t)u2 * 32768 : ybuf + (size_t)u1 * 32768);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * IMG);
   uint64_t* full = bars;                // [4]
   uint64_t* empty = full + 4;           // [4]
@@ -290,7 +292,7 @@ sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, 
     constexpr uint32_t HI = sdesc_hi(1024u);
     const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u);
     const uint32_t b_lo[3] = {sdesc_lo(smem_u32(xbuf), 16u), sdesc_lo(smem_u32(ybuf), (uint32_t)u1 * 16384u),
-                              sdesc_lo(smem_u32(xbuf), (uint32_t)u2 * 16384u)};
+                              sdesc_lo(smem_u32(zbuf), (uint32_t)u2 * 16384u)};
     uint32_t it = 0, tile_it = 0, unit_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
       for (int l = 0; l < 3; ++l) {
@@ -327,8 +329,8 @@ sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, 
     const int r = e & 127, hh = e >> 7;  // gather: column r, chunk parity hh
     const float* biasv = reinterpret_cast<const float*>(blob);
     uint32_t unit_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      // ---- gather: [features (D) | xyz - centre (3) | 0] of column r into the K-major input operand ----
+    // ---- gather: [features (D) | xyz - centre (3) | 0] of column r of `tile` into the K-major input operand ----
+    auto gather = [&](int tile) {
       {
         const long long col = (long long)tile * NT + r;
         const bool ok = col < total;
@@ -379,9 +381,15 @@ sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, 
         fence_proxy_async_smem();
         mbar_arrive(in_ready);
       }
+    };
+    // With its own region for the layer-2 output, the input of the NEXT tile is gathered as soon as layer 1 of this
+    // tile is complete, under the tensor work of layers 2 and 3.
+    if (z_off && (int)blockIdx.x < num_tiles) gather(blockIdx.x);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (!z_off) gather(tile);
       int boff = 0;
       for (int l = 0; l < 3; ++l) {
-        unsigned char* dst = l == 0 ? ybuf : xbuf;
+        unsigned char* dst = l == 0 ? ybuf : zbuf;
         const uint32_t mnblk = (uint32_t)units[l] * 16384u;  // bytes between 64-column blocks of this layer's output
         for (int u = 0; u < units[l]; ++u, ++unit_it) {
           const uint32_t buf = unit_it & 1u;
@@ -450,6 +458,7 @@ sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, 
           }
         }
         boff += units[l] * 128;
+        if (l == 0 && z_off && tile + (int)gridDim.x < num_tiles) gather(tile + gridDim.x);
       }
     }
   }
@@ -514,8 +523,13 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
     const char* ev = getenv("PPT_SA_FUSED");
     use_fused = ev ? (atoi(ev) != 0) : 1;
   }
-  const size_t x_bytes = (size_t)d.kc0 * IMG > (size_t)d.u2 * 32768 ? (size_t)d.kc0 * IMG : (size_t)d.u2 * 32768;
-  const size_t fixed = x_bytes + (size_t)d.u1 * 32768 + 256;
+  // separate regions for the input and the layer-2 output (-> gather prefetch) when they fit with a 3-stage ring
+  const size_t sep_fixed = (size_t)d.kc0 * IMG + (size_t)d.u1 * 32768 + (size_t)d.u2 * 32768 + 256;
+  const bool sep = sep_fixed + 3 * (size_t)IMG <= 232448;
+  const size_t x_bytes = sep ? (size_t)d.kc0 * IMG
+                             : ((size_t)d.kc0 * IMG > (size_t)d.u2 * 32768 ? (size_t)d.kc0 * IMG : (size_t)d.u2 * 32768);
+  const size_t fixed = sep ? sep_fixed : x_bytes + (size_t)d.u1 * 32768 + 256;
+  const uint32_t z_off = sep ? (uint32_t)(x_bytes + (size_t)d.u1 * 32768) : 0u;
   int nstage = 0;
   for (int n = 4; n >= 2 && !nstage; --n)
     if (fixed + (size_t)n * IMG <= 232448) nstage = n;
@@ -528,7 +542,7 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
     }
     if (ns == 128) PPT_RETURN_IF_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * c3 * sizeof(float), st));
     kf<<<grid, SAF_THREADS, fixed + (size_t)nstage * IMG, st>>>(xyz, feats, new_xyz, idx, blob, out, N, S, ns, D, d.kc0,
-                                                              d.u1, d.u2, d.u3, c3, nstage, (uint32_t)x_bytes,
+                                                              d.u1, d.u2, d.u3, c3, nstage, (uint32_t)x_bytes, z_off,
                                                               (uint32_t)d.w1(), (uint32_t)d.w2(), (uint32_t)d.w3(),
                                                               groups, total, tiles);
     return ppt_launch_status();
