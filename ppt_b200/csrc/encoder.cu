@@ -377,15 +377,18 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
             tmem_ld32(t_addr + jj * 32, v);
             if (g0 + jj < num_groups) {
               const float cv = ccur[u < 4 ? u : 0][jj] / act_scale;  // act_scale is a power of two
-              float a1 = 0.f, a2 = 0.f;
+              // packed f32x2 arithmetic (FFMA2 / FADD2): this epilogue is issue-bound, three instructions per element
+              // pair instead of per element
+              float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+              const float2 inv2 = make_float2(inv_true, inv_true), cv2 = make_float2(cv, cv);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float y = fmaf(v[i], inv_true, cv);
-                a1 += y;
-                a2 = fmaf(y, y, a2);
+              for (int i = 0; i < 32; i += 2) {
+                const float2 y = __ffma2_rn(make_float2(v[i], v[i + 1]), inv2, cv2);
+                a1 = __fadd2_rn(a1, y);
+                a2 = __ffma2_rn(y, y, a2);
               }
-              s1 += a1;
-              s2 += a2;
+              s1 += a1.x + a1.y;
+              s2 += a2.x + a2.y;
             }
           }
           st_sum[u < 4 ? u : 0] += (double)s1;
