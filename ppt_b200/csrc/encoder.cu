@@ -5,7 +5,8 @@
 // composes first_conv.3 with the per-point half of second_conv.0 and packs every
 // weight into swizzled operand images (ppt_b200/encoder_pack.py).  Four launches:
 //
-//   stage1        per 128-point tile: h1 = relu(W1'x + b1') (K = 3, CUDA cores) ->
+//   stage1        per 128-point tile: h1 = relu(W1'x + b1') as one K = 16 tcgen05.mma (hi/lo parts along K;
+//                 encoder_stage1_tc_kernel; the CUDA-core variant is encoder_stage_kernel<STAGE 1>) ->
 //                 tcgen05: W2 h1 -> max over each 32-point group -> g   [groups, 256]
 //   group_linear  c = W3a' g + bias_c                                   [groups, 512] fp32
 //   stage2        per tile: relu(W32 h1 + c) -> h3 (shared memory only) ->
@@ -20,6 +21,10 @@
 // channels); h3 is written by channel-owning threads as an MN-major operand (16-byte
 // stores along the points), each pair of values converted, ReLU'd and saturated by one
 // F2FP instruction.
+//
+// Also here: the CTA-pair (cta_group::2) stage 2 (encoder_stage2_pair_kernel, experimental), the cls / pos_embed
+// token assembly (pos_hidden_kernel, group_linear_kernel<ASSEMBLE>) and the train-mode BatchNorm path
+// (bn_moments / bn_fold1 / bn_fold2, encoder_stage_kernel<BN_STATS / BN_APPLY>); DESIGN.md sections 8 and 9.
 //
 // Pipeline per CTA (persistent over tiles): warp 0 streams 16 KB weight images from
 // L2 with 1-D bulk async copies into a ring (full/empty mbarriers); warp 1 issues
