@@ -164,7 +164,6 @@ def config_block(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import torch_port  # seeded Encoder weights only (no compute from oracle/ on this path)
     from ppt_b200.tokenizer import PointTokenizer
     from ppt_b200 import ops
 
@@ -178,8 +177,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    torch.manual_seed(0)
     tok = PointTokenizer(N_GROUP, GROUP_SIZE, precision=args.precision).to(dev).eval()
-    tok.load_reference_state(torch_port.make_encoder_state())
+    # random-init weights of the reference's architecture (seeded); non-trivial BatchNorm running statistics so that
+    # the folded weights are not the identity case.  Nothing under oracle/ is used by this arm.
+    wg = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for m in tok.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=wg) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=wg) + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=wg) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=wg) * 0.1)
+    tok.encoder._packed = None
     tok.start_idx = 0
     B = BATCH_PER_GPU
     g = torch.Generator().manual_seed(1234 + rank)
@@ -255,8 +265,7 @@ def run_ours(args):
     # (x, pos) arguments of self.blocks (point_encoder.py:241-249); not part of `value` ----
     ms_assembled = pos_ms = ms_train = None
     if not args.no_widened:
-        tok.load_front_end_state(torch_port.make_front_end_state())
-        pos_blob = tok._pos_blob(dev)
+        pos_blob = tok._pos_blob(dev)  # the module's own (seeded) cls_token / cls_pos / pos_embed initialisation
         for i in range(3):
             tok.forward_assembled(resident[i % ROTATE])
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -336,8 +345,11 @@ def run_ours(args):
         # module's own Conv2d/BatchNorm2d stack (cuDNN fp32) on the same kernels' geometry ----
         from ppt_b200 import pointnet2 as ppt_pn2
         sa2 = ppt_pn2.PointNetSetAbstraction(128, 0.4, 64, 131, [128, 128, 256], False).to(dev).eval()
-        sa2.load_state_dict({k: v.to(dev) for k, v in torch_port.make_sa_state(131, [128, 128, 256], 11).items()},
-                            strict=False)
+        with torch.no_grad():
+            for m in sa2.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.running_mean.copy_(torch.randn(m.num_features, generator=wg).to(dev) * 0.1)
+                    m.running_var.copy_(torch.rand(m.num_features, generator=wg).to(dev) + 0.5)
         sa2.start_idx = 0
         pn = torch.randn(32, 512, 3, device=dev)
         sx = (pn / pn.norm(dim=-1, keepdim=True)).permute(0, 2, 1).contiguous()
