@@ -94,11 +94,10 @@ extern "C" PPT_EXPORT int ppt_ball_query(const float* xyz, const float* new_xyz,
   if (B == 0) return 0;
   const int resident = N < BQ_CHUNK ? ((N + 31) / 32) * 32 : BQ_CHUNK;
   const size_t smem = (size_t)resident * sizeof(float4);
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(BQ_CHUNK * sizeof(float4))));
-    configured = true;
   }
   const int tiles = (S + BQ_QPB - 1) / BQ_QPB;
   ball_query_kernel<<<(unsigned)(B * tiles), BQ_THREADS, smem, (cudaStream_t)stream>>>(xyz, new_xyz, idx_out, radius2,

@@ -17,6 +17,20 @@
     if (_e != cudaSuccess) return (int)_e;          \
   } while (0)
 
+// cudaFuncSetAttribute (dynamic shared-memory opt-in) is per device: a call site configures its kernel once per
+// device it is used on (one process normally drives one GPU, but nothing here should depend on that).
+struct PptOncePerDevice {
+  unsigned long long done = 0;
+  bool need() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+
 static inline int ppt_launch_status() { return (int)cudaPeekAtLastError(); }
 
 // ---- exact fp32 arithmetic of the reference's CPU path ----

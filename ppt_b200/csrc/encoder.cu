@@ -1559,8 +1559,8 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   constexpr size_t s1 = stage_smem_bytes<SPLIT, NT, 1>(), s2 = stage_smem_bytes<SPLIT, NT, 2>(),
                    sl = linear_smem_bytes<SPLIT>();
   static_assert(s2 <= 232448 && s1 <= 232448 && sl <= 232448, "shared memory budget (227 KB per CTA)");
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1tc));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
@@ -1570,7 +1570,6 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kda, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
-    configured = true;
   }
   const long long points = groups * 32;
   const int tiles = (int)((points + NT - 1) / NT);
@@ -1658,10 +1657,9 @@ int run_tokenizer(const float* nbhd, const float* center, const unsigned char* b
   const Workspace W(groups, SPLIT);
   auto kp = group_linear_kernel<FMT, SPLIT, 3, 2, true>;
   constexpr size_t sl = linear_smem_bytes<SPLIT>();
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
-    configured = true;
   }
   const int tiles128 = (int)((groups + 127) / 128);
   const int sms = num_sms();
@@ -1686,11 +1684,10 @@ int run_encoder_train(const float* nbhd, unsigned char* blob, const BnDevice& bn
   auto k2s = encoder_stage_kernel<FMT, SPLIT, NT, 2, 8, BN_STATS>;
   auto k2a = encoder_stage_kernel<FMT, SPLIT, NT, 2, 8, BN_APPLY>;
   constexpr size_t s2 = stage_smem_bytes<SPLIT, NT, 2>();
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-    configured = true;
   }
   const long long points = groups * 32;
   const int tiles = (int)((points + NT - 1) / NT);

@@ -181,10 +181,9 @@ int launch_fps(const float* xyz, const int64_t* start, int64_t* idx_out, float* 
                cudaStream_t st) {
   auto kern = fps_kernel<THREADS, PPT, CLUSTER>;
   const size_t smem = (size_t)THREADS * PPT * 12 + 64 * sizeof(int2) + 2 * CLUSTER * sizeof(FpsRecord);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PptOncePerDevice configured;  // per instantiation
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B * CLUSTER);

@@ -145,12 +145,11 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
 template <int W>
 int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                     int B, int N, int G, cudaStream_t st) {
-  static bool configured = false;
+  static PptOncePerDevice configured;
   const size_t slots = 2 * W * sizeof(int2);
-  if (!configured) {
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)spidx::MAX_N * 24 + slots)));
-    configured = true;
   }
   const size_t smem = (size_t)((N + 31) & ~31) * 24 + slots;
   fps_grid_kernel<W><<<B, W * 32, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,

@@ -136,11 +136,10 @@ extern "C" PPT_EXPORT int ppt_three_nn(const float* unknown, const float* known,
   if (B == 0) return 0;
   if (B > 65535) return PPT_ERANGE;
   const size_t smem = (size_t)(S < NN_CHUNK ? S : NN_CHUNK) * sizeof(float4);
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(NN_CHUNK * sizeof(float4))));
-    configured = true;
   }
   dim3 grid((N + NN_THREADS - 1) / NN_THREADS, B);
   three_nn_kernel<<<grid, NN_THREADS, smem, (cudaStream_t)stream>>>(unknown, known, dist_out, idx_out, N, S);

@@ -144,11 +144,10 @@ int launch_knn(const float* xyz, const float* query, int64_t* idx_out, float* di
   auto kern = knn_kernel<GROUP>;
   const int resident = N < KNN_CHUNK ? ((N + 31) / 32) * 32 : KNN_CHUNK;
   const size_t smem = (size_t)resident * sizeof(float4);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(KNN_CHUNK * sizeof(float4))));
-    configured = KNN_CHUNK * sizeof(float4);
   }
   const int tiles = (S + KNN_QPB - 1) / KNN_QPB;
   kern<<<(unsigned)(B * tiles), KNN_THREADS, smem, st>>>(xyz, query, idx_out, dist_out, nb_out, N, S, k, tiles);

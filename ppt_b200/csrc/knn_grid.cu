@@ -352,11 +352,10 @@ size_t ppt_index_bytes(int B, int N) {
 }
 
 int ppt_index_build(const float* xyz, void* index, int B, int N, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)prep_smem(GRID_MAX_N)));
-    configured = true;
   }
   knn_prepare_kernel<<<B, PREP_THREADS, prep_smem(N), st>>>(xyz, static_cast<unsigned char*>(index), N);
   return ppt_launch_status();
@@ -364,13 +363,12 @@ int ppt_index_build(const float* xyz, void* index, int B, int N, cudaStream_t st
 
 int ppt_knn_grid_search(const float* xyz, const float* query, const void* index, int64_t* idx_out, float* dist_out,
                         float* nb_out, int B, int N, int S, int k, bool group, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)search_smem(GRID_MAX_N)));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)search_smem(GRID_MAX_N)));
-    configured = true;
   }
   const unsigned char* ws = static_cast<const unsigned char*>(index);
   const int tiles = (S + SEARCH_QPB - 1) / SEARCH_QPB;

@@ -508,11 +508,10 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
   auto kl = pointwise_linear_kernel<FMT, false>;
   auto kp = pointwise_linear_kernel<FMT, true>;
   const size_t smem_max = (size_t)SA_MAX_KC * IMG + SA_NSTAGE * IMG + 256;
-  static bool configured = false;
-  if (!configured) {
+  static PptOncePerDevice configured;
+  if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    configured = true;
   }
   const int sms = num_sms_sa();
   const int grid = tiles < sms ? tiles : sms;
@@ -535,10 +534,9 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
     if (fixed + (size_t)n * IMG <= 232448) nstage = n;
   if (use_fused && nstage) {
     auto kf = sa_fused_kernel<FMT>;
-    static bool fused_configured = false;
-    if (!fused_configured) {
+    static PptOncePerDevice fused_configured;
+    if (fused_configured.need()) {
       PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-      fused_configured = true;
     }
     if (ns == 128) PPT_RETURN_IF_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * c3 * sizeof(float), st));
     kf<<<grid, SAF_THREADS, fixed + (size_t)nstage * IMG, st>>>(xyz, feats, new_xyz, idx, blob, out, N, S, ns, D, d.kc0,
