@@ -196,3 +196,40 @@ def test_pos_embed_packing_matches_abi_sizes():
     with pytest.raises(ValueError):
         ep.pack_pos_embed({"0.weight": torch.zeros(64, 3), "0.bias": torch.zeros(64), "2.weight": torch.zeros(384, 64),
                            "2.bias": torch.zeros(384)}, front["cls_token"], front["cls_pos"], 0)
+
+
+def test_sa_mlp_packing_matches_abi_sizes_and_folds_batchnorm():
+    """Row f1 host side: blob sizes agree with the library for every level of models/pointnet2/pointnet2.py that the
+    fused path covers, unsupported stacks are refused, and Conv + eval-BatchNorm folding is exact (fp64)."""
+    from ppt_b200 import _lib, encoder_pack as ep
+    from oracle import torch_port
+    lib = _lib.load()
+    levels = [(3, [64, 64, 128]), (131, [128, 128, 256]), (259, [256, 512, 1024]), (3, [32, 32, 64]), (3, [64, 96, 128]),
+              (323, [128, 128, 256])]
+    for c0, mlp in levels:
+        sd = torch_port.make_sa_state(c0, mlp, 5)
+        convs, bns = torch.nn.ModuleList(), torch.nn.ModuleList()
+        last = c0
+        for w in mlp:
+            convs.append(torch.nn.Conv2d(last, w, 1))
+            bns.append(torch.nn.BatchNorm2d(w))
+            last = w
+        holder = torch.nn.Module()
+        holder.mlp_convs, holder.mlp_bns = convs, bns
+        holder.load_state_dict(sd, strict=False)
+        blob, dims = ep.pack_sa_mlp(convs, bns, xyz_first=True, mode=0)
+        assert dims == (c0, *mlp)
+        assert blob.numel() == ep.sa_mlp_packed_bytes(*dims) == lib.ppt_sa_mlp_packed_bytes(*dims)
+        assert lib.ppt_sa_mlp_workspace_bytes(1000, *dims) > 0
+        # folded affine map == conv + eval BN on random input (fp64)
+        x = torch.randn(7, c0, dtype=torch.float64)
+        w, b = ep.fold_conv_bn(convs[0].weight, convs[0].bias, bns[0].weight, bns[0].bias, bns[0].running_mean,
+                               bns[0].running_var, bns[0].eps)
+        ref = torch.nn.functional.batch_norm(
+            torch.nn.functional.conv2d(x.view(7, c0, 1, 1), convs[0].weight.double(), convs[0].bias.double()),
+            bns[0].running_mean.double(), bns[0].running_var.double(), bns[0].weight.double(), bns[0].bias.double(),
+            False, 0.1, bns[0].eps).view(7, -1)
+        assert float((x @ w.T + b - ref).abs().max()) < 1e-12
+    assert lib.ppt_sa_mlp_packed_bytes(643, 256, 512, 1024) == -2      # PPT_ERANGE: > 512 input channels
+    with pytest.raises(ValueError):
+        ep.pack_sa_mlp(convs[:2], bns[:2], True, 0)
