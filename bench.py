@@ -390,7 +390,7 @@ def run_ours(args):
     # HostPipeline: H2D of the clouds, the kernels and D2H of tokens + centres on three streams,
     # two slots in flight; every step's inputs start in pinned host memory and its results end there.
     from ppt_b200.tokenizer import HostPipeline
-    pipe = HostPipeline(tok, B, N_POINTS, depth=2, device=dev)
+    pipe = HostPipeline(tok, B, N_POINTS, depth=int(os.environ.get("PPT_E2E_DEPTH", "2")), device=dev)
     sums = []
 
     def feed(count):
@@ -405,7 +405,7 @@ def run_ours(args):
     ms_e2e_local = (time.perf_counter() - t0) * 1e3  # host clock: the region ends with data on the host
     barrier()
     ms_e2e = max_over_ranks(ms_e2e_local)
-    checksum = float(pipe.out_tokens[(args.steps - 1) % 2].double().abs().sum())
+    checksum = float(pipe.out_tokens[(args.steps - 1) % pipe.depth].double().abs().sum())
 
     if world > 1:
         dist.destroy_process_group()
