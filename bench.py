@@ -161,10 +161,94 @@ def config_block(args):
             % (ROTATE, ROTATE * BATCH_PER_GPU * N_POINTS * 12 / 1e6)}
 
 
+def make_tokenizer(precision):
+    """The bench's tokenizer on the CPU: random-init weights of the reference's architecture (seeded), with
+    non-trivial BatchNorm running statistics so that the folded weights are not the identity case.  Shared with
+    oracle/gen_golden.py (which loads the same weights into the unmodified reference modules to make
+    tests/golden/bench_cfg2.npz) and the cfg-2-size parity tests."""
+    import torch
+    from ppt_b200.tokenizer import PointTokenizer
+    torch.manual_seed(0)
+    tok = PointTokenizer(N_GROUP, GROUP_SIZE, precision=precision).eval()
+    wg = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for m in tok.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=wg) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=wg) + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=wg) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=wg) * 0.1)
+    tok.encoder._packed = None
+    tok.start_idx = 0
+    return tok
+
+
+def make_host_batches(rank, count, batch=BATCH_PER_GPU, pin=True):
+    """`count` distinct synthetic batches of uniform-cube clouds for `rank` (seed 1234 + rank), on the host."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    out = [torch.rand(batch, N_POINTS, 3, generator=g) * 2 - 1 for _ in range(count)]
+    return [h.pin_memory() for h in out] if pin else out
+
+
+# ---- parity at the benchmarked size (tests/golden/bench_cfg2.npz, made by oracle/gen_golden.py from the
+# unmodified reference on rank 0's first batch with make_tokenizer's weights) ----
+CFG2_FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_cfg2.npz")
+TOKEN_TOL = {"fp16": 1e-3, "bf16": 8e-3, "fp32": 1e-5}
+
+
+def check_cfg2_parity(fps_idx, center, knn_idx, neighborhood, tokens, precision, fixture_path=CFG2_FIXTURE):
+    """Compares one step's outputs on rank 0's first batch (CPU tensors) with the reference-generated fixture:
+    FPS indices / centres bit-exact (sha256), kNN index sets and canonicalised neighbourhoods bit-exact outside the
+    reference's own k-boundary tie rows, tokens norm-relative within the precision's tolerance on the
+    stored rows plus a per-group checksum over ALL 65 536 groups.  Returns a dict with "ok"."""
+    import hashlib
+    import numpy as np
+    import torch
+    if not os.path.exists(fixture_path):
+        return {"ok": False, "why": "fixture missing: " + fixture_path}
+    f = np.load(fixture_path, allow_pickle=False)
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    res = {}
+    res["fps"] = sha(fps_idx.numpy()) == str(f["fps_sha"])
+    res["center"] = sha(center.numpy()) == str(f["center_sha"])
+    tie = torch.zeros(knn_idx.shape[:2], dtype=torch.bool)
+    tr = torch.from_numpy(f["tie_rows"].astype(np.int64))
+    if tr.numel():
+        tie[tr[:, 0], tr[:, 1]] = True
+    order = knn_idx.argsort(dim=-1)
+    ks = torch.gather(knn_idx, 2, order).clone()
+    nbc = torch.gather(neighborhood, 2, order.unsqueeze(-1).expand_as(neighborhood)).clone()
+    ks[tie] = 0
+    nbc[tie] = 0
+    res["knn_sets"] = sha(ks.numpy()) == str(f["knn_sorted_sha"])
+    res["neighborhood"] = sha(nbc.numpy()) == str(f["nb_canon_sha"])
+    tol = TOKEN_TOL[precision]
+    rows = torch.from_numpy(f["token_clouds"].astype(np.int64))
+    step = int(f["token_group_step"])
+    ref = torch.from_numpy(f["tokens"]).double()
+    got = tokens[rows][:, ::step].double()
+    keep = ~tie[rows][:, ::step]
+    d = (got - ref)[keep]
+    res["token_max_rel"] = float(d.abs().max() / ref[keep].abs().max())
+    res["token_rms_rel"] = float(d.norm() / ref[keep].norm())
+    gsum, gabs = torch.from_numpy(f["group_sum"]).double(), torch.from_numpy(f["group_abs"]).double()
+    # a group's token sum is off by at most tol * sum|ref| if every element is within tol * |ref|_max-ish; a group
+    # that received another group's points is off by O(1) of it
+    dev = ((tokens.double().sum(-1) - gsum).abs() / gabs)[~tie]
+    res["group_sum_max_dev"] = float(dev.max())
+    res["tokens"] = res["token_max_rel"] <= tol and res["token_rms_rel"] <= tol and res["group_sum_max_dev"] <= tol
+    res["tie_rows"] = int(tie.sum())
+    res["ok"] = all(res[k] for k in ("fps", "center", "knn_sets", "neighborhood", "tokens"))
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from ppt_b200.tokenizer import PointTokenizer
     from ppt_b200 import ops
 
     rank = int(os.environ.get("RANK", "0"))
@@ -177,23 +261,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    torch.manual_seed(0)
-    tok = PointTokenizer(N_GROUP, GROUP_SIZE, precision=args.precision).to(dev).eval()
-    # random-init weights of the reference's architecture (seeded); non-trivial BatchNorm running statistics so that
-    # the folded weights are not the identity case.  Nothing under oracle/ is used by this arm.
+    # Nothing under oracle/ is used by this arm.
+    tok = make_tokenizer(args.precision).to(dev)
     wg = torch.Generator().manual_seed(0)
-    with torch.no_grad():
-        for m in tok.modules():
-            if isinstance(m, torch.nn.BatchNorm1d):
-                m.running_mean.copy_(torch.randn(m.num_features, generator=wg) * 0.1)
-                m.running_var.copy_(torch.rand(m.num_features, generator=wg) + 0.5)
-                m.weight.copy_(torch.rand(m.num_features, generator=wg) + 0.5)
-                m.bias.copy_(torch.randn(m.num_features, generator=wg) * 0.1)
-    tok.encoder._packed = None
-    tok.start_idx = 0
     B = BATCH_PER_GPU
-    g = torch.Generator().manual_seed(1234 + rank)
-    host = [(torch.rand(B, N_POINTS, 3, generator=g) * 2 - 1).pin_memory() for _ in range(ROTATE)]
+    host = make_host_batches(rank, ROTATE)
     resident = [h.to(dev) for h in host]
     zeros = torch.zeros(B, dtype=torch.int64, device=dev)
 
@@ -215,7 +287,7 @@ def run_ours(args):
                              lambda: ops.fps(xyz, N_GROUP, zeros, return_centers=True, index=index))
         nb = timed_op(phase_events, "knn_group", lambda: ops.knn_group(xyz, center, GROUP_SIZE, index=index))
         blob, mode = tok.encoder._blob(dev)
-        return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events), center
+        return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events), center, nb
 
     def barrier():
         if world > 1:
@@ -256,6 +328,27 @@ def run_ours(args):
             step(i)
         barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- parity of the timed configuration: the very step() that was timed, on rank 0's first batch, against the
+    # fixture recorded from the unmodified reference (tests/golden/bench_cfg2.npz) ----
+    parity = None
+    if rank == 0:
+        import hashlib
+        import numpy as np
+        fx = np.load(CFG2_FIXTURE, allow_pickle=False) if os.path.exists(CFG2_FIXTURE) else None
+        wsum = hashlib.sha256(b"".join(np.ascontiguousarray(v.detach().cpu().numpy()).tobytes()
+                                       for _, v in sorted(tok.state_dict().items()))).hexdigest()
+        xsum = hashlib.sha256(host[0].numpy().tobytes()).hexdigest()
+        if fx is None:
+            parity = {"ok": False, "why": "tests/golden/bench_cfg2.npz missing"}
+        elif str(fx["xyz_sha"]) != xsum or str(fx["weights_sha"]) != wsum:
+            parity = {"ok": False, "why": "this torch build draws different synthetic inputs / weights than the one "
+                                          "that made the fixture (%s)" % str(fx["torch_version"])}
+        else:
+            tokens0, center0, nb0 = step(0)
+            fps0 = ops.fps(resident[0], N_GROUP, zeros)
+            _, knn0 = ops.knn_group(resident[0], center0, GROUP_SIZE, return_idx=True)
+            parity = check_cfg2_parity(fps0.cpu(), center0.cpu(), knn0.cpu(), nb0.cpu(), tokens0.cpu(), args.precision)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     per_phase = {}
     for name, a, b in phase_events:
@@ -499,9 +592,13 @@ def run_ours(args):
                 "d2h_bytes_per_step": B * N_GROUP * (384 + 3) * 4, "ms_per_step": ms_e2e / args.steps,
                 "checksum": checksum},
         # spatial index build, fps, knn_search, stage1, group_linear, stage2, group_linear
+        "parity_checked": bool(parity and parity["ok"]), "parity": parity,
         "gpu_launches": 7 * args.steps, "roofline": roofline, "roofline_all": roofline_all, "widened": widened, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
+    if parity is not None and not parity["ok"] and "why" not in parity:
+        sys.stderr.write("bench.py: PARITY FAILURE against tests/golden/bench_cfg2.npz: %r\n" % (parity,))
+        sys.exit(3)
 
 
 def main():

@@ -319,11 +319,59 @@ def gen_front_end(ns):
     print("front end x", tuple(seen["x"].shape), "pos absmax", float(seen["pos"].abs().max()))
 
 
+def gen_bench_cfg2(ns):
+    """BASELINE configs[1] at bench.py's own size and weights: rank 0's first batch (128 clouds x 8192 points,
+    seed 1234) through the UNMODIFIED reference Group (dvae.py:152-181) + Encoder (dvae.py:184-215) + reduce_dim
+    (point_encoder.py:133,239) carrying bench.make_tokenizer's seeded weights.  Stores digests of the index work
+    (k-boundary tie rows zeroed, F6), the fp32 tokens of two clouds (every 4th group) and a per-group token
+    checksum for all 65 536 groups; bench.check_cfg2_parity consumes it on the GPU box."""
+    import bench
+    tok = bench.make_tokenizer("fp16")
+    xyz = bench.make_host_batches(0, 1, pin=False)[0]
+    B, G, K = xyz.shape[0], bench.N_GROUP, bench.GROUP_SIZE
+    enc = ns.dvae.Encoder(256).eval()
+    enc.load_state_dict(tok.encoder.state_dict())
+    reduce_dim = torch.nn.Linear(256, 384)
+    reduce_dim.load_state_dict(tok.reduce_dim.state_dict())
+    fps_all, center_all, knn_all, nb_all, tok_all, tie_all = [], [], [], [], [], []
+    group = ns.dvae.Group(G, K)
+    for lo in range(0, B, 16):
+        part = xyz[lo:lo + 16]
+        with refimport.fixed_fps_start(0), torch.no_grad():
+            fps_all.append(ns.misc.farthest_point_sample(part, G))
+            nb, center = group(part)
+            sqd = ns.dvae.square_distance(center, part)
+            knn = ns.dvae.knn_point(K, part, center)
+            tok_all.append(reduce_dim(enc(nb)))
+        tie_all.append(torch.from_numpy(knn_tie_rows(sqd, K)))
+        center_all.append(center)
+        knn_all.append(knn)
+        nb_all.append(nb)
+        print("bench_cfg2 clouds", lo + 16, flush=True)
+    fps_idx, center, knn, nb, tokens, tie = (torch.cat(v) for v in (fps_all, center_all, knn_all, nb_all, tok_all, tie_all))
+    assert torch.equal(center, torch_port.take_rows(xyz, fps_idx))
+    knn_sorted = knn.sort(-1).values.clone()
+    nb_c = canon_group(nb, knn).clone()
+    knn_sorted[tie] = 0
+    nb_c[tie] = 0
+    clouds, step = np.array([0, B - 1]), 4
+    wsum = hashlib.sha256(b"".join(np.ascontiguousarray(v.detach().numpy()).tobytes()
+                                   for _, v in sorted(tok.state_dict().items()))).hexdigest()
+    np.savez_compressed(os.path.join(OUT, "bench_cfg2.npz"), B=B, N=xyz.shape[1], G=G, K=K,
+                        torch_version=torch.__version__, xyz_sha=digest(xyz.numpy()), weights_sha=wsum,
+                        fps_sha=digest(fps_idx.numpy()), center_sha=digest(center.numpy()),
+                        knn_sorted_sha=digest(knn_sorted.numpy()), nb_canon_sha=digest(nb_c.numpy()),
+                        tie_rows=np.argwhere(tie.numpy()).astype(np.int32),
+                        token_clouds=clouds, token_group_step=step, tokens=tokens[clouds][:, ::step].numpy(),
+                        group_sum=tokens.double().sum(-1).float().numpy(), group_abs=tokens.double().abs().sum(-1).float().numpy())
+    print("bench_cfg2: tie rows", int(tie.sum()), "token absmax", float(tokens.abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1:  # regenerate one fixture only: front_end | encoder_train
         {"front_end": gen_front_end, "encoder_train": gen_encoder_train, "graph_feature": gen_graph_feature,
-         "loader_fps": gen_loader_fps, "sa_mlp": gen_sa_mlp}[sys.argv[1]](refimport.load())
+         "loader_fps": gen_loader_fps, "sa_mlp": gen_sa_mlp, "bench_cfg2": gen_bench_cfg2}[sys.argv[1]](refimport.load())
         return
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     ns = refimport.load()
@@ -344,6 +392,7 @@ def main():
     gen_graph_feature(ns)
     gen_loader_fps(ns)
     gen_sa_mlp(ns)
+    gen_bench_cfg2(ns)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("fixtures total bytes", tot)
 

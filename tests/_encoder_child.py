@@ -26,9 +26,9 @@ def main():
         groups = int(case)
         g = torch.Generator().manual_seed(groups)
         nb = (torch.rand(1, groups, 32, 3, generator=g) - 0.5) * 0.4
-        with torch.no_grad():
-            ref_feat = torch_port.encoder_forward(sd, nb)
-            ref_tok = torch_port.tokens_forward(sd, nb)
+        with torch.no_grad():  # chunked: the port materialises every [groups, C, 32] intermediate
+            ref_feat = torch.cat([torch_port.encoder_forward(sd, c) for c in nb.split(8192, dim=1)], dim=1)
+            ref_tok = torch.nn.functional.linear(ref_feat, sd["reduce_dim.weight"], sd["reduce_dim.bias"])
     blob = encoder_pack.pack_encoder(sd, mode).cuda()
     tok, feat = ops.encoder_forward(nb.cuda(), blob, mode=mode, return_features=True)
     torch.cuda.synchronize()

@@ -27,8 +27,9 @@ def run_child(case, mode, env=None):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("case", ["golden", "4", "1", "131", "1500", "16384"])
+@pytest.mark.parametrize("case", ["golden", "4", "1", "131", "1500", "16384", "65536"])
 def test_encoder_tokens(case, mode):
+    """"65536" = BASELINE configs[1]: 128 clouds x 512 groups, the size bench.py times."""
     r = run_child(case, mode)
     assert r["finite"] and r["repeatable"], r
     for key in ("tokens", "features"):

@@ -233,3 +233,31 @@ def test_sa_mlp_packing_matches_abi_sizes_and_folds_batchnorm():
     assert lib.ppt_sa_mlp_packed_bytes(643, 256, 512, 1024) == -2      # PPT_ERANGE: > 512 input channels
     with pytest.raises(ValueError):
         ep.pack_sa_mlp(convs[:2], bns[:2], True, 0)
+
+
+def test_cfg2_fixture_checker_and_port_at_the_benchmarked_size():
+    """tests/golden/bench_cfg2.npz (from the unmodified reference) against the torch-op port on the full 128-cloud
+    batch, through the very checker bench.py and the GPU tests use: pins the fixture, the checker and the port at
+    BASELINE configs[1] size.  Tolerance 1e-5: both sides are fp32."""
+    import bench
+    from oracle import torch_port
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    tok = bench.make_tokenizer("fp32")
+    sd = {k: v for k, v in tok.encoder.state_dict().items()}
+    sd["reduce_dim.weight"], sd["reduce_dim.bias"] = tok.reduce_dim.weight.detach(), tok.reduce_dim.bias.detach()
+    xyz = bench.make_host_batches(0, 1, pin=False)[0]
+    fps_idx, center, knn, nb, toks = [], [], [], [], []
+    with torch.no_grad():
+        for part in xyz.split(16):
+            f = torch_port.fps_indices(part, bench.N_GROUP, 0)
+            c = torch_port.take_rows(part, f)
+            k = torch_port.knn_indices(bench.GROUP_SIZE, part, c)
+            n = torch_port.take_rows(part, k) - c.unsqueeze(2)
+            fps_idx.append(f), center.append(c), knn.append(k), nb.append(n), toks.append(torch_port.tokens_forward(sd, n))
+    r = bench.check_cfg2_parity(torch.cat(fps_idx), torch.cat(center), torch.cat(knn), torch.cat(nb), torch.cat(toks), "fp32")
+    assert r["ok"], r
+    # and the checker does notice a group that received another group's points
+    bad = torch.cat(toks).clone()
+    bad[5, 7], bad[5, 8] = bad[5, 8].clone(), bad[5, 7].clone()
+    r = bench.check_cfg2_parity(torch.cat(fps_idx), torch.cat(center), torch.cat(knn), torch.cat(nb), bad, "fp32")
+    assert not r["ok"] and not r["tokens"]
