@@ -328,3 +328,36 @@ def test_loader_fps_drop_in_matches_reference_fixture():
     assert np.array_equal(bidx[0], f["a.indices"][:64])
     with pytest.raises(TypeError):
         data.farthest_point_sample(f["a.point"].astype(np.float64), 8)
+
+
+def test_patch_reference_on_the_real_reference_tree_with_cuda_tensors():
+    """`refonly`: runs only where both a GPU and the reference tree (PPT_REFERENCE_ROOT, default /root/reference) exist.
+    patch_reference() on the UNMODIFIED modules: Group / Encoder / knn_point / PointTransformer.forward on CUDA tensors go
+    through the kernels and agree with the same modules on CPU tensors (which keep the reference's own code)."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference tree not present on this box (PPT_REFERENCE_ROOT)")
+    from ppt_b200 import patch
+    ns = refimport.load()
+    torch.manual_seed(0)
+    xyz = cloud("U", 2, 2048, 77)
+    grp, enc = ns.dvae.Group(64, 32), ns.dvae.Encoder(256).eval()
+    enc.load_state_dict({k: v for k, v in torch_port.make_encoder_state().items() if k in torch_port.ENCODER_KEYS},
+                        strict=False)
+    with refimport.fixed_fps_start(0), torch.no_grad():
+        nb_ref, c_ref = grp(xyz)
+        f_ref = enc(nb_ref)
+        k_ref = ns.dvae.knn_point(8, xyz, c_ref)
+    names = patch.patch_reference()
+    try:
+        assert "Group.forward" in " ".join(names) and "Encoder.forward" in " ".join(names)
+        with refimport.fixed_fps_start(0), torch.no_grad():
+            nb, c = grp.cuda()(xyz.cuda())
+            f = enc.cuda()(nb)
+            k = ns.dvae.knn_point(8, xyz.cuda(), c)
+        assert torch.equal(c.cpu(), c_ref)
+        assert torch.equal(nb.cpu().sort(2)[0], nb_ref.sort(2)[0])       # neighbour order inside a group is unspecified
+        assert torch.equal(k.cpu().sort(-1)[0], k_ref.sort(-1)[0])
+        assert float((f.cpu() - f_ref).abs().max() / f_ref.abs().max()) < 1e-3
+    finally:
+        patch.unpatch_reference()
