@@ -183,11 +183,15 @@ def make_tokenizer(precision):
     return tok
 
 
-def make_host_batches(rank, count, batch=BATCH_PER_GPU, pin=True):
-    """`count` distinct synthetic batches of uniform-cube clouds for `rank` (seed 1234 + rank), on the host."""
+def make_host_batches(rank, count, batch=BATCH_PER_GPU, pin=True, device=None):
+    """`count` distinct synthetic batches of uniform-cube clouds for `rank` (seed 1234 + rank), on the host; pinned
+    (on `device`'s NUMA node when given) unless pin=False."""
     import torch
     g = torch.Generator().manual_seed(1234 + rank)
     out = [torch.rand(batch, N_POINTS, 3, generator=g) * 2 - 1 for _ in range(count)]
+    if pin and device is not None:
+        from ppt_b200 import hostmem
+        return [hostmem.pinned_copy(h, device) for h in out]
     return [h.pin_memory() for h in out] if pin else out
 
 
@@ -265,7 +269,7 @@ def run_ours(args):
     tok = make_tokenizer(args.precision).to(dev)
     wg = torch.Generator().manual_seed(0)
     B = BATCH_PER_GPU
-    host = make_host_batches(rank, ROTATE)
+    host = make_host_batches(rank, ROTATE, device=dev)
     resident = [h.to(dev) for h in host]
     zeros = torch.zeros(B, dtype=torch.int64, device=dev)
 
@@ -279,7 +283,7 @@ def run_ours(args):
         events.append((name, a, b))
         return out
 
-    def step(i, phase_events=None):
+    def step(i, phase_events=None, clock_acc=None):
         # identical to PointTokenizer.forward, with an event pair around every launch when asked
         xyz = resident[i % ROTATE]
         index = timed_op(phase_events, "spatial_index", lambda: ops.spatial_index(xyz))
@@ -287,7 +291,7 @@ def run_ours(args):
                              lambda: ops.fps(xyz, N_GROUP, zeros, return_centers=True, index=index))
         nb = timed_op(phase_events, "knn_group", lambda: ops.knn_group(xyz, center, GROUP_SIZE, index=index))
         blob, mode = tok.encoder._blob(dev)
-        return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events), center, nb
+        return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events, clock_acc=clock_acc), center, nb
 
     def barrier():
         if world > 1:
@@ -325,7 +329,7 @@ def run_ours(args):
     # clock64 cycles of every launch): the SM clock inside the dominant kernel
     with ops.Stage2ClockTrace(dev) as clock_trace:
         for i in range(args.steps):
-            step(i)
+            step(i, clock_acc=clock_trace.acc)
         barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
 
@@ -481,24 +485,42 @@ def run_ours(args):
 
     # ---- timed region 2: end to end through the public API with pinned host buffers ----
     # HostPipeline: H2D of the clouds, the kernels and D2H of tokens + centres on three streams,
-    # two slots in flight; every step's inputs start in pinned host memory and its results end there.
+    # `depth` slots in flight; every step's inputs start in pinned host memory and its results end there.
+    # Two legs: tokens reach the host as fp16 (PPT_TOKENS_F16: the headline `e2e`, half the PCIe bytes) and as fp32
+    # (the reference's dtype; `e2e.fp32_tokens`).
     from ppt_b200.tokenizer import HostPipeline
-    pipe = HostPipeline(tok, B, N_POINTS, depth=int(os.environ.get("PPT_E2E_DEPTH", "2")), device=dev)
-    sums = []
 
     def feed(count):
         for i in range(count):
             yield host[i % ROTATE]
 
-    pipe.run(feed(3))
-    barrier()
-    t0 = time.perf_counter()
-    pipe.run(feed(args.steps), on_result=lambda i, t, c: sums.append(float(t[0, 0, 0])))
-    torch.cuda.synchronize()
-    ms_e2e_local = (time.perf_counter() - t0) * 1e3  # host clock: the region ends with data on the host
-    barrier()
-    ms_e2e = max_over_ranks(ms_e2e_local)
-    checksum = float(pipe.out_tokens[(args.steps - 1) % pipe.depth].double().abs().sum())
+    def run_e2e(token_dtype):
+        pipe = HostPipeline(tok, B, N_POINTS, depth=int(os.environ.get("PPT_E2E_DEPTH", "3")), device=dev,
+                            token_dtype=token_dtype)
+        first = {}
+
+        def keep(i, t, c):
+            if i == 0:  # batch 0 = the fixture's batch: keep a copy for the parity check below
+                first["tokens"], first["center"] = t.clone(), c.clone()
+
+        pipe.run(feed(3))
+        barrier()
+        t0 = time.perf_counter()
+        pipe.run(feed(args.steps), on_result=keep)
+        torch.cuda.synchronize()
+        ms_local = (time.perf_counter() - t0) * 1e3  # host clock: the region ends with data on the host
+        barrier()
+        return max_over_ranks(ms_local), first
+
+    ms_e2e16, first16 = run_e2e(torch.float16)
+    ms_e2e32, first32 = run_e2e(torch.float32)
+    parity_e2e = None
+    if rank == 0 and parity is not None and parity.get("ok"):
+        # the tokens that reached the host through the public pipeline, against the same fixture
+        r16 = check_cfg2_parity(fps0.cpu(), first16["center"], knn0.cpu(), nb0.cpu(), first16["tokens"].float(), args.precision)
+        r32 = check_cfg2_parity(fps0.cpu(), first32["center"], knn0.cpu(), nb0.cpu(), first32["tokens"], args.precision)
+        parity_e2e = {"fp16_tokens": {k: r16[k] for k in ("ok", "token_max_rel", "token_rms_rel", "group_sum_max_dev")},
+                      "fp32_tokens": {k: r32[k] for k in ("ok", "token_max_rel", "token_rms_rel", "group_sum_max_dev")}}
 
     if world > 1:
         dist.destroy_process_group()
@@ -513,7 +535,7 @@ def run_ours(args):
     peaks = load_peaks()
     clouds_total = B * world * args.steps
     value = clouds_total / (ms_total * 1e-3)
-    e2e_value = clouds_total / (ms_e2e * 1e-3)
+    e2e_value = clouds_total / (ms_e2e16 * 1e-3)
     s2_ms = statistics.mean(per_phase["stage2"])
     points = B * N_GROUP * GROUP_SIZE
     achieved_tf = points * STAGE2_FLOP_PER_POINT / (s2_ms * 1e-3) / 1e12
@@ -589,8 +611,11 @@ def run_ours(args):
         "data": "synthetic (uniform cube clouds, seeded random-init Encoder weights)",
         "config": config_block(args), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_POINTS * 12,
-                "d2h_bytes_per_step": B * N_GROUP * (384 + 3) * 4, "ms_per_step": ms_e2e / args.steps,
-                "checksum": checksum},
+                "d2h_bytes_per_step": B * N_GROUP * (384 * 2 + 3 * 4), "ms_per_step": ms_e2e16 / args.steps,
+                "token_dtype": "fp16 (PPT_TOKENS_F16: the fp32 tokens rounded once more in the last kernel's epilogue)",
+                "pinned": "NUMA-local (ppt_b200.hostmem)", "parity": parity_e2e,
+                "fp32_tokens": {"value": clouds_total / (ms_e2e32 * 1e-3), "unit": UNIT,
+                                "d2h_bytes_per_step": B * N_GROUP * (384 + 3) * 4, "ms_per_step": ms_e2e32 / args.steps}},
         # spatial index build, fps, knn_search, stage1, group_linear, stage2, group_linear
         "parity_checked": bool(parity and parity["ok"]), "parity": parity,
         "gpu_launches": 7 * args.steps, "roofline": roofline, "roofline_all": roofline_all, "widened": widened, "cpu_baseline": cpu,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PPT_B200_ABI_VERSION 1
+#define PPT_B200_ABI_VERSION 2
 
 #define PPT_EINVAL (-1) /* bad shape / null pointer */
 #define PPT_ERANGE (-2) /* size outside what the kernel supports */
@@ -174,6 +174,17 @@ int ppt_encoder_forward_phases(const float *neighborhood, const void *packed, vo
                                float *features_out, float *tokens_out, int64_t num_groups, int mode,
                                int phases, void *stream);
 
+/* The general entry point behind the two above.
+ *   flags: PPT_TOKENS_F16 -- tokens_out is [num_groups, 384] IEEE fp16 (the fp32 result rounded once more, saturating):
+ *          half the bytes for a caller that ships tokens to the host or feeds an fp16/autocast transformer;
+ *   clock_acc: NULL, or a device int64[2] the caller zeroed: CTA 0 of the stage-2 launch adds its lifetime in
+ *          nanoseconds (globaltimer) to [0] and in SM cycles (clock64) to [1] -- [1]/[0] is the SM clock in GHz inside
+ *          that kernel (measurement aid; selects a separately compiled copy of the kernel, the library keeps no state). */
+#define PPT_TOKENS_F16 1
+int ppt_encoder_forward_ex(const float *neighborhood, const void *packed, void *workspace,
+                           float *features_out, void *tokens_out, int64_t num_groups, int mode,
+                           int phases, int flags, void *clock_acc, void *stream);
+
 /* ---- Encoder.forward under model.train(): batch-statistics BatchNorm --------
  * PPT trains with model.train() (main_cls.py:169), which puts the FROZEN Encoder's two BatchNorm1d layers
  * (models/pointbert/dvae.py:190,196) in batch-statistics mode: they normalise with the mean / biased variance
@@ -229,11 +240,6 @@ int ppt_selftest_umma_pair(const float *a, const float *b, float *d, int N, int 
  * period_ns into out [samples][2] int64, on `stream` -- run it on a side stream next to the kernels under
  * test to see the SM clock inside them (DESIGN.md "clocks under load"). */
 int ppt_clock_probe(void *out, int samples, int64_t period_ns, void *stream);
-
-/* Measurement aid without any perturbation: while `acc` (device int64[2], zeroed by the caller) is set, CTA 0 of
- * every Encoder stage-2 launch adds its lifetime in nanoseconds (globaltimer) to acc[0] and in SM cycles (clock64)
- * to acc[1]; acc[1] / acc[0] is the SM clock in GHz inside that kernel.  NULL switches it off (the default). */
-int ppt_set_clock_trace(void *acc);
 
 #ifdef __cplusplus
 }

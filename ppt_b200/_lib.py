@@ -4,7 +4,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PPT_B200_LIB") or os.path.join(_HERE, "libppt_b200.so")  # override: A/B builds
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c = ctypes
 _p, _i, _f, _i64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64
@@ -46,13 +46,13 @@ SIGNATURES = {
     "ppt_encoder_workspace_bytes": (_i64, [_i64, _i]),
     "ppt_encoder_forward": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p]),
     "ppt_encoder_forward_phases": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p]),
+    "ppt_encoder_forward_ex": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p]),
     "ppt_encoder_train_workspace_bytes": (_i64, [_i64, _i]),
     "ppt_encoder_forward_train": (_i, [_p, _p, _c.POINTER(EncoderBn), _p, _p, _p, _i64, _i, _p]),
     "ppt_posembed_packed_bytes": (_i64, [_i]),
     "ppt_tokenizer_workspace_bytes": (_i64, [_i64, _i]),
     "ppt_tokenizer_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
     "ppt_clock_probe": (_i, [_p, _i, _i64, _p]),
-    "ppt_set_clock_trace": (_i, [_p]),
     "ppt_selftest_umma": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "ppt_selftest_umma_pair": (_i, [_p, _p, _p, _i, _i, _i, _p]),
 }

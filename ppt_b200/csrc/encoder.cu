@@ -1171,7 +1171,7 @@ template <uint32_t FMT, int SPLIT, int NUNITS, int KCH = 4, bool ASSEMBLE = fals
 __global__ void __launch_bounds__(LIN_THREADS, 1)
 group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned char* __restrict__ wsec,
                     const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ out,
-                    long long num_groups, int num_tiles, int rows_per_cloud) {
+                    long long num_groups, int num_tiles, int rows_per_cloud, int out_f16) {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int NT = 128;                      // groups per tile (MMA N)
   constexpr int NOUT = NUNITS * 128;
@@ -1272,7 +1272,13 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
           float v[32];
           tmem_ld32(t_addr + j * 32, v);
           const long long g0 = (long long)tile * NT + j * 32;
-          if (!ASSEMBLE) {
+          if (!ASSEMBLE && out_f16) {
+            // 16-bit rows (PPT_TOKENS_F16): same values rounded once more to fp16 (saturating), half the bytes
+            uint16_t* out16 = reinterpret_cast<uint16_t*>(out);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (g0 + i < num_groups) out16[(g0 + i) * NOUT + o] = to_operand<FMT_F16>(fmaf(v[i], inv_scale, bo));
+          } else if (!ASSEMBLE) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (g0 + i < num_groups) out[(g0 + i) * NOUT + o] = fmaf(v[i], inv_scale, bo);
@@ -1491,8 +1497,6 @@ constexpr size_t linear_smem_bytes() {
   return (size_t)4 * SPLIT * IMG + (size_t)NSTAGE * SPLIT * IMG + 256;
 }
 
-long long* g_clock_trace = nullptr;  // ppt_set_clock_trace
-
 int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -1527,7 +1531,8 @@ struct Workspace {
 // phases: bit 0 stage1, bit 1 group_linear(c), bit 2 stage2, bit 3 group_linear(tokens)
 template <uint32_t FMT, int SPLIT, int NT>
 int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws, float* features_out,
-                float* tokens_out, long long groups, int phases, cudaStream_t st, int rows_per_cloud = 0) {
+                float* tokens_out, long long groups, int phases, cudaStream_t st, int rows_per_cloud = 0,
+                int tokens_f16 = 0, long long* clock_acc = nullptr) {
   const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
   // stage 1 is bound by its epilogue side (layer-1 build + max): 16 epilogue warps where 32 columns each fit
@@ -1589,7 +1594,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   }
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
-                                        scales + 1, cbuf, groups, tiles128, 0);
+                                        scales + 1, cbuf, groups, tiles128, 0, 0);
   if (phases & 4) {
     if (SPLIT == 1 && use_pair) {
       const int ptiles = (int)((points + 255) / 256);
@@ -1638,14 +1643,14 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
         }
       }
     } else {
-      (g_clock_trace ? k2clk : k2)<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out,
-                                                                        groups, tiles, nullptr, nullptr, g_clock_trace);
+      (clock_acc ? k2clk : k2)<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out,
+                                                                    groups, tiles, nullptr, nullptr, clock_acc);
     }
   }
   if ((phases & 8) && tokens_out)
     (rows_per_cloud > 0 ? kda : kd)<<<grid_g, LIN_THREADS, sl, st>>>(
         ws + W.t_img, blob + L.WR(), reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,
-        groups, tiles128, rows_per_cloud);
+        groups, tiles128, rows_per_cloud, rows_per_cloud > 0 ? 0 : tokens_f16);
   return ppt_launch_status();
 }
 
@@ -1670,7 +1675,7 @@ int run_tokenizer(const float* nbhd, const float* center, const unsigned char* b
   kp<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.h_img, pblob + PosBlobLayout::W2(),
                                       reinterpret_cast<const float*>(pblob + PosBlobLayout::b2()),
                                       reinterpret_cast<const float*>(pblob + PosBlobLayout::scales()), pos_out, groups,
-                                      tiles128, rows_per_cloud);
+                                      tiles128, rows_per_cloud, 0);
   if (!x_out) return ppt_launch_status();
   return run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, x_out, groups, 15, st, rows_per_cloud);
 }
@@ -1723,9 +1728,13 @@ extern "C" PPT_EXPORT int64_t ppt_encoder_workspace_bytes(int64_t num_groups, in
   return (int64_t)Workspace(num_groups, mode == PPT_ENC_FP16X3 ? 2 : 1).total;
 }
 
-extern "C" PPT_EXPORT int ppt_encoder_forward_phases(const float* neighborhood, const void* packed, void* workspace,
-                                                     float* features_out, float* tokens_out, int64_t num_groups,
-                                                     int mode, int phases, void* stream) {
+extern "C" PPT_EXPORT int ppt_encoder_forward_ex(const float* neighborhood, const void* packed, void* workspace,
+                                                 float* features_out, void* tokens_out_v, int64_t num_groups, int mode,
+                                                 int phases, int flags, void* clock_acc_v, void* stream) {
+  float* tokens_out = static_cast<float*>(tokens_out_v);
+  const int tokens_f16 = (flags & PPT_TOKENS_F16) ? 1 : 0;
+  long long* clock_acc = static_cast<long long*>(clock_acc_v);
+  if (flags & ~PPT_TOKENS_F16) return PPT_EINVAL;
   if (!neighborhood || !packed || !workspace || (!tokens_out && !features_out) || num_groups < 1) return PPT_EINVAL;
   if (num_groups > (1ll << 31) / 32) return PPT_ERANGE;
   if ((reinterpret_cast<uintptr_t>(packed) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PPT_EINVAL;
@@ -1735,16 +1744,23 @@ extern "C" PPT_EXPORT int ppt_encoder_forward_phases(const float* neighborhood, 
   switch (mode) {
     case PPT_ENC_FP16:
       return run_encoder<tc05::FMT_F16, 1, 128>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
-                                                st);
+                                                st, 0, tokens_f16, clock_acc);
     case PPT_ENC_BF16:
       return run_encoder<tc05::FMT_BF16, 1, 128>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
-                                                 st);
+                                                 st, 0, tokens_f16, clock_acc);
     case PPT_ENC_FP16X3:
       return run_encoder<tc05::FMT_F16, 2, 64>(neighborhood, blob, ws, features_out, tokens_out, num_groups, phases,
-                                               st);
+                                               st, 0, tokens_f16, clock_acc);
     default:
       return PPT_EINVAL;
   }
+}
+
+extern "C" PPT_EXPORT int ppt_encoder_forward_phases(const float* neighborhood, const void* packed, void* workspace,
+                                                     float* features_out, float* tokens_out, int64_t num_groups,
+                                                     int mode, int phases, void* stream) {
+  return ppt_encoder_forward_ex(neighborhood, packed, workspace, features_out, tokens_out, num_groups, mode, phases, 0,
+                                nullptr, stream);
 }
 
 extern "C" PPT_EXPORT int ppt_encoder_forward(const float* neighborhood, const void* packed, void* workspace,
@@ -1833,7 +1849,3 @@ extern "C" PPT_EXPORT int ppt_encoder_forward_train(const float* neighborhood, v
   }
 }
 
-extern "C" PPT_EXPORT int ppt_set_clock_trace(void* acc) {
-  g_clock_trace = static_cast<long long*>(acc);
-  return 0;
-}

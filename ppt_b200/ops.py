@@ -309,28 +309,43 @@ _workspaces = {}
 
 def _workspace(key, nbytes):
     """Scratch owned by the host layer (the C ABI never allocates); grown on demand, one per
-    (device, purpose) key."""
+    (device, purpose, STREAM): kernels of one stream run in order, so reuse within a stream is safe, and two
+    streams (or two threads driving their own streams) never share a buffer.  A buffer that is outgrown is
+    released to torch's caching allocator, which keeps it reserved for this stream until its queued work is done."""
+    dev = key[0]
+    key = key + (torch.cuda.current_stream(dev).cuda_stream,)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=key[0])
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         _workspaces[key] = buf
     return buf
+
+
+def release_workspaces():
+    """Drops every cached scratch buffer (e.g. after a stream has been destroyed)."""
+    _workspaces.clear()
 
 
 def encoder_packed_bytes(mode):
     return int(_lib.load().ppt_encoder_packed_bytes(mode))
 
 
+TOKENS_F16 = 1  # PPT_TOKENS_F16
 ENC_PHASE_NAMES = ("stage1", "group_linear_c", "stage2", "group_linear_tokens")
 
 
-def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, want_tokens=True, phase_events=None):
+def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, want_tokens=True, phase_events=None,
+                    token_dtype=torch.float32, clock_acc=None):
     """neighborhood [..., 32, 3] fp32 (CUDA) -> tokens [..., 384] (and Encoder features [..., 256]).
 
     `packed` is the uint8 CUDA blob from ppt_b200.encoder_pack.pack_encoder(state_dict, mode).
     `phase_events`: optional list; when given, the four launches are issued one by one and a
     (name, start_event, end_event) triple per launch is appended (for per-kernel timing on
-    the launching stream)."""
+    the launching stream).
+    `token_dtype`: torch.float32 (the reference's dtype) or torch.float16 (PPT_TOKENS_F16: the same values
+    rounded once more to fp16 in the last kernel's epilogue -- half the bytes to ship).
+    `clock_acc`: optional int64[2] CUDA tensor (zeroed by the caller) that receives ns / SM cycles of the
+    stage-2 kernel's CTA 0 (measurement aid, Stage2ClockTrace)."""
     _need_cuda(neighborhood, packed)
     nb = _f32(neighborhood)
     if nb.dim() < 3 or nb.shape[-1] != 3 or nb.shape[-2] != 32:
@@ -345,21 +360,27 @@ def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, 
         raise ValueError("packed weight blob does not match mode %d" % mode)
     if not (want_tokens or return_features):
         raise ValueError("nothing to compute")
-    tokens = torch.empty(lead + (384,), dtype=torch.float32, device=nb.device) if want_tokens else None
+    if token_dtype not in (torch.float32, torch.float16):
+        raise ValueError("token_dtype must be torch.float32 or torch.float16")
+    flags = TOKENS_F16 if token_dtype == torch.float16 else 0
+    tokens = torch.empty(lead + (384,), dtype=token_dtype, device=nb.device) if want_tokens else None
     feats = torch.empty(lead + (256,), dtype=torch.float32, device=nb.device) if return_features else None
     if groups == 0:
         return (tokens, feats) if return_features else tokens
+    if clock_acc is not None and not (clock_acc.is_cuda and clock_acc.dtype == torch.int64 and clock_acc.numel() >= 2):
+        raise ValueError("clock_acc must be a CUDA int64[2] tensor")
     ws = _workspace((nb.device, "encoder"), lib.ppt_encoder_workspace_bytes(groups, mode))
     with torch.cuda.device(nb.device):
         if phase_events is None:
-            _lib.check(lib.ppt_encoder_forward_phases(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens),
-                                                      groups, mode, 15, _stream(nb)), "ppt_encoder_forward")
+            _lib.check(lib.ppt_encoder_forward_ex(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens), groups,
+                                                  mode, 15, flags, _ptr(clock_acc), _stream(nb)), "ppt_encoder_forward")
         else:
             for bit, name in enumerate(ENC_PHASE_NAMES):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                _lib.check(lib.ppt_encoder_forward_phases(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens),
-                                                          groups, mode, 1 << bit, _stream(nb)), "ppt_encoder_" + name)
+                _lib.check(lib.ppt_encoder_forward_ex(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens), groups,
+                                                      mode, 1 << bit, flags, _ptr(clock_acc), _stream(nb)),
+                           "ppt_encoder_" + name)
                 e1.record()
                 phase_events.append((name, e0, e1))
     return (tokens, feats) if return_features else tokens
@@ -459,19 +480,18 @@ def selftest_umma_pair(a, b, mode=ENC_FP16, b_mn_major=False):
 
 
 class Stage2ClockTrace:
-    """SM clock inside the Encoder's stage-2 kernel, without perturbing it: CTA 0 of every launch adds its lifetime
-    in ns and in SM cycles to a device accumulator (ppt_set_clock_trace).  Use as a context manager; .mhz after."""
+    """SM clock inside the Encoder's stage-2 kernel, without perturbing it: pass `.acc` as encoder_forward's
+    `clock_acc` and CTA 0 of every such launch adds its lifetime in ns and in SM cycles to it.  Use as a context
+    manager; .mhz after.  (No library state: the accumulator travels with the call.)"""
 
     def __init__(self, device):
         self.acc = torch.zeros(2, dtype=torch.int64, device=device)
         self.mhz = None
 
     def __enter__(self):
-        _lib.check(_lib.load().ppt_set_clock_trace(_ptr(self.acc)), "ppt_set_clock_trace")
         return self
 
     def __exit__(self, *exc):
-        _lib.load().ppt_set_clock_trace(None)
         torch.cuda.synchronize(self.acc.device)
         ns, cyc = (int(v) for v in self.acc.cpu())
         self.mhz = cyc / ns * 1e3 if ns > 0 else None

@@ -165,17 +165,20 @@ class Encoder(nn.Module):
         feature = self.second_conv(torch.cat([glob.expand(-1, -1, n), feature], dim=1))
         return torch.max(feature, dim=2, keepdim=False)[0].reshape(bs, g, self.encoder_channel)
 
-    def forward_tokens(self, point_groups):
-        """(B,G,32,3) -> reduce_dim(Encoder(point_groups)) : (B,G,384), one fused pipeline."""
+    def forward_tokens(self, point_groups, token_dtype=torch.float32):
+        """(B,G,32,3) -> reduce_dim(Encoder(point_groups)) : (B,G,384), one fused pipeline.
+        token_dtype=torch.float16 stores the tokens as fp16 (eval mode: in the last kernel's epilogue)."""
         if self._reduce_dim is None:
             raise RuntimeError("attach_reduce_dim() first")
         if self.training:
             if self._train_fusable(point_groups):
-                return train_forward(self, point_groups, self._state_for_pack, ops.ENC_MODES[self.precision],
-                                     want_tokens=True)
-            return self._reduce_dim(self._forward_torch(point_groups))
+                out = train_forward(self, point_groups, self._state_for_pack, ops.ENC_MODES[self.precision],
+                                    want_tokens=True)
+            else:
+                out = self._reduce_dim(self._forward_torch(point_groups))
+            return out if token_dtype == torch.float32 else out.to(token_dtype)
         blob, mode = self._blob(point_groups.device)
-        return ops.encoder_forward(point_groups, blob, mode=mode)
+        return ops.encoder_forward(point_groups, blob, mode=mode, token_dtype=token_dtype)
 
     # -- reference API ----------------------------------------------------------------------------
     def forward(self, point_groups):

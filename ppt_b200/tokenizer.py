@@ -75,10 +75,11 @@ class PointTokenizer(nn.Module):
         return ops.knn_group(xyz, center, self.group_size, index=index), center
 
     @torch.no_grad()
-    def forward(self, xyz, return_neighborhood=False):
-        """xyz [B,N,3] (CUDA) -> tokens [B,G,384], center [B,G,3] (, neighborhood [B,G,32,3])."""
+    def forward(self, xyz, return_neighborhood=False, token_dtype=torch.float32):
+        """xyz [B,N,3] (CUDA) -> tokens [B,G,384], center [B,G,3] (, neighborhood [B,G,32,3]).
+        token_dtype: torch.float32 (the reference's dtype) or torch.float16 (half the bytes; adds one fp16 rounding)."""
         neighborhood, center = self.group(xyz)
-        tokens = self.encoder.forward_tokens(neighborhood)
+        tokens = self.encoder.forward_tokens(neighborhood, token_dtype=token_dtype)
         if return_neighborhood:
             return tokens, center, neighborhood
         return tokens, center
@@ -92,15 +93,22 @@ class HostPipeline:
     data-loader-fed caller uses (pc.to(gpu) ... features.cpu(), main_cls.py:188-189,
     lp_feat_extractor.py:53-56), and what bench.py reports as `e2e`."""
 
-    def __init__(self, tokenizer, batch, points, depth=2, device=None):
+    def __init__(self, tokenizer, batch, points, depth=2, device=None, token_dtype=torch.float32, numa_local=True):
+        """token_dtype: dtype of the tokens that reach the host (fp32 = the reference's; fp16 halves the D2H bytes,
+        which bound this path on PCIe).  numa_local: allocate the pinned output buffers on the NUMA node the GPU
+        hangs off (hostmem.pinned_empty), so the DMA does not cross the socket interconnect."""
+        from . import hostmem
         self.tok = tokenizer
         self.device = device or next(tokenizer.parameters()).device
         self.depth = depth
+        self.token_dtype = token_dtype
         G = tokenizer.num_group
         D = tokenizer.reduce_dim.out_features
+        alloc = (lambda shape, dt: hostmem.pinned_empty(shape, dt, self.device)) if numa_local else \
+            (lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory())
         self.dev_in = [torch.empty((batch, points, 3), dtype=torch.float32, device=self.device) for _ in range(depth)]
-        self.out_tokens = [torch.empty((batch, G, D), dtype=torch.float32).pin_memory() for _ in range(depth)]
-        self.out_center = [torch.empty((batch, G, 3), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.out_tokens = [alloc((batch, G, D), token_dtype) for _ in range(depth)]
+        self.out_center = [alloc((batch, G, 3), torch.float32) for _ in range(depth)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_run = [torch.cuda.Event() for _ in range(depth)]
@@ -127,7 +135,7 @@ class HostPipeline:
                 self.ev_in[slot].record(self.s_in)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(self.ev_in[slot])
-                tokens, center = self.tok(self.dev_in[slot])
+                tokens, center = self.tok(self.dev_in[slot], token_dtype=self.token_dtype)
                 self.ev_consumed[slot].record(self.s_run)
                 self.ev_run[slot].record(self.s_run)
             with torch.cuda.stream(self.s_out):

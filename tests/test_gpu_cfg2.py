@@ -40,3 +40,45 @@ def test_tokenizer_cfg2_halves_agree():
     a = a.clone()
     b, _ = tok(xyz[64:].contiguous())
     assert torch.equal(full[:64], a) and torch.equal(full[64:], b)
+
+
+def test_fp16_token_output_is_the_fp32_output_rounded_once():
+    """PPT_TOKENS_F16 (ops.encoder_forward token_dtype=float16): the last kernel's epilogue stores round-to-nearest
+    fp16 of exactly the value it would have stored as fp32."""
+    tok = bench.make_tokenizer("fp16").cuda()
+    xyz = bench.make_host_batches(0, 1, batch=8, pin=False)[0].cuda()
+    t32, c32 = tok(xyz)
+    t16, c16 = tok(xyz, token_dtype=torch.float16)
+    assert t16.dtype == torch.float16 and torch.equal(c16, c32)
+    assert torch.equal(t16, t32.half())
+
+
+def test_two_streams_do_not_share_scratch():
+    """ops._workspace is keyed by (device, purpose, stream): two tokenizer calls in flight on two streams give
+    the results of the same calls run one after the other (shared scratch raced)."""
+    tok = bench.make_tokenizer("fp16").cuda()
+    a, b = (t.cuda() for t in bench.make_host_batches(0, 2, batch=32, pin=False))
+    want_a, want_b = tok(a)[0].clone(), tok(b)[0].clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            got_a = tok(a)[0]
+        with torch.cuda.stream(s2):
+            got_b = tok(b)[0]
+        torch.cuda.synchronize()
+        assert torch.equal(got_a, want_a) and torch.equal(got_b, want_b)
+
+
+def test_host_pipeline_delivers_the_same_tokens():
+    from ppt_b200.tokenizer import HostPipeline
+    tok = bench.make_tokenizer("fp16").cuda()
+    host = bench.make_host_batches(0, 4, batch=16)
+    want = [tok(h.cuda())[0].cpu() for h in host]
+    for dt in (torch.float32, torch.float16):
+        pipe = HostPipeline(tok, 16, bench.N_POINTS, depth=3, device=torch.device("cuda", 0), token_dtype=dt)
+        got = {}
+        pipe.run(iter(host), on_result=lambda i, t, c: got.__setitem__(i, t.clone()))
+        assert sorted(got) == [0, 1, 2, 3]
+        for i in range(4):
+            assert torch.equal(got[i], want[i].to(dt))
