@@ -68,7 +68,8 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   }
   __syncthreads();
 
-  unsigned far = (unsigned)start[b];
+  const int64_t s0 = start[b];  // the reference indexes xyz[start] (raises when out of range): clamp instead
+  unsigned far = (unsigned)(s0 < 0 ? 0 : (s0 >= N ? N - 1 : s0));
   float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
   int64_t* out = idx_out + (size_t)b * G;
   float* cout = centers_out ? centers_out + (size_t)b * G * 3 : nullptr;

@@ -22,7 +22,10 @@ __global__ void gather_kernel(const float* __restrict__ points, const int64_t* _
     const size_t e = e0 + t;
     if (e < total) {
       const int m = (int)(e / C), c = (int)(e - (size_t)m * C);
-      v[t] = __ldg(src + (size_t)ib[m] * C + c);
+      const int64_t n = ib[m];
+      // an index outside [0, N) (e.g. query_ball_point's empty-ball sentinel N, which makes the reference raise
+      // an IndexError) yields NaN instead of an out-of-bounds read
+      v[t] = (uint64_t)n < (uint64_t)N ? __ldg(src + (size_t)n * C + c) : __int_as_float(0x7fc00000);
     } else {
       v[t] = 0.f;
     }
@@ -60,7 +63,9 @@ __global__ void group_concat_kernel(const float* __restrict__ xyz, const float* 
       const int row = (int)(e / C), c = (int)(e - (size_t)row * C);
       const int64_t n = ib[row];
       const int cx = c - xyz_lo;
-      if (cx >= 0 && cx < 3) {
+      if ((uint64_t)n >= (uint64_t)N) {
+        v[t] = __int_as_float(0x7fc00000);  // out-of-range index: NaN, never an out-of-bounds read
+      } else if (cx >= 0 && cx < 3) {
         const int s = row / K;
         v[t] = __fsub_rn(__ldg(cloud + (size_t)n * 3 + cx), __ldg(ctr + (size_t)s * 3 + cx));
       } else {

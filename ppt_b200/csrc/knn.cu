@@ -121,10 +121,13 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ query, int64
     if (dist_out) dist_out[o] = top[u].d;
     if (GROUP) {
       // dvae.py:177-180: neighborhood = xyz[idx] - center  (one fp32 subtract each)
-      const float* p = cloud + (size_t)top[u].i * 3;
-      nb_out[o * 3 + 0] = __fsub_rn(p[0], qx[u]);
-      nb_out[o * 3 + 1] = __fsub_rn(p[1], qy[u]);
-      nb_out[o * 3 + 2] = __fsub_rn(p[2], qz[u]);
+      // NaN coordinates leave unfilled slots (index 0x7fffffff): NaN rows, not an out-of-bounds read
+      const bool ok = (unsigned)top[u].i < (unsigned)N;
+      const float* p = cloud + (size_t)(ok ? top[u].i : 0) * 3;
+      const float nanv = __int_as_float(0x7fc00000);
+      nb_out[o * 3 + 0] = ok ? __fsub_rn(p[0], qx[u]) : nanv;
+      nb_out[o * 3 + 1] = ok ? __fsub_rn(p[1], qy[u]) : nanv;
+      nb_out[o * 3 + 2] = ok ? __fsub_rn(p[2], qz[u]) : nanv;
     }
   }
 }

@@ -326,10 +326,12 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
       if (idx_out) idx_out[o] = (int64_t)ti;
       if (dist_out) dist_out[o] = key_dist(t.key);
       if (GROUP) {
-        const float* p = cloud + (size_t)ti * 3;
-        nb_out[o * 3 + 0] = __fsub_rn(p[0], qx);
-        nb_out[o * 3 + 1] = __fsub_rn(p[1], qy);
-        nb_out[o * 3 + 2] = __fsub_rn(p[2], qz);
+        const bool ok = (unsigned)ti < (unsigned)N;  // NaN coordinates leave unfilled slots: NaN rows, no wild read
+        const float* p = cloud + (size_t)(ok ? ti : 0) * 3;
+        const float nanv = __int_as_float(0x7fc00000);
+        nb_out[o * 3 + 0] = ok ? __fsub_rn(p[0], qx) : nanv;
+        nb_out[o * 3 + 1] = ok ? __fsub_rn(p[1], qy) : nanv;
+        nb_out[o * 3 + 2] = ok ? __fsub_rn(p[2], qz) : nanv;
       }
     }
   }

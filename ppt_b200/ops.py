@@ -35,6 +35,13 @@ def _ptr(t):
 AUTO = "auto"
 
 
+def _xyz3(name, t):
+    """The geometry kernels are written for 3-D coordinates (stride 3 in the C ABI): anything else is an error here,
+    never a silently wrong answer (feature-space kNN etc. must stay on the caller's torch code; patch.py does that)."""
+    if t.dim() != 3 or t.shape[-1] != 3:
+        raise ValueError("%s must be [B, N, 3] (got %s)" % (name, tuple(t.shape)))
+
+
 def spatial_index(xyz):
     """Builds the per-cloud spatial index used by fps / knn / knn_group to skip far-away rows of the
     cloud (results are bit-identical with and without it).  Returns None where it does not apply
@@ -60,10 +67,9 @@ def fps(xyz, npoint, start, return_centers=False, index=AUTO):
     """farthest_point_sample with a given start index tensor [B] -> idx [B,npoint] (int64).
     index: AUTO (build one if it applies), None (plain kernel), or the result of spatial_index(xyz)."""
     _need_cuda(xyz, start)
+    _xyz3("xyz", xyz)
     xyz = _f32(xyz)
     B, N, C = xyz.shape
-    if C != 3:
-        raise ValueError("xyz must be [B,N,3]")
     start = _i64(start)
     idx = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
     centers = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device) if return_centers else None
@@ -76,6 +82,7 @@ def fps(xyz, npoint, start, return_centers=False, index=AUTO):
 
 def square_distance(src, dst):
     _need_cuda(src, dst)
+    _xyz3("src", src), _xyz3("dst", dst)
     src, dst = _f32(src), _f32(dst)
     B, S, _ = src.shape
     N = dst.shape[1]
@@ -88,6 +95,7 @@ def square_distance(src, dst):
 
 def knn(k, xyz, query, return_dist=False, index=AUTO):
     _need_cuda(xyz, query)
+    _xyz3("xyz", xyz), _xyz3("query", query)
     xyz, query = _f32(xyz), _f32(query)
     B, N, _ = xyz.shape
     S = query.shape[1]
@@ -102,6 +110,7 @@ def knn(k, xyz, query, return_dist=False, index=AUTO):
 
 def knn_group(xyz, center, k, return_idx=False, index=AUTO):
     _need_cuda(xyz, center)
+    _xyz3("xyz", xyz), _xyz3("center", center)
     xyz, center = _f32(xyz), _f32(center)
     B, N, _ = xyz.shape
     G = center.shape[1]
@@ -116,6 +125,7 @@ def knn_group(xyz, center, k, return_idx=False, index=AUTO):
 
 def ball_query(radius, nsample, xyz, new_xyz):
     _need_cuda(xyz, new_xyz)
+    _xyz3("xyz", xyz), _xyz3("new_xyz", new_xyz)
     xyz, new_xyz = _f32(xyz), _f32(new_xyz)
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
@@ -128,10 +138,7 @@ def ball_query(radius, nsample, xyz, new_xyz):
     return idx
 
 
-def gather(points, idx):
-    """index_points: points [B,N,C], idx [B,...] -> [B,...,C]."""
-    _need_cuda(points, idx)
-    points, idx = _f32(points), _i64(idx)
+def _gather_fwd(points, idx):
     B, N, C = points.shape
     M = idx[0].numel() if B else 0
     out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
@@ -141,15 +148,43 @@ def gather(points, idx):
     return out
 
 
-def group_concat(xyz, new_xyz, points, idx, xyz_first=True):
-    _need_cuda(xyz, new_xyz, points, idx)
-    xyz, new_xyz, idx = _f32(xyz), _f32(new_xyz), _i64(idx)
+def _scatter_rows(grad_rows, idx, N):
+    """Adjoint of a row gather: grad_rows [B, M, C] accumulated into [B, N, C] at rows idx [B, M] (torch
+    scatter_add: the backward is not on PPT's hot path -- its backbones are frozen -- it only has to be right)."""
+    B, M, C = grad_rows.shape
+    out = torch.zeros((B, N, C), dtype=grad_rows.dtype, device=grad_rows.device)
+    return out.scatter_add_(1, idx.reshape(B, M, 1).expand(B, M, C), grad_rows)
+
+
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        ctx.save_for_backward(idx)
+        ctx.N = points.shape[1]
+        return _gather_fwd(points, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, C = grad_out.shape[0], grad_out.shape[-1]
+        return _scatter_rows(_f32(grad_out).reshape(B, -1, C), idx.reshape(B, -1), ctx.N), None
+
+
+def gather(points, idx):
+    """index_points: points [B,N,C], idx [B,...] -> [B,...,C].  Differentiable w.r.t. points."""
+    _need_cuda(points, idx)
+    points, idx = _f32(points), _i64(idx)
+    if points.dim() != 3 or idx.dim() < 2 or idx.shape[0] != points.shape[0]:
+        raise ValueError("gather: points [B,N,C], idx [B,...]")
+    if points.requires_grad and torch.is_grad_enabled():
+        return _Gather.apply(points, idx)
+    return _gather_fwd(points, idx)
+
+
+def _group_concat_fwd(xyz, new_xyz, points, idx, xyz_first):
     B, N, _ = xyz.shape
     _, S, K = idx.shape
-    D = 0
-    if points is not None:
-        points = _f32(points)
-        D = points.shape[2]
+    D = 0 if points is None else points.shape[2]
     out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         _lib.check(_lib.load().ppt_group_concat(_ptr(xyz), _ptr(new_xyz), _ptr(points), _ptr(idx), _ptr(out), B, N, S,
@@ -157,8 +192,48 @@ def group_concat(xyz, new_xyz, points, idx, xyz_first=True):
     return out
 
 
+class _GroupConcat(torch.autograd.Function):
+    """out[b,s,j] = cat(xyz[b,idx] - new_xyz[b,s], points[b,idx]) (or features first): gradients for xyz, new_xyz
+    and points, so an unfrozen PointNet++ backbone trains correctly through the grouping."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, points, idx, xyz_first):
+        ctx.save_for_backward(idx)
+        ctx.N, ctx.xyz_first, ctx.has_points = xyz.shape[1], xyz_first, points is not None
+        return _group_concat_fwd(xyz, new_xyz, points, idx, xyz_first)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        g = _f32(grad_out)
+        B, S, K, C = g.shape
+        lo = 0 if ctx.xyz_first else C - 3
+        g_xyz = g[..., lo:lo + 3]
+        flat = idx.reshape(B, S * K)
+        d_xyz = _scatter_rows(g_xyz.reshape(B, S * K, 3).contiguous(), flat, ctx.N)
+        d_new = -g_xyz.sum(dim=2)
+        d_pts = None
+        if ctx.has_points:
+            g_f = g[..., 3:] if ctx.xyz_first else g[..., :C - 3]
+            d_pts = _scatter_rows(g_f.reshape(B, S * K, C - 3).contiguous(), flat, ctx.N)
+        return d_xyz, d_new, d_pts, None, None
+
+
+def group_concat(xyz, new_xyz, points, idx, xyz_first=True):
+    _need_cuda(xyz, new_xyz, points, idx)
+    _xyz3("xyz", xyz), _xyz3("new_xyz", new_xyz)
+    xyz, new_xyz, idx = _f32(xyz), _f32(new_xyz), _i64(idx)
+    if points is not None:
+        points = _f32(points)
+    if torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad
+                                    or (points is not None and points.requires_grad)):
+        return _GroupConcat.apply(xyz, new_xyz, points, idx, xyz_first)
+    return _group_concat_fwd(xyz, new_xyz, points, idx, xyz_first)
+
+
 def three_nn(unknown, known):
     _need_cuda(unknown, known)
+    _xyz3("unknown", unknown), _xyz3("known", known)
     unknown, known = _f32(unknown), _f32(known)
     B, N, _ = unknown.shape
     S = known.shape[1]

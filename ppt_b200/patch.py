@@ -35,13 +35,59 @@ _FUNCTIONS = {
     },
     "models.pointbert.point_encoder": {},  # PointTransformer.forward (class patch below)
     "models.pointmlp.pointMLP": {
-        "farthest_point_sample": pointbert.farthest_point_sample, "index_points": pointbert.index_points,
+        "furthest_point_sample": pointbert.farthest_point_sample,  # sic: pointMLP.py:64 spells it "furthest"
+        "index_points": pointbert.index_points,
         "knn_point": pointbert.knn_point, "square_distance": pointbert.square_distance,
         "query_ball_point": pointnet2.query_ball_point,
     },
 }
 
 _installed = []  # (owner, attribute, original)
+missing = []     # 'module.attribute' entries of the table that the imported tree did not have (last patch_reference call)
+
+
+# ---- the envelope the kernels cover; anything else keeps the reference's own code ----------------------------
+def _f32_cuda(*tensors):
+    return all(t.is_cuda and t.dtype == torch.float32 for t in tensors)
+
+
+def _is_xyz(*tensors):
+    return all(t.dim() == 3 and t.shape[-1] == 3 for t in tensors)
+
+
+def _ok_fps(xyz, npoint, *a, **k):
+    return _f32_cuda(xyz) and _is_xyz(xyz) and 1 <= xyz.shape[1] <= 65536 and npoint >= 1
+
+
+def _ok_fps_data(data, number, *a, **k):
+    return _ok_fps(data, number)
+
+
+def _ok_index_points(points, idx, *a, **k):
+    return (_f32_cuda(points) and points.dim() == 3 and idx.dtype == torch.int64 and idx.dim() in (2, 3)
+            and points.shape[0] <= 65535)
+
+
+def _ok_sqdist(src, dst, *a, **k):
+    return _f32_cuda(src, dst) and _is_xyz(src, dst) and src.shape[1] <= 65535 and src.shape[0] <= 65535
+
+
+def _ok_knn(nsample, xyz, new_xyz, *a, **k):
+    return _f32_cuda(xyz, new_xyz) and _is_xyz(xyz, new_xyz) and 1 <= nsample <= min(32, xyz.shape[1])
+
+
+def _ok_ball(radius, nsample, xyz, new_xyz, *a, **k):
+    return _f32_cuda(xyz, new_xyz) and _is_xyz(xyz, new_xyz) and nsample >= 1
+
+
+def _ok_sample_and_group(npoint, radius, nsample, xyz, points, *a, **k):
+    return (_ok_fps(xyz, npoint) and nsample >= 1 and xyz.shape[0] <= 65535
+            and (points is None or (_f32_cuda(points) and points.dim() == 3)))
+
+
+_SUPPORTED = {"fps": _ok_fps_data, "farthest_point_sample": _ok_fps, "furthest_point_sample": _ok_fps,
+              "index_points": _ok_index_points, "square_distance": _ok_sqdist, "knn_point": _ok_knn,
+              "query_ball_point": _ok_ball, "sample_and_group": _ok_sample_and_group}
 
 
 def _first_tensor(args, kwargs):
@@ -51,12 +97,20 @@ def _first_tensor(args, kwargs):
     return None
 
 
-def _divert_cuda(original, replacement):
+def _divert_cuda(original, replacement, supported=None):
+    """CUDA fp32 arguments inside the kernels' envelope (3-D coordinates, k <= 32, N <= 65536, ...) go to
+    `replacement`; CPU tensors, other dtypes, feature-space inputs and out-of-envelope sizes keep running the
+    reference's own code -- never an error or a wrong answer where the reference had a right one."""
     @functools.wraps(original)
     def wrapper(*args, **kwargs):
         t = _first_tensor(args, kwargs)
         if t is not None and t.is_cuda:
-            return replacement(*args, **kwargs)
+            try:
+                ok = supported is None or supported(*args, **kwargs)
+            except Exception:
+                ok = False
+            if ok:
+                return replacement(*args, **kwargs)
         return original(*args, **kwargs)
 
     wrapper.__ppt_b200_original__ = original
@@ -70,10 +124,7 @@ def _set(owner, name, value):
 
 def _group_forward(self, xyz):
     """Group.forward, models/pointbert/dvae.py:159-181."""
-    start = pointbert._draw_start(xyz)
-    index = ops.spatial_index(xyz)
-    _, center = ops.fps(xyz, self.num_group, start, return_centers=True, index=index)
-    return ops.knn_group(xyz, center, self.group_size, index=index), center
+    return pointbert.group_forward(xyz, self.num_group, self.group_size, pointbert._draw_start(xyz))
 
 
 def _encoder_forward(self, point_groups):
@@ -152,9 +203,12 @@ def _fp_forward(self, xyz1, xyz2, points1, points2):
 
 def patch_reference(modules=None):
     """Rebinds the hot-path names on every reference module that is importable.
-    Returns the list of patched 'module.attribute' names.  Idempotent."""
+    Returns the list of patched 'module.attribute' names; entries of the table that the tree does not have are
+    listed in `patch.missing` and reported with a warning (a silently unpatched function would leave the Python
+    loop in place).  Idempotent."""
     if _installed:
         return [getattr(o, "__name__", repr(o)) + "." + n for o, n, _ in _installed]
+    del missing[:]
     names = modules if modules is not None else list(_FUNCTIONS)
     for modname in names:
         mod = sys.modules.get(modname)
@@ -165,17 +219,24 @@ def patch_reference(modules=None):
                 continue  # optional backbone whose imports are unavailable
         for attr, repl in _FUNCTIONS.get(modname, {}).items():
             if hasattr(mod, attr):
-                _set(mod, attr, _divert_cuda(getattr(mod, attr), repl))
+                _set(mod, attr, _divert_cuda(getattr(mod, attr), repl, _SUPPORTED.get(attr)))
+            else:
+                missing.append(modname + "." + attr)
         if modname == "models.pointbert.dvae":
             orig_g, orig_e = mod.Group.forward, mod.Encoder.forward
 
             def group_fwd(self, xyz, _o=orig_g):
-                return _group_forward(self, xyz) if xyz.is_cuda else _o(self, xyz)
+                ok = _f32_cuda(xyz) and _is_xyz(xyz) and xyz.shape[1] <= 65536 and \
+                    1 <= self.group_size <= min(32, xyz.shape[1])
+                return _group_forward(self, xyz) if ok else _o(self, xyz)
 
             def enc_fwd(self, pg, _o=orig_e):
                 if pg.is_cuda and self.training and pointbert.train_forward_fusable(self, pg):
                     return _encoder_forward_train(self, pg)
-                fused = pg.is_cuda and not self.training and pg.shape[2] == 32 and self.encoder_channel == 256
+                # forward-only kernels: an unfrozen fine-tune (anything here wants a gradient) keeps the torch layers
+                frozen = not pointbert._needs_grad(pg, *self.parameters())
+                fused = (_f32_cuda(pg) and not self.training and frozen and pg.dim() == 4 and pg.shape[2] == 32
+                         and pg.shape[3] == 3 and self.encoder_channel == 256)
                 return _encoder_forward(self, pg) if fused else _o(self, pg)
 
             _set(mod.Group, "forward", group_fwd)
@@ -193,7 +254,7 @@ def patch_reference(modules=None):
                 orig_f = cls.forward
 
                 def fp_fwd(self, xyz1, xyz2, points1, points2, _o=orig_f):
-                    if xyz1.is_cuda:
+                    if _f32_cuda(xyz1, xyz2, points2) and xyz1.shape[1] == 3 and (xyz2.shape[2] == 1 or xyz2.shape[2] >= 3):
                         return _fp_forward(self, xyz1, xyz2, points1, points2)
                     return _o(self, xyz1, xyz2, points1, points2)
 
@@ -213,7 +274,7 @@ def patch_reference(modules=None):
                 orig_s = ssg.forward
 
                 def ssg_fwd(self, xyz, points, _o=orig_s):
-                    if xyz.is_cuda:
+                    if _f32_cuda(xyz) and xyz.shape[1] == 3 and xyz.shape[0] <= 65535:
                         if not hasattr(self, "start_idx"):
                             self.start_idx = None
                         return pointnet2.PointNetSetAbstraction.forward(self, xyz, points)  # fused shared MLP in eval
@@ -225,14 +286,28 @@ def patch_reference(modules=None):
                 orig_m = msg.forward
 
                 def msg_fwd(self, xyz, points, _o=orig_m):
-                    if xyz.is_cuda:
+                    if _f32_cuda(xyz) and xyz.shape[1] == 3 and xyz.shape[0] <= 65535:
                         if not hasattr(self, "start_idx"):
                             self.start_idx = None
                         return pointnet2.PointNetSetAbstractionMsg.forward(self, xyz, points)
                     return _o(self, xyz, points)
 
                 _set(msg, "forward", msg_fwd)
+    if missing:
+        import warnings
+        warnings.warn("ppt_b200.patch: not found in the imported tree (left unpatched): " + ", ".join(missing))
     return [getattr(o, "__name__", repr(o)) + "." + n for o, n, _ in _installed]
+
+
+def invalidate(model):
+    """Drops every packed-weight cache hanging off `model`'s sub-modules.  The caches are keyed on (data_ptr,
+    _version), which misses writes through `param.data.copy_()` -- the reference's own loading idiom
+    (models/ULIP_models.py:507): call this after loading weights that way once a forward has already run."""
+    for m in model.modules():
+        for name in ("_ppt_key", "_ppt_blob", "_ppt_train_key", "_ppt_train_blob", "_ppt_front_key", "_ppt_front_blobs",
+                     "_ppt_sa_cache", "_packed", "_packed_key", "_pos_packed", "_pos_key"):
+            if name in m.__dict__:
+                object.__setattr__(m, name, {} if name == "_ppt_sa_cache" else None)
 
 
 def unpatch_reference():

@@ -33,14 +33,24 @@ def index_points(points, idx):
     return ops.gather(points, idx)
 
 
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def fps(data, number, start_idx=None):
     """models/pointbert/misc.py:12-24.  data [B,N,3] -> fps_data [B,number,3]."""
     start = _draw_start(data) if start_idx is None else _as_start(start_idx, data)
+    if _needs_grad(data):  # the gather is the differentiable part (index_points, misc.py:23)
+        return ops.gather(data, ops.fps(data.detach(), number, start))
     return ops.fps(data, number, start, return_centers=True)[1]
 
 
 def square_distance(src, dst):
     """models/pointbert/dvae.py:130-149.  src [B,N,C], dst [B,M,C] -> [B,N,M] (C = 3)."""
+    if _needs_grad(src, dst):  # the kernel is forward only: keep autograd's graph with the reference's own formula
+        dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+        dist = dist + torch.sum(src ** 2, -1).unsqueeze(-1)
+        return dist + torch.sum(dst ** 2, -1).unsqueeze(1)
     return ops.square_distance(src, dst)
 
 
@@ -48,6 +58,20 @@ def knn_point(nsample, xyz, new_xyz):
     """models/pointbert/dvae.py:116-127.  -> group_idx [B,S,nsample] int64.  The reference's
     topk(sorted=False) leaves the order unspecified; here it is ascending (distance, index)."""
     return ops.knn(nsample, xyz, new_xyz)
+
+
+def group_forward(xyz, num_group, group_size, start):
+    """Group.forward behind the start-index draw (dvae.py:163-180).  Indices come from the kernels either way; when
+    the coordinates need a gradient the two gathers go through the differentiable ops.gather."""
+    if _needs_grad(xyz):
+        x = xyz.detach()
+        index = ops.spatial_index(x)
+        center = ops.gather(xyz, ops.fps(x, num_group, start, index=index))
+        idx = ops.knn(group_size, x, center.detach(), index=index)
+        return ops.gather(xyz, idx) - center.unsqueeze(2), center
+    index = ops.spatial_index(xyz)  # one index serves both FPS and kNN
+    _, center = ops.fps(xyz, num_group, start, return_centers=True, index=index)
+    return ops.knn_group(xyz, center, group_size, index=index), center
 
 
 class Group(nn.Module):
@@ -62,10 +86,7 @@ class Group(nn.Module):
     def forward(self, xyz):
         """xyz [B,N,3] -> neighborhood [B,G,M,3], center [B,G,3]."""
         start = _draw_start(xyz) if self.start_idx is None else _as_start(self.start_idx, xyz)
-        index = ops.spatial_index(xyz)  # one index serves both FPS and kNN
-        _, center = ops.fps(xyz, self.num_group, start, return_centers=True, index=index)
-        neighborhood = ops.knn_group(xyz, center, self.group_size, index=index)
-        return neighborhood, center
+        return group_forward(xyz, self.num_group, self.group_size, start)
 
 
 def train_forward_fusable(module, point_groups, reduce_dim=None):
@@ -155,6 +176,21 @@ class Encoder(nn.Module):
             self._packed_key = key
         return self._packed, mode
 
+    def _grad_needed(self, point_groups):
+        params = list(self.parameters()) + (list(self._reduce_dim.parameters()) if self._reduce_dim is not None else [])
+        return _needs_grad(point_groups, *params)
+
+    def invalidate_packed(self):
+        """Drops the cached packed weights.  The cache is keyed on (data_ptr, _version) of every parameter and
+        buffer, which misses writes through `param.data` (the reference's loading idiom, models/ULIP_models.py:507):
+        call this after such a load if a forward has already run (load_state_dict does it by itself)."""
+        self._packed = None
+        self._packed_key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _train_fusable(self, point_groups):
         return train_forward_fusable(self, point_groups, self._reduce_dim)
 
@@ -177,6 +213,9 @@ class Encoder(nn.Module):
             else:
                 out = self._reduce_dim(self._forward_torch(point_groups))
             return out if token_dtype == torch.float32 else out.to(token_dtype)
+        if self._grad_needed(point_groups):  # the fused path is forward only
+            out = self._reduce_dim(self._forward_torch(point_groups))
+            return out if token_dtype == torch.float32 else out.to(token_dtype)
         blob, mode = self._blob(point_groups.device)
         return ops.encoder_forward(point_groups, blob, mode=mode, token_dtype=token_dtype)
 
@@ -188,8 +227,9 @@ class Encoder(nn.Module):
                 return train_forward(self, point_groups, self._state_for_pack, ops.ENC_MODES[self.precision],
                                      want_tokens=False)
             return self._forward_torch(point_groups)
-        if point_groups.shape[2] != 32 or self.encoder_channel != 256:
-            raise RuntimeError("fused Encoder is specialised for 32-point groups and encoder_dims=256 "
-                               "(models/pointbert/PointTransformer_8192point.yaml:17-24)")
+        if self._grad_needed(point_groups) or point_groups.shape[2] != 32 or self.encoder_channel != 256:
+            # a gradient is wanted (unfrozen fine-tune) or a shape the kernels are not specialised for
+            # (models/pointbert/PointTransformer_8192point.yaml:17-24): the module's own torch layers
+            return self._forward_torch(point_groups)
         blob, mode = self._blob(point_groups.device)
         return ops.encoder_forward(point_groups, blob, mode=mode, return_features=True, want_tokens=False)[1]

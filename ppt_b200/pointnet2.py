@@ -124,7 +124,7 @@ class PointNetSetAbstraction(nn.Module):
             else:
                 grouped = ops.group_concat(xyz, new_xyz, points, idx, xyz_first=True)
             new_points = _shared_mlp_max(grouped, self.mlp_convs, self.mlp_bns)
-        if self.remove_last:
+        if getattr(self, "remove_last", False):  # the models/pointbert copy of this class has no such attribute
             return new_points
         return new_xyz.permute(0, 2, 1), new_points
 

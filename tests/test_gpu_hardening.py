@@ -1,0 +1,182 @@
+"""Round-1 advisor findings, as tests: gradients survive the grouping ops, inputs outside the kernels' envelope
+keep the reference's own code (never an error or a wrong answer), out-of-range indices never read out of bounds."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_port
+from oracle.inputs import cloud
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def test_gather_and_group_concat_backward_match_autograd():
+    from ppt_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, N, S, K, D = 2, 200, 17, 9, 13
+    xyz = cloud("U", B, N, 5).cuda()
+    idx = torch.randint(0, N, (B, S, K), generator=g).cuda()
+    new_xyz = xyz[:, :S].contiguous()
+    for xyz_first in (True, False):
+        a = [xyz.clone().requires_grad_(True), new_xyz.clone().requires_grad_(True),
+             torch.randn(B, N, D, generator=g).cuda().requires_grad_(True)]
+        b = [t.detach().clone().requires_grad_(True) for t in a]
+        out = ops.group_concat(a[0], a[1], a[2], idx, xyz_first=xyz_first)
+        gx = torch_port.take_rows(b[0], idx) - b[1].unsqueeze(2)
+        gf = torch_port.take_rows(b[2], idx)
+        ref = torch.cat([gx, gf] if xyz_first else [gf, gx], dim=-1)
+        assert torch.equal(out, ref)
+        w = torch.randn_like(ref)
+        (out * w).sum().backward()
+        (ref * w).sum().backward()
+        for x, y in zip(a, b):
+            assert torch.allclose(x.grad, y.grad, rtol=1e-5, atol=1e-6)
+    p = torch.randn(B, N, D, generator=g).cuda().requires_grad_(True)
+    q = p.detach().clone().requires_grad_(True)
+    out, ref = ops.gather(p, idx), torch_port.take_rows(q, idx)
+    assert out.requires_grad and torch.equal(out, ref)
+    w = torch.randn_like(ref)
+    (out * w).sum().backward()
+    (ref * w).sum().backward()
+    assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_backward_through_two_stacked_set_abstraction_levels():
+    """An unfrozen PointNet++ fine-tune: the first level's convolution must receive a gradient through the second
+    level's grouping (it was silently cut in round 1).  Reference = the same weights with torch-op grouping."""
+    from ppt_b200 import pointnet2
+    torch.manual_seed(2)
+    sa1 = pointnet2.PointNetSetAbstraction(64, 0.4, 16, 3, [16, 16, 32], False).cuda().train()
+    sa2 = pointnet2.PointNetSetAbstraction(16, 0.8, 8, 32 + 3, [32, 32, 64], False).cuda().train()
+    sa1.start_idx = sa2.start_idx = 0
+    xyz = cloud("S", 2, 256, 3).cuda().permute(0, 2, 1).contiguous()
+
+    def run(group):
+        for m in (sa1, sa2):
+            m.zero_grad()
+        x1, f1 = group(sa1, xyz, None)
+        x2, f2 = group(sa2, x1, f1)
+        f2.square().sum().backward()
+        return f2.detach().clone(), sa1.mlp_convs[0].weight.grad.clone(), sa2.mlp_convs[0].weight.grad.clone()
+
+    def torch_group(m, xyz_cf, feats_cf):
+        x = xyz_cf.permute(0, 2, 1)
+        f = None if feats_cf is None else feats_cf.permute(0, 2, 1)
+        fidx = torch_port.fps_indices(x, m.npoint, 0)
+        new_xyz = torch_port.take_rows(x, fidx)
+        idx = torch_port.ball_indices(m.radius, m.nsample, x, new_xyz)
+        grouped = torch_port.take_rows(x, idx) - new_xyz.unsqueeze(2)
+        if f is not None:
+            grouped = torch.cat([grouped, torch_port.take_rows(f, idx)], dim=-1)
+        return new_xyz.permute(0, 2, 1), pointnet2._shared_mlp_max(grouped, m.mlp_convs, m.mlp_bns)
+
+    out_a, g1_a, g2_a = run(lambda m, x, f: m(x, f))
+    out_b, g1_b, g2_b = run(torch_group)
+    assert torch.allclose(out_a, out_b, rtol=1e-4, atol=1e-5)
+    assert float(g1_a.abs().sum()) > 0, "first level received no gradient"
+    assert torch.allclose(g1_a, g1_b, rtol=1e-3, atol=1e-5) and torch.allclose(g2_a, g2_b, rtol=1e-3, atol=1e-5)
+
+
+def test_encoder_with_unfrozen_weights_keeps_autograd():
+    from ppt_b200 import pointbert
+    enc = pointbert.Encoder(256).cuda().eval()
+    nb = (torch.rand(1, 4, 32, 3, device="cuda") - 0.5) * 0.4
+    out = enc(nb)                      # parameters require grad: the torch layers run and the graph exists
+    assert out.requires_grad
+    out.sum().backward()
+    assert enc.first_conv[0].weight.grad is not None
+    for p in enc.parameters():
+        p.requires_grad_(False)
+    assert not enc(nb).requires_grad   # frozen (PPT's recipe): the fused kernels
+
+
+def _stand_in(modname, **attrs):
+    names = modname.split(".")
+    mods = {".".join(names[:i + 1]): types.ModuleType(".".join(names[:i + 1])) for i in range(len(names))}
+    mods[modname].__dict__.update(attrs)
+    return mods
+
+
+def test_patched_names_fall_back_outside_the_kernel_envelope():
+    """Feature-space kNN ([B,N,6]), k > 32, fp64 and S < 3 inputs must reach the tree's own code through the patch."""
+    from ppt_b200 import patch
+    calls = []
+
+    def knn_point(nsample, xyz, new_xyz):
+        calls.append(("knn", tuple(xyz.shape), nsample, xyz.dtype))
+        return torch_port.knn_indices(nsample, xyz, new_xyz)
+
+    def square_distance(src, dst):
+        calls.append(("sqd", tuple(src.shape)))
+        return torch_port.pairwise_sqdist(src, dst)
+
+    def furthest_point_sample(xyz, npoint):
+        calls.append(("fps", tuple(xyz.shape)))
+        return torch_port.fps_indices(xyz, npoint, 0)
+
+    def index_points(points, idx):
+        calls.append(("idx", tuple(points.shape)))
+        return torch_port.take_rows(points, idx)
+
+    mods = _stand_in("models.pointmlp.pointMLP", knn_point=knn_point, square_distance=square_distance,
+                     furthest_point_sample=furthest_point_sample, index_points=index_points)
+    saved = {n: sys.modules.get(n) for n in mods}
+    sys.modules.update(mods)
+    try:
+        with pytest.warns(UserWarning, match="query_ball_point"):
+            names = patch.patch_reference(["models.pointmlp.pointMLP"])
+        assert "models.pointmlp.pointMLP.furthest_point_sample" in names      # pointMLP.py:64 spelling
+        assert "models.pointmlp.pointMLP.query_ball_point" in patch.missing
+        m = mods["models.pointmlp.pointMLP"]
+        xyz = cloud("U", 2, 300, 4).cuda()
+        m.knn_point(8, xyz, xyz[:, :10].contiguous())
+        m.furthest_point_sample(xyz, 16)
+        assert calls == [], "in-envelope CUDA calls go to the kernels"
+        feat6 = torch.randn(2, 300, 6, device="cuda")
+        got = m.knn_point(8, feat6, feat6[:, :10].contiguous())                # feature-space kNN
+        assert got.shape == (2, 10, 8) and calls[-1][0] == "knn"
+        m.knn_point(40, xyz, xyz[:, :10].contiguous())                         # k > 32
+        assert calls[-1] == ("knn", (2, 300, 3), 40, torch.float32)
+        m.knn_point(8, xyz.double(), xyz[:, :10].double().contiguous())        # fp64 stays fp64
+        assert calls[-1][3] == torch.float64
+        m.square_distance(feat6, feat6)
+        assert calls[-1] == ("sqd", (2, 300, 6))
+        n = len(calls)
+        p = torch.randn(2, 300, 5, device="cuda", requires_grad=True)
+        out = m.index_points(p, torch.randint(0, 300, (2, 7), device="cuda"))  # differentiable gather, on the kernels
+        assert len(calls) == n and out.requires_grad
+    finally:
+        patch.unpatch_reference()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_ops_reject_non_xyz_inputs_and_survive_bad_indices():
+    from ppt_b200 import ops
+    xyz = cloud("U", 1, 64, 1).cuda()
+    with pytest.raises(ValueError):
+        ops.knn(4, torch.randn(1, 64, 6, device="cuda"), xyz)
+    with pytest.raises(ValueError):
+        ops.square_distance(torch.randn(1, 8, 4, device="cuda"), xyz)
+    with pytest.raises(ValueError):
+        ops.ball_query(0.1, 4, xyz, torch.randn(1, 8, 2, device="cuda"))
+    # an out-of-range index (query_ball_point's empty-ball sentinel N) gives NaN rows, not a wild read
+    idx = torch.tensor([[0, 64, 5, -1]], device="cuda")
+    out = ops.gather(xyz, idx)
+    assert torch.equal(out[0, 0], xyz[0, 0]) and torch.equal(out[0, 2], xyz[0, 5])
+    assert out[0, 1].isnan().all() and out[0, 3].isnan().all()
+    gc = ops.group_concat(xyz, xyz[:, :1].contiguous(), None, idx.view(1, 1, 4))
+    assert gc[0, 0, 1].isnan().all() and not gc[0, 0, 0].isnan().any()
+    # a start index outside the cloud is clamped (the reference would raise)
+    a = ops.fps(xyz, 8, torch.tensor([10 ** 9], device="cuda"), index=None)
+    b = ops.fps(xyz, 8, torch.tensor([63], device="cuda"), index=None)
+    assert torch.equal(a, b)
