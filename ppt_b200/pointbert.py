@@ -10,6 +10,12 @@ import torch.nn as nn
 from . import encoder_pack, ops
 
 
+def _cops():
+    """torch.ops.ppt_b200.* while a tracer (torch.compile) is recording, else None: eager calls go straight to ctypes."""
+    from . import custom_ops
+    return custom_ops if custom_ops.use_custom_ops() else None
+
+
 def _draw_start(xyz):
     """The reference's own draw (models/pointbert/misc.py:59), so a seeded run consumes
     the RNG stream exactly as it does with the reference."""
@@ -20,7 +26,8 @@ def _draw_start(xyz):
 def farthest_point_sample(xyz, npoint, start_idx=None):
     """models/pointbert/misc.py:44-69.  xyz [B,N,3] -> centroids [B,npoint] int64."""
     start = _draw_start(xyz) if start_idx is None else _as_start(start_idx, xyz)
-    return ops.fps(xyz, npoint, start)
+    c = _cops()
+    return c.fps(xyz, npoint, start) if c else ops.fps(xyz, npoint, start)
 
 
 def _as_start(start_idx, xyz):
@@ -30,7 +37,8 @@ def _as_start(start_idx, xyz):
 
 def index_points(points, idx):
     """models/pointbert/misc.py:26-42.  points [B,N,C], idx [B,S] or [B,S,K] -> [B,S(,K),C]."""
-    return ops.gather(points, idx)
+    c = _cops()
+    return c.gather(points, idx) if c else ops.gather(points, idx)
 
 
 def _needs_grad(*tensors):
@@ -57,7 +65,8 @@ def square_distance(src, dst):
 def knn_point(nsample, xyz, new_xyz):
     """models/pointbert/dvae.py:116-127.  -> group_idx [B,S,nsample] int64.  The reference's
     topk(sorted=False) leaves the order unspecified; here it is ascending (distance, index)."""
-    return ops.knn(nsample, xyz, new_xyz)
+    c = _cops()
+    return c.knn(nsample, xyz, new_xyz) if c else ops.knn(nsample, xyz, new_xyz)
 
 
 def group_forward(xyz, num_group, group_size, start):
@@ -69,6 +78,9 @@ def group_forward(xyz, num_group, group_size, start):
         center = ops.gather(xyz, ops.fps(x, num_group, start, index=index))
         idx = ops.knn(group_size, x, center.detach(), index=index)
         return ops.gather(xyz, idx) - center.unsqueeze(2), center
+    c = _cops()
+    if c:
+        return c.group(xyz, num_group, group_size, start)
     index = ops.spatial_index(xyz)  # one index serves both FPS and kNN
     _, center = ops.fps(xyz, num_group, start, return_centers=True, index=index)
     return ops.knn_group(xyz, center, group_size, index=index), center

@@ -28,7 +28,9 @@ def farthest_point_sample(xyz, npoint, start_idx=None):
 
 def query_ball_point(radius, nsample, xyz, new_xyz):
     """models/pointnet2/pointnet2_utils.py:87-107.  -> group_idx [B,S,nsample] int64."""
-    return ops.ball_query(radius, nsample, xyz, new_xyz)
+    from .pointbert import _cops
+    c = _cops()
+    return c.ball_query(float(radius), nsample, xyz, new_xyz) if c else ops.ball_query(radius, nsample, xyz, new_xyz)
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, start_idx=None):
@@ -173,6 +175,11 @@ def three_nn_interpolate(xyz1, xyz2, points2):
     S = xyz2.shape[1]
     if S == 1:
         return points2.repeat(1, N, 1)
+    from .pointbert import _cops
+    c = _cops()
+    if c:
+        dist, idx = c.three_nn(xyz1, xyz2)
+        return c.three_interpolate(points2, idx, dist)
     dist, idx = ops.three_nn(xyz1, xyz2)
     return ops.three_interpolate(points2, idx, dist)
 

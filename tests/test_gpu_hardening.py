@@ -180,3 +180,24 @@ def test_ops_reject_non_xyz_inputs_and_survive_bad_indices():
     a = ops.fps(xyz, 8, torch.tensor([10 ** 9], device="cuda"), index=None)
     b = ops.fps(xyz, 8, torch.tensor([63], device="cuda"), index=None)
     assert torch.equal(a, b)
+
+
+def test_torch_compile_traces_the_patched_functions_as_custom_ops():
+    """Under torch.compile the wrappers switch from ctypes to torch.ops.ppt_b200.* (opaque, fake-shaped ops)."""
+    from ppt_b200 import pointbert, pointnet2
+    xyz = cloud("U", 2, 1024, 6).cuda()
+
+    def fn(x):
+        idx = pointbert.farthest_point_sample(x, 64, start_idx=0)
+        c = pointbert.index_points(x, idx)
+        nn_idx = pointbert.knn_point(8, x, c)
+        ball = pointnet2.query_ball_point(0.3, 16, x, c)
+        return c * 2.0, nn_idx, ball
+
+    want = fn(xyz)
+    try:
+        got = torch.compile(fn, fullgraph=True, backend="eager")(xyz)
+    except Exception as e:  # pragma: no cover
+        pytest.fail("torch.compile could not trace the custom ops: %r" % (e,))
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)

@@ -261,3 +261,24 @@ def test_cfg2_fixture_checker_and_port_at_the_benchmarked_size():
     bad[5, 7], bad[5, 8] = bad[5, 8].clone(), bad[5, 7].clone()
     r = bench.check_cfg2_parity(torch.cat(fps_idx), torch.cat(center), torch.cat(knn), torch.cat(nb), bad, "fp32")
     assert not r["ok"] and not r["tokens"]
+
+
+def test_custom_ops_are_registered_with_fake_shapes():
+    """torch.ops.ppt_b200.* (SURVEY.md section 7 step 2): the fake-tensor implementations give a tracer the
+    reference's output shapes and dtypes without touching a GPU."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from ppt_b200 import custom_ops  # noqa: F401  (registers)
+    with FakeTensorMode():
+        xyz = torch.empty(2, 100, 3, device="cuda")
+        start = torch.empty(2, dtype=torch.int64, device="cuda")
+        assert torch.ops.ppt_b200.fps(xyz, 8, start).shape == (2, 8)
+        nb, c = torch.ops.ppt_b200.group(xyz, 8, 4, start)
+        assert nb.shape == (2, 8, 4, 3) and c.shape == (2, 8, 3)
+        idx = torch.ops.ppt_b200.knn(5, xyz, c)
+        assert idx.shape == (2, 8, 5) and idx.dtype == torch.int64
+        assert torch.ops.ppt_b200.ball_query(0.2, 16, xyz, c).shape == (2, 8, 16)
+        assert torch.ops.ppt_b200.gather(torch.empty(2, 100, 7, device="cuda"), idx).shape == (2, 8, 5, 7)
+        d, i = torch.ops.ppt_b200.three_nn(xyz, c)
+        assert d.shape == (2, 100, 3) and i.dtype == torch.int64
+        assert torch.ops.ppt_b200.three_interpolate(torch.empty(2, 8, 6, device="cuda"), i, d).shape == (2, 100, 6)
+        assert torch.ops.ppt_b200.encoder_tokens(nb.new_empty(2, 8, 32, 3), torch.empty(10, dtype=torch.uint8, device="cuda"), 0).shape == (2, 8, 384)
