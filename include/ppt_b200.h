@@ -142,7 +142,10 @@ int ppt_graph_feature_grad(const float *grad_out, const int64_t *idx, float *gra
  *   packed: ppt_b200/encoder_pack.py:pack_sa_mlp (BatchNorm folded, layer-1 columns in [features, xyz] order),
  *   ppt_sa_mlp_packed_bytes(D + 3, c1, c2, c3) bytes (PPT_ERANGE if a layer has more than 512 input channels);
  *   workspace: ppt_sa_mlp_workspace_bytes(B*S*nsample, D + 3, c1, c2, c3) bytes;
- *   out [B, c3, S] f32 (channel-first, as the module returns it).  mode: PPT_ENC_FP16 or PPT_ENC_BF16. */
+ *   out [B, c3, S] f32 (channel-first, as the module returns it).  mode: PPT_ENC_FP16 or PPT_ENC_BF16, optionally
+ *   | PPT_SA_PER_LAYER: one kernel per layer with the activations as operand images in `workspace` (the fallback
+ *   taken by itself when a level's activations do not fit in shared memory) instead of the single fused kernel. */
+#define PPT_SA_PER_LAYER 0x100
 int64_t ppt_sa_mlp_packed_bytes(int c0, int c1, int c2, int c3);
 int64_t ppt_sa_mlp_workspace_bytes(int64_t num_columns, int c0, int c1, int c2, int c3);
 int ppt_sa_mlp_forward(const float *xyz, const float *feats, const float *new_xyz, const int64_t *idx,
@@ -231,10 +234,6 @@ int ppt_tokenizer_forward(const float *neighborhood, const float *center, const 
  * same smem layouts, descriptors and epilogue the Encoder uses).
  *   a [128,K] f32, b [N,K] f32 -> d [128,N] f32 = a * b^T with operands rounded to `mode`'s type. */
 int ppt_selftest_umma(const float *a, const float *b, float *d, int N, int K, int mode, void *stream);
-
-/* The same through a CTA pair (tcgen05 cta_group::2, cluster of two CTAs):
- *   a [256,K] f32, b [N,K] f32 -> d [256,N] f32.  N in {64,128,192,256}, mode bits 0-2 as above. */
-int ppt_selftest_umma_pair(const float *a, const float *b, float *d, int N, int K, int mode, void *stream);
 
 /* Measurement aid (bench.py): one device thread records (globaltimer ns, clock64 cycles) pairs every
  * period_ns into out [samples][2] int64, on `stream` -- run it on a side stream next to the kernels under

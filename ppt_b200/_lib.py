@@ -54,7 +54,6 @@ SIGNATURES = {
     "ppt_tokenizer_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
     "ppt_clock_probe": (_i, [_p, _i, _i64, _p]),
     "ppt_selftest_umma": (_i, [_p, _p, _p, _i, _i, _i, _p]),
-    "ppt_selftest_umma_pair": (_i, [_p, _p, _p, _i, _i, _i, _p]),
 }
 
 _lib = None

@@ -6,7 +6,7 @@
 // weight into swizzled operand images (ppt_b200/encoder_pack.py).  Four launches:
 //
 //   stage1        per 128-point tile: h1 = relu(W1'x + b1') as one K = 16 tcgen05.mma (hi/lo parts along K;
-//                 encoder_stage1_tc_kernel; the CUDA-core variant is encoder_stage_kernel<STAGE 1>) ->
+//                 encoder_stage1_tc_kernel) ->
 //                 tcgen05: W2 h1 -> max over each 32-point group -> g   [groups, 256]
 //   group_linear  c = W3a' g + bias_c                                   [groups, 512] fp32
 //   stage2        per tile: relu(W32 h1 + c) -> h3 (shared memory only) ->
@@ -22,9 +22,10 @@
 // stores along the points), each pair of values converted, ReLU'd and saturated by one
 // F2FP instruction.
 //
-// Also here: the CTA-pair (cta_group::2) stage 2 (encoder_stage2_pair_kernel, experimental), the cls / pos_embed
-// token assembly (pos_hidden_kernel, group_linear_kernel<ASSEMBLE>) and the train-mode BatchNorm path
-// (bn_moments / bn_fold1 / bn_fold2, encoder_stage_kernel<BN_STATS / BN_APPLY>); DESIGN.md sections 8 and 9.
+// Also here: the cls / pos_embed token assembly (pos_hidden_kernel, group_linear_kernel<ASSEMBLE>) and the
+// train-mode BatchNorm path (bn_moments / bn_fold1 / bn_fold2, encoder_stage_kernel<BN_STATS / BN_APPLY>);
+// DESIGN.md section 9.  (A cta_group::2 variant of stage 2 was built and measured in round 1 -- same time, more
+// code -- and removed in round 2; DESIGN.md section 8 keeps what it showed.)
 //
 // Pipeline per CTA (persistent over tiles): warp 0 streams 16 KB weight images from
 // L2 with 1-D bulk async copies into a ring (full/empty mbarriers); warp 1 issues
@@ -44,10 +45,6 @@ using namespace tc05;
 constexpr int LIN_THREADS = 192;      // group_linear: producer, MMA, 4 epilogue warps
 constexpr int LIN_EPI = 128;
 constexpr uint32_t IMG = 16384;       // one operand image: 128 rows x 64 K x 2 B
-#ifndef PPT_RING_PIECES
-#define PPT_RING_PIECES 1
-#endif
-constexpr int RING_PIECES = PPT_RING_PIECES;  // bulk copies per ring stage in the stage-2 producer
 constexpr uint32_t MNBLK = 65536;     // MN-major h3: bytes between 64-point blocks (64 K-atoms x 1 KB)
 
 // ---- packed weight blob (ppt_b200/encoder_pack.py) -----------------------------------
@@ -227,12 +224,7 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
             const uint32_t s = r.stage<NSTAGE>();
             mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
             mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-            // PIECES concurrent copies per stage (same barrier, same bytes): tuning knob for the copy latency
-            const unsigned char* src = blob + sec + (size_t)(blk * nkc + kc) * STAGE_BYTES;
-#pragma unroll
-            for (int pc = 0; pc < RING_PIECES; ++pc)
-              bulk_g2s(ring + s * STAGE_BYTES + pc * (STAGE_BYTES / RING_PIECES), src + pc * (STAGE_BYTES / RING_PIECES),
-                       STAGE_BYTES / RING_PIECES, &full[s]);
+            bulk_g2s(ring + s * STAGE_BYTES, blob + sec + (size_t)(blk * nkc + kc) * STAGE_BYTES, STAGE_BYTES, &full[s]);
             ++r.it;
           }
         }
@@ -705,463 +697,6 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
 }
 
 // ======================================================================================
-// stage 2 on CTA pairs (tcgen05 cta_group::2)
-// ======================================================================================
-// The single-CTA stage 2 re-reads 4 KB of weights and 4 KB of activations from shared memory for every
-// M128 x N128 x K16 instruction (64 tensor cycles) and streams 384 KB of weights per 128-point tile from L2.
-// Here two CTAs of a cluster work on a pair-tile of 256 points with M = 256 instructions, and the operand
-// roles are swapped with respect to the single-CTA kernel -- activations are A (points = M = accumulator
-// lanes), weights are B (channels = N = accumulator columns):
-//   * CTA r owns points [128 r, 128 r + 128) of the tile: its rows of every A operand (h1, h3) and of every
-//     accumulator.  An epilogue thread owns one point and writes that point's row of h3, K-major, into its
-//     own CTA's shared memory: no activation crosses between the CTAs (a first version with channels on the
-//     lanes pushed half of h3 through DSMEM and ran at half the speed);
-//   * CTA r streams only its half of the channels of every weight block (its half of B; the hardware shares
-//     it with the peer): half the ring traffic per CTA, half the L2 traffic per point;
-//   * only the last layer (W4 h3, whose output is max-pooled, not fed to another layer) goes back to weights = A:
-//     K-major rows of h3 serve as either operand, and with channels on the lanes the max over a group's 32
-//     points is a max over a thread's registers (a first version reduced over lanes with CREDUX.MAX and spent
-//     2800 cycles per tile on it);
-//   * hand-offs that involve both CTAs (operands ready, accumulators drained, ring stage filled) go through
-//     mbarriers of the leader CTA (remote arrivals from the peer).
-// Tensor memory: columns [0, 256) the W4 h3 accumulator (256 channels), [256, 384) and [384, 512) two
-// accumulators for the 128-channel units of W32 h1.  Per iteration the leader issues, in this fixed order,
-//     P0  G4' G5'  P1  G6' G7'  P2  G0 G1  P3  G2 G3
-// (Pv = W32 unit v of the current tile: N = 128, K = 128; Gc = W4 K-chunk c: N = 256, K = 64, primed = of the
-// PREVIOUS tile; 512 tensor cycles each), one ring stage per item.  Every hand-off through the epilogue warps
-// (accumulator -> h3 -> next instruction, a chain of ~2000 cycles of barrier wake-ups, tcgen05.ld, conversion,
-// proxy fence and a possibly remote arrive) is given five or six items of slack: Gc follows unit c / 2 by
-// six items, unit v + 2 reuses unit v's accumulator five items later.  h3 lives in four chunk slots (chunk c in
-// slot c % 4; g_done[slot] says when its reader has finished), and the weight ring is six stages deep --
-// enough to cover L2 latency plus the hop through the peer.  The first iteration has no primed items and one
-// extra iteration after the last tile has only primed ones; absent items still take their ring stage (the
-// producer arrives without a copy, the issuer commits without instructions) so that stage indices and phases
-// stay compile-time constants.
-// Warp roles per CTA: 0 weight producer, 1 issuer of the P items (leader) / ring-stage forwarder (peer),
-// 2-9 epilogue, 10 issuer of the G items (leader only).
-// Item i of the per-iteration schedule: 0..3 = W32 unit v (current tile), 4 + c = W4 chunk c (c >= 4: of the
-// previous tile).
-__host__ __device__ constexpr int pair_sched(int i) {
-  constexpr int code[12] = {0, 8, 9, 1, 10, 11, 2, 4, 5, 3, 6, 7};
-  return code[i];
-}
-
-template <uint32_t FMT>
-__global__ void __launch_bounds__(352, 1)
-encoder_stage2_pair_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
-                           const float* __restrict__ cbuf, unsigned char* __restrict__ out_img,
-                           float* __restrict__ features_out, long long num_groups, int num_ptiles,
-                           long long* __restrict__ trace) {
-  // Debug timeline (PPT_PAIR_TRACE): clock64 of the leader CTA of pair 0 at the events of iterations < 32,
-  // trace[it * 64 + slot]; slots 0-11 item issued (after commit), 12-23 item's waits satisfied, 32-35 unit v
-  // accumulator seen full by epilogue warp 2, 36-39 unit v h3 handed over, 40 group max accumulator seen full,
-  // 41 group max handed back, 42 h1 built.
-#define PAIR_TRACE(it_, slot_)                                                                    \
-  do {                                                                                            \
-    if (trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it_) < 32) trace[(it_) * 64 + (slot_)] = clock64(); \
-  } while (0)
-  constexpr int NSTAGE = 6, EPW = 8, NTC = 128;      // NTC: points per CTA per pair-tile
-  constexpr uint32_t H1_BYTES = 2u * NTC * 128u;     // K-major: 2 chunks x [128 points x 64 channels]
-  constexpr uint32_t H3_BYTES = 4u * IMG;            // K-major [128 points x 64 channels] chunks: chunk c in slot c % 4
-  constexpr int TCOLS = 512;
-  constexpr uint32_t ACC_G3 = 0, ACC_P2 = 256;       // tensor-memory columns
-  constexpr int ITEMS = 12;                          // ring stages per tile and CTA
-  static_assert(ITEMS % NSTAGE == 0 && (ITEMS / NSTAGE) % 2 == 0, "static ring schedule");
-
-  if (trace && threadIdx.x == 0 && (blockIdx.x & 1) == 0) {
-    trace[32 * 64 + (blockIdx.x >> 1) * 2] = clock64();
-    if (blockIdx.x == 0) {
-      unsigned long long ns;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-      trace[32 * 64 + 200] = (long long)ns;
-    }
-  }
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* h1buf = smem;
-  unsigned char* h3buf = h1buf + H1_BYTES;
-  unsigned char* ring = h3buf + H3_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * IMG);
-  uint64_t* full = bars;                    // [6] own ring stage landed
-  uint64_t* empty = full + NSTAGE;          // [6] stage consumed (commit, multicast to both CTAs)
-  uint64_t* full_peer = empty + NSTAGE;     // [6] leader only: the peer's stage landed
-  uint64_t* p2_full = full_peer + NSTAGE;   // [2] W32 accumulator complete (commit, multicast)
-  uint64_t* g3_full = p2_full + 2;          // [1] W4 accumulator complete (commit, multicast)
-  uint64_t* max_done = g3_full + 1;         // [1] leader only: the W4 accumulator was drained by both CTAs
-  uint64_t* h1_ready = max_done + 1;        // [1] leader only: h1 of both CTAs written
-  uint64_t* h3_ready = h1_ready + 1;        // [8] leader only: h3 chunk c written (and its accumulator half read)
-  uint64_t* g_done = h3_ready + 8;          // [4] the W4 chunk in h3 slot s was consumed (commit, multicast)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_done + 4);
-  float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 512);
-  float* c_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512 + 2048);  // [8 warps][256]
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const BlobLayout L{1u};
-  const float* sc = reinterpret_cast<const float*>(blob + L.scales());
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&full_peer[s], 1); }
-    for (int i = 0; i < 2; ++i) mbar_init(&p2_full[i], 1);
-    mbar_init(g3_full, 1);
-    mbar_init(max_done, 2 * EPW);
-    mbar_init(h1_ready, 2 * EPW);
-    for (int i = 0; i < 8; ++i) mbar_init(&h3_ready[i], EPW);  // 4 warps (one column half) of each CTA
-    for (int i = 0; i < 4; ++i) mbar_init(&g_done[i], 1);
-    mbar_fence_init();
-  }
-  if (tid < 128) {
-    float4 w = __ldg(reinterpret_cast<const float4*>(blob + L.w1()) + tid);
-    const float s = __ldg(sc + 5);
-    w.x *= s; w.y *= s; w.z *= s; w.w *= s;
-    w1s[tid] = w;
-  }
-  if (warp == 1) tmem_alloc_pair<TCOLS>(tmem_slot);
-  fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();  // barrier inits of both CTAs are visible before any remote arrive
-  fence_after_sync();
-  const uint32_t tbase = *tmem_slot;
-  if (tbase != 0) __trap();  // 512 columns = the whole tensor memory of the SM
-  const int ntiles = pair < num_ptiles ? (num_ptiles - pair + npairs - 1) / npairs : 0;  // tiles of this pair
-
-  if (warp == 0) {
-    // ===================== weight producer: this CTA's half of every weight block =====================
-    if (lane == 0) {
-      for (int it = 0; it <= ntiles; ++it) {
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          const int code = pair_sched(i);
-          const int st = i % NSTAGE;
-          const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
-          const bool present = code >= 8 ? it >= 1 : it < ntiles;
-          mbar_wait_relaxed(&empty[st], sph ^ 1u);
-          if (!present) {
-            mbar_arrive(&full[st]);  // the stage is taken without a copy
-          } else if (code < 4) {
-            // W32 unit v = code, both K chunks: rows [64 rank, 64 rank + 64) of each 128-row image (8 KB, contiguous)
-            mbar_arrive_expect_tx(&full[st], IMG);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              bulk_g2s(ring + st * IMG + k * (IMG / 2), blob + L.W32() + (uint32_t)(code * 2 + k) * IMG + rank * (IMG / 2),
-                       IMG / 2, &full[st]);
-          } else {
-            // W4 chunk c = code - 4: channels [128 rank, 128 rank + 128)
-            mbar_arrive_expect_tx(&full[st], IMG);
-            bulk_g2s(ring + st * IMG, blob + L.W4() + (rank * 8u + (uint32_t)(code - 4)) * IMG, IMG, &full[st]);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1 && rank != 0) {
-    // ===================== peer: tell the leader when a ring stage has landed here =====================
-    for (int it = 0; it <= ntiles; ++it) {
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) {
-        mbar_wait(&full[i % NSTAGE], (uint32_t)(i / NSTAGE) & 1u);
-        if (lane == 0) mbar_arrive_peer(&full_peer[i % NSTAGE], 0);
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== leader, warp 1: issues the W32 h1 units (P items) =====================
-    // Two warps issue the tensor instructions (this one the P items, warp 10 the G items): the instruction
-    // stream around each tcgen05.mma (descriptor moves into uniform registers, elect, commit) costs about as
-    // many cycles as the instruction runs, so a single issuing warp caps the tensor pipe near 60 %.
-    // Fully unrolled per iteration: every item has a compile-time ring stage and phase.
-    constexpr uint32_t idesc_p = make_idesc(FMT, 256, 128, 0);
-    constexpr uint32_t HI = sdesc_hi(1024u);
-    const uint32_t w_lo0 = sdesc_lo(smem_u32(ring), 16u);
-    const uint32_t h1_lo = sdesc_lo(smem_u32(h1buf), 16u);
-    uint32_t tpar = 0;  // parity of the tile counter
-    for (int it = 0; it <= ntiles; ++it, tpar ^= 1u) {
-      const bool cur = it < ntiles;
-      if (cur) mbar_wait(h1_ready, tpar);
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) {
-        const int code = pair_sched(i);
-        if (code >= 4) continue;
-        const int v = code;
-        const int st = i % NSTAGE;
-        const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
-        const uint32_t w_lo = w_lo0 + (uint32_t)st * (IMG >> 4);
-        if (cur) {
-          // the accumulator of unit v was last read by the epilogue of unit v - 2 (this tile: chunks 2v-4, 2v-3)
-          // or of unit v + 2 of the previous tile (chunks 2v+4, 2v+5)
-          const int c0 = v >= 2 ? 2 * v - 4 : 2 * v + 4;
-          const uint32_t dpar = v >= 2 ? tpar : tpar ^ 1u;
-          mbar_wait(&h3_ready[c0], dpar);
-          mbar_wait(&h3_ready[c0 + 1], dpar);
-        }
-        mbar_wait(&full[st], sph);
-        mbar_wait(&full_peer[st], sph);
-        fence_after_sync();
-        PAIR_TRACE(it, 12 + i);
-        if (cur) {
-          const uint32_t d_tmem = ACC_P2 + (uint32_t)(v & 1) * 128u;
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16)
-              umma_f16_pair_elect(d_tmem, sdesc_join(h1_lo + (uint32_t)kk * ((NTC * 128u) >> 4) + (uint32_t)k16 * 2u, HI),
-                                  sdesc_join(w_lo + (uint32_t)kk * (IMG >> 5) + (uint32_t)k16 * 2u, HI), idesc_p,
-                                  (kk == 0 && k16 == 0) ? 0u : 1u);
-        }
-        umma_commit_pair_elect(&empty[st], 3);
-        if (cur) umma_commit_pair_elect(&p2_full[v & 1], 3);
-        PAIR_TRACE(it, i);
-      }
-    }
-  } else if (warp == 10) {
-    // ===================== leader, warp 10: issues the W4 h3 chunks (G items); idle in the peer =====================
-    if (rank == 0) {
-      constexpr uint32_t idesc_g = make_idesc(FMT, 256, 256, 0);
-      constexpr uint32_t HI = sdesc_hi(1024u);
-      const uint32_t w_lo0 = sdesc_lo(smem_u32(ring), 16u);
-      const uint32_t h3_lo = sdesc_lo(smem_u32(h3buf), 16u);
-      uint32_t tpar = 0;
-      for (int it = 0; it <= ntiles; ++it, tpar ^= 1u) {
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          const int code = pair_sched(i);
-          if (code < 4) continue;
-          const int c = code - 4;
-          const int st = i % NSTAGE;
-          const uint32_t sph = (uint32_t)(i / NSTAGE) & 1u;
-          const uint32_t w_lo = w_lo0 + (uint32_t)st * (IMG >> 4);
-          const bool present = c >= 4 ? it >= 1 : it < ntiles;
-          const uint32_t par = c >= 4 ? tpar ^ 1u : tpar;  // parity of the tile this chunk belongs to
-          if (present) {
-            if (c == 0) mbar_wait(max_done, tpar ^ 1u);  // the W4 accumulator of the previous tile is in registers
-            mbar_wait(&h3_ready[c], par);
-          }
-          mbar_wait(&full[st], sph);
-          mbar_wait(&full_peer[st], sph);
-          fence_after_sync();
-          PAIR_TRACE(it, 12 + i);
-          if (present) {
-#pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16)
-              // operand roles swapped back for this layer: A = W4 (channels on the lanes), B = h3 (points on the
-              // columns; K-major rows of h3 serve as either operand), so the group max is a max over registers
-              umma_f16_pair_elect(ACC_G3, sdesc_join(w_lo + (uint32_t)k16 * 2u, HI),
-                                  sdesc_join(h3_lo + (uint32_t)(c & 3) * (IMG >> 4) + (uint32_t)k16 * 2u, HI), idesc_g,
-                                  (c == 0 && k16 == 0) ? 0u : 1u);
-          }
-          umma_commit_pair_elect(&empty[st], 3);
-          if (present) {
-            umma_commit_pair_elect(&g_done[c & 3], 3);  // h3 slot c % 4 may be overwritten
-            if (c == 7) umma_commit_pair_elect(g3_full, 3);
-          }
-          PAIR_TRACE(it, i);
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue warps (2..9) of both CTAs =====================
-    const int quad = warp & 3;               // accumulator lanes [32 quad, 32 quad + 32) = group `quad` of this CTA
-    const int part = (warp - 2) >> 2;        // column half of every accumulator
-    const int prow = quad * 32 + lane;       // this thread's point (row of h3)
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const float* bias_b4 = reinterpret_cast<const float*>(blob + L.b4());
-    const float inv_g3 = __ldg(sc + 3), act_scale = __ldg(sc + 5), grp_scale = __ldg(sc + 6);
-    const float inv_p2s = __ldg(sc + 2) * act_scale;
-
-    auto arrive_leader = [&](uint64_t* bar) {  // one arrival per warp, after every lane has fenced its writes
-      __syncwarp();
-      if (lane == 0) mbar_arrive_peer(bar, 0);
-    };
-
-    // h1 of this CTA's 128 points (CUDA cores, K = 3), K-major.  Warp w computes channels [16 w, 16 w + 16) -- its 16
-    // weight rows are read from shared memory once (broadcast) and stay in registers -- for the four points
-    // lane, lane + 32, lane + 64, lane + 96 of every lane: 4 independent FFMA chains per weight instead of one
-    // shared-memory load per 3 FFMAs (which left these 8 warps latency-bound: 1800 cycles per tile).
-    const int hw = warp - 2;  // 0..7
-    float px[4], py[4], pz[4];
-    auto fetch_point = [&](int tile) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        px[j] = py[j] = pz[j] = 0.f;
-        const long long gp = (long long)tile * 256 + (long long)rank * NTC + lane + 32 * j;
-        if (tile < num_ptiles && gp < num_groups * 32) {
-          const float* src = nbhd + gp * 3;
-          px[j] = __ldg(src); py[j] = __ldg(src + 1); pz[j] = __ldg(src + 2);
-        }
-      }
-    };
-    int trace_it = 99;
-    auto build_h1 = [&](int tile_after) {
-      float x[4], y[4], z[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { x[j] = px[j]; y[j] = py[j]; z[j] = pz[j]; }
-      fetch_point(tile_after);
-      if (warp == 2) PAIR_TRACE(trace_it, 43);
-#pragma unroll
-      for (int c8 = 0; c8 < 16; c8 += 8) {
-        float4 w[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) w[t] = w1s[hw * 16 + c8 + t];
-        const int ch = hw * 16 + c8;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = fmaf(w[t].z, z[j], fmaf(w[t].y, y[j], fmaf(w[t].x, x[j], w[t].w)));
-          store_relu8<FMT, 1>(h1buf, (uint32_t)(ch >> 6) * (NTC * 128u) + sw128_kmajor_off(lane + 32 * j, ch & 63), 0u, v);
-        }
-      }
-      if (warp == 2) PAIR_TRACE(trace_it, 44);
-      fence_proxy_async_smem();
-      if (warp == 2) PAIR_TRACE(trace_it, 45);
-      arrive_leader(h1_ready);
-    };
-
-    // c[group][ch] for the channels this warp handles (unit v: 128 v + 64 part + [0, 64)), staged per tile in a
-    // warp-private kilobyte of shared memory: c_w[64 v + j]
-    float* c_w = c_s + (warp - 2) * 256;
-    float4 cpre[2];
-    auto fetch_c = [&](int tile) {
-      const long long g = (long long)tile * 8 + (long long)rank * 4 + quad;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int f = 4 * (lane + 32 * h);  // position in c_w
-        cpre[h] = (tile < num_ptiles && g < num_groups)
-                      ? __ldg(reinterpret_cast<const float4*>(cbuf + g * 512 + (f >> 6) * 128 + part * 64 + (f & 63)))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto stage_c = [&]() {
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        reinterpret_cast<float4*>(c_w)[lane + 32 * h] = make_float4(cpre[h].x * act_scale, cpre[h].y * act_scale,
-                                                                    cpre[h].z * act_scale, cpre[h].w * act_scale);
-      __syncwarp();
-    };
-
-    if (ntiles > 0) {
-      fetch_point(pair);
-      fetch_c(pair);
-      build_h1(pair + npairs);
-      stage_c();
-    }
-
-    // one relu unit: h3[point][ch] = relu(acc + c[group][ch]) for ch = 128 v + 64 part + [0, 64) = chunk 2 v + part
-    auto relu_unit = [&](int v) {
-      const uint32_t t_addr = lane_base + ACC_P2 + (uint32_t)(v & 1) * 128u + (uint32_t)part * 64u;
-      uint32_t r0[32], r1[32];
-      tmem_ld32_async(t_addr, r0);
-      tmem_ld32_async(t_addr + 32, r1);
-      tmem_wait_ld();
-      const uint32_t img = (uint32_t)((2 * v + part) & 3) * IMG;
-      // the slot still holds chunk 2v+part-4 (this tile) or 2v+part+4 (previous tile) until its G item is complete;
-      // each slot's barrier completes twice per tile
-      mbar_wait(&g_done[(2 * v + part) & 3], v < 2 ? 1u : 0u);
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        float x[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 cv = reinterpret_cast<const float4*>(c_w + v * 64 + jj * 32)[i];  // broadcast
-          x[4 * i + 0] = fmaf(__uint_as_float(jj ? r1[4 * i + 0] : r0[4 * i + 0]), inv_p2s, cv.x);
-          x[4 * i + 1] = fmaf(__uint_as_float(jj ? r1[4 * i + 1] : r0[4 * i + 1]), inv_p2s, cv.y);
-          x[4 * i + 2] = fmaf(__uint_as_float(jj ? r1[4 * i + 2] : r0[4 * i + 2]), inv_p2s, cv.z);
-          x[4 * i + 3] = fmaf(__uint_as_float(jj ? r1[4 * i + 3] : r0[4 * i + 3]), inv_p2s, cv.w);
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          store_relu8<FMT, 1>(h3buf, img + sw128_kmajor_off(prow, jj * 32 + q4 * 8), 0u, x + q4 * 8);
-      }
-      fence_proxy_async_smem();
-      fence_before_sync();
-      arrive_leader(&h3_ready[2 * v + part]);
-    };
-
-    // per-group max of W4 h3 of tile `tile`.  This accumulator has channels on the lanes (CTA r: 128 r + lane) and
-    // the pair-tile's 256 points on the columns (32 columns = one group), so the max is over a thread's registers.
-    auto max_unit = [&](int tile, uint32_t par) {
-      const int ch = (int)rank * 128 + quad * 32 + lane;
-      const float b4v = __ldg(bias_b4 + ch);
-      mbar_wait(g3_full, par);
-      fence_after_sync();
-#pragma unroll 1
-      for (int jj = 0; jj < 4; jj += 2) {
-        uint32_t r0[32], r1[32];
-        const uint32_t t_addr = lane_base + ACC_G3 + (uint32_t)part * 128u + (uint32_t)jj * 32u;
-        tmem_ld32_async(t_addr, r0);
-        tmem_ld32_async(t_addr + 32, r1);
-        tmem_wait_ld();
-        if (jj == 2) {  // the accumulator is in registers: hand it back before reducing
-          fence_before_sync();
-          arrive_leader(max_done);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float mx = __uint_as_float(h ? r1[0] : r0[0]);
-#pragma unroll
-          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(h ? r1[i] : r0[i]));
-          mx *= inv_g3;
-          const long long g = (long long)tile * 8 + part * 4 + jj + h;
-          if (g < num_groups) {
-            const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * IMG;
-            store_operand<FMT, 1>(out_img + img, sw128_kmajor_off((int)(g & 127), ch & 63), IMG, mx * grp_scale);
-            if (features_out) features_out[g * 256 + ch] = mx + b4v;
-          }
-        }
-      }
-    };
-
-    // Program order per iteration: unit 0 of the current tile, the group max of the previous tile (its last chunk
-    // G7' is issued between P1 and P2; G0 needs the accumulator back and unit 2 needs G0 / G1 complete before it may
-    // overwrite their h3 slots), units 1 and 2, then -- as soon as unit 3's accumulator is full, i.e. every W32 h1
-    // instruction of the tile is complete -- h1 of the next tile, then unit 3.  Measured with PPT_PAIR_TRACE: the
-    // iteration period (8.4 k cycles against 6.1 k of tensor work) is the dependency cycle through these eight
-    // warps; the max placed after unit 1 instead lengthens it (8.7 k).
-    uint32_t tpar = 0;
-    for (int it = 0; it <= ntiles; ++it, tpar ^= 1u) {
-      const int tile = pair + it * npairs;
-      const bool cur = it < ntiles;
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (v == 1 && it >= 1) {
-          max_unit(tile - npairs, tpar ^ 1u);
-          if (warp == 2) PAIR_TRACE(it, 41);
-        }
-        if (!cur) continue;
-        mbar_wait(&p2_full[v & 1], (uint32_t)(v >> 1) & 1u);  // each accumulator completes twice per tile
-        fence_after_sync();
-        if (warp == 2) PAIR_TRACE(it, 32 + v);
-        if (v == 3) {
-          const int next = tile + npairs;
-          trace_it = it;
-          fetch_c(next);
-          if (next < num_ptiles) build_h1(next + npairs);
-        }
-        if (warp == 2 && v == 3) PAIR_TRACE(it, 42);
-        relu_unit(v);
-        if (warp == 2) PAIR_TRACE(it, 36 + v);
-        if (v == 3) stage_c();  // after the last read of this tile's c values
-      }
-    }
-  }
-
-  __syncwarp();
-  fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();  // neither CTA may exit (or free tensor memory) while the other can still reach it
-  if (warp == 1) tmem_dealloc_pair<TCOLS>(tbase);
-  if (trace && threadIdx.x == 0 && (blockIdx.x & 1) == 0) {
-    trace[32 * 64 + (blockIdx.x >> 1) * 2 + 1] = clock64();
-    if (blockIdx.x == 0) {
-      unsigned long long ns;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-      trace[32 * 64 + 201] = (long long)ns;
-    }
-  }
-}
-
-// ======================================================================================
 // group_linear: out[row(g)][o] = sum_k W[o][k] * act[g][k] + bias[o], act given as operand images
 // (K = 64 KCH).  row(g) = g, or -- rows_per_cloud = G > 0, the token-assembly layout of
 // models/pointbert/point_encoder.py:245-246 -- g + g / G + 1: every cloud's G rows follow one row that
@@ -1535,43 +1070,22 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
                 int tokens_f16 = 0, long long* clock_acc = nullptr) {
   const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
-  // stage 1 is bound by its epilogue side (layer-1 build + max): 16 epilogue warps where 32 columns each fit
-  constexpr int EPW1 = NT >= 128 ? 16 : 8, EPW2 = 8;
-  auto k1 = encoder_stage_kernel<FMT, SPLIT, NT, 1, EPW1>;
+  constexpr int EPW2 = 8;
   auto k1tc = encoder_stage1_tc_kernel<FMT, SPLIT, NT, 8>;
   constexpr size_t s1tc = stage1_tc_smem_bytes<SPLIT, NT>();
   static_assert(s1tc <= 232448, "shared memory budget (227 KB per CTA)");
-  static int use_tc = -1;  // tuning knob: PPT_STAGE1_TC=0 selects the CUDA-core layer-1 variant
-  if (use_tc < 0) {
-    const char* ev = getenv("PPT_STAGE1_TC");
-    use_tc = ev ? (atoi(ev) != 0) : 1;
-  }
-  // PPT_STAGE2_PAIR=1 selects the CTA-pair (cta_group::2) stage 2.  It is bit-compatible with the single-CTA
-  // kernel's tolerance and parity-tested, but as of round 1 it is ~8 % slower (0.635 ms against 0.585 ms on the
-  // 128-cloud step: every P -> epilogue -> G hand-off crosses the pair and the tile pipeline is not yet deep
-  // enough to hide those hops), so the single-CTA kernel stays the default.
-  static int use_pair = -1;
-  if (use_pair < 0) {
-    const char* ev = getenv("PPT_STAGE2_PAIR");
-    use_pair = ev ? (atoi(ev) != 0) : 0;
-  }
-  auto k2p = encoder_stage2_pair_kernel<FMT>;
   auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
   auto k2clk = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2, BN_EVAL, true>;
   auto kb = group_linear_kernel<FMT, SPLIT, 4>;
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
   auto kda = group_linear_kernel<FMT, SPLIT, 3, 4, true>;
-  constexpr size_t s1 = stage_smem_bytes<SPLIT, NT, 1>(), s2 = stage_smem_bytes<SPLIT, NT, 2>(),
-                   sl = linear_smem_bytes<SPLIT>();
-  static_assert(s2 <= 232448 && s1 <= 232448 && sl <= 232448, "shared memory budget (227 KB per CTA)");
+  constexpr size_t s2 = stage_smem_bytes<SPLIT, NT, 2>(), sl = linear_smem_bytes<SPLIT>();
+  static_assert(s2 <= 232448 && sl <= 232448, "shared memory budget (227 KB per CTA)");
   static PptOncePerDevice configured;
   if (configured.need()) {
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1tc));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2clk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2p, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)stage_smem_bytes<1, 128, 2>()));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kda, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
@@ -1585,68 +1099,13 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   const float* scales = reinterpret_cast<const float*>(blob + L.scales());
   // Rows of the last operand-image tile beyond `groups` are never written; they only feed accumulator
   // columns that are never stored.
-  if (phases & 1) {
-    if (use_tc)
-      k1tc<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles);
-    else
-      k1<<<grid_t, (EPW1 + 2) * 32, s1, st>>>(nbhd, blob, nullptr, ws + W.g_img, nullptr, groups, tiles, nullptr,
-                                              nullptr, nullptr);
-  }
+  if (phases & 1) k1tc<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles);
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
                                         scales + 1, cbuf, groups, tiles128, 0, 0);
-  if (phases & 4) {
-    if (SPLIT == 1 && use_pair) {
-      const int ptiles = (int)((points + 255) / 256);
-      const int npairs = ptiles < sms / 2 ? ptiles : sms / 2;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * npairs);
-      cfg.blockDim = dim3(352);
-      cfg.dynamicSmemBytes = stage_smem_bytes<1, 128, 2>();
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      const unsigned char* blob_c = blob;
-      unsigned char* timg = ws + W.t_img;
-      // PPT_PAIR_TRACE=1: a 16 KB device buffer receives the timeline of pair 0 (see the kernel); it is printed
-      // to stderr (with a synchronisation) -- debugging only
-      static long long* trace = nullptr;
-      static int want_trace = -1;
-      if (want_trace < 0) {
-        const char* ev = getenv("PPT_PAIR_TRACE");
-        want_trace = ev ? atoi(ev) : 0;
-        if (want_trace) {
-          cudaMalloc(&trace, (32 * 64 + 256) * sizeof(long long));
-          cudaMemset(trace, 0, (32 * 64 + 256) * sizeof(long long));
-        }
-      }
-      PPT_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, k2p, nbhd, blob_c, (const float*)cbuf, timg, features_out, groups,
-                                            ptiles, trace));
-      if (want_trace > 0 && trace) {
-        --want_trace;  // print the first `want_trace` launches
-        cudaStreamSynchronize(st);
-        static long long host[32 * 64 + 256];
-        cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "PAIRSPAN");  // per leader CTA: kernel-entry to kernel-exit cycles on its SM
-        for (int k = 0; k < 74; ++k) fprintf(stderr, " %lld", host[32 * 64 + 2 * k + 1] - host[32 * 64 + 2 * k]);
-        fprintf(stderr, "\nPAIRCLOCK pair0 %lld cycles in %lld ns\n", host[32 * 64 + 1] - host[32 * 64],
-                host[32 * 64 + 201] - host[32 * 64 + 200]);
-        for (int it = 0; it < 32; ++it) {
-          fprintf(stderr, "PAIRTRACE %d", it);
-          for (int k = 0; k < 46; ++k) fprintf(stderr, " %lld", host[it * 64 + k] ? host[it * 64 + k] - host[12] : 0ll);
-          fprintf(stderr, "\n");
-        }
-      }
-    } else {
-      (clock_acc ? k2clk : k2)<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out,
-                                                                    groups, tiles, nullptr, nullptr, clock_acc);
-    }
-  }
+  if (phases & 4)
+    (clock_acc ? k2clk : k2)<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups,
+                                                                  tiles, nullptr, nullptr, clock_acc);
   if ((phases & 8) && tokens_out)
     (rows_per_cloud > 0 ? kda : kd)<<<grid_g, LIN_THREADS, sl, st>>>(
         ws + W.t_img, blob + L.WR(), reinterpret_cast<const float*>(blob + L.bias_tok()), scales + 4, tokens_out,

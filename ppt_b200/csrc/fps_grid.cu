@@ -17,8 +17,6 @@
 //  * lane j keeps row (w + 32 j)'s box, max and argmax POSITION, so the skip test of all rows of a
 //    warp is one pass and every argmax level is ONE max-reduction plus a ballot; the original-index
 //    tie-break (torch.max keeps the first index, F4) runs only when the ballot shows an actual tie.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "spatial_index.cuh"
 
@@ -162,13 +160,6 @@ int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, i
 
 int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                  int B, int N, int G, cudaStream_t st) {
-  static int warps = 0;
-  if (!warps) {  // tuning knob; the default is what measured best on B200
-    const char* e = getenv("PPT_FPS_GRID_WARPS");
-    warps = e ? atoi(e) : 16;
-    if (warps != 8 && warps != 16 && warps != 32) warps = 16;
-  }
-  if (warps == 8) return launch_fps_grid<8>(xyz, start, index, idx_out, centers_out, B, N, G, st);
-  if (warps == 16) return launch_fps_grid<16>(xyz, start, index, idx_out, centers_out, B, N, G, st);
-  return launch_fps_grid<32>(xyz, start, index, idx_out, centers_out, B, N, G, st);
+  // 16 warps: what measured best on B200 (8 and 32 were within 5 % and slower)
+  return launch_fps_grid<16>(xyz, start, index, idx_out, centers_out, B, N, G, st);
 }

@@ -72,35 +72,61 @@ __device__ __forceinline__ float interp3(float w0, float a, float w1, float b, f
   return __fadd_rn(__fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b)), __fmul_rn(w2, c));
 }
 
-// One warp per unknown point; lanes stride the channels (coalesced rows of feats / out).
+// One warp per FOUR unknown points; lanes stride the channels (coalesced rows of feats / out).  Lanes 0-3 each
+// fetch one point's three (distance, index) pairs and run its six IEEE divisions -- once per point instead of once
+// per lane -- and broadcast the weights; the twelve row loads of a channel chunk are issued before the four stores.
+constexpr int TI_PTS = 4;
+
 __global__ void __launch_bounds__(256)
 three_interpolate_kernel(const float* __restrict__ feats, const int64_t* __restrict__ idx,
-                         const float* __restrict__ dist, float* __restrict__ out, int N, int S, int D) {
-  const int b = blockIdx.y;
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (n >= N) return;
+                         const float* __restrict__ dist, float* __restrict__ out, long long total, int N, int S, int D) {
   const int lane = threadIdx.x & 31;
-  const size_t o = ((size_t)b * N + n) * 3;
-  float w0, w1, w2;
-  interp_weights(dist + o, w0, w1, w2);
-  const float* f0 = feats + ((size_t)b * S + idx[o]) * D;
-  const float* f1 = feats + ((size_t)b * S + idx[o + 1]) * D;
-  const float* f2 = feats + ((size_t)b * S + idx[o + 2]) * D;
-  float* y = out + ((size_t)b * N + n) * D;
+  const long long p0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * TI_PTS;  // global point index b * N + n
+  if (p0 >= total) return;
+  float mw0 = 0.f, mw1 = 0.f, mw2 = 0.f;
+  long long mr0 = 0, mr1 = 0, mr2 = 0;  // feats row (b * S + idx) of the three neighbours
+  if (lane < TI_PTS && p0 + lane < total) {
+    const size_t o = (size_t)(p0 + lane) * 3;
+    interp_weights(dist + o, mw0, mw1, mw2);
+    const long long base = ((p0 + lane) / N) * S;
+    mr0 = base + idx[o]; mr1 = base + idx[o + 1]; mr2 = base + idx[o + 2];
+  }
+  float w0[TI_PTS], w1[TI_PTS], w2[TI_PTS];
+  const float *f0[TI_PTS], *f1[TI_PTS], *f2[TI_PTS];
+#pragma unroll
+  for (int j = 0; j < TI_PTS; ++j) {
+    w0[j] = __shfl_sync(PPT_FULL_MASK, mw0, j); w1[j] = __shfl_sync(PPT_FULL_MASK, mw1, j);
+    w2[j] = __shfl_sync(PPT_FULL_MASK, mw2, j);
+    f0[j] = feats + (size_t)__shfl_sync(PPT_FULL_MASK, mr0, j) * D;
+    f1[j] = feats + (size_t)__shfl_sync(PPT_FULL_MASK, mr1, j) * D;
+    f2[j] = feats + (size_t)__shfl_sync(PPT_FULL_MASK, mr2, j) * D;
+  }
+  float* y = out + (size_t)p0 * D;
+  const int npts = total - p0 < TI_PTS ? (int)(total - p0) : TI_PTS;
   if ((D & 3) == 0) {
     for (int c = lane * 4; c < D; c += 128) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(f0 + c));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(f1 + c));
-      const float4 cc = __ldg(reinterpret_cast<const float4*>(f2 + c));
-      float4 r;
-      r.x = interp3(w0, a.x, w1, bb.x, w2, cc.x);
-      r.y = interp3(w0, a.y, w1, bb.y, w2, cc.y);
-      r.z = interp3(w0, a.z, w1, bb.z, w2, cc.z);
-      r.w = interp3(w0, a.w, w1, bb.w, w2, cc.w);
-      *reinterpret_cast<float4*>(y + c) = r;
+      float4 a[TI_PTS], bb[TI_PTS], cc[TI_PTS];
+#pragma unroll
+      for (int j = 0; j < TI_PTS; ++j) {
+        a[j] = __ldg(reinterpret_cast<const float4*>(f0[j] + c));
+        bb[j] = __ldg(reinterpret_cast<const float4*>(f1[j] + c));
+        cc[j] = __ldg(reinterpret_cast<const float4*>(f2[j] + c));
+      }
+#pragma unroll
+      for (int j = 0; j < TI_PTS; ++j) {
+        if (j >= npts) break;
+        float4 r;
+        r.x = interp3(w0[j], a[j].x, w1[j], bb[j].x, w2[j], cc[j].x);
+        r.y = interp3(w0[j], a[j].y, w1[j], bb[j].y, w2[j], cc[j].y);
+        r.z = interp3(w0[j], a[j].z, w1[j], bb[j].z, w2[j], cc[j].z);
+        r.w = interp3(w0[j], a[j].w, w1[j], bb[j].w, w2[j], cc[j].w);
+        __stcs(reinterpret_cast<float4*>(y + (size_t)j * D + c), r);  // written once: streaming store
+      }
     }
   } else {
-    for (int c = lane; c < D; c += 32) y[c] = interp3(w0, __ldg(f0 + c), w1, __ldg(f1 + c), w2, __ldg(f2 + c));
+    for (int j = 0; j < npts; ++j)
+      for (int c = lane; c < D; c += 32)
+        y[(size_t)j * D + c] = interp3(w0[j], __ldg(f0[j] + c), w1[j], __ldg(f1[j] + c), w2[j], __ldg(f2[j] + c));
   }
 }
 
@@ -150,9 +176,10 @@ extern "C" PPT_EXPORT int ppt_three_interpolate(const float* feats, const int64_
                                      int N, int S, int D, void* stream) {
   if (!feats || !idx || !dist || !out || B < 0 || N < 1 || S < 1 || D < 1) return PPT_EINVAL;
   if (B == 0) return 0;
-  if (B > 65535) return PPT_ERANGE;
-  dim3 grid((N + 7) / 8, B);
-  three_interpolate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feats, idx, dist, out, N, S, D);
+  const long long total = (long long)B * N;
+  const long long blocks = (total + 8 * TI_PTS - 1) / (8 * TI_PTS);
+  if (blocks > 0x7fffffffll) return PPT_ERANGE;
+  three_interpolate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(feats, idx, dist, out, total, N, S, D);
   return ppt_launch_status();
 }
 

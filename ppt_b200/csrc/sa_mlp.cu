@@ -7,7 +7,7 @@
 //   sa_fused_kernel            the default: gather + centre subtraction + concat -> three tensor-core layers -> max
 //                              over nsample in ONE kernel per 128-column tile, activations resident in shared memory;
 //   sa_gather_image_kernel,    the first version and the fallback when the activation regions do not fit
-//   pointwise_linear_kernel    (PPT_SA_FUSED=0 selects it): the gather writes the fp16 K-major operand images of
+//   pointwise_linear_kernel    (PPT_SA_PER_LAYER in `mode` selects it): the gather writes the fp16 K-major operand images of
 //                              layer 1 to HBM, then one kernel per layer = relu(W' act + b') on the tensor core (the
 //                              group_linear pipeline of encoder.cu); layers 1, 2 store the next layer's operand images,
 //                              the last one max-pools over each group's accumulator columns and stores [B, C3, S].
@@ -500,7 +500,7 @@ struct SaDims {
 template <uint32_t FMT>
 int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
                const unsigned char* blob, unsigned char* ws, float* out, int B, int N, int S, int ns, int D,
-               const SaDims& d, int c3, cudaStream_t st) {
+               const SaDims& d, int c3, bool use_fused, cudaStream_t st) {
   const long long groups = (long long)B * S, total = groups * ns;
   const long long tiles_ll = (total + 127) / 128;
   if (tiles_ll > 0x7fffffffll) return PPT_ERANGE;
@@ -516,12 +516,8 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
   const int sms = num_sms_sa();
   const int grid = tiles < sms ? tiles : sms;
   const float* bias = reinterpret_cast<const float*>(blob);
-  // single-kernel path: activations stay in shared memory (PPT_SA_FUSED=0 forces the per-layer kernels)
-  static int use_fused = -1;
-  if (use_fused < 0) {
-    const char* ev = getenv("PPT_SA_FUSED");
-    use_fused = ev ? (atoi(ev) != 0) : 1;
-  }
+  // single-kernel path: activations stay in shared memory; the per-layer kernels are the fallback for layer widths
+  // whose activation regions do not fit (and can be forced with PPT_SA_PER_LAYER in `mode`, for cross-checks)
   // separate regions for the input and the layer-2 output (-> gather prefetch) when they fit with a 3-stage ring
   const size_t sep_fixed = (size_t)d.kc0 * IMG + (size_t)d.u1 * 32768 + (size_t)d.u2 * 32768 + 256;
   const bool sep = sep_fixed + 3 * (size_t)IMG <= 232448;
@@ -583,11 +579,13 @@ extern "C" PPT_EXPORT int ppt_sa_mlp_forward(const float* xyz, const float* feat
   if (c1 < 1 || c2 < 1 || c3 < 1 || !d.ok()) return PPT_ERANGE;
   const unsigned char* blob = static_cast<const unsigned char*>(packed);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const bool use_fused = !(mode & PPT_SA_PER_LAYER);
+  mode &= ~PPT_SA_PER_LAYER;
   if (mode == PPT_ENC_FP16)
     return run_sa_mlp<tc05::FMT_F16>(xyz, D > 0 ? feats : nullptr, new_xyz, idx, blob, ws, out, B, N, S, nsample, D, d, c3,
-                                     (cudaStream_t)stream);
+                                     use_fused, (cudaStream_t)stream);
   if (mode == PPT_ENC_BF16)
     return run_sa_mlp<tc05::FMT_BF16>(xyz, D > 0 ? feats : nullptr, new_xyz, idx, blob, ws, out, B, N, S, nsample, D, d,
-                                      c3, (cudaStream_t)stream);
+                                      c3, use_fused, (cudaStream_t)stream);
   return PPT_EINVAL;
 }

@@ -113,114 +113,7 @@ umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restric
   if (warp == 1) tmem_dealloc<ST_TMEM_COLS>(tbase);
 }
 
-// ---- CTA-pair variant: D[256,N] = A[256,K] * B[N,K]^T on two CTAs (cta_group::2) ----
-template <uint32_t FMT>
-__global__ void __launch_bounds__(ST_THREADS, 1)
-umma_pair_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, int N,
-                          int K, int b_mn) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int kchunks = K / 64, NH = N / 2;                    // this CTA's half of B
-  const uint32_t a_bytes = (uint32_t)kchunks * 16384u;
-  const uint32_t b_bytes = (uint32_t)NH * (uint32_t)K * 2u;
-  unsigned char* sA = smem;
-  unsigned char* sB = sA + a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_bytes);  // [0] mma done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tbase = *tmem_slot;
-
-  const float* a_mine = a + (size_t)rank * 128 * K;
-  for (int e = tid; e < 128 * K; e += ST_THREADS) {
-    const int m = e / K, k = e - m * K;
-    *reinterpret_cast<uint16_t*>(sA + (uint32_t)(k >> 6) * 16384u + sw128_kmajor_off(m, k & 63)) =
-        to_operand<FMT>(a_mine[e]);
-  }
-  const float* b_mine = b + (size_t)rank * NH * K;
-  const uint32_t mn_block = (uint32_t)(K / 8) * 1024u;
-  for (int e = tid; e < NH * K; e += ST_THREADS) {
-    const int n = e / K, k = e - n * K;
-    const uint32_t off = b_mn ? sw128_mnmajor_off(n, k, mn_block)
-                              : (uint32_t)(k >> 6) * ((uint32_t)NH * 128u) + sw128_kmajor_off(n, k & 63);
-    *reinterpret_cast<uint16_t*>(sB + off) = to_operand<FMT>(b_mine[e]);
-  }
-  fence_proxy_async_smem();
-  cluster_sync_all();  // both halves of both operands are in place
-
-  if (rank == 0 && warp == 0) {
-    fence_after_sync();
-    const uint32_t idesc = make_idesc(FMT, 256, N, b_mn);
-    const uint32_t aaddr = smem_u32(sA), baddr = smem_u32(sB);
-    uint32_t acc = 0;
-    for (int kc = 0; kc < kchunks; ++kc)
-      for (int k16 = 0; k16 < 4; ++k16) {
-        const uint64_t adesc = make_sdesc(aaddr + kc * 16384u + k16 * 32u, 16u, 1024u);
-        uint64_t bdesc;
-        if (b_mn) {
-          const uint32_t k0 = (uint32_t)kc * 64u + (uint32_t)k16 * 16u;
-          bdesc = make_sdesc(baddr + (k0 >> 3) * 1024u, mn_block, 1024u);
-        } else {
-          bdesc = make_sdesc(baddr + kc * ((uint32_t)NH * 128u) + k16 * 32u, 16u, 1024u);
-        }
-        umma_f16_pair_elect(tbase, adesc, bdesc, idesc, acc);
-        acc = 1;
-      }
-    umma_commit_pair_elect(&bars[0], 3);
-  }
-
-  mbar_wait(&bars[0], 0);
-  fence_after_sync();
-  const int m = (int)rank * 128 + warp * 32 + lane;
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float v[32];
-    tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) d[(size_t)m * N + c0 + i] = v[i];
-  }
-  fence_before_sync();
-  cluster_sync_all();
-  if (warp == 1) tmem_dealloc_pair<512>(tbase);
-}
-
 }  // namespace
-
-// CTA-pair GEMM self-test: a [256,K], b [N,K] -> d [256,N].  mode bits as below (no split, no packed image).
-extern "C" PPT_EXPORT int ppt_selftest_umma_pair(const float* a, const float* b, float* d, int N, int K, int mode,
-                                                 void* stream) {
-  if (!a || !b || !d) return PPT_EINVAL;
-  const int prec = mode & 3, b_mn = (mode >> 2) & 1;
-  if (prec > PPT_ENC_BF16) return PPT_EINVAL;
-  if (N < 64 || N > 256 || (N % 64) != 0 || K < 64 || (K % 64) != 0) return PPT_ERANGE;
-  if (b_mn && (N % 128) != 0) return PPT_ERANGE;
-  const size_t smem = (size_t)(K / 64) * 16384 + (size_t)(N / 2) * K * 2 + 64;
-  if (smem > 220 * 1024) return PPT_ERANGE;
-  auto kern = prec == PPT_ENC_FP16 ? umma_pair_selftest_kernel<tc05::FMT_F16> : umma_pair_selftest_kernel<tc05::FMT_BF16>;
-  PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2);
-  cfg.blockDim = dim3(ST_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PPT_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b, d, N, K, b_mn));
-  return ppt_launch_status();
-}
 
 // mode: bits [0,2) = PPT_ENC_FP16 / PPT_ENC_BF16 / PPT_ENC_FP16X3; bit 2 = B operand MN-major;
 // bit 3 = `a` points at a packed operand image (ppt_b200/encoder_pack.py: pack_kmajor) instead of fp32.

@@ -339,7 +339,10 @@ def sa_mlp_supported(c0, c1, c2, c3, nsample):
     return nsample in (16, 32, 64, 128) and _lib.load().ppt_sa_mlp_packed_bytes(c0, c1, c2, c3) > 0
 
 
-def sa_mlp_forward(xyz, feats, new_xyz, idx, packed, dims, mode=ENC_FP16):
+SA_PER_LAYER = 0x100  # PPT_SA_PER_LAYER
+
+
+def sa_mlp_forward(xyz, feats, new_xyz, idx, packed, dims, mode=ENC_FP16, per_layer=False):
     """Grouping gather + 3 x (Conv 1x1 + BN + ReLU) + max over nsample of a PointNet++ set-abstraction level
     (models/pointnet2/pointnet2_utils.py:196-201, 256-261; eval mode).  xyz [B,N,3], feats [B,N,D] or None,
     new_xyz [B,S,3], idx [B,S,nsample] int64; `packed`, `dims` from encoder_pack.pack_sa_mlp -> [B, c3, S]."""
@@ -360,7 +363,8 @@ def sa_mlp_forward(xyz, feats, new_xyz, idx, packed, dims, mode=ENC_FP16):
     ws = _workspace((xyz.device, "sa_mlp"), lib.ppt_sa_mlp_workspace_bytes(B * S * ns, c0, c1, c2, c3))
     with torch.cuda.device(xyz.device):
         _lib.check(lib.ppt_sa_mlp_forward(_ptr(xyz), _ptr(feats) if D > 0 else None, _ptr(new_xyz), _ptr(idx), _ptr(packed),
-                                          _ptr(ws), _ptr(out), B, N, S, ns, D, c1, c2, c3, mode, _stream(xyz)),
+                                          _ptr(ws), _ptr(out), B, N, S, ns, D, c1, c2, c3,
+                                          mode | (SA_PER_LAYER if per_layer else 0), _stream(xyz)),
                    "ppt_sa_mlp_forward")
     return out
 
@@ -540,18 +544,6 @@ def tokenizer_forward(neighborhood, center, enc_packed, pos_packed, mode=ENC_FP1
                                              _ptr(ws), _ptr(x), _ptr(pos), B * G, G, mode, _stream(ct)),
                    "ppt_tokenizer_forward")
     return x, pos
-
-
-def selftest_umma_pair(a, b, mode=ENC_FP16, b_mn_major=False):
-    """D[256,N] = A[256,K] @ B[N,K]^T on a CTA pair (tcgen05 cta_group::2)."""
-    _need_cuda(a, b)
-    a, b = _f32(a), _f32(b)
-    N, K = b.shape
-    d = torch.empty((256, N), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
-        _lib.check(_lib.load().ppt_selftest_umma_pair(_ptr(a), _ptr(b), _ptr(d), N, K, mode | (4 if b_mn_major else 0),
-                                                      _stream(a)), "ppt_selftest_umma_pair")
-    return d
 
 
 class Stage2ClockTrace:

@@ -79,7 +79,8 @@ def _fused_mlp_max(owner, key, xyz, points, new_xyz, idx, convs, bns, xyz_first)
         blob, dims = encoder_pack.pack_sa_mlp(convs, bns, xyz_first, mode)
         cache[key] = (ckey, blob.to(xyz.device), dims)
     _, blob, dims = cache[key]
-    return ops.sa_mlp_forward(xyz, points, new_xyz, idx, blob, dims, mode=mode)
+    return ops.sa_mlp_forward(xyz, points, new_xyz, idx, blob, dims, mode=mode,
+                              per_layer=bool(getattr(owner, "ppt_sa_per_layer", False)))
 
 
 def _shared_mlp_max(new_points, convs, bns):

@@ -44,6 +44,7 @@ def main():
     mod = mod.cuda().eval()
     mod.start_idx = 0
     mod.ppt_precision = precision
+    mod.ppt_sa_per_layer = len(sys.argv) > 3 and sys.argv[3] == "0"
     with torch.no_grad():
         new_xyz, out = mod(*args)
         fused_calls = len(calls)

@@ -35,14 +35,3 @@ def test_encoder_tokens(case, mode):
     for key in ("tokens", "features"):
         assert r[key]["max"] <= TOL[mode], (key, r)
         assert r[key]["rms"] <= TOL[mode], (key, r)
-
-
-@pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("case", ["golden", "1", "7", "131", "1500", "16384"])
-def test_encoder_tokens_cta_pair_stage2(case, mode):
-    """The experimental cta_group::2 stage 2 (PPT_STAGE2_PAIR=1): same tolerances, ragged tails included."""
-    r = run_child(case, mode, env={"PPT_STAGE2_PAIR": "1"})
-    assert r["finite"] and r["repeatable"], r
-    for key in ("tokens", "features"):
-        assert r[key]["max"] <= TOL[mode], (key, r)
-        assert r[key]["rms"] <= TOL[mode], (key, r)

@@ -15,13 +15,13 @@ CHILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_sa_mlp_child.
 TOL = {"fp16": 2e-3, "bf16": 1.5e-2}  # three chained layers with 16-bit operands, norm-relative
 
 
-@pytest.mark.parametrize("single_kernel", ["1", "0"])  # PPT_SA_FUSED: activations in shared memory / per-layer kernels
+@pytest.mark.parametrize("single_kernel", ["1", "0"])  # activations in shared memory / per-layer kernels (PPT_SA_PER_LAYER)
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("case", ["ssg2", "ssg3", "msg1"])
 def test_sa_mlp_modules(case, precision, single_kernel):
     try:
-        out = subprocess.run([sys.executable, CHILD, case, precision], capture_output=True, text=True, timeout=300,
-                             env=dict(os.environ, PPT_SA_FUSED=single_kernel))
+        out = subprocess.run([sys.executable, CHILD, case, precision, single_kernel], capture_output=True, text=True,
+                             timeout=300)
     except subprocess.TimeoutExpired:
         pytest.fail("sa_mlp child hung (killed after 300 s)")
     assert out.returncode == 0, out.stderr[-3000:]

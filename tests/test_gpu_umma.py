@@ -30,22 +30,3 @@ def test_umma_selftest(N, K, mode, b_mn, packed):
     err = json.loads(out.stdout.strip().splitlines()[-1])["rel_err"]
     # operands are rounded identically on both sides; only fp32 accumulation order differs
     assert err < (2e-5 if mode == 2 else 1e-5), err
-
-
-PAIR_CHILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_umma_pair_child.py")
-# N, K, mode, B MN-major
-PAIR_VARIANTS = [(256, 128, 0, 0), (128, 256, 0, 0), (256, 64, 1, 0), (64, 128, 0, 0), (256, 128, 0, 1),
-                 (256, 256, 0, 1), (128, 128, 1, 1)]
-
-
-@pytest.mark.parametrize("N,K,mode,b_mn", PAIR_VARIANTS)
-def test_umma_pair_selftest(N, K, mode, b_mn):
-    """tcgen05 cta_group::2: two CTAs of a cluster run one M = 256 MMA (layout / descriptor / commit pinning)."""
-    try:
-        out = subprocess.run([sys.executable, PAIR_CHILD] + [str(v) for v in (N, K, mode, b_mn)],
-                             capture_output=True, text=True, timeout=120)
-    except subprocess.TimeoutExpired:
-        pytest.fail("CTA-pair self-test hung (killed after 120 s)")
-    assert out.returncode == 0, out.stderr[-2000:]
-    r = json.loads(out.stdout.strip().splitlines()[-1])
-    assert r["rel_err"] < 1e-5, r

@@ -55,4 +55,4 @@ for name, fn in kernels.items():
     torch.cuda.synchronize()
     m = probe.mhz()
     out[name] = {"sm_mhz_mean": round(m[0], 1), "sm_mhz_min_200us": round(m[1], 1), "sm_mhz_max_200us": round(m[2], 1)}
-print(json.dumps({"pair": os.environ.get("PPT_STAGE2_PAIR", "0"), "clocks_inside_kernels": out}))
+print(json.dumps({"clocks_inside_kernels": out}))
