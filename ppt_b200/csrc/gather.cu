@@ -99,7 +99,7 @@ gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_
   // CONCAT: out row = [xyz - centre | feats] (or feats first), C = 3 + D; else: out row = points row, C = D
   const int lane = threadIdx.x & 31;
   const int C = CONCAT ? D + 3 : D;
-  const int xyz_lo = xyz_first ? 0 : D, feat_lo = xyz_first ? 3 : 0;
+  const int xyz_lo = xyz_first ? 0 : D, feat_lo = (CONCAT && xyz_first) ? 3 : 0;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const float nanv = __int_as_float(0x7fc00000);
   for (long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GR_ROWS; row0 < total_rows;
