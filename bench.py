@@ -293,6 +293,16 @@ def measure_other_kernels(dev, peaks, issue_peak, steps):
                                   "hbm_frac": B * (N * 12 + S * 12 + S * ns * 8) / (ms * 1e-3) / 1e9 / hbm,
                                   "note": "first-nsample early exit: executes far fewer than the S x N x 7 of a full scan "
                                           "(effective rate, may exceed 1); 4 MB of output, launch-latency sized"}
+    # the same kernel with the batch scaled x16 (512 clouds): what it does once the launch is amortised
+    Bb = 512
+    xb = sphere(Bb, N)
+    cb_ = ops.gather(xb, ops.fps(xb, S, torch.zeros(Bb, dtype=torch.int64, device=dev)))
+    ms = _time_launches(lambda i: ops.ball_query(0.2, ns, xb, cb_), steps)
+    out["ball_query_cfg3_sa1_batch512"] = {"shape": "B=512, N=1024, S=512, r=0.2, nsample=32", "bound": "sm_issue", "ms": ms,
+                                           "unit": "lane-instr/s", "achieved": Bb * S * N * 7 / (ms * 1e-3),
+                                           "peak": issue_peak,
+                                           "hbm_frac": Bb * (N * 12 + S * 12 + S * ns * 8) / (ms * 1e-3) / 1e9 / hbm}
+    del xb, cb_
     # -- cfg 3 (SSG level 2) grouping gather: [B,128,64,131] fp32 = 4.29 MB per cloud, batch 64 (275 MB > L2)
     B, N, S, K, D = 64, 512, 128, 64, 128
     x2 = sphere(B, N)

@@ -85,11 +85,13 @@ __global__ void group_concat_kernel(const float* __restrict__ xyz, const float* 
   }
 }
 
-// Wide rows (C >= 32): one warp per output row, lanes stride the columns -- every load and store instruction of the
-// warp covers 128 contiguous bytes of one source / destination row (the element-wise kernels above spend a divide, an
-// 8-byte index load and a scattered 4-byte load per element, and reached 18 % of the HBM peak at C = 131).  Four rows
-// per warp and step, their index loads and the first column loads issued before anything is stored.
-constexpr int GR_ROWS = 4;
+// Wide rows (C >= 32).  The element-wise kernels above spend a divide, an 8-byte index load and a scattered 4-byte
+// load per element and reached 18 % of the HBM peak at C = 131; a warp-per-row version with direct 4-byte stores
+// reached 27 % (rows of 131 floats start at odd 4-byte offsets, so every store straddles sectors).  Here a block
+// assembles GR_ROWS consecutive output rows in shared memory -- warps fetch whole source rows with 16-byte loads --
+// and then writes the block's contiguous slice of the output with 16-byte ALIGNED stores (GR_ROWS * C * 4 bytes is a
+// multiple of 16 for every C), so the HBM sees full-sector streaming writes.
+constexpr int GR_ROWS = 32;
 
 template <bool CONCAT>
 __global__ void __launch_bounds__(256)
@@ -97,46 +99,63 @@ gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_
                    const int64_t* __restrict__ idx, float* __restrict__ out, long long total_rows, int rows_per_cloud,
                    int N, int K, int D, int xyz_first) {
   // CONCAT: out row = [xyz - centre | feats] (or feats first), C = 3 + D; else: out row = points row, C = D
-  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) float stage[];  // [GR_ROWS][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = CONCAT ? D + 3 : D;
   const int xyz_lo = xyz_first ? 0 : D, feat_lo = (CONCAT && xyz_first) ? 3 : 0;
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const float nanv = __int_as_float(0x7fc00000);
-  for (long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GR_ROWS; row0 < total_rows;
-       row0 += nwarps * GR_ROWS) {
-    long long mine = -1;
-    if (lane < GR_ROWS && row0 + lane < total_rows) mine = __ldg(idx + row0 + lane);
+  const bool vec = (D & 3) == 0;
+  for (long long row0 = (long long)blockIdx.x * GR_ROWS; row0 < total_rows; row0 += (long long)gridDim.x * GR_ROWS) {
+    const int nrows = total_rows - row0 < GR_ROWS ? (int)(total_rows - row0) : GR_ROWS;
 #pragma unroll
-    for (int r = 0; r < GR_ROWS; ++r) {
+    for (int rr = 0; rr < GR_ROWS / 8; ++rr) {
+      const int r = warp + 8 * rr;
+      if (r >= nrows) continue;  // warp-uniform
       const long long row = row0 + r;
-      if (row >= total_rows) break;  // warp-uniform
-      const long long n = __shfl_sync(PPT_FULL_MASK, mine, r);
+      const long long n = __ldg(idx + row);  // same address in every lane: one broadcast load
       const long long b = row / rows_per_cloud;
       const bool ok = (unsigned long long)n < (unsigned long long)N;  // out-of-range index: NaN row, no wild read
       const float* frow = points + ((size_t)b * N + (ok ? n : 0)) * D;
-      float* orow = out + (size_t)row * C;
+      float* srow = stage + r * C;
       if (CONCAT && lane < 3) {
         const long long s = (row - b * rows_per_cloud) / K;
         const float p = __ldg(xyz + ((size_t)b * N + (ok ? n : 0)) * 3 + lane);
         const float c = __ldg(new_xyz + ((size_t)b * (rows_per_cloud / K) + s) * 3 + lane);
-        orow[xyz_lo + lane] = ok ? __fsub_rn(p, c) : nanv;
+        srow[xyz_lo + lane] = ok ? __fsub_rn(p, c) : nanv;
       }
-      for (int c = lane; c < D; c += 32) {
-        const float v = __ldg(frow + c);
-        __stcs(orow + feat_lo + c, ok ? v : nanv);  // written once, never re-read here: streaming store
+      if (vec) {
+        for (int c = lane * 4; c < D; c += 128) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(frow + c));
+          if (!ok) v = make_float4(nanv, nanv, nanv, nanv);
+          float* d = srow + feat_lo + c;  // 4-byte aligned only (C is odd in the concat case)
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+      } else {
+        for (int c = lane; c < D; c += 32) srow[feat_lo + c] = ok ? __ldg(frow + c) : nanv;
       }
     }
+    __syncthreads();
+    const int total = nrows * C;
+    float* dst = out + (size_t)row0 * C;  // 16-byte aligned: row0 is a multiple of GR_ROWS
+    const int total4 = total & ~3;
+    for (int i = threadIdx.x * 4; i < total4; i += 1024)
+      __stcs(reinterpret_cast<float4*>(dst + i), *reinterpret_cast<const float4*>(stage + i));  // written once: streaming
+    if (threadIdx.x < total - total4) dst[total4 + threadIdx.x] = stage[total4 + threadIdx.x];
+    __syncthreads();
   }
 }
 
 }  // namespace
 
-static int gather_rows_grid(long long total_rows) {
+static int gather_rows_launch_dims(long long total_rows, int C, size_t* smem) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long want = (total_rows + 8 * GR_ROWS - 1) / (8 * GR_ROWS);  // 8 warps per block
-  const long long cap = (long long)sms * 8;                               // 8 resident blocks per SM
+  *smem = (size_t)GR_ROWS * C * sizeof(float);
+  const long long want = (total_rows + GR_ROWS - 1) / GR_ROWS;
+  int per_sm = (int)((200 * 1024) / (*smem + 1024));
+  per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
+  const long long cap = (long long)sms * per_sm;
   return (int)(want < cap ? want : cap);
 }
 
@@ -144,10 +163,16 @@ extern "C" PPT_EXPORT int ppt_gather(const float* points, const int64_t* idx, fl
                           void* stream) {
   if (!points || !idx || !out || B < 0 || N < 1 || C < 1 || M < 0) return PPT_EINVAL;
   if (B == 0 || M == 0) return 0;
-  if (C >= 32) {
+  if (C >= 32 && C <= 1024) {
     const long long rows = (long long)B * M;
-    gather_rows_kernel<false><<<gather_rows_grid(rows), 256, 0, (cudaStream_t)stream>>>(
-        nullptr, nullptr, points, idx, out, rows, M, N, 1, C, 1);
+    size_t smem;
+    const int grid = gather_rows_launch_dims(rows, C, &smem);
+    static PptOncePerDevice configured;
+    if (configured.need())
+      PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(gather_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              GR_ROWS * 1024 * 4));
+    gather_rows_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(nullptr, nullptr, points, idx, out, rows, M, N, 1,
+                                                                         C, 1);
     return ppt_launch_status();
   }
   if (B > 65535) return PPT_ERANGE;
@@ -162,10 +187,16 @@ extern "C" PPT_EXPORT int ppt_group_concat(const float* xyz, const float* new_xy
   if (!xyz || !new_xyz || !idx || !out || B < 0 || N < 1 || S < 1 || K < 1 || D < 0) return PPT_EINVAL;
   if (D > 0 && !points) return PPT_EINVAL;
   if (B == 0) return 0;
-  if (D >= 32) {
+  if (D >= 32 && D + 3 <= 1024) {
     const long long rows = (long long)B * S * K;
-    gather_rows_kernel<true><<<gather_rows_grid(rows), 256, 0, (cudaStream_t)stream>>>(
-        xyz, new_xyz, points, idx, out, rows, S * K, N, K, D, xyz_first);
+    size_t smem;
+    const int grid = gather_rows_launch_dims(rows, D + 3, &smem);
+    static PptOncePerDevice configured;
+    if (configured.need())
+      PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(gather_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              GR_ROWS * 1024 * 4));
+    gather_rows_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(xyz, new_xyz, points, idx, out, rows, S * K, N, K,
+                                                                        D, xyz_first);
     return ppt_launch_status();
   }
   if (B > 65535) return PPT_ERANGE;
