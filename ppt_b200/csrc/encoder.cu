@@ -63,7 +63,8 @@ struct BlobLayout {
   __host__ __device__ uint32_t W4() const { return W32() + 8 * split * IMG; }    // 2 x 8
   __host__ __device__ uint32_t WR() const { return W4() + 16 * split * IMG; }    // 3 x 4
   __host__ __device__ uint32_t W1T() const { return WR() + 12 * split * IMG; }   // layer-1 image (1, unsplit)
-  __host__ __device__ uint32_t total() const { return W1T() + IMG; }
+  __host__ __device__ uint32_t W32F() const { return W1T() + IMG; }             // W32 as fp32 [512][128] (train statistics)
+  __host__ __device__ uint32_t total() const { return W32F() + 512u * 128u * 4u; }
 };
 
 struct Ring {  // position in a ring of mbarrier-guarded stages
@@ -119,6 +120,53 @@ __device__ __forceinline__ void store_relu8(unsigned char* base, uint32_t off, u
       lo[t] = pack2<FMT, false>(fmaxf(v[2 * t], 0.f) - h.x, fmaxf(v[2 * t + 1], 0.f) - h.y);
     }
     *reinterpret_cast<uint4*>(base + split_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// store_relu8 that also returns the sum of the eight values AS STORED (operand rounding included): the train-mode
+// statistics are those of the activations the tensor core actually multiplies.
+template <uint32_t FMT, int SPLIT>
+__device__ __forceinline__ float store_relu8_sum(unsigned char* base, uint32_t off, uint32_t split_bytes, const float* v) {
+  uint32_t hi[4];
+  float s = 0.f;
+  float2 h[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    hi[t] = pack2<FMT, true>(v[2 * t], v[2 * t + 1]);
+    h[t] = unpack2<FMT>(hi[t]);
+    s += h[t].x + h[t].y;
+  }
+  *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (SPLIT == 2) {
+    uint32_t lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      lo[t] = pack2<FMT, false>(fmaxf(v[2 * t], 0.f) - h[t].x, fmaxf(v[2 * t + 1], 0.f) - h[t].y);
+      const float2 l = unpack2<FMT>(lo[t]);
+      s += l.x + l.y;
+    }
+    *reinterpret_cast<uint4*>(base + split_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  return s;
+}
+
+// Gram matrix of one 64-point chunk of h1: G[i][j] += sum_p h1[p][i] h1[p][j].  The MN-major h1 buffer (points =
+// MN, channels = K) read with the roles swapped is a K-major operand with channels as rows and points as K (same
+// bytes, same swizzle), so the chunk serves as BOTH operands of an M128 x N128 x K64 product.  Split mode:
+// hi*hi + hi*lo + lo*hi like every other product.
+template <int SPLIT>
+__device__ __forceinline__ void issue_gram_k64(uint32_t d_tmem, uint32_t h_lo, uint32_t split_step, uint32_t idesc,
+                                               bool first) {
+  constexpr uint32_t HI = sdesc_hi(1024u);
+#pragma unroll
+  for (int k16 = 0; k16 < 4; ++k16) {
+#pragma unroll
+    for (int pass = 0; pass < (SPLIT == 2 ? 3 : 1); ++pass) {
+      const uint32_t sa = pass == 2 ? 1 : 0, sb = pass == 1 ? 1 : 0;
+      const uint64_t ad = sdesc_join(h_lo + sa * split_step + (uint32_t)k16 * 2u, HI);
+      const uint64_t bd = sdesc_join(h_lo + sb * split_step + (uint32_t)k16 * 2u, HI);
+      umma_f16_elect(d_tmem, ad, bd, idesc, (first && k16 == 0 && pass == 0) ? 0u : 1u);
+    }
   }
 }
 
@@ -492,10 +540,20 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 // and the epilogue warps convert L1(n+1) while those units run:
 //   MMA      : L1(n+1) | unit0(n) unit1(n)
 //   epilogue : convert(n+1) -> h1[(n+1)%2] | point rows X(n+2) | max-epilogue unit0(n), unit1(n)
-template <uint32_t FMT, int SPLIT, int NT, int EPW>
+//
+// TRAIN (model.train(), batch-statistics BatchNorm of second_conv.1): the same pass also produces what the
+// statistics of y = W32 h1 + c need, so that no extra pass over the points exists:
+//   * the Gram matrix G = sum_p h1_p h1_p^T of this CTA's points, accumulated on the tensor core in a fourth
+//     accumulator (128 x 128 fp32 in tensor memory for the CTA's whole lifetime; the h1 buffer doubles as both
+//     operands) and written once at the end to gram_out[blockIdx.x];
+//   * the per-group MEAN of h1 (sum of the operand values as stored / 32) as operand images s_img for the
+//     small per-group GEMM W32 s (group_stats_kernel).
+// Padding points (beyond the last group) get all-zero operand rows (no bias slot), so their h1 is exactly 0.
+template <uint32_t FMT, int SPLIT, int NT, int EPW, bool TRAIN = false>
 __global__ void __launch_bounds__((EPW + 2) * 32, 1)
 encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
-                         unsigned char* __restrict__ out_img, long long num_groups, int num_tiles) {
+                         unsigned char* __restrict__ out_img, long long num_groups, int num_tiles,
+                         unsigned char* __restrict__ s_img, float* __restrict__ gram_out) {
   constexpr int GPT = NT / 32;
   constexpr int EPI_THREADS = EPW * 32;
   constexpr int CPW = NT / (EPW / 4);
@@ -506,7 +564,7 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
   constexpr uint32_t H1_BYTES = (NT / 64) * H1BLK;             // one split part of one buffer
   constexpr uint32_t H1_BUF = SPLIT * H1_BYTES;
   constexpr uint32_t STAGE_BYTES = SPLIT * IMG;
-  constexpr int TCOLS = NT >= 128 ? 512 : 256;                 // two unit accumulators + the layer-1 accumulator
+  constexpr int TCOLS = (TRAIN || NT >= 128) ? 512 : 256;      // two unit accumulators + layer 1 (+ the Gram matrix)
 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* w1img = smem;                                   // [16 KB]
@@ -521,7 +579,8 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
   uint64_t* l1_full = x_ready + 2;         // [1]
   uint64_t* l1_empty = l1_full + 1;        // [1]
   uint64_t* w1_full = l1_empty + 1;        // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w1_full + 1);
+  uint64_t* gram_full = w1_full + 1;       // [1] TRAIN: every Gram product of this CTA is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gram_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BlobLayout L{(uint32_t)SPLIT};
@@ -534,6 +593,7 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
     mbar_init(l1_full, 1);
     mbar_init(l1_empty, EPI_THREADS);
     mbar_init(w1_full, 1);
+    mbar_init(gram_full, 1);
     mbar_fence_init();
   }
   // the unused 96 bytes of every point row must be finite zeros (they sit in K slots the MMA never reads,
@@ -547,6 +607,7 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   const uint32_t l1_tmem = tbase + 2u * NT;
+  const uint32_t gram_tmem = tbase + 3u * NT;  // TRAIN: 128 columns
 
   if (warp == 0) {
     // ===================== producer: every weight of this kernel, once =====================
@@ -588,8 +649,18 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
           issue_k64<SPLIT, true>(tbase + (uint32_t)(u * NT), a_lo0 + (uint32_t)(u * 2 + kc) * (STAGE_BYTES >> 4),
                                  h1_lo + (uint32_t)kc * 512u, H1_BYTES >> 4, idesc_mn, kc == 0);
         umma_commit_elect(&acc_full[u]);
+        if (TRAIN && u == 0) {
+          // Gram products of this tile, between the two units: unit 1's commit (acc_full[1]) then also covers
+          // them, and that is what the epilogue warps wait for before this h1 buffer is overwritten
+          const uint32_t g_lo = sdesc_lo(smem_u32(h1buf) + (n & 1u) * H1_BUF, 16u);
+#pragma unroll
+          for (int kc = 0; kc < NT / 64; ++kc)
+            issue_gram_k64<SPLIT>(gram_tmem, g_lo + (uint32_t)kc * (H1BLK >> 4), H1_BYTES >> 4,
+                                  make_idesc(FMT, 128, 128, 0), n == 0 && kc == 0);
+        }
       }
     }
+    if (TRAIN) umma_commit_elect(gram_full);
   } else {
     // ===================== epilogue warps =====================
     const int e = tid - 64;
@@ -600,12 +671,15 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
     const float inv_p1 = __ldg(sc + 0), grp_scale = __ldg(sc + 6);
 
     float nx = 0.f, ny = 0.f, nz = 0.f;  // this thread's point for the NEXT build_x (threads e < NT)
+    bool nvalid = false;
     auto fetch_point = [&](int tile) {
       nx = ny = nz = 0.f;
+      nvalid = false;
       const long long gp = (long long)tile * NT + e;
       if (e < NT && tile < num_tiles && gp < num_groups * 32) {
         const float* src = nbhd + gp * 3;
         nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
+        nvalid = true;
       }
     };
     // point rows of tile index n: [x_hi y_hi z_hi | x_lo y_lo z_lo | x_hi y_hi z_hi | 1 | 1 | 0 ...]
@@ -614,7 +688,8 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
         const uint32_t hxy = pack2<FMT, false>(nx, ny), hz1 = pack2<FMT, false>(nz, 1.0f);
         const float2 fxy = unpack2<FMT>(hxy), fz = unpack2<FMT>(hz1);
         const uint32_t lxy = pack2<FMT, false>(nx - fxy.x, ny - fxy.y), lz = pack2<FMT, false>(nz - fz.x, 0.f);
-        const uint32_t hx = hxy & 0xffffu, hy = hxy >> 16, hz = hz1 & 0xffffu, one = hz1 >> 16;
+        // TRAIN: a padding point gets no bias slot either, so its h1 is exactly zero (Gram matrix, group sums)
+        const uint32_t hx = hxy & 0xffffu, hy = hxy >> 16, hz = hz1 & 0xffffu, one = (TRAIN && !nvalid) ? 0u : hz1 >> 16;
         const uint32_t lx = lxy & 0xffffu, ly = lxy >> 16, lzz = lz & 0xffffu;
         // k: 0 xh 1 yh | 2 zh 3 xl | 4 yl 5 zl | 6 xh 7 yh || 8 zh 9 one | 10 one 11 0 | 0 | 0
         const uint4 p0 = make_uint4(hx | (hy << 16), hz | (lx << 16), ly | (lzz << 16), hx | (hy << 16));
@@ -638,11 +713,21 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
       for (int jj = 0; jj < GH; ++jj) {
         float v[32];
         tmem_ld32(t_addr + jj * 32, v);
+        float gsum = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int pt = col0 + jj * 32 + q * 8;
           const uint32_t off = (uint32_t)(pt >> 6) * H1BLK + krow + ((((uint32_t)(pt & 63) >> 3) ^ sw) << 4);
-          store_relu8<FMT, SPLIT>(dst, off, H1_BYTES, v + q * 8);
+          if (TRAIN) gsum += store_relu8_sum<FMT, SPLIT>(dst, off, H1_BYTES, v + q * 8);
+          else store_relu8<FMT, SPLIT>(dst, off, H1_BYTES, v + q * 8);
+        }
+        if (TRAIN) {
+          // group mean of channel m (in act_scale units, like h1 itself): K-major operand image, K = 128 -> 2 chunks
+          const long long g = ((long long)blockIdx.x + (long long)n * gridDim.x) * GPT + part * GH + jj;
+          if (g < num_groups) {
+            const size_t img = ((size_t)(g >> 7) * 2 + (size_t)(m >> 6)) * (SPLIT * IMG);
+            store_operand<FMT, SPLIT>(s_img + img, sw128_kmajor_off((int)(g & 127), m & 63), IMG, gsum * 0.03125f);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -689,6 +774,20 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
         mbar_arrive(&acc_empty[u]);
       }
     }
+    if (TRAIN && t0 < num_tiles) {
+      // this CTA's Gram matrix: row m (this thread's channel), columns [64 part, 64 part + 64)
+      mbar_wait(gram_full, 0);
+      fence_after_sync();
+      float* grow = gram_out + ((size_t)blockIdx.x * 128 + m) * 128 + part * (128 / (EPW / 4));
+#pragma unroll
+      for (int jj = 0; jj < 128 / (EPW / 4) / 32; ++jj) {
+        float v[32];
+        tmem_ld32(gram_tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * (128 / (EPW / 4)) + jj * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) grow[jj * 32 + i] = v[i];
+      }
+      fence_before_sync();
+    }
   }
 
   fence_before_sync();
@@ -702,7 +801,13 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
 // models/pointbert/point_encoder.py:245-246 -- g + g / G + 1: every cloud's G rows follow one row that
 // belongs to the cls token.  G >= 32 so that a run of 32 consecutive groups crosses at most one cloud boundary.
 // ======================================================================================
-template <uint32_t FMT, int SPLIT, int NUNITS, int KCH = 4, bool ASSEMBLE = false>
+//
+// STATS (train-mode BatchNorm of second_conv.1): act = per-group means of h1 (s_img of
+// encoder_stage1_tc_kernel<TRAIN>), W = W32, `bias` = the per-group term c [groups, 512].  Nothing is stored per
+// group; instead, with t = W32 . mean_g(h1) for channel o, the sums over the group's 32 points of y = W32 h1 + c
+//   sum y   = 32 (t + c),      sum y^2 = (Gram term, bn_fold2_kernel) + 64 c t + 32 c^2
+// are accumulated per channel (fp32 within a 128-group tile, fp64 across) and added to stats[o] / stats[512 + o].
+template <uint32_t FMT, int SPLIT, int NUNITS, int KCH = 4, bool ASSEMBLE = false, bool STATS = false>
 __global__ void __launch_bounds__(LIN_THREADS, 1)
 group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned char* __restrict__ wsec,
                     const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ out,
@@ -793,21 +898,34 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
     const int m = quad * 32 + lane;
     const float inv_scale = __ldg(inv_scale_ptr);
     uint32_t unit_it = 0;
+    double st1[STATS ? NUNITS : 1], st2[STATS ? NUNITS : 1];
+#pragma unroll
+    for (int u = 0; u < (STATS ? NUNITS : 1); ++u) st1[u] = st2[u] = 0.0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < NUNITS; ++u, ++unit_it) {
         const int buf = unit_it & 1;
         const int o = u * 128 + m;
-        const float bo = __ldg(bias + o);
+        const float bo = STATS ? 0.f : __ldg(bias + o);
         mbar_wait(&acc_full[buf], (unit_it >> 1) & 1u);
         fence_after_sync();
         const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * NT);
+        float a1 = 0.f, a2 = 0.f;
 #pragma unroll
         for (int j = 0; j < NT / 32; ++j) {
           float v[32];
           tmem_ld32(t_addr + j * 32, v);
           const long long g0 = (long long)tile * NT + j * 32;
-          if (!ASSEMBLE && out_f16) {
+          if (STATS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (g0 + i < num_groups) {
+                const float t = v[i] * inv_scale;
+                const float c = __ldg(bias + (g0 + i) * 512 + o);  // c [groups, 512]: a warp reads 128 contiguous bytes
+                a1 += t + c;
+                a2 = fmaf(c, fmaf(2.f, t, c), a2);
+              }
+          } else if (!ASSEMBLE && out_f16) {
             // 16-bit rows (PPT_TOKENS_F16): same values rounded once more to fp16 (saturating), half the bytes
             uint16_t* out16 = reinterpret_cast<uint16_t*>(out);
 #pragma unroll
@@ -829,8 +947,17 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
               if (i < limit) (i < wrap ? p0 : p1)[i * NOUT] = fmaf(v[i], inv_scale, bo);
           }
         }
+        if (STATS) { st1[u] += (double)a1; st2[u] += (double)a2; }
         fence_before_sync();
         mbar_arrive(&acc_empty[buf]);
+      }
+    }
+    if (STATS) {
+      double* stats = reinterpret_cast<double*>(out);
+#pragma unroll
+      for (int u = 0; u < NUNITS; ++u) {
+        atomicAdd(stats + u * 128 + m, 32.0 * st1[u]);
+        atomicAdd(stats + 512 + u * 128 + m, 32.0 * st2[u]);
       }
     }
   }
@@ -997,12 +1124,36 @@ bn_fold1_kernel(BnDevice bn, const double* __restrict__ mom, long long npoints, 
   if (ch == 0 && bn.bn1_nbt) *bn.bn1_nbt += 1;
 }
 
-__global__ void __launch_bounds__(512)
-bn_fold2_kernel(BnDevice bn, const double* __restrict__ stats, long long npoints, float* __restrict__ bn_vec) {
-  const int ch = threadIdx.x;
+// Sum of the per-CTA Gram matrices (fp32 partials of encoder_stage1_tc_kernel<TRAIN>) in fp64, scaled back from the
+// activation scale: gram[i][j] = sum over every point of h1_i h1_j.
+__global__ void __launch_bounds__(256)
+bn_gram_reduce_kernel(const float* __restrict__ parts, int nparts, double inv_act2, double* __restrict__ gram) {
+  const int e = blockIdx.x * 256 + threadIdx.x;  // 0 .. 16383
+  double a = 0.0;
+  for (int p = 0; p < nparts; ++p) a += (double)parts[(size_t)p * 16384 + e];
+  gram[e] = a * inv_act2;
+}
+
+// One block per channel k of second_conv.1: sum_p y_k^2 = w_k^T G w_k (fp64, w = the exact fp32 W32 row) + the c terms
+// already in stats[512 + k] (group_linear_kernel<STATS>); then scale / shift and the running statistics.
+__global__ void __launch_bounds__(128)
+bn_fold2_kernel(BnDevice bn, const double* __restrict__ stats, const double* __restrict__ gram,
+                const float* __restrict__ w32f, long long npoints, float* __restrict__ bn_vec) {
+  const int ch = blockIdx.x, i = threadIdx.x;
+  const float* w = w32f + (size_t)ch * 128;
+  double r = 0.0;
+  for (int j = 0; j < 128; ++j) r += gram[i * 128 + j] * (double)w[j];
+  r *= (double)w[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  __shared__ double part[4];
+  if ((i & 31) == 0) part[i >> 5] = r;
+  __syncthreads();
+  if (i != 0) return;
+  const double quad = part[0] + part[1] + part[2] + part[3];
   const double n = (double)npoints;
   const double mean = stats[ch] / n;
-  double var = stats[512 + ch] / n - mean * mean;
+  double var = (stats[512 + ch] + quad) / n - mean * mean;
   var = var < 0.0 ? 0.0 : var;
   const double s = (double)bn.bn2_w[ch] / sqrt(var + (double)bn.eps);
   bn_vec[ch] = (float)s;
@@ -1058,9 +1209,15 @@ struct Workspace {
     bn_mom = total_tokenizer;
     bn_stats = bn_mom + 16 * sizeof(double);
     bn_vec = bn_stats + 1024 * sizeof(double);
-    total_train = bn_vec + 1024 * sizeof(float);
+    // group means of h1 as operand images (K = 128: 2 chunks per 128-group tile), the Gram matrix in fp64 and one
+    // fp32 partial per CTA (at most MAX_CTAS)
+    s_img = (bn_vec + 1024 * sizeof(float) + 1023) & ~(size_t)1023;
+    gram = s_img + tiles128 * 2 * (size_t)split * IMG;
+    gram_parts = gram + 16384 * sizeof(double);
+    total_train = gram_parts + (size_t)MAX_CTAS * 16384 * sizeof(float);
   }
-  size_t bn_mom, bn_stats, bn_vec, total_train;
+  static constexpr int MAX_CTAS = 256;
+  size_t bn_mom, bn_stats, bn_vec, s_img, gram, gram_parts, total_train;
 };
 
 // phases: bit 0 stage1, bit 1 group_linear(c), bit 2 stage2, bit 3 group_linear(tokens)
@@ -1071,7 +1228,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
   constexpr int EPW2 = 8;
-  auto k1tc = encoder_stage1_tc_kernel<FMT, SPLIT, NT, 8>;
+  auto k1tc = encoder_stage1_tc_kernel<FMT, SPLIT, NT, 8, false>;
   constexpr size_t s1tc = stage1_tc_smem_bytes<SPLIT, NT>();
   static_assert(s1tc <= 232448, "shared memory budget (227 KB per CTA)");
   auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
@@ -1099,7 +1256,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   const float* scales = reinterpret_cast<const float*>(blob + L.scales());
   // Rows of the last operand-image tile beyond `groups` are never written; they only feed accumulator
   // columns that are never stored.
-  if (phases & 1) k1tc<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles);
+  if (phases & 1) k1tc<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles, nullptr, nullptr);
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
                                         scales + 1, cbuf, groups, tiles128, 0, 0);
@@ -1144,31 +1301,47 @@ int run_tokenizer(const float* nbhd, const float* center, const unsigned char* b
 template <uint32_t FMT, int SPLIT, int NT>
 int run_encoder_train(const float* nbhd, unsigned char* blob, const BnDevice& bn, unsigned char* ws,
                       float* features_out, float* tokens_out, long long groups, cudaStream_t st) {
+  const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
-  auto k2s = encoder_stage_kernel<FMT, SPLIT, NT, 2, 8, BN_STATS>;
+  auto k1t = encoder_stage1_tc_kernel<FMT, SPLIT, NT, 8, true>;
+  auto kst = group_linear_kernel<FMT, SPLIT, 4, 2, false, true>;
   auto k2a = encoder_stage_kernel<FMT, SPLIT, NT, 2, 8, BN_APPLY>;
-  constexpr size_t s2 = stage_smem_bytes<SPLIT, NT, 2>();
+  constexpr size_t s1tc = stage1_tc_smem_bytes<SPLIT, NT>(), s2 = stage_smem_bytes<SPLIT, NT, 2>(),
+                   sl = linear_smem_bytes<SPLIT>();
   static PptOncePerDevice configured;
   if (configured.need()) {
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1tc));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   }
   const long long points = groups * 32;
   const int tiles = (int)((points + NT - 1) / NT);
-  const int sms = num_sms();
-  const int grid_t = tiles < sms ? tiles : sms;
+  const int tiles128 = (int)((groups + 127) / 128);
+  const int sms = num_sms() < Workspace::MAX_CTAS ? num_sms() : Workspace::MAX_CTAS;
+  const int grid_t = tiles < sms ? tiles : sms, grid_g = tiles128 < sms ? tiles128 : sms;
   double* mom = reinterpret_cast<double*>(ws + W.bn_mom);
   double* stats = reinterpret_cast<double*>(ws + W.bn_stats);
   float* bn_vec = reinterpret_cast<float*>(ws + W.bn_vec);
   float* cbuf = reinterpret_cast<float*>(ws + W.c_buf);
+  double* gram = reinterpret_cast<double*>(ws + W.gram);
+  float* gram_parts = reinterpret_cast<float*>(ws + W.gram_parts);
+  const float* scales = reinterpret_cast<const float*>(blob + L.scales());
   PPT_RETURN_IF_CUDA(cudaMemsetAsync(mom, 0, (16 + 1024) * sizeof(double), st));
+  // first_conv.1: exact batch statistics from the point moments, folded into W1'
   const long long want = (points + 255) / 256;
   bn_moments_kernel<<<(int)(want < 4 * sms ? want : 4 * sms), 256, 0, st>>>(nbhd, points, mom);
   bn_fold1_kernel<FMT><<<1, 128, 0, st>>>(bn, mom, points, blob, (uint32_t)SPLIT);
-  int rc = run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, nullptr, groups, 3, st);  // stage 1, c (raw weights)
+  // stage 1 (raw weights) + the Gram matrix and group means of h1; then c = W3a g + bias (raw weights)
+  k1t<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles, ws + W.s_img, gram_parts);
+  int rc = run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, nullptr, groups, 2, st);
   if (rc) return rc;
-  k2s<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, nullptr, nullptr, groups, tiles, stats, nullptr, nullptr);
-  bn_fold2_kernel<<<1, 512, 0, st>>>(bn, stats, points, bn_vec);
+  // second_conv.1: sum y and the c-dependent part of sum y^2 (per-group GEMM W32 . mean h1 on the tensor core),
+  // the quadratic part from the Gram matrix; scale / shift; running statistics
+  kst<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.s_img, blob + L.W32(), cbuf, scales + 2, reinterpret_cast<float*>(stats),
+                                       groups, tiles128, 0, 0);
+  const float act = SPLIT == 2 ? 64.f : 1.f;  // encoder_pack.ACT_SCALE (h1 operands are stored times this)
+  bn_gram_reduce_kernel<<<64, 256, 0, st>>>(gram_parts, grid_t, 1.0 / ((double)act * act), gram);
+  bn_fold2_kernel<<<512, 128, 0, st>>>(bn, stats, gram, reinterpret_cast<const float*>(blob + L.W32F()), points, bn_vec);
   k2a<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr, bn_vec,
                                         nullptr);
   if (tokens_out) return run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, tokens_out, groups, 8, st);

@@ -107,20 +107,27 @@ gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_
   const bool vec = (D & 3) == 0;
   for (long long row0 = (long long)blockIdx.x * GR_ROWS; row0 < total_rows; row0 += (long long)gridDim.x * GR_ROWS) {
     const int nrows = total_rows - row0 < GR_ROWS ? (int)(total_rows - row0) : GR_ROWS;
+    // one 64-bit division per 32-row step; the rows of the step are located from it with 32-bit arithmetic
+    // (a 64-bit divide per row and lane made the first version of this kernel issue-bound: 46 instructions per float)
+    const long long b0 = row0 / rows_per_cloud;
+    const int in0 = (int)(row0 - b0 * rows_per_cloud);
 #pragma unroll
     for (int rr = 0; rr < GR_ROWS / 8; ++rr) {
       const int r = warp + 8 * rr;
       if (r >= nrows) continue;  // warp-uniform
       const long long row = row0 + r;
       const long long n = __ldg(idx + row);  // same address in every lane: one broadcast load
-      const long long b = row / rows_per_cloud;
+      const unsigned in = (unsigned)(in0 + r);
+      const unsigned over = in / (unsigned)rows_per_cloud;       // 0 unless the step crosses into the next cloud(s)
+      const unsigned in_cloud = in - over * (unsigned)rows_per_cloud;
+      const long long b = b0 + over;
       const bool ok = (unsigned long long)n < (unsigned long long)N;  // out-of-range index: NaN row, no wild read
       const float* frow = points + ((size_t)b * N + (ok ? n : 0)) * D;
       float* srow = stage + r * C;
       if (CONCAT && lane < 3) {
-        const long long s = (row - b * rows_per_cloud) / K;
+        const unsigned s = in_cloud / (unsigned)K, S = (unsigned)rows_per_cloud / (unsigned)K;
         const float p = __ldg(xyz + ((size_t)b * N + (ok ? n : 0)) * 3 + lane);
-        const float c = __ldg(new_xyz + ((size_t)b * (rows_per_cloud / K) + s) * 3 + lane);
+        const float c = __ldg(new_xyz + ((size_t)b * S + s) * 3 + lane);
         srow[xyz_lo + lane] = ok ? __fsub_rn(p, c) : nanv;
       }
       if (vec) {

@@ -27,7 +27,8 @@ Blob layout (bytes), mirrored by csrc/encoder.cu (EncoderBlob):
                          scales [8] = 1/(weight scale * operand scale) of the five GEMMs, point-activation
                          scale, group-operand scale, 0   (all 1.0 outside the fp32-parity mode)
     then W2 (2 units x 2 chunks), W3A (4 x 4), W32 (4 x 2), W4 (2 x 8), WR (3 x 4) operand images,
-    then W1T: the layer-1 image of layer1_image() (one 16 KB image in every mode).
+    then W1T: the layer-1 image of layer1_image() (one 16 KB image in every mode),
+    then W32F: W32 as plain fp32 [512][128] (train mode: second-moment statistics from the Gram matrix of h1).
 """
 import torch
 
@@ -36,6 +37,7 @@ ACT_SCALE = 64.0   # fp32-parity mode: h1/h3 operands (values up to 1023 before 
 GRP_SCALE = 64.0   # fp32-parity mode: g/t operands
 F32_SECTION_BYTES = 8192
 IMAGE_BYTES = 16384
+W32F_BYTES = 512 * 128 * 4
 # (name, rows, cols)
 SECTIONS = (("W2", 256, 128), ("W3A", 512, 256), ("W32", 512, 128), ("W4", 256, 512), ("WR", 384, 256))
 
@@ -59,7 +61,8 @@ def weight_scale(w):
 
 def packed_bytes(mode):
     n = sum((r // 128) * (c // 64) for _, r, c in SECTIONS)
-    return F32_SECTION_BYTES + n * split_of(mode) * IMAGE_BYTES + IMAGE_BYTES  # + the layer-1 image (W1T)
+    # + the layer-1 image (W1T) + W32 in fp32 [512][128] (W32F: the train-mode statistics use the exact weights)
+    return F32_SECTION_BYTES + n * split_of(mode) * IMAGE_BYTES + IMAGE_BYTES + W32F_BYTES
 
 
 def layer1_image(w1, dtype):
@@ -148,6 +151,7 @@ def pack_encoder(sd, mode):
     head[: f32.numel() * 4] = f32.view(torch.uint8)
     parts = [head] + [pack_kmajor((f[name] * ws[name]).to(torch.float32), dtype, split) for name, _, _ in SECTIONS]
     parts.append(layer1_image(f["W1"] * act, dtype))
+    parts.append(f["W32"].to(torch.float32).contiguous().view(torch.uint8).reshape(-1))
     blob = torch.cat(parts)
     assert blob.numel() == packed_bytes(mode), (blob.numel(), packed_bytes(mode))
     return blob

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()  # raises if any symbol is missing
     assert lib.ppt_abi_version() == _lib.ABI_VERSION
     assert b"invalid" in lib.ppt_strerror(-1)
-    assert lib.ppt_encoder_packed_bytes(0) == 925696 + 16384
+    assert lib.ppt_encoder_packed_bytes(0) == 925696 + 16384 + 512 * 128 * 4
     assert lib.ppt_posembed_packed_bytes(0) == 8192 + 6 * 16384
     assert lib.ppt_posembed_packed_bytes(2) == 8192 + 12 * 16384
     assert lib.ppt_tokenizer_workspace_bytes(128, 0) == lib.ppt_encoder_workspace_bytes(128, 0) + 2 * 16384
