@@ -898,11 +898,13 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
     const int m = quad * 32 + lane;
     const float inv_scale = __ldg(inv_scale_ptr);
     uint32_t unit_it = 0;
-    double st1[STATS ? NUNITS : 1], st2[STATS ? NUNITS : 1];
-#pragma unroll
-    for (int u = 0; u < (STATS ? NUNITS : 1); ++u) st1[u] = st2[u] = 0.0;
+    // STATS: this thread's fp64 accumulators, one pair per unit, in its own shared-memory slots (the unit loop is not
+    // unrolled -- unrolling it tripled the run time of every instantiation -- so they cannot live in registers)
+    double* sacc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bars) + 128) + (tid - 64) * 2;
+    if (STATS)
+      for (int u = 0; u < NUNITS; ++u) sacc[u * 2 * LIN_EPI] = sacc[u * 2 * LIN_EPI + 1] = 0.0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-#pragma unroll
+#pragma unroll 1
       for (int u = 0; u < NUNITS; ++u, ++unit_it) {
         const int buf = unit_it & 1;
         const int o = u * 128 + m;
@@ -947,17 +949,16 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
               if (i < limit) (i < wrap ? p0 : p1)[i * NOUT] = fmaf(v[i], inv_scale, bo);
           }
         }
-        if (STATS) { st1[u] += (double)a1; st2[u] += (double)a2; }
+        if (STATS) { sacc[u * 2 * LIN_EPI] += (double)a1; sacc[u * 2 * LIN_EPI + 1] += (double)a2; }
         fence_before_sync();
         mbar_arrive(&acc_empty[buf]);
       }
     }
     if (STATS) {
       double* stats = reinterpret_cast<double*>(out);
-#pragma unroll
       for (int u = 0; u < NUNITS; ++u) {
-        atomicAdd(stats + u * 128 + m, 32.0 * st1[u]);
-        atomicAdd(stats + 512 + u * 128 + m, 32.0 * st2[u]);
+        atomicAdd(stats + u * 128 + m, 32.0 * sacc[u * 2 * LIN_EPI]);
+        atomicAdd(stats + 512 + u * 128 + m, 32.0 * sacc[u * 2 * LIN_EPI + 1]);
       }
     }
   }
@@ -1180,7 +1181,8 @@ constexpr size_t stage1_tc_smem_bytes() {
 template <int SPLIT>
 constexpr size_t linear_smem_bytes() {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
-  return (size_t)4 * SPLIT * IMG + (size_t)NSTAGE * SPLIT * IMG + 256;
+  // operand tile + ring + barriers (128 B) + the STATS accumulators (4 units x 128 threads x 2 doubles)
+  return (size_t)4 * SPLIT * IMG + (size_t)NSTAGE * SPLIT * IMG + 128 + 4 * 2 * LIN_EPI * sizeof(double);
 }
 
 int num_sms() {
