@@ -31,7 +31,6 @@ constexpr int PREP_THREADS = 1024;
 constexpr int SEARCH_THREADS = 1024;     // 32 warps: the per-query work is latency-bound (shuffles), so
 constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;  // occupancy is what hides it
 constexpr int SEARCH_QPB = 128;          // queries per CTA
-constexpr int MERGE_MIN = 5;             // candidates in a row from which sort+merge beats serial insertion
 
 __device__ __forceinline__ unsigned spread4(unsigned v) {  // 4 bits -> every third bit
   return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
@@ -227,27 +226,44 @@ __device__ __forceinline__ void merge_row(TopList& t, unsigned long long key, in
   t.tau = __shfl_sync(PPT_FULL_MASK, t.key, k - 1);
 }
 
-__device__ __forceinline__ void scan_row(TopList& t, const float4* __restrict__ pts, const int* __restrict__ sidx,
-                                         int row, float qx, float qy, float qz, float qn, int k, int lane) {
+// Candidate buffer (one per warp, CAND_CAP keys in shared memory): a scanned row only FILTERS -- lanes whose key beats
+// the current k-th best (tau) append it with a ballot compaction, four instructions -- and the expensive part, a
+// 32-key bitonic sort plus merge into the list (~170 instructions), runs once per 32 collected candidates instead of
+// once per candidate-rich row.  tau is then older than it could be, which only makes the row pruning slightly less
+// sharp (a stale tau is still an upper bound of the final k-th distance, so the result stays exact).
+constexpr int CAND_CAP = 64;  // fewer than 32 pending + at most 32 from one row
+
+__device__ __forceinline__ void flush32(TopList& t, unsigned long long* __restrict__ buf, int& cnt, int k, int lane) {
+  __syncwarp();
+  merge_row(t, buf[lane], k, lane);            // the first 32 pending keys
+  const int rest = cnt - 32;                   // 0 .. 31 stay pending
+  const unsigned long long x = lane < rest ? buf[32 + lane] : 0ull;
+  __syncwarp();
+  if (lane < rest) buf[lane] = x;
+  cnt = rest;
+}
+
+__device__ __forceinline__ void flush_all(TopList& t, unsigned long long* __restrict__ buf, int& cnt, int k, int lane) {
+  if (cnt >= 32) flush32(t, buf, cnt, k, lane);
+  if (cnt > 0) {
+    __syncwarp();
+    merge_row(t, lane < cnt ? buf[lane] : KEY_INF, k, lane);
+    cnt = 0;
+  }
+}
+
+__device__ __forceinline__ void scan_row(TopList& t, unsigned long long* __restrict__ buf, int& cnt,
+                                         const float4* __restrict__ pts, const int* __restrict__ sidx, int row, float qx,
+                                         float qy, float qz, float qn, int k, int lane) {
   const float4 p = pts[row * 32 + lane];
   const unsigned long long key =
       make_key(ppt_pair_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w), sidx[row * 32 + lane]);
-  unsigned bal = __ballot_sync(PPT_FULL_MASK, key < t.tau);
-  if (__popc(bal) >= MERGE_MIN) {  // many candidates (seed rows, loose tau): one sort + merge
-    merge_row(t, key, k, lane);
-    return;
-  }
-  while (bal) {
-    const int src = __ffs(bal) - 1;
-    bal &= bal - 1;
-    const unsigned long long c = __shfl_sync(PPT_FULL_MASK, key, src);
-    if (!(c < t.tau)) continue;  // tau tightened since the vote (warp-uniform)
-    const int pos = __popc(__ballot_sync(PPT_FULL_MASK, t.key < c));
-    const unsigned long long up = __shfl_up_sync(PPT_FULL_MASK, t.key, 1);
-    if (lane == pos) t.key = c;
-    else if (lane > pos) t.key = up;
-    t.tau = __shfl_sync(PPT_FULL_MASK, t.key, k - 1);
-  }
+  const bool c = key < t.tau;
+  const unsigned bal = __ballot_sync(PPT_FULL_MASK, c);
+  if (!bal) return;
+  if (c) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = key;
+  cnt += __popc(bal);
+  if (cnt >= 32) flush32(t, buf, cnt, k, lane);
 }
 
 template <bool GROUP>
@@ -261,6 +277,7 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   float4* pts = reinterpret_cast<float4*>(smem_raw);     // [np]
   int* sidx = reinterpret_cast<int*>(pts + np);          // [np]
   RowBox* boxes = reinterpret_cast<RowBox*>(sidx + np);  // [rows]
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(boxes + rows) + (threadIdx.x >> 5) * CAND_CAP;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / tiles_per_cloud;
@@ -292,7 +309,9 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
     // seed: the rows around the query's own cell
     const int r0 = min(rows - 1, __ldg(cell_start + cell_of(qx, qy, qz, hdr.lo, hdr.inv)) >> 5);
     const int ra = max(0, r0 - 1), rz = min(rows - 1, r0 + 1);
-    for (int r = ra; r <= rz; ++r) scan_row(t, pts, sidx, r, qx, qy, qz, qn, k, lane);
+    int cnt = 0;
+    for (int r = ra; r <= rz; ++r) scan_row(t, cand, cnt, pts, sidx, r, qx, qy, qz, qn, k, lane);
+    flush_all(t, cand, cnt, k, lane);  // a tight tau before the pruning pass
 
     // every other row whose box may still contain a closer point
     for (int rb = 0; rb < rows; rb += 32) {
@@ -316,9 +335,10 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
         const float slr = __shfl_sync(PPT_FULL_MASK, slack, src);
         tau_d = key_dist(t.tau);
         if (lbr > tau_d + slr + 2e-6f * fabsf(tau_d)) continue;  // tau tightened meanwhile
-        scan_row(t, pts, sidx, rb + src, qx, qy, qz, qn, k, lane);
+        scan_row(t, cand, cnt, pts, sidx, rb + src, qx, qy, qz, qn, k, lane);
       }
     }
+    flush_all(t, cand, cnt, k, lane);
 
     if (lane < k) {
       const size_t o = ((size_t)b * S + q) * k + lane;
@@ -343,7 +363,7 @@ size_t prep_smem(int N) {
 }
 size_t search_smem(int N) {
   const size_t np = (size_t)((N + 31) / 32) * 32;
-  return np * 20 + (np / 32) * sizeof(RowBox);
+  return np * 20 + (np / 32) * sizeof(RowBox) + (size_t)SEARCH_WARPS * CAND_CAP * sizeof(unsigned long long);
 }
 
 }  // namespace
