@@ -973,6 +973,146 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
 }
 
 // ======================================================================================
+// train mode: c = W3a g + bias_c AND the second_conv.1 channel sums, one kernel (single-part operands)
+// ======================================================================================
+// group_linear(c) and group_linear<STATS> fused: per 128-group tile and 128-channel unit, two accumulators -- W3a . g
+// (K = 256) and W32 . mean_g(h1) (K = 128) -- are complete at the same time, so the epilogue writes c and forms
+// c t and c^2 from registers.  Run separately, the STATS kernel re-read the 134 MB of c it needs with 128-byte pieces
+// of 2 KB rows and took 187 us; fused, the statistics cost no memory traffic at all.  Four accumulators (two pairs,
+// 512 tensor-memory columns) so that the units of a tile still pipeline against the epilogue.
+template <uint32_t FMT>
+__global__ void __launch_bounds__(LIN_THREADS, 1)
+group_c_stats_kernel(const unsigned char* __restrict__ g_img, const unsigned char* __restrict__ s_img,
+                     const unsigned char* __restrict__ w3a_sec, const unsigned char* __restrict__ w32_sec,
+                     const float* __restrict__ bias_c, const float* __restrict__ scales, float* __restrict__ cbuf,
+                     double* __restrict__ stats, long long num_groups, int num_tiles) {
+  constexpr int NSTAGE = 4, NT = 128, KG = 4, KS = 2;
+  constexpr uint32_t B_BYTES = (uint32_t)(KG + KS) * IMG;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* bbuf = smem;                    // [g: 4 chunks | s: 2 chunks] x 16 KB
+  unsigned char* ring = bbuf + B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * IMG);
+  uint64_t* full = bars;
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* acc_full = empty + NSTAGE;   // [2] pair p: both accumulators of a unit complete
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint64_t* b_full = acc_empty + 2;
+  uint64_t* b_empty = b_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], LIN_EPI); }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring r;
+      uint32_t tile_it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        mbar_wait_relaxed(b_empty, (tile_it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(b_full, B_BYTES);
+        for (int kc = 0; kc < KG; ++kc) bulk_g2s(bbuf + kc * IMG, g_img + ((size_t)tile * KG + kc) * IMG, IMG, b_full);
+        for (int kc = 0; kc < KS; ++kc)
+          bulk_g2s(bbuf + (KG + kc) * IMG, s_img + ((size_t)tile * KS + kc) * IMG, IMG, b_full);
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u)
+          for (int kc = 0; kc < KG + KS; ++kc) {
+            const uint32_t s = r.stage<NSTAGE>();
+            mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
+            mbar_arrive_expect_tx(&full[s], IMG);
+            const unsigned char* src = kc < KG ? w3a_sec + (size_t)(u * KG + kc) * IMG
+                                               : w32_sec + (size_t)(u * KS + kc - KG) * IMG;
+            bulk_g2s(ring + s * IMG, src, IMG, &full[s]);
+            ++r.it;
+          }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(FMT, 128, NT, 0);
+    const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u), b_lo0 = sdesc_lo(smem_u32(bbuf), 16u);
+    uint32_t it = 0, tile_it = 0, unit_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      mbar_wait(b_full, tile_it & 1u);
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u, ++unit_it) {
+        const int p = unit_it & 1;
+        mbar_wait(&acc_empty[p], ((unit_it >> 1) & 1u) ^ 1u);
+        fence_after_sync();
+#pragma unroll
+        for (int kc = 0; kc < KG + KS; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE;
+          mbar_wait(&full[s], (it / NSTAGE) & 1u);
+          fence_after_sync();
+          const uint32_t d = tbase + (uint32_t)((2 * p + (kc < KG ? 0 : 1)) * NT);
+          issue_k64<1, false>(d, a_lo0 + s * (IMG >> 4), b_lo0 + (uint32_t)kc * (IMG >> 4), IMG >> 4, idesc,
+                              kc == 0 || kc == KG);
+          umma_commit_elect(&empty[s]);
+        }
+        umma_commit_elect(&acc_full[p]);
+        if (u == 3) umma_commit_elect(b_empty);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const float inv_c = __ldg(scales + 1), inv_t = __ldg(scales + 2);
+    double* sacc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bars) + 128) + (tid - 64) * 2;
+    for (int u = 0; u < 4; ++u) sacc[u * 2 * LIN_EPI] = sacc[u * 2 * LIN_EPI + 1] = 0.0;
+    uint32_t unit_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u, ++unit_it) {
+        const int p = unit_it & 1;
+        const int o = u * 128 + m;
+        const float bo = __ldg(bias_c + o);
+        mbar_wait(&acc_full[p], (unit_it >> 1) & 1u);
+        fence_after_sync();
+        const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * p * NT);
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < NT / 32; ++j) {
+          uint32_t rc[32], rt[32];
+          tmem_ld32_async(t_addr + j * 32, rc);
+          tmem_ld32_async(t_addr + NT + j * 32, rt);
+          tmem_wait_ld();
+          const long long g0 = (long long)tile * NT + j * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (g0 + i < num_groups) {
+              const float c = fmaf(__uint_as_float(rc[i]), inv_c, bo);
+              const float t = __uint_as_float(rt[i]) * inv_t;
+              cbuf[(g0 + i) * 512 + o] = c;
+              a1 += t + c;
+              a2 = fmaf(c, fmaf(2.f, t, c), a2);
+            }
+        }
+        sacc[u * 2 * LIN_EPI] += (double)a1;
+        sacc[u * 2 * LIN_EPI + 1] += (double)a2;
+        fence_before_sync();
+        mbar_arrive(&acc_empty[p]);
+      }
+    }
+    for (int u = 0; u < 4; ++u) {
+      atomicAdd(stats + u * 128 + m, 32.0 * sacc[u * 2 * LIN_EPI]);
+      atomicAdd(stats + 512 + u * 128 + m, 32.0 * sacc[u * 2 * LIN_EPI + 1]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tbase);
+}
+
+// ======================================================================================
 // pos_embed layer 1 + cls rows (models/pointbert/point_encoder.py:138-142, 241-247)
 // ======================================================================================
 // pos = Linear(128, 384)(GELU(Linear(3, 128)(center))).  The 3 -> 128 layer and the exact (erf) GELU run here
@@ -1339,12 +1479,23 @@ int run_encoder_train(const float* nbhd, unsigned char* blob, const BnDevice& bn
   bn_fold1_kernel<FMT><<<1, 128, 0, st>>>(bn, mom, points, blob, (uint32_t)SPLIT);
   // stage 1 (raw weights) + the Gram matrix and group means of h1; then c = W3a g + bias (raw weights)
   k1t<<<grid_t, (8 + 2) * 32, s1tc, st>>>(nbhd, blob, ws + W.g_img, groups, tiles, ws + W.s_img, gram_parts);
-  int rc = run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, nullptr, groups, 2, st);
-  if (rc) return rc;
   // second_conv.1: sum y and the c-dependent part of sum y^2 (per-group GEMM W32 . mean h1 on the tensor core),
   // the quadratic part from the Gram matrix; scale / shift; running statistics
-  kst<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.s_img, blob + L.W32(), cbuf, scales + 2, reinterpret_cast<float*>(stats),
-                                       groups, tiles128, 0, 0);
+  if (SPLIT == 1) {
+    auto kcs = group_c_stats_kernel<FMT>;
+    constexpr size_t scs = (size_t)6 * IMG + 4 * IMG + 128 + 4 * 2 * LIN_EPI * sizeof(double);
+    static PptOncePerDevice cs_configured;
+    if (cs_configured.need())
+      PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kcs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scs));
+    kcs<<<grid_g, LIN_THREADS, scs, st>>>(ws + W.g_img, ws + W.s_img, blob + L.W3A(), blob + L.W32(),
+                                          reinterpret_cast<const float*>(blob + L.bias_c()), scales, cbuf, stats, groups,
+                                          tiles128);
+  } else {
+    int rc = run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, nullptr, groups, 2, st);
+    if (rc) return rc;
+    kst<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.s_img, blob + L.W32(), cbuf, scales + 2, reinterpret_cast<float*>(stats),
+                                         groups, tiles128, 0, 0);
+  }
   const float act = SPLIT == 2 ? 64.f : 1.f;  // encoder_pack.ACT_SCALE (h1 operands are stored times this)
   bn_gram_reduce_kernel<<<64, 256, 0, st>>>(gram_parts, grid_t, 1.0 / ((double)act * act), gram);
   bn_fold2_kernel<<<512, 128, 0, st>>>(bn, stats, gram, reinterpret_cast<const float*>(blob + L.W32F()), points, bn_vec);
