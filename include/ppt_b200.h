@@ -132,6 +132,17 @@ int ppt_graph_feature(const float *x_q, const float *x_k, const int64_t *idx, fl
 int ppt_graph_feature_grad(const float *grad_out, const int64_t *idx, float *grad_xq, float *grad_xk,
                            int B, int C, int Nq, int Nk, int k, void *stream);
 
+/* DGCNN_Propagation layer behind its per-point GEMMs (models/pointbert/pointnet2_utils.py:382-390, 444-467; eval):
+ * the layer's Conv2d(2C -> Co, 1x1, no bias) on cat(x_k[idx] - x_q, x_q) is linear, so with W = [Wa | Wb] its output
+ * is U[:, idx] + V with U = Wa x_k [B,Co,Nk] and V = (Wb - Wa) x_q [B,Co,Nq] (two plain GEMMs the caller runs).
+ * This entry does the rest: GroupNorm(G groups, eps) statistics over (Co/G, Nq, k), affine (gamma, beta [Co]),
+ * LeakyReLU(slope) and the max over the k neighbours -> out [B,Co,Nq].  idx [B,Nq,k] int64 in [0,Nk), k <= 16.
+ *   workspace: ppt_edge_gn_workspace_bytes(B, G) bytes. */
+int64_t ppt_edge_gn_workspace_bytes(int B, int G);
+int ppt_edge_gn_max_forward(const float *U, const float *V, const int64_t *idx, const float *gamma, const float *beta,
+                            void *workspace, float *out, int B, int C, int Nq, int Nk, int k, int G, float eps,
+                            float slope, void *stream);
+
 /* ---- PointNet++ set-abstraction shared MLP + max-pool (tcgen05) --------------
  * PointNetSetAbstraction[Msg].forward behind the grouping, eval mode (models/pointnet2/pointnet2_utils.py:196-201,
  * 256-261): 3 x (Conv2d 1x1 + BatchNorm2d + ReLU) over [xyz - centre, features] of every (group, sample), then max

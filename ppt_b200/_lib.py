@@ -39,6 +39,8 @@ SIGNATURES = {
     "ppt_three_interpolate_grad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ppt_graph_feature": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "ppt_graph_feature_grad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "ppt_edge_gn_workspace_bytes": (_i64, [_i, _i]),
+    "ppt_edge_gn_max_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     "ppt_sa_mlp_packed_bytes": (_i64, [_i, _i, _i, _i]),
     "ppt_sa_mlp_workspace_bytes": (_i64, [_i64, _i, _i, _i, _i]),
     "ppt_sa_mlp_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

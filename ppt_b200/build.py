@@ -26,6 +26,7 @@ PER_FILE = {
     "gather.cu": ["-fmad=false"],
     "interp.cu": ["-fmad=false"],
     "graph_feature.cu": ["-fmad=false"],
+    "edge_conv.cu": [],
 }
 
 

@@ -334,6 +334,28 @@ def graph_feature(x_q, x_k, idx):
     return _graph_feature_fwd(x_q, x_k, idx)
 
 
+def edge_gn_max(U, V, idx, gn_weight, gn_bias, num_groups, eps=1e-5, negative_slope=0.2):
+    """The tail of a DGCNN_Propagation layer (models/pointbert/pointnet2_utils.py:382-390, 444-467) behind its two
+    per-point GEMMs: U [B,Co,Nk] = Wa x_k, V [B,Co,Nq] = (Wb - Wa) x_q, idx [B,Nq,k] int64 ->
+    max_j LeakyReLU(GroupNorm(U[:, :, idx[:, :, j]] + V)) : [B,Co,Nq].  Forward only."""
+    _need_cuda(U, V, idx, gn_weight, gn_bias)
+    U, V, idx = _f32(U), _f32(V), _i64(idx)
+    B, C, Nk = U.shape
+    Nq, k = idx.shape[1], idx.shape[2]
+    if tuple(V.shape) != (B, C, Nq) or idx.shape[0] != B or gn_weight.numel() != C or gn_bias.numel() != C:
+        raise ValueError("edge_gn_max: U [B,C,Nk], V [B,C,Nq], idx [B,Nq,k], weight / bias [C]")
+    lib = _lib.load()
+    out = torch.empty((B, C, Nq), dtype=torch.float32, device=U.device)
+    if B == 0:
+        return out
+    ws = _workspace((U.device, "edge_gn"), lib.ppt_edge_gn_workspace_bytes(B, num_groups))
+    with torch.cuda.device(U.device):
+        _lib.check(lib.ppt_edge_gn_max_forward(_ptr(U), _ptr(V), _ptr(idx), _ptr(_f32(gn_weight)), _ptr(_f32(gn_bias)),
+                                               _ptr(ws), _ptr(out), B, C, Nq, Nk, k, num_groups, float(eps),
+                                               float(negative_slope), _stream(U)), "ppt_edge_gn_max_forward")
+    return out
+
+
 def sa_mlp_supported(c0, c1, c2, c3, nsample):
     """Whether ppt_sa_mlp_forward covers this layer stack (<= 512 input channels per layer, nsample 16/32/64/128)."""
     return nsample in (16, 32, 64, 128) and _lib.load().ppt_sa_mlp_packed_bytes(c0, c1, c2, c3) > 0
