@@ -319,6 +319,25 @@ def gen_front_end(ns):
     print("front end x", tuple(seen["x"].shape), "pos absmax", float(seen["pos"].abs().max()))
 
 
+def gen_dgcnn(ns):
+    """The unmodified reference DGCNN_Propagation(k=4) (models/pointbert/pointnet2_utils.py:371-467) with seeded
+    weights on seeded inputs (regenerated by the tests from the seeds): its output, for the fused edge-conv path."""
+    dg = ns.pb_pn2.DGCNN_Propagation(k=4).eval()
+    sd = torch_port.make_dgcnn_state(31)
+    dg.load_state_dict(sd)
+    rec = {}
+    for tag, (B, Nk, Nq) in (("cross", (2, 64, 128)), ("up", (1, 96, 50))):
+        coor, f, coor_q, f_q = torch_port.dgcnn_inputs(4700 + Nk, B, Nk, Nq)
+        with torch.no_grad():
+            out = dg(coor, f, coor_q, f_q)
+            port = torch_port.dgcnn_forward(sd, coor, f, coor_q, f_q)
+        assert (out - port).abs().max() <= 1e-5 * out.abs().max()
+        rec[tag + ".out"] = out.numpy()
+        rec[tag + ".inputs_sha"] = digest(torch.cat([t.reshape(-1) for t in (coor, f, coor_q, f_q)]).numpy())
+    np.savez_compressed(os.path.join(OUT, "dgcnn.npz"), torch_version=torch.__version__, **rec)
+    print("dgcnn fixtures", {k: getattr(v, "shape", v) for k, v in rec.items()})
+
+
 def gen_bench_cfg2(ns):
     """BASELINE configs[1] at bench.py's own size and weights: rank 0's first batch (128 clouds x 8192 points,
     seed 1234) through the UNMODIFIED reference Group (dvae.py:152-181) + Encoder (dvae.py:184-215) + reduce_dim
@@ -371,7 +390,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1:  # regenerate one fixture only: front_end | encoder_train
         {"front_end": gen_front_end, "encoder_train": gen_encoder_train, "graph_feature": gen_graph_feature,
-         "loader_fps": gen_loader_fps, "sa_mlp": gen_sa_mlp, "bench_cfg2": gen_bench_cfg2}[sys.argv[1]](refimport.load())
+         "loader_fps": gen_loader_fps, "sa_mlp": gen_sa_mlp, "bench_cfg2": gen_bench_cfg2, "dgcnn": gen_dgcnn}[sys.argv[1]](refimport.load())
         return
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     ns = refimport.load()
@@ -393,6 +412,7 @@ def main():
     gen_loader_fps(ns)
     gen_sa_mlp(ns)
     gen_bench_cfg2(ns)
+    gen_dgcnn(ns)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("fixtures total bytes", tot)
 

@@ -238,3 +238,38 @@ def sa_mlp_max(grouped, sd, n_layers, conv_prefix="mlp_convs.", bn_prefix="mlp_b
                          sd["%s%d.weight" % (bn_prefix, i)], sd["%s%d.bias" % (bn_prefix, i)], False, 0.1, eps)
         x = F.relu(x)
     return torch.max(x, 2)[0]
+
+
+# ---- DGCNN_Propagation (models/pointbert/pointnet2_utils.py:371-467) -------------------------------------------
+def make_dgcnn_state(seed):
+    """Seeded weights with the reference module's parameter names (layer1.0 / layer1.1 / layer2.0 / layer2.1);
+    non-trivial GroupNorm affine parameters (fresh modules have weight 1 / bias 0)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, cout, cin in (("layer1", 512, 768), ("layer2", 384, 1024)):
+        sd[name + ".0.weight"] = (torch.rand(cout, cin, 1, 1, generator=g) * 2 - 1) * cin ** -0.5
+        sd[name + ".1.weight"] = torch.rand(cout, generator=g) + 0.5
+        sd[name + ".1.bias"] = torch.randn(cout, generator=g) * 0.1
+    sd["layer1.1.weight"][::7] *= -1.0   # negative scales: max over neighbours must come after the affine map
+    return sd
+
+
+def dgcnn_inputs(seed, B, Nk, Nq, C=384):
+    g = torch.Generator().manual_seed(seed)
+    unit = lambda n: torch.nn.functional.normalize(torch.randn(B, 3, n, generator=g), dim=1)
+    return unit(Nk), torch.randn(B, C, Nk, generator=g), unit(Nq), torch.randn(B, C, Nq, generator=g)
+
+
+def dgcnn_forward(sd, coor, f, coor_q, f_q, k=4):
+    """DGCNN_Propagation.forward restated with torch ops (edge features -> conv -> GroupNorm(4) -> LeakyReLU(0.2) ->
+    max over k, twice; the second graph is the queries' own)."""
+    F = torch.nn.functional
+
+    def layer(name, cq, xq, ck, xk):
+        feat, _ = graph_feature(cq, xq, ck, xk, k)
+        y = F.conv2d(feat, sd[name + ".0.weight"])
+        y = F.group_norm(y, 4, sd[name + ".1.weight"], sd[name + ".1.bias"], 1e-5)
+        return F.leaky_relu(y, 0.2).max(dim=-1)[0]
+
+    h = layer("layer1", coor_q, f_q, coor, f)
+    return layer("layer2", coor_q, h, coor_q, h)

@@ -261,6 +261,14 @@ def patch_reference(modules=None):
                 _set(cls, "forward", fp_fwd)
             dg = getattr(mod, "DGCNN_Propagation", None)
             if dg is not None:
+                orig_df = dg.forward
+
+                def dgcnn_fwd(self, coor, f, coor_q, f_q, _o=orig_df):
+                    if pointnet2.dgcnn_fusable(self, coor, f, coor_q, f_q):
+                        return pointnet2.dgcnn_propagation_forward(self, coor, f, coor_q, f_q)
+                    return _o(self, coor, f, coor_q, f_q)
+
+                _set(dg, "forward", dgcnn_fwd)
                 orig_gf = dg.get_graph_feature
 
                 def graph_fwd(self, coor_q, x_q, coor_k, x_k, _o=orig_gf):

@@ -207,9 +207,102 @@ class PointNetFeaturePropagation(nn.Module):
         else:
             new_points = interpolated
         new_points = new_points.permute(0, 2, 1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            new_points = F.relu(bn(conv(new_points)))
-        return new_points
+        return feature_propagation_mlp(self, new_points)
+
+
+def feature_propagation_mlp(module, x):
+    """The Conv1d + BatchNorm1d + ReLU stack of PointNetFeaturePropagation (models/pointnet2/pointnet2_utils.py:316-319)
+    on x [B, C, N].  Eval mode with nothing to differentiate: BatchNorm is folded into the convolution (one library
+    GEMM with a fused bias per layer, then ReLU in place -- no normalisation pass, no extra activation tensor); the
+    folded weights are cached per weight version.  Otherwise (training: these layers are trainable in the part-seg
+    head, models/ULIP_models.py:550-565) the module's own layers run."""
+    convs, bns = list(module.mlp_convs), list(module.mlp_bns)
+    params = [p for m in convs + bns for p in m.parameters()]
+    if module.training or (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))):
+        for conv, bn in zip(convs, bns):
+            x = F.relu(bn(conv(x)))
+        return x
+    tensors = params + [b for m in bns for b in m.buffers()]
+    key = (str(x.device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+    cache = module.__dict__.get("_ppt_fp_folded")
+    if cache is None or cache[0] != key:
+        folded = []
+        for conv, bn in zip(convs, bns):
+            w, b = encoder_pack.fold_conv_bn(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                             bn.eps)
+            folded.append((w.to(torch.float32).unsqueeze(-1).to(x.device), b.to(torch.float32).to(x.device)))
+        cache = (key, folded)
+        module.__dict__["_ppt_fp_folded"] = cache
+    for w, b in cache[1]:
+        x = F.relu_(F.conv1d(x, w, b))
+    return x
+
+
+class DGCNN_Propagation(nn.Module):
+    """models/pointbert/pointnet2_utils.py:371-467 -- same sub-module names (layer1 / layer2: Conv2d, GroupNorm(4),
+    LeakyReLU(0.2)), so part-seg checkpoints load."""
+
+    def __init__(self, k=16):
+        super().__init__()
+        self.k = k
+        self.layer1 = nn.Sequential(nn.Conv2d(768, 512, kernel_size=1, bias=False), nn.GroupNorm(4, 512),
+                                    nn.LeakyReLU(negative_slope=0.2))
+        self.layer2 = nn.Sequential(nn.Conv2d(1024, 384, kernel_size=1, bias=False), nn.GroupNorm(4, 384),
+                                    nn.LeakyReLU(negative_slope=0.2))
+
+    def get_graph_feature(self, coor_q, x_q, coor_k, x_k):
+        return get_graph_feature(coor_q, x_q, coor_k, x_k, self.k)
+
+    def forward(self, coor, f, coor_q, f_q):
+        """coor [B,3,Nk], f [B,C,Nk], coor_q [B,3,Nq], f_q [B,C,Nq] -> [B,384,Nq]."""
+        if dgcnn_fusable(self, coor, f, coor_q, f_q):
+            return dgcnn_propagation_forward(self, coor, f, coor_q, f_q)
+        x = self.layer1(self.get_graph_feature(coor_q, f_q, coor, f)).max(dim=-1, keepdim=False)[0]
+        return self.layer2(self.get_graph_feature(coor_q, x, coor_q, x)).max(dim=-1, keepdim=False)[0]
+
+
+def dgcnn_fusable(module, coor, f, coor_q, f_q):
+    """The fused edge-conv path is forward only (no BatchNorm here, so train / eval does not matter)."""
+    try:
+        conv1, gn1, act1 = module.layer1
+        conv2, gn2, act2 = module.layer2
+    except Exception:
+        return False
+    params = list(module.parameters())
+    if torch.is_grad_enabled() and (f.requires_grad or f_q.requires_grad or any(p.requires_grad for p in params)):
+        return False
+    ok_types = all(isinstance(c, nn.Conv2d) and c.bias is None and c.kernel_size == (1, 1) for c in (conv1, conv2)) and \
+        all(isinstance(g, nn.GroupNorm) and g.affine for g in (gn1, gn2)) and \
+        all(isinstance(a, nn.LeakyReLU) for a in (act1, act2))
+    return (ok_types and f.is_cuda and f.dtype == torch.float32 and coor.shape[1] == 3 and coor_q.shape[1] == 3
+            and conv1.in_channels == 2 * f.shape[1] and f_q.shape[1] == f.shape[1]
+            and conv2.in_channels == 2 * conv1.out_channels and 1 <= module.k <= min(16, coor.shape[2], coor_q.shape[2]))
+
+
+def _edge_layer(conv, gn, act, x_q, x_k, idx):
+    """Conv2d(cat(x_k[idx] - x_q, x_q)) -> GroupNorm -> LeakyReLU -> max over neighbours, with the linear convolution
+    split into U = Wa x_k and V = (Wb - Wa) x_q (two per-point library GEMMs; ops.edge_gn_max does the rest)."""
+    C = x_k.shape[1]
+    w = conv.weight.reshape(conv.out_channels, 2 * C)
+    wa, wb = w[:, :C], w[:, C:]
+    if x_q is x_k:
+        uv = torch.matmul(torch.cat([wa, wb - wa], dim=0), x_k)   # one GEMM for both
+        U, V = uv[:, :conv.out_channels], uv[:, conv.out_channels:]
+    else:
+        U, V = torch.matmul(wa, x_k), torch.matmul(wb - wa, x_q)
+    return ops.edge_gn_max(U, V, idx, gn.weight, gn.bias, gn.num_groups, gn.eps, act.negative_slope)
+
+
+@torch.no_grad()
+def dgcnn_propagation_forward(module, coor, f, coor_q, f_q):
+    """DGCNN_Propagation.forward (models/pointbert/pointnet2_utils.py:444-467) without the [B, 2C, Nq, k] edge tensor
+    and with k times fewer convolution FLOPs: kNN kernels for the two graphs, per-point GEMMs, fused
+    GroupNorm / LeakyReLU / max kernel (dense half; forward only)."""
+    cq = coor_q.permute(0, 2, 1).contiguous()
+    idx1 = ops.knn(module.k, coor.permute(0, 2, 1).contiguous(), cq)
+    h = _edge_layer(*module.layer1, f_q.contiguous(), f.contiguous(), idx1)
+    idx2 = ops.knn(module.k, cq, cq)
+    return _edge_layer(*module.layer2, h, h, idx2)
 
 
 def get_graph_feature(coor_q, x_q, coor_k, x_k, k):

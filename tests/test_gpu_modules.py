@@ -361,3 +361,56 @@ def test_patch_reference_on_the_real_reference_tree_with_cuda_tensors():
         assert float((f.cpu() - f_ref).abs().max() / f_ref.abs().max()) < 1e-3
     finally:
         patch.unpatch_reference()
+
+
+def test_dgcnn_propagation_fused_matches_the_reference_fixture():
+    """Row f4, dense half: DGCNN_Propagation.forward (models/pointbert/pointnet2_utils.py:444-467) with the edge
+    convolution split into per-point GEMMs and the fused GroupNorm / LeakyReLU / max kernel, against the output of the
+    unmodified reference module (tests/golden/dgcnn.npz); the unfused body (gradient needed) on the same kernels too."""
+    from oracle.inputs import digest
+    from ppt_b200 import ops, pointnet2
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dgcnn.npz"))
+    mod = pointnet2.DGCNN_Propagation(k=4)
+    mod.load_state_dict(torch_port.make_dgcnn_state(31))
+    mod = mod.cuda().eval()
+    calls = []
+    real = ops.edge_gn_max
+    ops.edge_gn_max = lambda *a, **k: calls.append(1) or real(*a, **k)
+    try:
+        for tag, (B, Nk, Nq) in (("cross", (2, 64, 128)), ("up", (1, 96, 50))):
+            inputs = torch_port.dgcnn_inputs(4700 + Nk, B, Nk, Nq)
+            assert digest(torch.cat([t.reshape(-1) for t in inputs]).numpy()) == str(f[tag + ".inputs_sha"])
+            want = torch.from_numpy(f[tag + ".out"])
+            n0 = len(calls)
+            with torch.no_grad():
+                got = mod(*(t.cuda() for t in inputs))
+            assert len(calls) == n0 + 2, "both layers must take the fused path"
+            assert got.shape == want.shape
+            assert float((got.cpu() - want).abs().max() / want.abs().max()) < 1e-4
+            n0 = len(calls)
+            got2 = mod(*(t.cuda() for t in inputs))     # parameters require grad: the module's own layers
+            assert len(calls) == n0 and got2.requires_grad
+            assert float((got2.detach().cpu() - want).abs().max() / want.abs().max()) < 1e-4
+    finally:
+        ops.edge_gn_max = real
+
+
+def test_feature_propagation_mlp_folded_in_eval_mode():
+    """PointNetFeaturePropagation's Conv1d + BatchNorm1d + ReLU stack with BatchNorm folded (eval, no gradient) equals
+    the module's own layers; train mode / gradients keep the layers."""
+    from ppt_b200 import pointnet2
+    torch.manual_seed(4)
+    fp = pointnet2.PointNetFeaturePropagation(19 + 24, [64, 32]).cuda().eval()
+    with torch.no_grad():
+        for bn in fp.mlp_bns:
+            bn.running_mean.normal_(0, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(2, 43, 300, device="cuda")
+    with torch.no_grad():
+        want = x
+        for conv, bn in zip(fp.mlp_convs, fp.mlp_bns):
+            want = torch.relu(bn(conv(want)))
+        got = pointnet2.feature_propagation_mlp(fp, x.clone())
+    assert "_ppt_fp_folded" in fp.__dict__ and float((got - want).abs().max()) < 1e-4
+    out = pointnet2.feature_propagation_mlp(fp, x.clone())      # grad enabled, trainable parameters
+    assert out.requires_grad
