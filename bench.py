@@ -606,7 +606,31 @@ def run_ours(args):
                       "+ ppt_group_concat + the module's Conv2d/BN2d/ReLU stack",
               "fused_ms": sa_fused_ms, "torch_layers_ms": sa_torch_ms, "mlp_flops": sa_flops}
 
-        f4 = {"graph_feature": {"shape": "B=32, C=384, 512 queries <- 256 keys, k=4", "bound": "hbm", "ms": gf_ms,
+        # dense half of f4: DGCNN_Propagation (k = 4) at the part-seg shapes (512 groups -> 256 points, then 256 -> 512,
+        # point_encoder.py:409-411), fused (per-point GEMMs + edge_gn_max kernel) vs the module's own layer stack on the
+        # same kNN / graph-feature kernels
+        dg = ppt_pn2.DGCNN_Propagation(k=4).to(dev).eval()
+        dB = 32
+        dk, dq = torch.randn(dB, 3, 512, device=dev), torch.randn(dB, 3, 256, device=dev)
+        fk, fq = torch.randn(dB, 384, 512, device=dev), torch.randn(dB, 384, 256, device=dev)
+
+        def time_dg(fused):
+            real = ppt_pn2.dgcnn_fusable
+            if not fused:
+                ppt_pn2.dgcnn_fusable = lambda *a: False
+            try:
+                with torch.no_grad():
+                    return _time_launches(lambda i: dg(dk, fk, dq, fq), args.steps)
+            finally:
+                ppt_pn2.dgcnn_fusable = real
+
+        dg_fused_ms, dg_layers_ms = time_dg(True), time_dg(False)
+        f4 = {"dgcnn_propagation": {"shape": "B=32, 512 keys -> 256 queries, C=384, k=4 (dgcnn_pro_2)",
+                                    "fused_ms": dg_fused_ms, "torch_layers_ms": dg_layers_ms,
+                                    "what": "edge convolution as two per-point GEMMs (cuBLAS) + edge_gn_max kernel "
+                                            "(GroupNorm statistics, affine, LeakyReLU, max over k) vs ppt_graph_feature + "
+                                            "Conv2d / GroupNorm / LeakyReLU / max layers"},
+              "graph_feature": {"shape": "B=32, C=384, 512 queries <- 256 keys, k=4", "bound": "hbm", "ms": gf_ms,
                                 "achieved": gf_bytes / (gf_ms * 1e-3) / 1e9, "unit": "GB/s",
                                 "bytes_per_launch": gf_bytes},
               "loader_fps_10000_to_1024": {"ms_per_cloud_single_call": loader_ms, "ms_per_cloud_batched_32": loader_batch_ms,
