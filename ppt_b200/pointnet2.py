@@ -279,17 +279,20 @@ def dgcnn_fusable(module, coor, f, coor_q, f_q):
             and conv2.in_channels == 2 * conv1.out_channels and 1 <= module.k <= min(16, coor.shape[2], coor_q.shape[2]))
 
 
-def _edge_layer(conv, gn, act, x_q, x_k, idx):
+def _edge_layer(conv, gn, act, x_q, x_k, idx, half):
     """Conv2d(cat(x_k[idx] - x_q, x_q)) -> GroupNorm -> LeakyReLU -> max over neighbours, with the linear convolution
-    split into U = Wa x_k and V = (Wb - Wa) x_q (two per-point library GEMMs; ops.edge_gn_max does the rest)."""
+    split into U = Wa x_k and V = (Wb - Wa) x_q (two per-point library GEMMs; ops.edge_gn_max does the rest).
+    half: fp16 operands / fp32 accumulate on the tensor cores (the fast mode, like the Encoder's; the reference's own
+    cuDNN convolution runs TF32 by default), else plain fp32 GEMMs."""
     C = x_k.shape[1]
     w = conv.weight.reshape(conv.out_channels, 2 * C)
-    wa, wb = w[:, :C], w[:, C:]
+    wa, wd = w[:, :C], w[:, C:] - w[:, :C]
+    cast = (lambda t: t.half()) if half else (lambda t: t)
     if x_q is x_k:
-        uv = torch.matmul(torch.cat([wa, wb - wa], dim=0), x_k)   # one GEMM for both
-        U, V = uv[:, :conv.out_channels], uv[:, conv.out_channels:]
+        uv = torch.matmul(cast(torch.cat([wa, wd], dim=0)), cast(x_k)).float()   # one GEMM for both
+        U, V = uv[:, :conv.out_channels].contiguous(), uv[:, conv.out_channels:].contiguous()
     else:
-        U, V = torch.matmul(wa, x_k), torch.matmul(wb - wa, x_q)
+        U, V = torch.matmul(cast(wa), cast(x_k)).float(), torch.matmul(cast(wd), cast(x_q)).float()
     return ops.edge_gn_max(U, V, idx, gn.weight, gn.bias, gn.num_groups, gn.eps, act.negative_slope)
 
 
@@ -298,11 +301,12 @@ def dgcnn_propagation_forward(module, coor, f, coor_q, f_q):
     """DGCNN_Propagation.forward (models/pointbert/pointnet2_utils.py:444-467) without the [B, 2C, Nq, k] edge tensor
     and with k times fewer convolution FLOPs: kNN kernels for the two graphs, per-point GEMMs, fused
     GroupNorm / LeakyReLU / max kernel (dense half; forward only)."""
+    half = getattr(module, "ppt_precision", "fp16") != "fp32"
     cq = coor_q.permute(0, 2, 1).contiguous()
     idx1 = ops.knn(module.k, coor.permute(0, 2, 1).contiguous(), cq)
-    h = _edge_layer(*module.layer1, f_q.contiguous(), f.contiguous(), idx1)
+    h = _edge_layer(*module.layer1, f_q.contiguous(), f.contiguous(), idx1, half)
     idx2 = ops.knn(module.k, cq, cq)
-    return _edge_layer(*module.layer2, h, h, idx2)
+    return _edge_layer(*module.layer2, h, h, idx2, half)
 
 
 def get_graph_feature(coor_q, x_q, coor_k, x_k, k):
