@@ -23,7 +23,7 @@
 // F2FP instruction.
 //
 // Also here: the cls / pos_embed token assembly (pos_hidden_kernel, group_linear_kernel<ASSEMBLE>) and the
-// train-mode BatchNorm path (bn_moments / bn_fold1 / bn_fold2, encoder_stage_kernel<BN_STATS / BN_APPLY>);
+// train-mode BatchNorm path (bn_moments / bn_fold1 / Gram statistics / bn_fold2, encoder_stage_kernel<BN_APPLY>);
 // DESIGN.md section 9.  (A cta_group::2 variant of stage 2 was built and measured in round 1 -- same time, more
 // code -- and removed in round 2; DESIGN.md section 8 keeps what it showed.)
 //
@@ -175,13 +175,10 @@ __device__ __forceinline__ void issue_gram_k64(uint32_t d_tmem, uint32_t h_lo, u
 // ======================================================================================
 // BN (stage 2 only; train-mode BatchNorm of second_conv.1, DESIGN.md "train mode"):
 //   BN_EVAL   the blob's W32 / c carry the folded running statistics (the inference path);
-//   BN_STATS  first pass of a training step: only the four W32 h1 units run, and instead of writing h3 the
-//             epilogue accumulates sum and sum of squares per channel of y = W32 h1 + c (raw, un-normalised
-//             weights) into bn_stats[0..511] / [512..1023] (fp64 atomics, one per channel, half and CTA);
-//   BN_APPLY  second pass: h3 = relu(s[ch] * y + t[ch]) with s = bn_vec[ch], t = bn_vec[512 + ch] from the
+//   BN_APPLY  training step: h3 = relu(s[ch] * y + t[ch]) with s = bn_vec[ch], t = bn_vec[512 + ch] from the
 //             batch statistics -- folded into the per-unit accumulator scale and the prefetched c values, so
 //             the inner loop is the same single FFMA per element as BN_EVAL.
-constexpr int BN_EVAL = 0, BN_STATS = 1, BN_APPLY = 2;
+constexpr int BN_EVAL = 0, BN_APPLY = 2;
 
 // CLK: measurement build of the same kernel (ppt_set_clock_trace).  A separate instantiation because even these few
 // instructions at kernel entry / exit changed ptxas's schedule of the MMA-issue loop and cost 7 % (0.59 -> 0.63 ms).
@@ -192,13 +189,13 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
                      unsigned char* __restrict__ out_img,     // stage 1: g images, stage 2: t images
                      float* __restrict__ features_out,        // stage 2, nullable: [groups, 256]
                      long long num_groups, int num_tiles,
-                     double* __restrict__ bn_stats = nullptr, const float* __restrict__ bn_vec = nullptr,
+                     double* __restrict__ /*unused*/ = nullptr, const float* __restrict__ bn_vec = nullptr,
                      long long* __restrict__ clock_acc = nullptr) {
   static_assert(BN == BN_EVAL || STAGE == 2, "batch statistics belong to stage 2");
 
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
   constexpr int GPT = NT / 32;                       // groups per tile
-  constexpr int NUNITS = STAGE == 1 ? 2 : (BN == BN_STATS ? 4 : 6);
+  constexpr int NUNITS = STAGE == 1 ? 2 : 6;
   constexpr int NH1 = STAGE == 1 ? 2 : 1;            // h1 buffers (stage 1 builds one tile ahead)
   constexpr uint32_t H1_BYTES = 2u * NT * 128u;      // one split part of one buffer: 2 K-chunks, K-major
   constexpr uint32_t H1_BUF = SPLIT * H1_BYTES;
@@ -337,7 +334,6 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
       u_scale[u] = BN == BN_APPLY ? __ldg(bn_vec + u * 128 + m) : 1.f;
       u_shift[u] = BN == BN_APPLY ? __ldg(bn_vec + 512 + u * 128 + m) : 0.f;
     }
-    double st_sum[4] = {0.0, 0.0, 0.0, 0.0}, st_sq[4] = {0.0, 0.0, 0.0, 0.0};  // BN_STATS
 
     // This thread's point of a tile, fetched one build ahead: the load comes from HBM (the neighbourhoods
     // are read here for the first time) and would otherwise stall the first FFMA of every build.
@@ -412,35 +408,7 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
         fence_after_sync();
         const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * NT + col0);
 
-        if (relu_unit && BN == BN_STATS) {
-          // y = acc + c over this thread's channel and valid points: fp32 sums per 32-point group, fp64 across
-          const float inv_true = __ldg(sc + 2);
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < GH; ++jj) {
-            float v[32];
-            tmem_ld32(t_addr + jj * 32, v);
-            if (g0 + jj < num_groups) {
-              const float cv = ccur[u < 4 ? u : 0][jj] / act_scale;  // act_scale is a power of two
-              // packed f32x2 arithmetic (FFMA2 / FADD2): this epilogue is issue-bound, three instructions per element
-              // pair instead of per element
-              float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
-              const float2 inv2 = make_float2(inv_true, inv_true), cv2 = make_float2(cv, cv);
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float2 y = __ffma2_rn(make_float2(v[i], v[i + 1]), inv2, cv2);
-                a1 = __fadd2_rn(a1, y);
-                a2 = __ffma2_rn(y, y, a2);
-              }
-              s1 += a1.x + a1.y;
-              s2 += a2.x + a2.y;
-            }
-          }
-          st_sum[u < 4 ? u : 0] += (double)s1;
-          st_sq[u < 4 ? u : 0] += (double)s2;
-          fence_before_sync();
-          mbar_arrive(&acc_empty[buf]);
-        } else if (relu_unit) {
+        if (relu_unit) {
           // h3[p][ch] = relu(acc + c[group][ch]); ch = u*128 + m is this thread's K index (MN-major B).
           const int ch = u * 128 + m;
           const float a_unit = BN == BN_APPLY ? inv_p2s * u_scale[u < 4 ? u : 0] : inv_p2s;
@@ -504,13 +472,6 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
       if (STAGE == 1) {
         const int next2 = tile + 2 * gridDim.x;
         if (next2 < num_tiles) build_h1(next2, tile_it & 1u, next2 + gridDim.x);
-      }
-    }
-    if (BN == BN_STATS) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        atomicAdd(bn_stats + u * 128 + m, st_sum[u]);
-        atomicAdd(bn_stats + 512 + u * 128 + m, st_sq[u]);
       }
     }
   }
@@ -1193,8 +1154,12 @@ pos_hidden_kernel(const float* __restrict__ center, const unsigned char* __restr
 // bn_moments_kernel reduces the nine first and second moments in fp64; bn_fold1_kernel folds the batch
 // statistics into W1' (fp32 rows for stage 2 and the K = 16 layer-1 operand image for stage 1, the layout of
 // encoder_pack.layer1_image) inside the caller's mutable blob and applies the momentum update to the
-// running statistics.  second_conv.1 sits behind a ReLU, so its statistics need a pass over the data
-// (encoder_stage_kernel<BN_STATS>); bn_fold2_kernel turns the sums into per-channel scale / shift.
+// running statistics.  second_conv.1 normalises y = W32 h1 + c_group behind a ReLU.  Its statistics need no pass of
+// their own either: with G = sum_p h1 h1^T (accumulated on the tensor core inside stage 1) and the per-group
+// means of h1,   sum y = 32 sum_g (W32 mean_g + c_g),   sum y^2 = w^T G w + sum_g (64 c_g (W32 mean_g) + 32 c_g^2)
+// per channel (group_c_stats_kernel / group_linear_kernel<STATS>, bn_gram_reduce_kernel); bn_fold2_kernel turns the
+// sums into per-channel scale / shift.  (Round 1 ran the four W32 units over every point a second time: +0.41 ms
+// per 128-cloud step; this is +0.13 ms.)
 __global__ void __launch_bounds__(256)
 bn_moments_kernel(const float* __restrict__ nbhd, long long npoints, double* __restrict__ mom) {
   double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
