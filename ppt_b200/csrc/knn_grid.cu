@@ -30,7 +30,6 @@ constexpr int GRID_MAX_N = spidx::MAX_N;
 constexpr int PREP_THREADS = 1024;
 constexpr int SEARCH_THREADS = 1024;     // 32 warps: the per-query work is latency-bound (shuffles), so
 constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;  // occupancy is what hides it
-constexpr int SEARCH_QPB = 128;          // queries per CTA
 
 __device__ __forceinline__ unsigned spread4(unsigned v) {  // 4 bits -> every third bit
   return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
@@ -271,7 +270,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, 1)
 knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query,
                   const unsigned char* __restrict__ workspace, int64_t* __restrict__ idx_out,
                   float* __restrict__ dist_out, float* __restrict__ nb_out, int N, int S, int k,
-                  int tiles_per_cloud) {
+                  long long total_queries) {
+  // Persistent, balanced: the B * S queries are cut into gridDim.x equal contiguous ranges (one CTA per SM), a CTA
+  // (re)loads the sorted cloud whenever its range crosses into the next cloud -- at most twice for ranges shorter
+  // than S.  (One CTA per (cloud, 128 queries) left the last of 3.46 waves at BASELINE configs[1] 54 % empty.)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = ((N + 31) / 32) * 32, rows = np / 32;
   float4* pts = reinterpret_cast<float4*>(smem_raw);     // [np]
@@ -280,12 +282,18 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(boxes + rows) + (threadIdx.x >> 5) * CAND_CAP;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x / tiles_per_cloud;
-  const int tile = blockIdx.x - b * tiles_per_cloud;
   const GridLayout L(N);
+  const float inf = __int_as_float(0x7f800000);
+  const long long per = (total_queries + gridDim.x - 1) / gridDim.x;
+  const long long q_lo = (long long)blockIdx.x * per;
+  const long long q_hi = q_lo + per < total_queries ? q_lo + per : total_queries;
+  for (long long base = q_lo; base < q_hi;) {
+  const int b = (int)(base / S);
+  const long long cloud_end = (long long)(b + 1) * S;
+  const long long seg_end = cloud_end < q_hi ? cloud_end : q_hi;
   const unsigned char* rec = workspace + (size_t)b * L.total;
   const float* cloud = xyz + (size_t)b * N * 3;
-
+  if (base != q_lo) __syncthreads();  // every warp is done with the previous cloud
   {  // contiguous in the record: pts | idx | boxes
     const uint4* src = reinterpret_cast<const uint4*>(rec + L.pts);
     uint4* dst = reinterpret_cast<uint4*>(smem_raw);
@@ -296,10 +304,8 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   const int* cell_start = reinterpret_cast<const int*>(rec + L.cells);
   __syncthreads();
 
-  const float inf = __int_as_float(0x7f800000);
-  for (int qq = warp; qq < SEARCH_QPB; qq += SEARCH_WARPS) {
-    const int q = tile * SEARCH_QPB + qq;
-    if (q >= S) break;  // warp-uniform
+  for (long long qg = base + warp; qg < seg_end; qg += SEARCH_WARPS) {
+    const int q = (int)(qg - (long long)b * S);
     const float* qp = query + ((size_t)b * S + q) * 3;
     const float qx = qp[0], qy = qp[1], qz = qp[2];
     const float qn = ppt_sqnorm3(qx, qy, qz);
@@ -355,6 +361,8 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
       }
     }
   }
+  base = seg_end;
+  }
 }
 
 size_t prep_smem(int N) {
@@ -393,12 +401,19 @@ int ppt_knn_grid_search(const float* xyz, const float* query, const void* index,
                                             (int)search_smem(GRID_MAX_N)));
   }
   const unsigned char* ws = static_cast<const unsigned char*>(index);
-  const int tiles = (S + SEARCH_QPB - 1) / SEARCH_QPB;
+  const long long total = (long long)B * S;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // one CTA per SM at N = 8192 (the sorted cloud fills most of its shared memory); never fewer than 32 queries each
+  const long long want = (total + SEARCH_WARPS - 1) / SEARCH_WARPS;
+  const int per_sm = search_smem(N) <= 100 * 1024 ? 2 : 1;  // small clouds: two CTAs (2048 threads) share an SM
+  const int grid = (int)(want < (long long)sms * per_sm ? want : (long long)sms * per_sm);
   if (group)
-    knn_search_kernel<true><<<B * tiles, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out,
-                                                                              nb_out, N, S, k, tiles);
+    knn_search_kernel<true><<<grid, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out, nb_out, N, S,
+                                                                         k, total);
   else
-    knn_search_kernel<false><<<B * tiles, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out,
-                                                                               nb_out, N, S, k, tiles);
+    knn_search_kernel<false><<<grid, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out, nb_out, N,
+                                                                          S, k, total);
   return ppt_launch_status();
 }
