@@ -1277,6 +1277,12 @@ bn_fold2_kernel(BnDevice bn, const double* __restrict__ stats, const double* __r
 // ======================================================================================
 // host side
 // ======================================================================================
+// Stage 2 runs 8 epilogue warps (64 accumulator columns per thread, 152 registers).  16 warps (32 columns each) were
+// measured in round 2: the 576-thread CTA caps a thread at 96 registers, the epilogue spills, and the kernel slows from
+// 0.56 to 0.75 ms -- the relu epilogues need registers more than they need warps.
+template <int NT>
+constexpr int stage2_epilogue_warps() { return 8; }
+
 template <int SPLIT, int NT, int STAGE>
 constexpr size_t stage_smem_bytes() {
   constexpr int NSTAGE = SPLIT == 2 ? 2 : 4;
@@ -1338,7 +1344,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
                 int tokens_f16 = 0, long long* clock_acc = nullptr) {
   const BlobLayout L{(uint32_t)SPLIT};
   const Workspace W(groups, SPLIT);
-  constexpr int EPW2 = 8;
+  constexpr int EPW2 = stage2_epilogue_warps<NT>();
   auto k1tc = encoder_stage1_tc_kernel<FMT, SPLIT, NT, 8, false>;
   constexpr size_t s1tc = stage1_tc_smem_bytes<SPLIT, NT>();
   static_assert(s1tc <= 232448, "shared memory budget (227 KB per CTA)");
@@ -1416,7 +1422,8 @@ int run_encoder_train(const float* nbhd, unsigned char* blob, const BnDevice& bn
   const Workspace W(groups, SPLIT);
   auto k1t = encoder_stage1_tc_kernel<FMT, SPLIT, NT, 8, true>;
   auto kst = group_linear_kernel<FMT, SPLIT, 4, 2, false, true>;
-  auto k2a = encoder_stage_kernel<FMT, SPLIT, NT, 2, 8, BN_APPLY>;
+  constexpr int EPW2 = stage2_epilogue_warps<NT>();
+  auto k2a = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2, BN_APPLY>;
   constexpr size_t s1tc = stage1_tc_smem_bytes<SPLIT, NT>(), s2 = stage_smem_bytes<SPLIT, NT, 2>(),
                    sl = linear_smem_bytes<SPLIT>();
   static PptOncePerDevice configured;
@@ -1464,8 +1471,8 @@ int run_encoder_train(const float* nbhd, unsigned char* blob, const BnDevice& bn
   const float act = SPLIT == 2 ? 64.f : 1.f;  // encoder_pack.ACT_SCALE (h1 operands are stored times this)
   bn_gram_reduce_kernel<<<64, 256, 0, st>>>(gram_parts, grid_t, 1.0 / ((double)act * act), gram);
   bn_fold2_kernel<<<512, 128, 0, st>>>(bn, stats, gram, reinterpret_cast<const float*>(blob + L.W32F()), points, bn_vec);
-  k2a<<<grid_t, (8 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr, bn_vec,
-                                        nullptr);
+  k2a<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles, nullptr, bn_vec,
+                                           nullptr);
   if (tokens_out) return run_encoder<FMT, SPLIT, NT>(nbhd, blob, ws, nullptr, tokens_out, groups, 8, st);
   return ppt_launch_status();
 }
