@@ -414,13 +414,17 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
           const float a_unit = BN == BN_APPLY ? inv_p2s * u_scale[u < 4 ? u : 0] : inv_p2s;
           const uint32_t krow = (uint32_t)(ch >> 3) * 1024u + (uint32_t)(ch & 7) * 128u;
           const uint32_t sw = (uint32_t)(ch & 7);
+          // both 32-column loads in flight before the first use: one tensor-memory round trip per unit, not two
+          uint32_t raw[GH][32];
+#pragma unroll
+          for (int jj = 0; jj < GH; ++jj) tmem_ld32_async(t_addr + jj * 32, raw[jj]);
+          tmem_wait_ld();
 #pragma unroll
           for (int jj = 0; jj < GH; ++jj) {
             float v[32];
-            tmem_ld32(t_addr + jj * 32, v);
             const float cv = ccur[u < 4 ? u : 0][jj];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], a_unit, cv);
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(raw[jj][i]), a_unit, cv);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int n = col0 + jj * 32 + q * 8;

@@ -105,30 +105,42 @@ gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_
   const int xyz_lo = xyz_first ? 0 : D, feat_lo = (CONCAT && xyz_first) ? 3 : 0;
   const float nanv = __int_as_float(0x7fc00000);
   const bool vec = (D & 3) == 0;
-  for (long long row0 = (long long)blockIdx.x * GR_ROWS; row0 < total_rows; row0 += (long long)gridDim.x * GR_ROWS) {
+  // (cloud, row inside the cloud) of the step's first row, advanced incrementally: two 64-bit divisions per thread in
+  // the whole kernel instead of one per step
+  const long long step = (long long)gridDim.x * GR_ROWS;
+  const long long step_b = step / rows_per_cloud;
+  const unsigned step_in = (unsigned)(step - step_b * rows_per_cloud);
+  long long b0 = ((long long)blockIdx.x * GR_ROWS) / rows_per_cloud;
+  unsigned in0 = (unsigned)((long long)blockIdx.x * GR_ROWS - b0 * rows_per_cloud);
+  for (long long row0 = (long long)blockIdx.x * GR_ROWS; row0 < total_rows; row0 += step) {
     const int nrows = total_rows - row0 < GR_ROWS ? (int)(total_rows - row0) : GR_ROWS;
-    // one 64-bit division per 32-row step; the rows of the step are located from it with 32-bit arithmetic
-    // (a 64-bit divide per row and lane made the first version of this kernel issue-bound: 46 instructions per float)
-    const long long b0 = row0 / rows_per_cloud;
-    const int in0 = (int)(row0 - b0 * rows_per_cloud);
+    // Index arithmetic once per row, not once per row and lane: lane r of every warp locates row r of the step (one
+    // 64-bit division per step, 32-bit ones per row), the four rows a warp then copies get their source row, centre
+    // row and validity by shuffle.  (A first version did this per lane and per row and was issue-bound: 680 warp
+    // instructions per 32-row step, 46 per float.)
+    const unsigned in = in0 + (unsigned)lane;
+    const unsigned over = in / (unsigned)rows_per_cloud;  // 0 unless the step crosses into the next cloud(s)
+    const long long bl = b0 + over;
+    const long long nl = lane < nrows ? __ldg(idx + row0 + lane) : 0;
+    const bool okl = (unsigned long long)nl < (unsigned long long)N;  // out-of-range index: NaN row, no wild read
+    const long long src_l = bl * N + (okl ? nl : 0);                  // row of `points` / `xyz`
+    long long ctr_l = 0;
+    if (CONCAT) ctr_l = bl * (rows_per_cloud / K) + (in - over * (unsigned)rows_per_cloud) / (unsigned)K;
 #pragma unroll
     for (int rr = 0; rr < GR_ROWS / 8; ++rr) {
       const int r = warp + 8 * rr;
       if (r >= nrows) continue;  // warp-uniform
-      const long long row = row0 + r;
-      const long long n = __ldg(idx + row);  // same address in every lane: one broadcast load
-      const unsigned in = (unsigned)(in0 + r);
-      const unsigned over = in / (unsigned)rows_per_cloud;       // 0 unless the step crosses into the next cloud(s)
-      const unsigned in_cloud = in - over * (unsigned)rows_per_cloud;
-      const long long b = b0 + over;
-      const bool ok = (unsigned long long)n < (unsigned long long)N;  // out-of-range index: NaN row, no wild read
-      const float* frow = points + ((size_t)b * N + (ok ? n : 0)) * D;
+      const long long src = __shfl_sync(PPT_FULL_MASK, src_l, r);
+      const bool ok = __shfl_sync(PPT_FULL_MASK, (int)okl, r) != 0;
+      const float* frow = points + (size_t)src * D;
       float* srow = stage + r * C;
-      if (CONCAT && lane < 3) {
-        const unsigned s = in_cloud / (unsigned)K, S = (unsigned)rows_per_cloud / (unsigned)K;
-        const float p = __ldg(xyz + ((size_t)b * N + (ok ? n : 0)) * 3 + lane);
-        const float c = __ldg(new_xyz + ((size_t)b * S + s) * 3 + lane);
-        srow[xyz_lo + lane] = ok ? __fsub_rn(p, c) : nanv;
+      if (CONCAT) {
+        const long long ctr = __shfl_sync(PPT_FULL_MASK, ctr_l, r);
+        if (lane < 3) {
+          const float pv = __ldg(xyz + (size_t)src * 3 + lane);
+          const float cv = __ldg(new_xyz + (size_t)ctr * 3 + lane);
+          srow[xyz_lo + lane] = ok ? __fsub_rn(pv, cv) : nanv;
+        }
       }
       if (vec) {
         for (int c = lane * 4; c < D; c += 128) {
@@ -149,6 +161,9 @@ gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_
       __stcs(reinterpret_cast<float4*>(dst + i), *reinterpret_cast<const float4*>(stage + i));  // written once: streaming
     if (threadIdx.x < total - total4) dst[total4 + threadIdx.x] = stage[total4 + threadIdx.x];
     __syncthreads();
+    b0 += step_b;
+    in0 += step_in;
+    if (in0 >= (unsigned)rows_per_cloud) { in0 -= (unsigned)rows_per_cloud; ++b0; }
   }
 }
 
