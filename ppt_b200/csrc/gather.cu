@@ -86,81 +86,115 @@ __global__ void group_concat_kernel(const float* __restrict__ xyz, const float* 
 }
 
 // Wide rows (C >= 32).  The element-wise kernels above spend a divide, an 8-byte index load and a scattered 4-byte
-// load per element and reached 18 % of the HBM peak at C = 131; a warp-per-row version with direct 4-byte stores
-// reached 27 % (rows of 131 floats start at odd 4-byte offsets, so every store straddles sectors).  Here a block
-// assembles GR_ROWS consecutive output rows in shared memory -- warps fetch whole source rows with 16-byte loads --
-// and then writes the block's contiguous slice of the output with 16-byte ALIGNED stores (GR_ROWS * C * 4 bytes is a
-// multiple of 16 for every C), so the HBM sees full-sector streaming writes.
-constexpr int GR_ROWS = 32;
+// load per element and reached 18 % of the HBM peak at C = 131.  Here a WARP owns GR_ROWS = 4 consecutive output rows:
+// 4 * C * 4 bytes is a multiple of 16 for every C, so the warp's slice of the output starts 16-byte aligned whatever
+// the row length.  Source rows are read with 16-byte loads; a row's feature span starts s = (r C + offset) mod 4
+// floats into an aligned 16-byte slot, so each aligned output slot is assembled from the lane's own float4 and its
+// left neighbour's (one shuffle, s is warp-uniform) and stored with one aligned 16-byte streaming store; only the
+// first and last slot of a span (shared with the coordinates / the neighbouring row) are written with scalar stores.
+// No shared memory, no barrier.  Row bookkeeping (cloud, centre row, validity) is done by lanes 0-3 for their row and
+// shuffled; the position inside the cloud advances incrementally (one 64-bit division per warp in the whole kernel).
+// History at C = 131 (fraction of the HBM peak): element-wise 18 %, warp-per-row with 4-byte stores 27 % (every store
+// straddles sectors), staged through shared memory 31-44 % (bank conflicts of the 4-byte staging stores, barriers),
+// per-lane 64-bit divides made the early versions issue-bound (46 instructions per float).
+constexpr int GR_ROWS = 4;
+constexpr int GR_WARPS = 8;
+
+__device__ __forceinline__ float4 shfl_up4(float4 v) {
+  return make_float4(__shfl_up_sync(PPT_FULL_MASK, v.x, 1), __shfl_up_sync(PPT_FULL_MASK, v.y, 1),
+                     __shfl_up_sync(PPT_FULL_MASK, v.z, 1), __shfl_up_sync(PPT_FULL_MASK, v.w, 1));
+}
+__device__ __forceinline__ float4 shfl_from4(float4 v, int src) {
+  return make_float4(__shfl_sync(PPT_FULL_MASK, v.x, src), __shfl_sync(PPT_FULL_MASK, v.y, src),
+                     __shfl_sync(PPT_FULL_MASK, v.z, src), __shfl_sync(PPT_FULL_MASK, v.w, src));
+}
 
 template <bool CONCAT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GR_WARPS * 32)
 gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, const float* __restrict__ points,
                    const int64_t* __restrict__ idx, float* __restrict__ out, long long total_rows, int rows_per_cloud,
                    int N, int K, int D, int xyz_first) {
   // CONCAT: out row = [xyz - centre | feats] (or feats first), C = 3 + D; else: out row = points row, C = D
-  extern __shared__ __align__(16) float stage[];  // [GR_ROWS][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = CONCAT ? D + 3 : D;
   const int xyz_lo = xyz_first ? 0 : D, feat_lo = (CONCAT && xyz_first) ? 3 : 0;
   const float nanv = __int_as_float(0x7fc00000);
   const bool vec = (D & 3) == 0;
-  // (cloud, row inside the cloud) of the step's first row, advanced incrementally: two 64-bit divisions per thread in
-  // the whole kernel instead of one per step
-  const long long step = (long long)gridDim.x * GR_ROWS;
+  const long long nwarps = (long long)gridDim.x * GR_WARPS;
+  const long long step = nwarps * GR_ROWS;
   const long long step_b = step / rows_per_cloud;
   const unsigned step_in = (unsigned)(step - step_b * rows_per_cloud);
-  long long b0 = ((long long)blockIdx.x * GR_ROWS) / rows_per_cloud;
-  unsigned in0 = (unsigned)((long long)blockIdx.x * GR_ROWS - b0 * rows_per_cloud);
-  for (long long row0 = (long long)blockIdx.x * GR_ROWS; row0 < total_rows; row0 += step) {
+  long long row0 = ((long long)blockIdx.x * GR_WARPS + warp) * GR_ROWS;
+  long long b0 = row0 / rows_per_cloud;
+  unsigned in0 = (unsigned)(row0 - b0 * rows_per_cloud);
+  for (; row0 < total_rows; row0 += step) {
     const int nrows = total_rows - row0 < GR_ROWS ? (int)(total_rows - row0) : GR_ROWS;
-    // Index arithmetic once per row, not once per row and lane: lane r of every warp locates row r of the step (one
-    // 64-bit division per step, 32-bit ones per row), the four rows a warp then copies get their source row, centre
-    // row and validity by shuffle.  (A first version did this per lane and per row and was issue-bound: 680 warp
-    // instructions per 32-row step, 46 per float.)
-    const unsigned in = in0 + (unsigned)lane;
-    const unsigned over = in / (unsigned)rows_per_cloud;  // 0 unless the step crosses into the next cloud(s)
-    const long long bl = b0 + over;
-    const long long nl = lane < nrows ? __ldg(idx + row0 + lane) : 0;
-    const bool okl = (unsigned long long)nl < (unsigned long long)N;  // out-of-range index: NaN row, no wild read
-    const long long src_l = bl * N + (okl ? nl : 0);                  // row of `points` / `xyz`
-    long long ctr_l = 0;
-    if (CONCAT) ctr_l = bl * (rows_per_cloud / K) + (in - over * (unsigned)rows_per_cloud) / (unsigned)K;
-#pragma unroll
-    for (int rr = 0; rr < GR_ROWS / 8; ++rr) {
-      const int r = warp + 8 * rr;
-      if (r >= nrows) continue;  // warp-uniform
-      const long long src = __shfl_sync(PPT_FULL_MASK, src_l, r);
-      const bool ok = __shfl_sync(PPT_FULL_MASK, (int)okl, r) != 0;
-      const float* frow = points + (size_t)src * D;
-      float* srow = stage + r * C;
-      if (CONCAT) {
-        const long long ctr = __shfl_sync(PPT_FULL_MASK, ctr_l, r);
-        if (lane < 3) {
-          const float pv = __ldg(xyz + (size_t)src * 3 + lane);
-          const float cv = __ldg(new_xyz + (size_t)ctr * 3 + lane);
-          srow[xyz_lo + lane] = ok ? __fsub_rn(pv, cv) : nanv;
-        }
-      }
-      if (vec) {
-        for (int c = lane * 4; c < D; c += 128) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(frow + c));
-          if (!ok) v = make_float4(nanv, nanv, nanv, nanv);
-          float* d = srow + feat_lo + c;  // 4-byte aligned only (C is odd in the concat case)
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-      } else {
-        for (int c = lane; c < D; c += 32) srow[feat_lo + c] = ok ? __ldg(frow + c) : nanv;
+    // lanes 8r .. 8r+7 locate row r (source row, validity); lanes 8r .. 8r+2 also write its three centred coordinates
+    const int rl = lane >> 3, jl = lane & 7;
+    float* dst = out + (size_t)row0 * C;  // 16-byte aligned: row0 is a multiple of 4
+    long long src_l = 0;
+    int ok_l = 0;
+    if (rl < nrows) {
+      const unsigned in = in0 + (unsigned)rl;
+      const unsigned over = in >= (unsigned)rows_per_cloud ? in / (unsigned)rows_per_cloud : 0u;
+      const long long bl = b0 + over;
+      const long long nl = __ldg(idx + row0 + rl);
+      ok_l = (unsigned long long)nl < (unsigned long long)N;  // out-of-range index: NaN row, no wild read
+      src_l = bl * N + (ok_l ? nl : 0);
+      if (CONCAT && jl < 3) {
+        const long long ctr = bl * (rows_per_cloud / K) + (in - over * (unsigned)rows_per_cloud) / (unsigned)K;
+        const float pv = __ldg(xyz + (size_t)src_l * 3 + jl);
+        const float cv = __ldg(new_xyz + (size_t)ctr * 3 + jl);
+        dst[rl * C + xyz_lo + jl] = ok_l ? __fsub_rn(pv, cv) : nanv;
       }
     }
-    __syncthreads();
-    const int total = nrows * C;
-    float* dst = out + (size_t)row0 * C;  // 16-byte aligned: row0 is a multiple of GR_ROWS
-    const int total4 = total & ~3;
-    for (int i = threadIdx.x * 4; i < total4; i += 1024)
-      __stcs(reinterpret_cast<float4*>(dst + i), *reinterpret_cast<const float4*>(stage + i));  // written once: streaming
-    if (threadIdx.x < total - total4) dst[total4 + threadIdx.x] = stage[total4 + threadIdx.x];
-    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < GR_ROWS; ++r) {
+      if (r >= nrows) break;  // warp-uniform
+      const long long src = __shfl_sync(PPT_FULL_MASK, src_l, r * 8);
+      const bool ok = __shfl_sync(PPT_FULL_MASK, ok_l, r * 8) != 0;
+      const float* frow = points + (size_t)src * D;
+      const int base = r * C + feat_lo;  // float offset of the feature span inside the slice
+      if (!vec) {
+        for (int c = lane; c < D; c += 32) dst[base + c] = ok ? __ldg(frow + c) : nanv;
+        continue;
+      }
+      const int sft = base & 3, nf = D >> 2;   // warp-uniform
+      float4* slot = reinterpret_cast<float4*>(dst) + (base >> 2);  // slot[f] holds span elements 4f - sft .. 4f - sft + 3
+      float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int f0 = 0; f0 < nf; f0 += 32) {
+        const int f = f0 + lane;
+        float4 v = make_float4(nanv, nanv, nanv, nanv);
+        if (f < nf && ok) v = __ldg(reinterpret_cast<const float4*>(frow) + f);
+        if (sft == 0) {
+          if (f < nf) __stcs(slot + f, v);  // written once: streaming store
+          continue;
+        }
+        float4 up = shfl_up4(v);
+        if (nf > 32) {  // rows longer than one warp pass: lane 0 continues from lane 31 of the previous pass
+          if (lane == 0) up = carry;
+          if (f0 + 32 < nf) carry = shfl_from4(v, 31);
+        }
+        float4 o;
+        if (sft == 1) o = make_float4(up.w, v.x, v.y, v.z);
+        else if (sft == 2) o = make_float4(up.z, up.w, v.x, v.y);
+        else o = make_float4(up.y, up.z, up.w, v.x);
+        if (f >= 1 && f < nf) {
+          __stcs(slot + f, o);
+        } else if (f == 0) {  // first slot of the span: its leading sft floats belong to the coordinates / the row before
+          float* p = reinterpret_cast<float*>(slot);
+          p[sft] = v.x;
+          if (sft <= 2) p[sft + 1] = v.y;
+          if (sft <= 1) p[sft + 2] = v.z;
+        }
+        if (f == nf - 1) {  // the span's last sft floats spill into the next slot
+          float* p = reinterpret_cast<float*>(slot + nf);
+          if (sft == 1) p[0] = v.w;
+          else if (sft == 2) { p[0] = v.z; p[1] = v.w; }
+          else { p[0] = v.y; p[1] = v.z; p[2] = v.w; }
+        }
+      }
+    }
     b0 += step_b;
     in0 += step_in;
     if (in0 >= (unsigned)rows_per_cloud) { in0 -= (unsigned)rows_per_cloud; ++b0; }
@@ -169,15 +203,12 @@ gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_
 
 }  // namespace
 
-static int gather_rows_launch_dims(long long total_rows, int C, size_t* smem) {
+static int gather_rows_grid(long long total_rows) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  *smem = (size_t)GR_ROWS * C * sizeof(float);
-  const long long want = (total_rows + GR_ROWS - 1) / GR_ROWS;
-  int per_sm = (int)((200 * 1024) / (*smem + 1024));
-  per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
-  const long long cap = (long long)sms * per_sm;
+  const long long want = (total_rows + GR_WARPS * GR_ROWS - 1) / (GR_WARPS * GR_ROWS);
+  const long long cap = (long long)sms * 8;  // 8 resident blocks of 8 warps per SM
   return (int)(want < cap ? want : cap);
 }
 
@@ -185,16 +216,10 @@ extern "C" PPT_EXPORT int ppt_gather(const float* points, const int64_t* idx, fl
                           void* stream) {
   if (!points || !idx || !out || B < 0 || N < 1 || C < 1 || M < 0) return PPT_EINVAL;
   if (B == 0 || M == 0) return 0;
-  if (C >= 32 && C <= 1024) {
+  if (C >= 32) {
     const long long rows = (long long)B * M;
-    size_t smem;
-    const int grid = gather_rows_launch_dims(rows, C, &smem);
-    static PptOncePerDevice configured;
-    if (configured.need())
-      PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(gather_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              GR_ROWS * 1024 * 4));
-    gather_rows_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(nullptr, nullptr, points, idx, out, rows, M, N, 1,
-                                                                         C, 1);
+    gather_rows_kernel<false><<<gather_rows_grid(rows), GR_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        nullptr, nullptr, points, idx, out, rows, M, N, 1, C, 1);
     return ppt_launch_status();
   }
   if (B > 65535) return PPT_ERANGE;
@@ -209,16 +234,10 @@ extern "C" PPT_EXPORT int ppt_group_concat(const float* xyz, const float* new_xy
   if (!xyz || !new_xyz || !idx || !out || B < 0 || N < 1 || S < 1 || K < 1 || D < 0) return PPT_EINVAL;
   if (D > 0 && !points) return PPT_EINVAL;
   if (B == 0) return 0;
-  if (D >= 32 && D + 3 <= 1024) {
+  if (D >= 32) {
     const long long rows = (long long)B * S * K;
-    size_t smem;
-    const int grid = gather_rows_launch_dims(rows, D + 3, &smem);
-    static PptOncePerDevice configured;
-    if (configured.need())
-      PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(gather_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              GR_ROWS * 1024 * 4));
-    gather_rows_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(xyz, new_xyz, points, idx, out, rows, S * K, N, K,
-                                                                        D, xyz_first);
+    gather_rows_kernel<true><<<gather_rows_grid(rows), GR_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        xyz, new_xyz, points, idx, out, rows, S * K, N, K, D, xyz_first);
     return ppt_launch_status();
   }
   if (B > 65535) return PPT_ERANGE;
