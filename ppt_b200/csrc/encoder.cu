@@ -423,8 +423,14 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
           for (int jj = 0; jj < GH; ++jj) {
             float v[32];
             const float cv = ccur[u < 4 ? u : 0][jj];
+            // packed f32x2 FMA (FFMA2): half the instructions of this issue-paced epilogue's arithmetic
+            const float2 a2 = make_float2(a_unit, a_unit), c2 = make_float2(cv, cv);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(raw[jj][i]), a_unit, cv);
+            for (int i = 0; i < 32; i += 2) {
+              const float2 y = __ffma2_rn(make_float2(__uint_as_float(raw[jj][i]), __uint_as_float(raw[jj][i + 1])), a2, c2);
+              v[i] = y.x;
+              v[i + 1] = y.y;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int n = col0 + jj * 32 + q * 8;
