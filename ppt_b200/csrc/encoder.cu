@@ -201,7 +201,12 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   constexpr uint32_t H1_BUF = SPLIT * H1_BYTES;
   constexpr uint32_t H3_BYTES = STAGE == 2 ? (NT / 64) * MNBLK : 0u;  // one split part, MN-major
   constexpr uint32_t STAGE_BYTES = SPLIT * IMG;
-  constexpr int TCOLS = 2 * NT;
+  // Accumulators in rotation (unit g of the CTA's unit sequence uses accumulator g % NACC).  Stage 2 keeps FOUR: the
+  // round trip accumulator full -> epilogue wakes -> tcgen05.ld -> convert -> proxy fence -> arrive -> issuer wakes is
+  // ~900 cycles of pure latency, longer than one W32 unit runs (~740), so with two accumulators every W32 unit waited
+  // for the epilogue of the unit before last; with four, the four W32 units of a tile issue back to back.
+  constexpr int NACC = STAGE == 2 ? 4 : 2;
+  constexpr int TCOLS = NACC * NT;
   constexpr int EPI_THREADS = EPW * 32;
   constexpr int CPW = NT / (EPW / 4);                // accumulator columns per epilogue thread
   constexpr int GH = CPW / 32;                       // groups per epilogue thread
@@ -214,11 +219,12 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_BYTES);
   uint64_t* full = bars;                   // [NSTAGE]
   uint64_t* empty = full + NSTAGE;         // [NSTAGE]
-  uint64_t* acc_full = empty + NSTAGE;     // [2]
-  uint64_t* acc_empty = acc_full + 2;      // [2]
-  uint64_t* h1_ready = acc_empty + 2;      // [2]
+  uint64_t* acc_full = empty + NSTAGE;     // [NACC]
+  uint64_t* acc_empty = acc_full + NACC;   // [NACC]
+  uint64_t* h1_ready = acc_empty + NACC;   // [2]
   uint64_t* h3_ready = h1_ready + 2;       // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h3_ready + 4);
+  static_assert((2 * 4 + 2 * NACC + 2 + 4) * 8 + 4 <= 192, "barrier block");
   float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [128]
   long long* clk0 = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(bars) + 192);  // [2], see below
 
@@ -237,7 +243,7 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_THREADS); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_THREADS); }
     for (int i = 0; i < 2; ++i) mbar_init(&h1_ready[i], EPI_THREADS);
     for (int i = 0; i < 4; ++i) mbar_init(&h3_ready[i], EPI_THREADS);
     mbar_fence_init();
@@ -290,9 +296,9 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
         for (int u = 0; u < NUNITS; ++u) {
           const bool g3 = STAGE == 2 && u >= 4;
           const int nkc = g3 ? 8 : 2;
-          const int buf = u & 1;
-          // accumulator `buf` is used NUNITS/2 times per tile: its n-th use has parity n & 1
-          const uint32_t use = tile_it * (NUNITS / 2) + (uint32_t)(u >> 1);
+          // unit g of this CTA's sequence: accumulator g % NACC, whose n-th use (n = g / NACC) has parity n & 1
+          const uint32_t g = tile_it * NUNITS + (uint32_t)u;
+          const uint32_t buf = g % NACC, use = g / NACC;
           mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
           fence_after_sync();
           const uint32_t d_tmem = tbase + (uint32_t)(buf * NT);
@@ -402,9 +408,10 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 
 #pragma unroll
       for (int u = 0; u < NUNITS; ++u) {
-        const int buf = u & 1;
+        const uint32_t gu = tile_it * NUNITS + (uint32_t)u;
+        const uint32_t buf = gu % NACC;
         const bool relu_unit = STAGE == 2 && u < 4;
-        mbar_wait(&acc_full[buf], (tile_it * (NUNITS / 2) + (uint32_t)(u >> 1)) & 1u);
+        mbar_wait(&acc_full[buf], (gu / NACC) & 1u);
         fence_after_sync();
         const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * NT + col0);
 
