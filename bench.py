@@ -625,7 +625,35 @@ def run_ours(args):
                 ppt_pn2.dgcnn_fusable = real
 
         dg_fused_ms, dg_layers_ms = time_dg(True), time_dg(False)
-        f4 = {"dgcnn_propagation": {"shape": "B=32, 512 keys -> 256 queries, C=384, k=4 (dgcnn_pro_2)",
+        # feature propagation 2048 <- 512 of the part-seg head (propagation_0: 19 + 384 -> 1536 -> 384), 32 clouds, eval:
+        # three_nn + fused interpolation / concat / two tensor-core layers vs three_nn + three_interpolate + the module's
+        # Conv1d / BatchNorm1d / ReLU layers (BatchNorm folded, cuDNN)
+        fpm = ppt_pn2.PointNetFeaturePropagation(384 + 19, [1536, 384]).to(dev).eval()
+        for prm in fpm.parameters():
+            prm.requires_grad_(False)
+        fB = 32
+        fx1, fx2 = torch.randn(fB, 3, 2048, device=dev), torch.randn(fB, 3, 512, device=dev)
+        fp1, fp2 = torch.randn(fB, 19, 2048, device=dev), torch.randn(fB, 384, 512, device=dev)
+
+        def time_fp(fused):
+            real = ppt_pn2._fused_fp_mlp
+            if not fused:
+                ppt_pn2._fused_fp_mlp = lambda *a: None
+            try:
+                with torch.no_grad():
+                    return _time_launches(lambda i: fpm(fx1, fx2, fp1, fp2), args.steps)
+            finally:
+                ppt_pn2._fused_fp_mlp = real
+
+        fp_fused_ms, fp_layers_ms = time_fp(True), time_fp(False)
+        fp_flops = 2.0 * fB * 2048 * (403 * 1536 + 1536 * 384)
+        f4 = {"feature_propagation": {"shape": "B=32, 2048 <- 512, 19 + 384 -> 1536 -> 384 (propagation_0)",
+                                      "fused_ms": fp_fused_ms, "torch_layers_ms": fp_layers_ms, "mlp_flops": fp_flops,
+                                      "fused_mlp_tflops": fp_flops / (fp_fused_ms * 1e-3) / 1e12,
+                                      "what": "three_nn + ppt_fp_mlp_forward (interpolation and concat fused into the operand "
+                                              "build, two tcgen05 layers) vs three_nn + three_interpolate + folded-BatchNorm "
+                                              "Conv1d layers"},
+              "dgcnn_propagation": {"shape": "B=32, 512 keys -> 256 queries, C=384, k=4 (dgcnn_pro_2)",
                                     "fused_ms": dg_fused_ms, "torch_layers_ms": dg_layers_ms,
                                     "what": "edge convolution as two per-point GEMMs (cuBLAS) + edge_gn_max kernel "
                                             "(GroupNorm statistics, affine, LeakyReLU, max over k) vs ppt_graph_feature + "

@@ -163,6 +163,25 @@ int ppt_sa_mlp_forward(const float *xyz, const float *feats, const float *new_xy
                        const void *packed, void *workspace, float *out, int B, int N, int S, int nsample, int D,
                        int c1, int c2, int c3, int mode, void *stream);
 
+/* ---- PointNetFeaturePropagation: three_interpolate + concat + two-layer MLP (tcgen05) ----------------------------
+ * PointNetFeaturePropagation.forward behind three_nn, eval mode (models/pointnet2/pointnet2_utils.py:304-319;
+ * the part-seg head's propagation_{0,1,2}: in = 384 + 3 (+16), mlp = [1536, 384], models/pointbert/point_encoder.py:300-302):
+ *     new_points = cat([points1, three_interpolate(points2, idx, dist)]) -> 2 x (Conv1d 1x1 + BatchNorm1d + ReLU)
+ * The interpolation and the concatenation happen while the first layer's fp16 operand images are built (neither the
+ * interpolated [B,N,D2] tensor nor the concatenated one exists); layer 1 keeps its input tile in shared memory, layer 2
+ * (K = c1 up to 4096) streams it in K blocks with all its output units resident in tensor memory.
+ *   points1 [B,D1,N] f32 channel-first (NULL iff D1 == 0); feats2 = points2 as [B,S,D2] f32 channel-last;
+ *   idx [B,N,3] i64, dist [B,N,3] f32 from ppt_three_nn (S >= 3);
+ *   packed: ppt_b200/encoder_pack.py:pack_fp_mlp (BatchNorm folded, layer-1 columns in [interpolated | points1] order),
+ *   ppt_fp_mlp_packed_bytes(D1 + D2, c1, c2) bytes (PPT_ERANGE if D1 + D2 > 512 or c2 > 512);
+ *   workspace: ppt_fp_mlp_workspace_bytes(B * N, D1 + D2, c1, c2) bytes;
+ *   out [B, c2, N] f32 channel-first (as the module returns it).  mode: PPT_ENC_FP16 or PPT_ENC_BF16.  Forward only. */
+int64_t ppt_fp_mlp_packed_bytes(int c0, int c1, int c2);
+int64_t ppt_fp_mlp_workspace_bytes(int64_t num_points, int c0, int c1, int c2);
+int ppt_fp_mlp_forward(const float *points1, const float *feats2, const int64_t *idx, const float *dist,
+                       const void *packed, void *workspace, float *out, int B, int N, int S, int D1, int D2,
+                       int c1, int c2, int mode, void *stream);
+
 /* ---- mini-PointNet patch Encoder + reduce_dim (tcgen05) ---------------------
  * Encoder.forward in eval mode, models/pointbert/dvae.py:201-215, followed by
  * reduce_dim, models/pointbert/point_encoder.py:133,239.

@@ -44,6 +44,9 @@ SIGNATURES = {
     "ppt_sa_mlp_packed_bytes": (_i64, [_i, _i, _i, _i]),
     "ppt_sa_mlp_workspace_bytes": (_i64, [_i64, _i, _i, _i, _i]),
     "ppt_sa_mlp_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ppt_fp_mlp_packed_bytes": (_i64, [_i, _i, _i]),
+    "ppt_fp_mlp_workspace_bytes": (_i64, [_i64, _i, _i, _i]),
+    "ppt_fp_mlp_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ppt_encoder_packed_bytes": (_i64, [_i]),
     "ppt_encoder_workspace_bytes": (_i64, [_i64, _i]),
     "ppt_encoder_forward": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p]),

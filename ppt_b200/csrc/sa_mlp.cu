@@ -219,6 +219,224 @@ pointwise_linear_kernel(const unsigned char* __restrict__ act_img, const unsigne
   if (warp == 1) tmem_dealloc<TCOLS>(tbase);
 }
 
+// ---- one layer with MORE input channels than fit in shared memory at once (K-blocked) ---------------------------
+// out = relu(W act + bias) for K up to 64 x 64 channels: the activation tile streams through two 4-chunk (64 KB)
+// buffers while ALL output units (U <= 4, c_out <= 512) keep their accumulators in tensor memory (U x 128 columns),
+// so every activation chunk is read once and multiplied with U weight chunks from the ring.  Used for the second
+// layer of the feature-propagation MLP (1536 -> 384, models/pointbert/point_encoder.py:300-302).
+//   OUT_F32 = false: store as the next layer's operand images [tile][2 U][16 KB];
+//   OUT_F32 = true : store fp32 channel-first, out[(b * c_out + o) * N + n] for column b * N + n.
+constexpr int KB_CHUNKS = 4;
+
+template <uint32_t FMT, bool OUT_F32>
+__global__ void __launch_bounds__(SA_THREADS, 1)
+pointwise_linear_kblock_kernel(const unsigned char* __restrict__ act_img, const unsigned char* __restrict__ wimg,
+                               const float* __restrict__ bias, unsigned char* __restrict__ out_img,
+                               float* __restrict__ out, int KC, int U, int c_out, int N, long long total_cols,
+                               int num_tiles) {
+  constexpr int NT = 128;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* bbuf = smem;                                   // [2][KB_CHUNKS][16 KB]
+  unsigned char* ring = bbuf + 2 * KB_CHUNKS * IMG;             // [SA_NSTAGE][16 KB] weights
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + SA_NSTAGE * IMG);
+  uint64_t* full = bars;
+  uint64_t* empty = full + SA_NSTAGE;
+  uint64_t* b_full = empty + SA_NSTAGE;    // [2]
+  uint64_t* b_empty = b_full + 2;          // [2]
+  uint64_t* acc_full = b_empty + 2;        // [1] all U accumulators of the tile complete
+  uint64_t* acc_empty = acc_full + 1;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = (KC + KB_CHUNKS - 1) / KB_CHUNKS;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < SA_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, SA_EPI);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, blk = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb, ++blk) {
+          const uint32_t slot = blk & 1u;
+          const int nch = KC - kb * KB_CHUNKS < KB_CHUNKS ? KC - kb * KB_CHUNKS : KB_CHUNKS;
+          mbar_wait_relaxed(&b_empty[slot], ((blk >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&b_full[slot], (uint32_t)nch * IMG);
+          for (int kc = 0; kc < nch; ++kc)
+            bulk_g2s(bbuf + (size_t)(slot * KB_CHUNKS + kc) * IMG,
+                     act_img + ((size_t)tile * KC + kb * KB_CHUNKS + kc) * IMG, IMG, &b_full[slot]);
+          for (int u = 0; u < U; ++u)
+            for (int kc = 0; kc < nch; ++kc, ++it) {
+              const uint32_t s = it % SA_NSTAGE;
+              mbar_wait_relaxed(&empty[s], ((it / SA_NSTAGE) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&full[s], IMG);
+              bulk_g2s(ring + s * IMG, wimg + ((size_t)u * KC + kb * KB_CHUNKS + kc) * IMG, IMG, &full[s]);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(FMT, 128, NT, 0);
+    constexpr uint32_t HI = sdesc_hi(1024u);
+    const uint32_t a_lo0 = sdesc_lo(smem_u32(ring), 16u), b_lo0 = sdesc_lo(smem_u32(bbuf), 16u);
+    uint32_t it = 0, blk = 0, tile_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      mbar_wait(acc_empty, (tile_it & 1u) ^ 1u);  // the previous tile's accumulators are drained
+      fence_after_sync();
+      for (int kb = 0; kb < nkb; ++kb, ++blk) {
+        const uint32_t slot = blk & 1u;
+        const int nch = KC - kb * KB_CHUNKS < KB_CHUNKS ? KC - kb * KB_CHUNKS : KB_CHUNKS;
+        mbar_wait(&b_full[slot], (blk >> 1) & 1u);
+        fence_after_sync();
+        for (int u = 0; u < U; ++u)
+          for (int kc = 0; kc < nch; ++kc, ++it) {
+            const uint32_t s = it % SA_NSTAGE;
+            mbar_wait(&full[s], (it / SA_NSTAGE) & 1u);
+            fence_after_sync();
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_f16_elect(tbase + (uint32_t)(u * NT), sdesc_join(a_lo0 + s * (IMG >> 4) + (uint32_t)k16 * 2u, HI),
+                             sdesc_join(b_lo0 + (slot * KB_CHUNKS + (uint32_t)kc) * (IMG >> 4) + (uint32_t)k16 * 2u, HI),
+                             idesc, (kb == 0 && kc == 0 && k16 == 0) ? 0u : 1u);
+            umma_commit_elect(&empty[s]);
+          }
+        umma_commit_elect(&b_empty[slot]);  // every MMA that reads this activation block is complete
+      }
+      umma_commit_elect(acc_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      mbar_wait(acc_full, tile_it & 1u);
+      fence_after_sync();
+      for (int u = 0; u < U; ++u) {
+        const int o = u * 128 + m;
+        const float bo = __ldg(bias + o);
+        const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(u * NT);
+#pragma unroll 1
+        for (int j = 0; j < NT / 32; ++j) {
+          float v[32];
+          tmem_ld32(t_addr + j * 32, v);
+          const long long col0 = (long long)tile * NT + j * 32;
+          if (!OUT_F32) {
+            unsigned char* dst = out_img + ((size_t)tile * (2 * U) + (size_t)(o >> 6)) * IMG;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              *reinterpret_cast<uint16_t*>(dst + sw128_kmajor_off(j * 32 + i, o & 63)) =
+                  to_operand<FMT>(fmaxf(v[i] + bo, 0.f));
+          } else if (o < c_out) {
+            const long long b0 = col0 / N;
+            const int n0 = (int)(col0 - b0 * N);
+            if (col0 + 32 <= total_cols && n0 + 32 <= N && (N & 3) == 0 && (n0 & 3) == 0) {
+              float4* dst = reinterpret_cast<float4*>(out + (b0 * c_out + o) * N + n0);  // 32 consecutive points
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                dst[q] = make_float4(fmaxf(v[4 * q] + bo, 0.f), fmaxf(v[4 * q + 1] + bo, 0.f),
+                                     fmaxf(v[4 * q + 2] + bo, 0.f), fmaxf(v[4 * q + 3] + bo, 0.f));
+            } else {
+#pragma unroll 1
+              for (int i = 0; i < 32; ++i) {
+                const long long col = col0 + i;
+                if (col < total_cols) {
+                  const long long b = col / N;
+                  out[(b * c_out + o) * N + (col - b * N)] = fmaxf(v[i] + bo, 0.f);
+                }
+              }
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(acc_empty);
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tbase);
+}
+
+// ---- feature propagation: three_interpolate + concat -> layer-1 operand images ------------------------------------
+// PointNetFeaturePropagation.forward (models/pointnet2/pointnet2_utils.py:297-313) up to the MLP: column = one point
+// (b, n); channel order [interpolated (D2) | points1 (D1) | zero padding] (the reference concatenates
+// [points1, interpolated]; layer 1's weight columns are permuted to match on the host, which keeps the 16-byte loads of
+// the three neighbour rows aligned).  The interpolation is the arithmetic of ppt_three_interpolate;
+// the fp32 [B, N, D2] interpolated tensor and the concatenated [B, D1 + D2, N] tensor never exist.
+template <uint32_t FMT>
+__global__ void __launch_bounds__(256)
+fp_build_image_kernel(const float* __restrict__ points1, const float* __restrict__ feats2,
+                      const int64_t* __restrict__ idx, const float* __restrict__ dist, unsigned char* __restrict__ img,
+                      int N, int S, int D1, int D2, int KC, long long total) {
+  const int r = threadIdx.x & 127, hh = threadIdx.x >> 7;
+  const long long tiles = (total + 127) / 128;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long col = tile * 128 + r;
+    const bool ok = col < total;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    const float *f0 = feats2, *f1 = feats2, *f2 = feats2;
+    long long b = 0;
+    int n = 0;
+    if (ok) {
+      b = col / N;
+      n = (int)(col - b * N);
+      const float r0 = __fdiv_rn(1.0f, __fadd_rn(__ldg(dist + col * 3), 1e-8f));
+      const float r1 = __fdiv_rn(1.0f, __fadd_rn(__ldg(dist + col * 3 + 1), 1e-8f));
+      const float r2 = __fdiv_rn(1.0f, __fadd_rn(__ldg(dist + col * 3 + 2), 1e-8f));
+      const float nrm = __fadd_rn(__fadd_rn(r0, r1), r2);
+      w0 = __fdiv_rn(r0, nrm); w1 = __fdiv_rn(r1, nrm); w2 = __fdiv_rn(r2, nrm);
+      auto row = [&](int j) {
+        long long s = __ldg(idx + col * 3 + j);
+        s = s < 0 ? 0 : (s >= S ? S - 1 : s);
+        return feats2 + (b * S + s) * D2;
+      };
+      f0 = row(0); f1 = row(1); f2 = row(2);
+    }
+    unsigned char* base = img + (size_t)tile * KC * IMG;
+    for (int c8 = hh * 8; c8 < KC * 64; c8 += 16) {
+      float v[8];
+      if (ok && c8 + 8 <= D2 && (D2 & 3) == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(f0 + c8 + 4 * h));
+          const float4 e = __ldg(reinterpret_cast<const float4*>(f1 + c8 + 4 * h));
+          const float4 g = __ldg(reinterpret_cast<const float4*>(f2 + c8 + 4 * h));
+          v[4 * h + 0] = __fadd_rn(__fadd_rn(__fmul_rn(w0, a.x), __fmul_rn(w1, e.x)), __fmul_rn(w2, g.x));
+          v[4 * h + 1] = __fadd_rn(__fadd_rn(__fmul_rn(w0, a.y), __fmul_rn(w1, e.y)), __fmul_rn(w2, g.y));
+          v[4 * h + 2] = __fadd_rn(__fadd_rn(__fmul_rn(w0, a.z), __fmul_rn(w1, e.z)), __fmul_rn(w2, g.z));
+          v[4 * h + 3] = __fadd_rn(__fadd_rn(__fmul_rn(w0, a.w), __fmul_rn(w1, e.w)), __fmul_rn(w2, g.w));
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int c = c8 + t;
+          float x = 0.f;
+          if (ok && c < D2)
+            x = __fadd_rn(__fadd_rn(__fmul_rn(w0, __ldg(f0 + c)), __fmul_rn(w1, __ldg(f1 + c))), __fmul_rn(w2, __ldg(f2 + c)));
+          else if (ok && c < D2 + D1)
+            x = __ldg(points1 + (b * D1 + (c - D2)) * N + n);  // channel-first: consecutive threads, consecutive points
+          v[t] = x;
+        }
+      }
+      uint4 w;
+      w.x = pack2<FMT, false>(v[0], v[1]); w.y = pack2<FMT, false>(v[2], v[3]);
+      w.z = pack2<FMT, false>(v[4], v[5]); w.w = pack2<FMT, false>(v[6], v[7]);
+      *reinterpret_cast<uint4*>(base + (size_t)(c8 >> 6) * IMG + sw128_kmajor_off(r, c8 & 63)) = w;
+    }
+  }
+}
+
 // ---- the three layers in ONE kernel: activations never leave shared memory ---------------------------------
 // Tile = 128 (group, sample) columns.  Per tile: the 8 epilogue warps gather [features | xyz - centre] into the
 // K-major input operand (region X); layer 1 -> ReLU -> MN-major operand in region Y; layer 2 -> ReLU -> MN-major
@@ -553,6 +771,85 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
   return ppt_launch_status();
 }
 
+
+
+// ---- feature-propagation MLP (two layers) -------------------------------------------------------------------------
+struct FpDims {
+  int kc0, u1, u2;
+  __host__ FpDims(int c0, int c1, int c2) : kc0((c0 + 63) / 64), u1((c1 + 127) / 128), u2((c2 + 127) / 128) {}
+  // blob: fp32 biases [128 (u1 + u2)] padded to 1 KB, then W1 [u1][kc0], W2 [u2][2 u1] images
+  size_t bias_bytes() const { return (((size_t)(u1 + u2) * 128 * 4) + 1023) & ~(size_t)1023; }
+  size_t w1() const { return bias_bytes(); }
+  size_t w2() const { return w1() + (size_t)u1 * kc0 * IMG; }
+  size_t total() const { return w2() + (size_t)u2 * 2 * u1 * IMG; }
+  bool ok() const { return kc0 >= 1 && kc0 <= SA_MAX_KC && u1 >= 1 && u2 >= 1 && u2 <= 4 && 2 * u1 <= 64; }
+  size_t ws_total(long long tiles) const { return (size_t)tiles * (kc0 + 2 * u1) * IMG; }
+};
+
+template <uint32_t FMT>
+int run_fp_mlp(const float* points1, const float* feats2, const int64_t* idx, const float* dist,
+               const unsigned char* blob, unsigned char* ws, float* out, int B, int N, int S, int D1, int D2,
+               const FpDims& d, int c2, cudaStream_t st) {
+  const long long total = (long long)B * N;
+  const long long tiles_ll = (total + 127) / 128;
+  if (tiles_ll > 0x7fffffffll) return PPT_ERANGE;
+  const int tiles = (int)tiles_ll;
+  auto k1 = pointwise_linear_kernel<FMT, false>;
+  auto k2 = pointwise_linear_kblock_kernel<FMT, true>;
+  const size_t smem1 = (size_t)d.kc0 * IMG + SA_NSTAGE * IMG + 256;
+  const size_t smem2 = (size_t)2 * KB_CHUNKS * IMG + SA_NSTAGE * IMG + 256;
+  static PptOncePerDevice configured;
+  if (configured.need()) {
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)SA_MAX_KC * IMG + SA_NSTAGE * IMG + 256)));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  }
+  const int sms = num_sms_sa();
+  const int grid = tiles < sms ? tiles : sms;
+  const float* bias = reinterpret_cast<const float*>(blob);
+  unsigned char* img0 = ws;
+  unsigned char* img1 = ws + (size_t)tiles * d.kc0 * IMG;
+  fp_build_image_kernel<FMT><<<tiles < 8 * sms ? tiles : 8 * sms, 256, 0, st>>>(points1, feats2, idx, dist, img0, N, S, D1,
+                                                                               D2, d.kc0, total);
+  k1<<<grid, SA_THREADS, smem1, st>>>(img0, blob + d.w1(), bias, img1, nullptr, d.kc0, d.u1, 0, 32, 1, 0, total, tiles);
+  k2<<<grid, SA_THREADS, smem2, st>>>(img1, blob + d.w2(), bias + d.u1 * 128, nullptr, out, 2 * d.u1, d.u2, c2, N, total,
+                                      tiles);
+  return ppt_launch_status();
+}
+
+}  // namespace
+
+extern "C" PPT_EXPORT int64_t ppt_fp_mlp_packed_bytes(int c0, int c1, int c2) {
+  if (c0 < 1 || c1 < 1 || c2 < 1) return PPT_EINVAL;
+  const FpDims d(c0, c1, c2);
+  return d.ok() ? (int64_t)d.total() : PPT_ERANGE;
+}
+
+extern "C" PPT_EXPORT int64_t ppt_fp_mlp_workspace_bytes(int64_t num_points, int c0, int c1, int c2) {
+  if (num_points < 1 || c0 < 1 || c1 < 1 || c2 < 1) return PPT_EINVAL;
+  const FpDims d(c0, c1, c2);
+  return d.ok() ? (int64_t)d.ws_total((num_points + 127) / 128) : PPT_ERANGE;
+}
+
+extern "C" PPT_EXPORT int ppt_fp_mlp_forward(const float* points1, const float* feats2, const int64_t* idx,
+                                             const float* dist, const void* packed, void* workspace, float* out, int B,
+                                             int N, int S, int D1, int D2, int c1, int c2, int mode, void* stream) {
+  if (!feats2 || !idx || !dist || !packed || !workspace || !out || B < 1 || N < 1 || S < 1 || D1 < 0 || D2 < 1)
+    return PPT_EINVAL;
+  if (D1 > 0 && !points1) return PPT_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(packed) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PPT_EINVAL;
+  const FpDims d(D1 + D2, c1, c2);
+  if (c1 < 1 || c2 < 1 || !d.ok()) return PPT_ERANGE;
+  const unsigned char* blob = static_cast<const unsigned char*>(packed);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  if (mode == PPT_ENC_FP16)
+    return run_fp_mlp<tc05::FMT_F16>(points1, feats2, idx, dist, blob, ws, out, B, N, S, D1, D2, d, c2, (cudaStream_t)stream);
+  if (mode == PPT_ENC_BF16)
+    return run_fp_mlp<tc05::FMT_BF16>(points1, feats2, idx, dist, blob, ws, out, B, N, S, D1, D2, d, c2, (cudaStream_t)stream);
+  return PPT_EINVAL;
+}
+
+namespace {
 }  // namespace
 
 extern "C" PPT_EXPORT int64_t ppt_sa_mlp_packed_bytes(int c0, int c1, int c2, int c3) {

@@ -254,3 +254,41 @@ def pack_sa_mlp(convs, bns, xyz_first, mode):
     blob = torch.cat([head] + parts)
     assert blob.numel() == sa_mlp_packed_bytes(c0, c1, c2, c3), (blob.numel(), sa_mlp_packed_bytes(c0, c1, c2, c3))
     return blob, (c0, c1, c2, c3)
+
+
+# ---- PointNetFeaturePropagation MLP (models/pointnet2/pointnet2_utils.py:273-279, 316-319) -------------------------
+def fp_mlp_packed_bytes(c0, c1, c2):
+    kc0, u1, u2 = (c0 + 63) // 64, (c1 + 127) // 128, (c2 + 127) // 128
+    bias = ((u1 + u2) * 128 * 4 + 1023) // 1024 * 1024
+    return bias + (u1 * kc0 + u2 * 2 * u1) * IMAGE_BYTES
+
+
+def pack_fp_mlp(convs, bns, d1, mode):
+    """Two Conv1d(1x1) + BatchNorm1d pairs (eval mode) -> uint8 CPU blob for ppt_fp_mlp_forward.  The module's input is
+    cat([points1 (d1 channels), interpolated]); the kernel's operand order is [interpolated | points1], so layer 1's
+    columns move (the interpolated rows are then read with aligned 16-byte loads)."""
+    if len(convs) != 2 or mode not in (ENC_FP16, ENC_BF16):
+        raise ValueError("fused FP MLP: exactly two layers, fp16 or bf16 operands")
+    dtype = operand_dtype(mode)
+    folded = [fold_conv_bn(c.weight, c.bias, b.weight, b.bias, b.running_mean, b.running_var, b.eps)
+              for c, b in zip(convs, bns)]
+    w1 = folded[0][0]
+    w1 = torch.cat([w1[:, d1:], w1[:, :d1]], dim=1)
+    w2 = folded[1][0]
+    c0, c1, c2 = w1.shape[1], w1.shape[0], w2.shape[0]
+    if w2.shape[1] != c1:
+        raise ValueError("layer shapes do not chain")
+    u1, u2 = (c1 + 127) // 128, (c2 + 127) // 128
+    bias = torch.zeros((u1 + u2) * 128, dtype=torch.float32)
+    bias[:c1] = folded[0][1].to(torch.float32)
+    bias[u1 * 128: u1 * 128 + c2] = folded[1][1].to(torch.float32)
+    parts = []
+    for w, rows, k in ((w1, u1 * 128, (c0 + 63) // 64 * 64), (w2, u2 * 128, 2 * u1 * 64)):
+        wp = torch.zeros(rows, k, dtype=torch.float32)
+        wp[: w.shape[0], : w.shape[1]] = w.to(torch.float32)
+        parts.append(pack_kmajor(wp, dtype, 1))
+    head = torch.zeros((bias.numel() * 4 + 1023) // 1024 * 1024, dtype=torch.uint8)
+    head[: bias.numel() * 4] = bias.view(torch.uint8)
+    blob = torch.cat([head] + parts)
+    assert blob.numel() == fp_mlp_packed_bytes(c0, c1, c2), (blob.numel(), fp_mlp_packed_bytes(c0, c1, c2))
+    return blob, (c0, c1, c2)

@@ -356,6 +356,42 @@ def edge_gn_max(U, V, idx, gn_weight, gn_bias, num_groups, eps=1e-5, negative_sl
     return out
 
 
+def fp_mlp_supported(c0, c1, c2):
+    """Whether ppt_fp_mlp_forward covers a two-layer feature-propagation MLP c0 -> c1 -> c2 (c0 <= 512, c2 <= 512)."""
+    return _lib.load().ppt_fp_mlp_packed_bytes(c0, c1, c2) > 0
+
+
+def fp_mlp_forward(points1, feats2, idx, dist, packed, dims, mode=ENC_FP16):
+    """three_interpolate + concat + two-layer Conv1d/BatchNorm1d/ReLU MLP of PointNetFeaturePropagation (eval mode,
+    models/pointnet2/pointnet2_utils.py:304-319).  points1 [B,D1,N] channel-first or None, feats2 [B,S,D2]
+    channel-last, idx / dist [B,N,3] from three_nn; `packed`, `dims` from encoder_pack.pack_fp_mlp -> [B, c2, N]."""
+    _need_cuda(feats2, idx, dist, packed)
+    feats2, idx, dist = _f32(feats2), _i64(idx), _f32(dist)
+    B, S, D2 = feats2.shape
+    N = idx.shape[1]
+    c0, c1, c2 = dims
+    D1 = c0 - D2
+    if D1 > 0:
+        _need_cuda(points1)
+        points1 = _f32(points1)
+        if tuple(points1.shape) != (B, D1, N):
+            raise ValueError("points1 must be [B, %d, N] (channel-first)" % D1)
+    elif D1 < 0:
+        raise ValueError("packed MLP expects fewer input channels than feats2 has")
+    if tuple(idx.shape) != (B, N, 3) or tuple(dist.shape) != (B, N, 3):
+        raise ValueError("idx / dist must be [B, N, 3]")
+    lib = _lib.load()
+    if packed.dtype != torch.uint8 or packed.numel() != lib.ppt_fp_mlp_packed_bytes(c0, c1, c2):
+        raise ValueError("packed FP-MLP blob does not match its dims")
+    out = torch.empty((B, c2, N), dtype=torch.float32, device=feats2.device)
+    ws = _workspace((feats2.device, "fp_mlp"), lib.ppt_fp_mlp_workspace_bytes(B * N, c0, c1, c2))
+    with torch.cuda.device(feats2.device):
+        _lib.check(lib.ppt_fp_mlp_forward(_ptr(points1) if D1 > 0 else None, _ptr(feats2), _ptr(idx), _ptr(dist), _ptr(packed),
+                                          _ptr(ws), _ptr(out), B, N, S, D1, D2, c1, c2, mode, _stream(feats2)),
+                   "ppt_fp_mlp_forward")
+    return out
+
+
 def sa_mlp_supported(c0, c1, c2, c3, nsample):
     """Whether ppt_sa_mlp_forward covers this layer stack (<= 512 input channels per layer, nsample 16/32/64/128)."""
     return nsample in (16, 32, 64, 128) and _lib.load().ppt_sa_mlp_packed_bytes(c0, c1, c2, c3) > 0

@@ -313,7 +313,8 @@ def invalidate(model):
     (models/ULIP_models.py:507): call this after loading weights that way once a forward has already run."""
     for m in model.modules():
         for name in ("_ppt_key", "_ppt_blob", "_ppt_train_key", "_ppt_train_blob", "_ppt_front_key", "_ppt_front_blobs",
-                     "_ppt_sa_cache", "_packed", "_packed_key", "_pos_packed", "_pos_key"):
+                     "_ppt_sa_cache", "_packed", "_packed_key", "_pos_packed", "_pos_key", "_ppt_fp_packed",
+                     "_ppt_fp_folded"):
             if name in m.__dict__:
                 object.__setattr__(m, name, {} if name == "_ppt_sa_cache" else None)
 

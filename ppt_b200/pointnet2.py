@@ -200,6 +200,9 @@ class PointNetFeaturePropagation(nn.Module):
 
     def forward(self, xyz1, xyz2, points1, points2):
         """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        fused = _fused_fp_mlp(self, xyz1, xyz2, points1, points2)
+        if fused is not None:
+            return fused
         interpolated = three_nn_interpolate(xyz1.permute(0, 2, 1).contiguous(), xyz2.permute(0, 2, 1).contiguous(),
                                             points2.permute(0, 2, 1).contiguous())
         if points1 is not None:
@@ -208,6 +211,36 @@ class PointNetFeaturePropagation(nn.Module):
             new_points = interpolated
         new_points = new_points.permute(0, 2, 1)
         return feature_propagation_mlp(self, new_points)
+
+
+def _fused_fp_mlp(module, xyz1, xyz2, points1, points2):
+    """three_nn, then interpolation + concat + the two-layer MLP on the tensor cores (ops.fp_mlp_forward; SURVEY.md section
+    8 row f4, dense half).  Eval mode with nothing to differentiate, two layers, <= 512 input and output channels, at
+    least three known points; otherwise None and the caller runs the unfused path."""
+    convs, bns = list(module.mlp_convs), list(module.mlp_bns)
+    if module.training or len(convs) != 2 or not xyz1.is_cuda or xyz2.shape[2] < 3:
+        return None
+    params = [p for m in convs + bns for p in m.parameters()]
+    tensors_in = [t for t in (xyz1, xyz2, points1, points2) if t is not None]
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors_in) or any(p.requires_grad for p in params)):
+        return None
+    if any(t.dtype != torch.float32 for t in tensors_in):
+        return None
+    d1 = 0 if points1 is None else points1.shape[1]
+    c0, c1, c2 = d1 + points2.shape[1], convs[0].out_channels, convs[1].out_channels
+    mode = ops.ENC_MODES[getattr(module, "ppt_precision", "fp16")]
+    if convs[0].in_channels != c0 or mode not in (ops.ENC_FP16, ops.ENC_BF16) or not ops.fp_mlp_supported(c0, c1, c2):
+        return None
+    tensors = params + [b for m in bns for b in m.buffers()]
+    key = (mode, str(xyz1.device)) + tuple((t.data_ptr(), t._version) for t in tensors)
+    cache = module.__dict__.get("_ppt_fp_packed")
+    if cache is None or cache[0] != key:
+        blob, dims = encoder_pack.pack_fp_mlp(convs, bns, d1, mode)
+        cache = (key, blob.to(xyz1.device), dims)
+        module.__dict__["_ppt_fp_packed"] = cache
+    dist, idx = ops.three_nn(xyz1.permute(0, 2, 1).contiguous(), xyz2.permute(0, 2, 1).contiguous())
+    return ops.fp_mlp_forward(None if points1 is None else points1.contiguous(), points2.permute(0, 2, 1).contiguous(),
+                              idx, dist, cache[1], cache[2], mode=mode)
 
 
 def feature_propagation_mlp(module, x):

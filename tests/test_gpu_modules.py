@@ -416,3 +416,50 @@ def test_feature_propagation_mlp_folded_in_eval_mode():
     assert "_ppt_fp_folded" in fp.__dict__ and float((got - want).abs().max()) < 1e-4
     out = pointnet2.feature_propagation_mlp(fp, x.clone())      # grad enabled, trainable parameters
     assert out.requires_grad
+
+
+@pytest.mark.parametrize("shape", [(2, 1000, 77, 19, 384, 1536, 384), (1, 300, 64, 0, 96, 256, 128), (2, 256, 512, 3, 384, 1536, 384)])
+def test_feature_propagation_fused_on_tensor_cores(shape):
+    """Row f4, dense half: PointNetFeaturePropagation.forward in eval mode -- three_nn + (interpolation + concat fused
+    into the operand build) + the two-layer Conv1d/BatchNorm1d/ReLU MLP on tcgen05 (ops.fp_mlp_forward) -- against the
+    same module's fp32 torch layers on the torch-op interpolation (the reference's own arithmetic, bit-identical on CPU,
+    tests/test_host_cpu.py).  Shapes: the part-seg head's propagation_0 (19 + 384 -> 1536 -> 384, ragged point count),
+    no skip features, and propagation_1 (3 + 384)."""
+    from ppt_b200 import ops, pointnet2
+    B, N, S, D1, D2, C1, C2 = shape
+    torch.manual_seed(N)
+    fp = pointnet2.PointNetFeaturePropagation(D1 + D2, [C1, C2]).eval()
+    with torch.no_grad():
+        for bn in fp.mlp_bns:
+            bn.running_mean.normal_(0, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_(0, 0.1)
+    for p in fp.parameters():
+        p.requires_grad_(False)   # the fused path is forward only
+    xyz1, xyz2 = cloud("S", B, N, 21), cloud("S", B, S, 22)
+    p1 = torch.randn(B, D1, N) if D1 else None
+    p2 = torch.randn(B, D2, S)
+    with torch.no_grad():
+        interp = torch_port.three_nn_interpolate(xyz1, xyz2, p2.permute(0, 2, 1))
+        x = interp.permute(0, 2, 1) if p1 is None else torch.cat([p1, interp.permute(0, 2, 1)], dim=1)
+        want = x
+        for conv, bn in zip(fp.mlp_convs, fp.mlp_bns):
+            want = torch.relu(bn(conv(want)))
+    fp = fp.cuda()
+    calls = []
+    real = ops.fp_mlp_forward
+    ops.fp_mlp_forward = lambda *a, **k: calls.append(1) or real(*a, **k)
+    try:
+        got = fp(xyz1.permute(0, 2, 1).cuda(), xyz2.permute(0, 2, 1).cuda(), None if p1 is None else p1.cuda(), p2.cuda())
+        assert calls == [1], "the tensor-core path must have run"
+        assert got.shape == want.shape and got.is_contiguous() and bool(torch.isfinite(got).all())
+        d = got.double().cpu() - want.double()
+        # two chained layers with fp16 operands, norm-relative like the Encoder's tokens
+        assert float(d.abs().max() / want.abs().max()) < 2e-3 and float(d.norm() / want.double().norm()) < 1e-3
+        fp.train()
+        n0 = len(calls)
+        fp(xyz1.permute(0, 2, 1).cuda(), xyz2.permute(0, 2, 1).cuda(), None if p1 is None else p1.cuda(), p2.cuda())
+        assert len(calls) == n0, "train mode keeps the module's own layers (batch statistics)"
+    finally:
+        ops.fp_mlp_forward = real
