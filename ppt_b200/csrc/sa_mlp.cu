@@ -707,7 +707,11 @@ struct SaDims {
   size_t w2() const { return w1() + (size_t)u1 * kc0 * IMG; }
   size_t w3() const { return w2() + (size_t)u2 * 2 * u1 * IMG; }
   size_t total() const { return w3() + (size_t)u3 * 2 * u2 * IMG; }
-  bool ok() const { return kc0 <= SA_MAX_KC && 2 * u1 <= SA_MAX_KC && 2 * u2 <= SA_MAX_KC && u3 <= 8; }
+  // layer 1 may be wider than shared memory holds (MSG level 3: 643 channels) when its <= 4 output units fit in
+  // tensor memory: the K-blocked kernel streams it
+  bool ok() const {
+    return (kc0 <= SA_MAX_KC || (kc0 <= 64 && u1 <= 4)) && 2 * u1 <= SA_MAX_KC && 2 * u2 <= SA_MAX_KC && u3 <= 8;
+  }
   // workspace: the three activation image sets
   size_t ws0(long long tiles) const { (void)tiles; return 0; }
   size_t ws1(long long tiles) const { return (size_t)tiles * kc0 * IMG; }
@@ -762,6 +766,15 @@ int run_sa_mlp(const float* xyz, const float* feats, const float* new_xyz, const
   sa_gather_image_kernel<FMT><<<tiles < 8 * sms ? tiles : 8 * sms, 256, 0, st>>>(xyz, feats, new_xyz, idx, ws + d.ws0(tiles),
                                                                                N, S, ns, D, d.kc0, total);
   auto smem = [](int kc) { return (size_t)kc * IMG + SA_NSTAGE * IMG + 256; };
+  if (d.kc0 > SA_MAX_KC) {  // wide input (MSG level 3): K-blocked layer 1
+    auto kb = pointwise_linear_kblock_kernel<FMT, false>;
+    const size_t smem_kb = (size_t)2 * KB_CHUNKS * IMG + SA_NSTAGE * IMG + 256;
+    static PptOncePerDevice kb_configured;
+    if (kb_configured.need())
+      PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kb));
+    kb<<<grid, SA_THREADS, smem_kb, st>>>(ws + d.ws0(tiles), blob + d.w1(), bias, ws + d.ws1(tiles), nullptr, d.kc0, d.u1, 0,
+                                          1, total, tiles);
+  } else
   kl<<<grid, SA_THREADS, smem(d.kc0), st>>>(ws + d.ws0(tiles), blob + d.w1(), bias, ws + d.ws1(tiles), nullptr, d.kc0,
                                             d.u1, 0, ns, S, groups, total, tiles);
   kl<<<grid, SA_THREADS, smem(2 * d.u1), st>>>(ws + d.ws1(tiles), blob + d.w2(), bias + d.u1 * 128, ws + d.ws2(tiles),

@@ -463,3 +463,38 @@ def test_feature_propagation_fused_on_tensor_cores(shape):
         assert len(calls) == n0, "train mode keeps the module's own layers (batch statistics)"
     finally:
         ops.fp_mlp_forward = real
+
+
+def test_set_abstraction_msg_level3_wide_input_on_tensor_cores():
+    """MSG level 3 (models/pointnet2/pointnet2.py:47: group_all over 128 points with 640 + 3 input channels, MLP
+    [256, 512, 1024]) was the one level left on the torch layers in round 1 (more input channels than the fused kernel
+    keeps in shared memory): its first layer now runs K-blocked.  Against the module's own fp32 layers."""
+    from ppt_b200 import ops, pointnet2
+    torch.manual_seed(5)
+    sa = pointnet2.PointNetSetAbstraction(None, None, None, 640 + 3, [256, 512, 1024], True).eval()
+    with torch.no_grad():
+        for bn in sa.mlp_bns:
+            bn.running_mean.normal_(0, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+    for p in sa.parameters():
+        p.requires_grad_(False)
+    sa = sa.cuda()
+    xyz = cloud("S", 3, 128, 31).permute(0, 2, 1).contiguous().cuda()
+    feats = torch.randn(3, 640, 128, device="cuda")
+    calls = []
+    real = ops.sa_mlp_forward
+    ops.sa_mlp_forward = lambda *a, **k: calls.append(1) or real(*a, **k)
+    try:
+        _, got = sa(xyz, feats)
+        assert calls == [1], "the tensor-core path must have run"
+        supported = ops.sa_mlp_supported
+        ops.sa_mlp_supported = lambda *a: False
+        try:
+            _, want = sa(xyz, feats)
+        finally:
+            ops.sa_mlp_supported = supported
+    finally:
+        ops.sa_mlp_forward = real
+    assert got.shape == want.shape == (3, 1024, 1)
+    d = (got - want).double()
+    assert float(d.abs().max() / want.abs().max()) < 2e-3 and float(d.norm() / want.double().norm()) < 2e-3

@@ -230,7 +230,8 @@ def test_sa_mlp_packing_matches_abi_sizes_and_folds_batchnorm():
             bns[0].running_mean.double(), bns[0].running_var.double(), bns[0].weight.double(), bns[0].bias.double(),
             False, 0.1, bns[0].eps).view(7, -1)
         assert float((x @ w.T + b - ref.detach()).abs().max()) < 1e-12
-    assert lib.ppt_sa_mlp_packed_bytes(643, 256, 512, 1024) == -2      # PPT_ERANGE: > 512 input channels
+    assert lib.ppt_sa_mlp_packed_bytes(643, 256, 512, 1024) > 0        # MSG level 3: K-blocked first layer
+    assert lib.ppt_sa_mlp_packed_bytes(643, 1024, 512, 1024) == -2     # PPT_ERANGE: wide input AND more than 4 output units
     with pytest.raises(ValueError):
         ep.pack_sa_mlp(convs[:2], bns[:2], True, 0)
 
