@@ -31,6 +31,10 @@ def farthest_point_sample(xyz, npoint, start_idx=None):
 
 
 def _as_start(start_idx, xyz):
+    if isinstance(start_idx, int):
+        # a fill kernel, not a host-to-device copy: torch.as_tensor(int, device=cuda) is a synchronous pageable copy that
+        # would stall the host behind everything queued on the stream (it cost the host->host pipeline its overlap)
+        return torch.full((xyz.shape[0],), start_idx, dtype=torch.long, device=xyz.device)
     s = torch.as_tensor(start_idx, dtype=torch.long, device=xyz.device)
     return s.expand(xyz.shape[0]).contiguous() if s.dim() == 0 else s
 
