@@ -849,7 +849,9 @@ def run_ours(args):
 
         widened["f3_train_mode_batchnorm"] = {
             "what": "Group + Encoder with batch-statistics BatchNorm (forward only, running stats updated in place) + "
-                    "reduce_dim; adds bn_moments, bn_fold1, stage-2 statistics pass (the four W32 h1 units), bn_fold2",
+                    "reduce_dim; adds bn_moments, bn_fold1, the Gram matrix of h1 and group means inside stage 1, "
+                    "group_c_stats (c and the channel sums in one kernel), bn_gram_reduce, bn_fold2 -- no second pass over "
+                    "the points",
             "value": clouds_total / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / args.steps,
             "extra_ms_over_eval": (ms_train - ms_total) / args.steps}
 
