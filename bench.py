@@ -792,9 +792,9 @@ def run_ours(args):
     roofline = {"kernel": "encoder_stage_kernel<stage 2> (relu(W32 h1 + c) -> h3 -> W4 h3 -> group max)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for the same 128-cloud launch, from
-                # the ncu --set full capture summarised in profiles/ncu_r1_summary.md (160.1 MB + 21.4 MB); the
+                # the ncu --set full capture summarised in profiles/ncu_r2_summary.md (159.8 MB + 23.4 MB); the
                 # algorithmic bytes are 25 MB neighbourhoods + 134 MB per-group bias in + 33.6 MB group operands out
-                "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 181.5e6 if B == 128 else None,
+                "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 183.2e6 if B == 128 else None,
                 "peak_source": "%s cuBLAS bf16 burst (MEASURED_PEAKS.json)" % peaks["source"],
                 "flops_per_launch": points * STAGE2_FLOP_PER_POINT, "ms_per_launch": s2_ms,
                 "phase_ms": {k: statistics.mean(v) for k, v in per_phase.items()}}
