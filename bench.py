@@ -409,15 +409,18 @@ def run_ours(args):
         events.append((name, a, b))
         return out
 
-    def step(i, phase_events=None, clock_acc=None):
-        # identical to PointTokenizer.forward, with an event pair around every launch when asked
+    def step(i, phase_events=None, clock_acc=None, only_stage2=False):
+        # identical to PointTokenizer.forward, with an event pair around every launch when asked -- or, in the timed
+        # region (only_stage2), around the dominant kernel alone: seven event pairs per step cost the step 2-3 %
         xyz = resident[i % ROTATE]
-        index = timed_op(phase_events, "spatial_index", lambda: ops.spatial_index(xyz))
-        _, center = timed_op(phase_events, "fps",
+        geo_events = None if only_stage2 else phase_events
+        index = timed_op(geo_events, "spatial_index", lambda: ops.spatial_index(xyz))
+        _, center = timed_op(geo_events, "fps",
                              lambda: ops.fps(xyz, N_GROUP, zeros, return_centers=True, index=index))
-        nb = timed_op(phase_events, "knn_group", lambda: ops.knn_group(xyz, center, GROUP_SIZE, index=index))
+        nb = timed_op(geo_events, "knn_group", lambda: ops.knn_group(xyz, center, GROUP_SIZE, index=index))
         blob, mode = tok.encoder._blob(dev)
-        return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events, clock_acc=clock_acc), center, nb
+        return ops.encoder_forward(nb, blob, mode=mode, phase_events=phase_events, clock_acc=clock_acc,
+                                   only_phase="stage2" if (only_stage2 and phase_events is not None) else None), center, nb
 
     def barrier():
         if world > 1:
@@ -447,10 +450,15 @@ def run_ours(args):
     t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
-        step(i, phase_events)
+        step(i, phase_events, only_stage2=True)   # the dominant kernel is timed live, inside the timed region
     e1.record()
     barrier()
     t_wall1 = time.time()
+    # every other kernel of the step: the same steps once more with an event pair around each launch (untimed)
+    all_events = []
+    for i in range(args.steps):
+        step(i, all_events)
+    barrier()
     # untimed repeat of the same steps with the measurement build of stage 2 (CTA 0 accumulates globaltimer ns and
     # clock64 cycles of every launch): the SM clock inside the dominant kernel
     with ops.Stage2ClockTrace(dev) as clock_trace:
@@ -481,7 +489,10 @@ def run_ours(args):
             parity = check_cfg2_parity(fps0.cpu(), center0.cpu(), knn0.cpu(), nb0.cpu(), tokens0.cpu(), args.precision)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     per_phase = {}
-    for name, a, b in phase_events:
+    for name, a, b in all_events:
+        if name != "stage2":
+            per_phase.setdefault(name, []).append(a.elapsed_time(b))
+    for name, a, b in phase_events:   # stage 2: from the timed region itself
         per_phase.setdefault(name, []).append(a.elapsed_time(b))
 
     # ---- widened row f2: the same step with the cls rows and pos_embed(center), i.e. the

@@ -472,13 +472,14 @@ ENC_PHASE_NAMES = ("stage1", "group_linear_c", "stage2", "group_linear_tokens")
 
 
 def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, want_tokens=True, phase_events=None,
-                    token_dtype=torch.float32, clock_acc=None):
+                    token_dtype=torch.float32, clock_acc=None, only_phase=None):
     """neighborhood [..., 32, 3] fp32 (CUDA) -> tokens [..., 384] (and Encoder features [..., 256]).
 
     `packed` is the uint8 CUDA blob from ppt_b200.encoder_pack.pack_encoder(state_dict, mode).
     `phase_events`: optional list; when given, the four launches are issued one by one and a
     (name, start_event, end_event) triple per launch is appended (for per-kernel timing on
-    the launching stream).
+    the launching stream).  `only_phase` (with phase_events): bracket just that launch (e.g. "stage2") and issue the
+    launches before / after it together, so that timing the dominant kernel perturbs the step as little as possible.
     `token_dtype`: torch.float32 (the reference's dtype) or torch.float16 (PPT_TOKENS_F16: the same values
     rounded once more to fp16 in the last kernel's epilogue -- half the bytes to ship).
     `clock_acc`: optional int64[2] CUDA tensor (zeroed by the caller) that receives ns / SM cycles of the
@@ -511,6 +512,19 @@ def encoder_forward(neighborhood, packed, mode=ENC_FP16, return_features=False, 
         if phase_events is None:
             _lib.check(lib.ppt_encoder_forward_ex(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens), groups,
                                                   mode, 15, flags, _ptr(clock_acc), _stream(nb)), "ppt_encoder_forward")
+        elif only_phase is not None:
+            bit = ENC_PHASE_NAMES.index(only_phase)
+            for mask, name in (((1 << bit) - 1, None), (1 << bit, only_phase), (15 & ~((2 << bit) - 1), None)):
+                if not mask:
+                    continue
+                if name:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                _lib.check(lib.ppt_encoder_forward_ex(_ptr(nb), _ptr(packed), _ptr(ws), _ptr(feats), _ptr(tokens), groups,
+                                                      mode, mask, flags, _ptr(clock_acc), _stream(nb)), "ppt_encoder_forward")
+                if name:
+                    e1.record()
+                    phase_events.append((name, e0, e1))
         else:
             for bit, name in enumerate(ENC_PHASE_NAMES):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
