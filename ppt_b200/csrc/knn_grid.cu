@@ -234,7 +234,14 @@ constexpr int CAND_CAP = 64;  // fewer than 32 pending + at most 32 from one row
 
 __device__ __forceinline__ void flush32(TopList& t, unsigned long long* __restrict__ buf, int& cnt, int k, int lane) {
   __syncwarp();
-  merge_row(t, buf[lane], k, lane);            // the first 32 pending keys
+  if (t.tau == KEY_INF && __all_sync(PPT_FULL_MASK, t.key == KEY_INF)) {  // empty list (first seed row): a sort is enough
+    unsigned long long key = buf[lane];
+    bitonic_sort32(key, lane);
+    t.key = key;
+    t.tau = __shfl_sync(PPT_FULL_MASK, t.key, k - 1);
+  } else {
+    merge_row(t, buf[lane], k, lane);          // the first 32 pending keys
+  }
   const int rest = cnt - 32;                   // 0 .. 31 stay pending
   const unsigned long long x = lane < rest ? buf[32 + lane] : 0ull;
   __syncwarp();
@@ -280,6 +287,10 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   int* sidx = reinterpret_cast<int*>(pts + np);          // [np]
   RowBox* boxes = reinterpret_cast<RowBox*>(sidx + np);  // [rows]
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(boxes + rows) + (threadIdx.x >> 5) * CAND_CAP;
+  // one box per BATCH of 32 consecutive rows (1024 Morton-ordered points): a query tests these first and only looks
+  // at the row boxes of batches its tau-ball reaches
+  RowBox* bbox = reinterpret_cast<RowBox*>(reinterpret_cast<unsigned long long*>(boxes + rows) + SEARCH_WARPS * CAND_CAP);
+  const int nbatch = (rows + 31) >> 5;  // <= 8
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const GridLayout L(N);
@@ -303,6 +314,17 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   const CloudHeader hdr = *reinterpret_cast<const CloudHeader*>(rec);
   const int* cell_start = reinterpret_cast<const int*>(rec + L.cells);
   __syncthreads();
+  if (warp < nbatch) {
+    const int r = warp * 32 + lane;
+    RowBox bx;
+    bx.lo[0] = bx.lo[1] = bx.lo[2] = inf; bx.hi[0] = bx.hi[1] = bx.hi[2] = -inf; bx.npmax = 0.f; bx.unused = 0.f;
+    if (r < rows) bx = boxes[r];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { bx.lo[c] = warp_min(bx.lo[c]); bx.hi[c] = warp_max(bx.hi[c]); }
+    bx.npmax = warp_max(bx.npmax);
+    if (lane == 0) bbox[warp] = bx;
+  }
+  __syncthreads();
 
   for (long long qg = base + warp; qg < seg_end; qg += SEARCH_WARPS) {
     const int q = (int)(qg - (long long)b * S);
@@ -319,8 +341,25 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
     for (int r = ra; r <= rz; ++r) scan_row(t, cand, cnt, pts, sidx, r, qx, qy, qz, qn, k, lane);
     flush_all(t, cand, cnt, k, lane);  // a tight tau before the pruning pass
 
-    // every other row whose box may still contain a closer point
-    for (int rb = 0; rb < rows; rb += 32) {
+    // batches of 32 rows the tau-ball reaches (tau only shrinks from here on, so a batch rejected now stays rejected)
+    unsigned bmask;
+    {
+      float lbb = inf, slb = 0.f;
+      if (lane < nbatch) {
+        const RowBox bx = bbox[lane];
+        const float dx = fmaxf(fmaxf(bx.lo[0] - qx, qx - bx.hi[0]), 0.f);
+        const float dy = fmaxf(fmaxf(bx.lo[1] - qy, qy - bx.hi[1]), 0.f);
+        const float dz = fmaxf(fmaxf(bx.lo[2] - qz, qz - bx.hi[2]), 0.f);
+        lbb = dx * dx + dy * dy + dz * dz;
+        slb = 2e-6f * (qn + bx.npmax);
+      }
+      const float tau0 = key_dist(t.tau);
+      bmask = __ballot_sync(PPT_FULL_MASK, !(lbb > tau0 + slb + 2e-6f * fabsf(tau0)));
+    }
+    // every other row (of those batches) whose box may still contain a closer point
+    while (bmask) {
+      const int rb = (__ffs(bmask) - 1) << 5;
+      bmask &= bmask - 1;
       const int r = rb + lane;
       float lb = inf, slack = 0.f;
       if (r < rows && (r < ra || r > rz)) {
@@ -371,7 +410,8 @@ size_t prep_smem(int N) {
 }
 size_t search_smem(int N) {
   const size_t np = (size_t)((N + 31) / 32) * 32;
-  return np * 20 + (np / 32) * sizeof(RowBox) + (size_t)SEARCH_WARPS * CAND_CAP * sizeof(unsigned long long);
+  return np * 20 + (np / 32) * sizeof(RowBox) + (size_t)SEARCH_WARPS * CAND_CAP * sizeof(unsigned long long) +
+         8 * sizeof(RowBox);
 }
 
 }  // namespace
