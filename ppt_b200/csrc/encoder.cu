@@ -42,8 +42,10 @@ namespace {
 using namespace tc05;
 
 // stage kernels: producer warp, MMA warp, EPW epilogue warps (8, or 16 where the epilogue side is the bottleneck)
-constexpr int LIN_THREADS = 192;      // group_linear: producer, MMA, 4 epilogue warps
-constexpr int LIN_EPI = 128;
+constexpr int LIN_EPW = 4;                           // group_linear: producer, MMA, 4 epilogue warps (8 measured the same:
+constexpr int LIN_THREADS = (LIN_EPW + 2) * 32;      // 39 vs 39 us -- the output stores are not what limits these kernels)
+constexpr int LIN_EPI = LIN_EPW * 32;
+constexpr int LIN_JPW = 4 / (LIN_EPW / 4);           // 32-column chunks of a 128-column accumulator per epilogue warp
 constexpr uint32_t IMG = 16384;       // one operand image: 128 rows x 64 K x 2 B
 constexpr uint32_t MNBLK = 65536;     // MN-major h3: bytes between 64-point blocks (64 K-atoms x 1 KB)
 
@@ -891,8 +893,9 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
         fence_after_sync();
         const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * NT);
         float a1 = 0.f, a2 = 0.f;
+        const int j0 = ((warp - 2) >> 2) * LIN_JPW;
 #pragma unroll
-        for (int j = 0; j < NT / 32; ++j) {
+        for (int j = j0; j < j0 + LIN_JPW; ++j) {
           float v[32];
           tmem_ld32(t_addr + j * 32, v);
           const long long g0 = (long long)tile * NT + j * 32;
@@ -1057,8 +1060,9 @@ group_c_stats_kernel(const unsigned char* __restrict__ g_img, const unsigned cha
         fence_after_sync();
         const uint32_t t_addr = tbase + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * p * NT);
         float a1 = 0.f, a2 = 0.f;
+        const int j0 = ((warp - 2) >> 2) * LIN_JPW;
 #pragma unroll 1
-        for (int j = 0; j < NT / 32; ++j) {
+        for (int j = j0; j < j0 + LIN_JPW; ++j) {
           uint32_t rc[32], rt[32];
           tmem_ld32_async(t_addr + j * 32, rc);
           tmem_ld32_async(t_addr + NT + j * 32, rt);
