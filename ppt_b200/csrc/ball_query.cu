@@ -1,9 +1,8 @@
-// Ball query for sm_100a: tiled scan in index order with warp-ballot compaction.
+// Ball query for sm_100a: one thread per query, the cloud broadcast from shared memory, scanned in index order.
 //
 // Replaces query_ball_point (models/pointnet2/pointnet2_utils.py:87-107 and its
 // copies).  The reference materialises a (B,S,N) int64 tensor and fully sorts it;
-// here each warp scans the cloud once per four queries and stops as soon as all
-// four have `nsample` members.  Membership is !(d > radius^2) with d from the
+// here each query scans the cloud once and stops as soon as it has `nsample` members.  Membership is !(d > radius^2) with d from the
 // reference's matmul-form distance, members keep ascending
 // index order, the tail is padded with the first member, and a query without any
 // member yields N in every slot (the reference's sentinel).
@@ -11,79 +10,69 @@
 
 namespace {
 
-constexpr int BQ_THREADS = 256;
-constexpr int BQ_WARPS = BQ_THREADS / 32;
-constexpr int BQ_QW = 4;
-constexpr int BQ_QPB = BQ_WARPS * BQ_QW;  // 32 queries per CTA
+constexpr int BQ_THREADS = 128;   // queries per CTA: one thread per query
 constexpr int BQ_CHUNK = 8192;
 
+// One THREAD per query scans the cloud in index order; the points are broadcast from shared memory (every lane of a
+// warp reads the same float4), so a pair costs the seven distance operations, one compare and a rarely taken append --
+// no cross-lane traffic, and the four-point unroll gives the scheduler independent chains.  (Round 1 used a warp per
+// four queries with ballot compaction: 15 lane-instructions per pair and a dependent ballot -> popc -> store chain per
+// row; 17 % of the issue peak at batch 512.)  A query that has its nsample members stops scanning; a warp leaves the
+// chunk loop when all of its queries have.
 __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int64_t* __restrict__ idx_out,
                   float thr, int N, int S, int nsample, int tiles_per_cloud) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* pts = reinterpret_cast<float4*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int b = blockIdx.x / tiles_per_cloud;
-  const int q0 = (blockIdx.x - b * tiles_per_cloud) * BQ_QPB + warp * BQ_QW;
+  const int q = (blockIdx.x - b * tiles_per_cloud) * BQ_THREADS + tid;
+  const bool live = q < S;
   const float* cloud = xyz + (size_t)b * N * 3;
-  const unsigned lt_mask = (1u << lane) - 1u;
-
-  float qx[BQ_QW], qy[BQ_QW], qz[BQ_QW], qn[BQ_QW];
-  int cnt[BQ_QW], first[BQ_QW];
-  int64_t* out[BQ_QW];
-#pragma unroll
-  for (int u = 0; u < BQ_QW; ++u) {
-    const int q = min(q0 + u, S - 1);
-    const float* p = new_xyz + ((size_t)b * S + q) * 3;
-    qx[u] = p[0]; qy[u] = p[1]; qz[u] = p[2];
-    qn[u] = ppt_sqnorm3(qx[u], qy[u], qz[u]);
-    cnt[u] = q0 + u < S ? 0 : nsample;  // surplus queries are born complete
-    first[u] = N;
-    out[u] = idx_out + ((size_t)b * S + q) * nsample;
-  }
+  const float* qp = new_xyz + ((size_t)b * S + (live ? q : S - 1)) * 3;
+  const float qx = qp[0], qy = qp[1], qz = qp[2];
+  const float qn = ppt_sqnorm3(qx, qy, qz);
+  int64_t* out = idx_out + ((size_t)b * S + (live ? q : 0)) * nsample;
+  int cnt = live ? 0 : nsample;  // surplus threads are born complete
+  int first = N;
 
   for (int c0 = 0; c0 < N; c0 += BQ_CHUNK) {
     const int cn = min(BQ_CHUNK, N - c0);
-    const int rows = (cn + 31) >> 5;
     if (c0) __syncthreads();
-    for (int n = tid; n < rows * 32; n += BQ_THREADS) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // padding is excluded by the n < N test below
-      if (n < cn) {
-        const float* p = cloud + (size_t)(c0 + n) * 3;
-        v.x = p[0]; v.y = p[1]; v.z = p[2];
-        v.w = ppt_sqnorm3(v.x, v.y, v.z);
-      }
+    for (int n = tid; n < cn; n += BQ_THREADS) {
+      const float* p = cloud + (size_t)(c0 + n) * 3;
+      float4 v;
+      v.x = p[0]; v.y = p[1]; v.z = p[2];
+      v.w = ppt_sqnorm3(v.x, v.y, v.z);
       pts[n] = v;
     }
     __syncthreads();
-
-    for (int r = 0; r < rows; ++r) {
-      bool open = false;
+    if (__all_sync(PPT_FULL_MASK, cnt >= nsample)) continue;  // warp-uniform (the barriers above stay matched)
+    int s = 0;
+    for (; s + 4 <= cn && cnt < nsample; s += 4) {
+      float d[4];
 #pragma unroll
-      for (int u = 0; u < BQ_QW; ++u) open |= cnt[u] < nsample;
-      if (!open) break;  // warp-uniform: all four queries are full
-      const float4 p = pts[r * 32 + lane];
-      const int n = c0 + r * 32 + lane;
+      for (int t = 0; t < 4; ++t) {
+        const float4 p = pts[s + t];  // same address in every lane: broadcast
+        d[t] = ppt_pair_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
+      }
 #pragma unroll
-      for (int u = 0; u < BQ_QW; ++u) {
-        const float d = ppt_pair_sqdist(qx[u], qy[u], qz[u], qn[u], p.x, p.y, p.z, p.w);
-        const bool member = n < N && !(d > thr);
-        const unsigned bal = __ballot_sync(PPT_FULL_MASK, member);
-        if (bal && cnt[u] < nsample) {
-          if (cnt[u] == 0) first[u] = c0 + r * 32 + __ffs(bal) - 1;
-          const int slot = cnt[u] + __popc(bal & lt_mask);
-          if (member && slot < nsample) out[u][slot] = (int64_t)n;
-          cnt[u] += __popc(bal);
+      for (int t = 0; t < 4; ++t)
+        if (!(d[t] > thr) && cnt < nsample) {
+          if (cnt == 0) first = c0 + s + t;
+          out[cnt++] = (int64_t)(c0 + s + t);
         }
+    }
+    for (; s < cn && cnt < nsample; ++s) {
+      const float4 p = pts[s];
+      if (!(ppt_pair_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w) > thr)) {
+        if (cnt == 0) first = c0 + s;
+        out[cnt++] = (int64_t)(c0 + s);
       }
     }
   }
-
-#pragma unroll
-  for (int u = 0; u < BQ_QW; ++u) {
-    if (q0 + u >= S) continue;
-    for (int slot = cnt[u] + lane; slot < nsample; slot += 32) out[u][slot] = (int64_t)first[u];
-  }
+  if (live)
+    for (int slot = cnt; slot < nsample; ++slot) out[slot] = (int64_t)first;
 }
 
 }  // namespace
@@ -99,7 +88,7 @@ extern "C" PPT_EXPORT int ppt_ball_query(const float* xyz, const float* new_xyz,
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(BQ_CHUNK * sizeof(float4))));
   }
-  const int tiles = (S + BQ_QPB - 1) / BQ_QPB;
+  const int tiles = (S + BQ_THREADS - 1) / BQ_THREADS;
   ball_query_kernel<<<(unsigned)(B * tiles), BQ_THREADS, smem, (cudaStream_t)stream>>>(xyz, new_xyz, idx_out, radius2,
                                                                                       N, S, nsample, tiles);
   return ppt_launch_status();
