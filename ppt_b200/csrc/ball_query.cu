@@ -75,6 +75,81 @@ ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_x
     for (int slot = cnt; slot < nsample; ++slot) out[slot] = (int64_t)first;
 }
 
+// ---- small problems: a warp per four queries, ballot compaction (more warps in flight when there are few queries) ----
+constexpr int BQW_THREADS = 256;
+constexpr int BQW_WARPS = BQW_THREADS / 32;
+constexpr int BQW_QW = 4;
+constexpr int BQW_QPB = BQW_WARPS * BQW_QW;  // 32 queries per CTA
+
+__global__ void __launch_bounds__(BQW_THREADS)
+ball_query_warp_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int64_t* __restrict__ idx_out,
+                  float thr, int N, int S, int nsample, int tiles_per_cloud) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* pts = reinterpret_cast<float4*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / tiles_per_cloud;
+  const int q0 = (blockIdx.x - b * tiles_per_cloud) * BQW_QPB + warp * BQW_QW;
+  const float* cloud = xyz + (size_t)b * N * 3;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  float qx[BQW_QW], qy[BQW_QW], qz[BQW_QW], qn[BQW_QW];
+  int cnt[BQW_QW], first[BQW_QW];
+  int64_t* out[BQW_QW];
+#pragma unroll
+  for (int u = 0; u < BQW_QW; ++u) {
+    const int q = min(q0 + u, S - 1);
+    const float* p = new_xyz + ((size_t)b * S + q) * 3;
+    qx[u] = p[0]; qy[u] = p[1]; qz[u] = p[2];
+    qn[u] = ppt_sqnorm3(qx[u], qy[u], qz[u]);
+    cnt[u] = q0 + u < S ? 0 : nsample;  // surplus queries are born complete
+    first[u] = N;
+    out[u] = idx_out + ((size_t)b * S + q) * nsample;
+  }
+
+  for (int c0 = 0; c0 < N; c0 += BQ_CHUNK) {
+    const int cn = min(BQ_CHUNK, N - c0);
+    const int rows = (cn + 31) >> 5;
+    if (c0) __syncthreads();
+    for (int n = tid; n < rows * 32; n += BQW_THREADS) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // padding is excluded by the n < N test below
+      if (n < cn) {
+        const float* p = cloud + (size_t)(c0 + n) * 3;
+        v.x = p[0]; v.y = p[1]; v.z = p[2];
+        v.w = ppt_sqnorm3(v.x, v.y, v.z);
+      }
+      pts[n] = v;
+    }
+    __syncthreads();
+
+    for (int r = 0; r < rows; ++r) {
+      bool open = false;
+#pragma unroll
+      for (int u = 0; u < BQW_QW; ++u) open |= cnt[u] < nsample;
+      if (!open) break;  // warp-uniform: all four queries are full
+      const float4 p = pts[r * 32 + lane];
+      const int n = c0 + r * 32 + lane;
+#pragma unroll
+      for (int u = 0; u < BQW_QW; ++u) {
+        const float d = ppt_pair_sqdist(qx[u], qy[u], qz[u], qn[u], p.x, p.y, p.z, p.w);
+        const bool member = n < N && !(d > thr);
+        const unsigned bal = __ballot_sync(PPT_FULL_MASK, member);
+        if (bal && cnt[u] < nsample) {
+          if (cnt[u] == 0) first[u] = c0 + r * 32 + __ffs(bal) - 1;
+          const int slot = cnt[u] + __popc(bal & lt_mask);
+          if (member && slot < nsample) out[u][slot] = (int64_t)n;
+          cnt[u] += __popc(bal);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int u = 0; u < BQW_QW; ++u) {
+    if (q0 + u >= S) continue;
+    for (int slot = cnt[u] + lane; slot < nsample; slot += 32) out[u][slot] = (int64_t)first[u];
+  }
+}
+
 }  // namespace
 
 extern "C" PPT_EXPORT int ppt_ball_query(const float* xyz, const float* new_xyz, int64_t* idx_out, float radius2, int B, int N,
@@ -87,9 +162,19 @@ extern "C" PPT_EXPORT int ppt_ball_query(const float* xyz, const float* new_xyz,
   if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(BQ_CHUNK * sizeof(float4))));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(ball_query_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(BQ_CHUNK * sizeof(float4))));
   }
-  const int tiles = (S + BQ_THREADS - 1) / BQ_THREADS;
-  ball_query_kernel<<<(unsigned)(B * tiles), BQ_THREADS, smem, (cudaStream_t)stream>>>(xyz, new_xyz, idx_out, radius2,
-                                                                                      N, S, nsample, tiles);
+  // thread-per-query needs enough queries to fill the machine (measured: 16 k queries 47 us vs 31 us for the warp
+  // variant; 262 k queries 164 us vs 295 us)
+  if ((long long)B * S >= 131072) {
+    const int tiles = (S + BQ_THREADS - 1) / BQ_THREADS;
+    ball_query_kernel<<<(unsigned)(B * tiles), BQ_THREADS, smem, (cudaStream_t)stream>>>(xyz, new_xyz, idx_out, radius2,
+                                                                                        N, S, nsample, tiles);
+  } else {
+    const int tiles = (S + BQW_QPB - 1) / BQW_QPB;
+    ball_query_warp_kernel<<<(unsigned)(B * tiles), BQW_THREADS, smem, (cudaStream_t)stream>>>(xyz, new_xyz, idx_out,
+                                                                                              radius2, N, S, nsample, tiles);
+  }
   return ppt_launch_status();
 }

@@ -156,6 +156,20 @@ def test_ball_query_bit_exact(ops, N, S, r, ns):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("r,ns,N", [(0.2, 32, 1024), (0.8, 128, 700), (0.05, 16, 9000)])
+def test_ball_query_large_batch_thread_per_query_kernel(ops, r, ns, N):
+    """>= 131072 queries take the thread-per-query kernel (the small cases above take the warp-per-four-queries one):
+    bit-exact against the C oracle, including full balls (early exit), empty-ish balls and a cloud longer than one
+    shared-memory chunk."""
+    B, S = (260, 512) if N <= 1024 else (33, 4000)
+    xyz = cloud("S", B, N, 900 + N)
+    new_xyz = xyz[:, :S].contiguous()
+    assert B * S >= 131072
+    want = cpu.query_ball_point(r, ns, xyz.numpy(), new_xyz.numpy())
+    got = ops.ball_query(r, ns, dev(xyz), dev(new_xyz)).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_ball_query_empty_ball_yields_sentinel_N(ops):
     xyz = cloud("S", 1, 100, 1)
     far = torch.full((1, 3, 3), 10.0)
