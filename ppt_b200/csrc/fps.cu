@@ -215,8 +215,9 @@ extern "C" PPT_EXPORT int ppt_fps(const float* xyz, const int64_t* start, int64_
   if (N <= 2048) return launch_fps<512, 4, 1>(xyz, start, idx_out, centers_out, B, N, G, st);
   if (N <= 4096) return launch_fps<512, 8, 1>(xyz, start, idx_out, centers_out, B, N, G, st);
   if (N <= 8192) return launch_fps<1024, 8, 1>(xyz, start, idx_out, centers_out, B, N, G, st);
-  if (N <= 16384) return launch_fps<1024, 8, 2>(xyz, start, idx_out, centers_out, B, N, G, st);
-  if (N <= 32768) return launch_fps<1024, 8, 4>(xyz, start, idx_out, centers_out, B, N, G, st);
+  if (N <= 16384) return launch_fps<512, 8, 4>(xyz, start, idx_out, centers_out, B, N, G, st);
+  // 8 CTAs of 512 threads per cloud: 0.577 ms for 8 x 32768 -> 512 against 0.684 ms with 4 CTAs of 1024 threads
+  if (N <= 32768) return launch_fps<512, 8, 8>(xyz, start, idx_out, centers_out, B, N, G, st);
   if (N <= 65536) return launch_fps<1024, 8, 8>(xyz, start, idx_out, centers_out, B, N, G, st);
   return PPT_ERANGE;
 }
