@@ -329,20 +329,26 @@ def measure_other_kernels(dev, peaks, issue_peak, steps):
     out["three_interpolate_cfg4"] = {"shape": "B=64, 2048 <- 512, D=384", "bound": "hbm", "ms": ms, "unit": "GB/s",
                                      "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "bytes_per_launch": nbytes,
                                      "bytes_per_cloud": nbytes // B}
-    # -- cfg 5 stress: 8 clouds x 32 768 points, FPS 512 + kNN 32 (no spatial index at this size)
+    # -- cfg 5 stress: 8 clouds x 32 768 points, FPS 512 + kNN 32.  FPS: plain cluster kernel (the bucketed one keeps a
+    #    cloud's state in shared memory: up to 8192 points); kNN: spatial index built in place + pruned search with the
+    #    sorted cloud read from L2 (the index build is INSIDE the timed call), and the full scan beside it
     B, N = 8, 32768
     big = [sphere(B, N) for _ in range(2)]
     z = torch.zeros(B, dtype=torch.int64, device=dev)
     ms_f = _time_launches(lambda i: ops.fps(big[i % 2], N_GROUP, z, return_centers=True), max(3, steps // 3))
     cb = [ops.fps(x, N_GROUP, z, return_centers=True)[1] for x in big]
     ms_k = _time_launches(lambda i: ops.knn_group(big[i % 2], cb[i % 2], GROUP_SIZE), max(3, steps // 3))
-    out["fps_stress_8x32768"] = {"shape": "B=8, 32768 -> 512 (4-CTA cluster per cloud)", "bound": "sm_issue", "ms": ms_f,
+    ms_kf = _time_launches(lambda i: ops.knn_group(big[i % 2], cb[i % 2], GROUP_SIZE, index=None), max(3, steps // 3))
+    out["fps_stress_8x32768"] = {"shape": "B=8, 32768 -> 512 (8-CTA cluster per cloud)", "bound": "sm_issue", "ms": ms_f,
                                  "unit": "lane-instr/s", "achieved": B * N_GROUP * N * 11 / (ms_f * 1e-3),
                                  "peak": issue_peak, "clouds_per_s": B / (ms_f * 1e-3),
-                                 "note": "8 clouds occupy 32 of 148 SMs: the fraction is of the whole GPU's issue rate"}
-    out["knn_group_stress_8x32768"] = {"shape": "B=8, 512 queries over 32768 points, k=32 (full scan)", "bound": "sm_issue",
-                                       "ms": ms_k, "unit": "lane-instr/s", "achieved": B * N_GROUP * N * 7 / (ms_k * 1e-3),
-                                       "peak": issue_peak, "clouds_per_s": B / (ms_k * 1e-3)}
+                                 "note": "8 clouds occupy 64 of 148 SMs: the fraction is of the whole GPU's issue rate"}
+    out["knn_group_stress_8x32768"] = {"shape": "B=8, 512 queries over 32768 points, k=32 (index build + pruned search)",
+                                       "bound": "sm_issue", "ms": ms_k, "ms_full_scan": ms_kf, "unit": "lane-instr/s",
+                                       "achieved": B * N_GROUP * N * 7 / (ms_k * 1e-3), "peak": issue_peak,
+                                       "clouds_per_s": B / (ms_k * 1e-3),
+                                       "note": "effective rate of the full scan's algorithmic work; the pruned search "
+                                               "executes far less (may exceed 1)"}
     for v in out.values():
         v["frac"] = v["achieved"] / v["peak"]
     return out

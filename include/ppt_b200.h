@@ -45,8 +45,9 @@ const char *ppt_strerror(int code);
 
 /* Spatial index of a batch of clouds (Morton-cell order + per-row bounding boxes), shared by
  * ppt_fps and ppt_knn / ppt_knn_group: with it they skip the parts of a cloud that cannot change the
- * result -- the outputs are bit-identical with and without it.  Supported for 512 <= N <= 8192
- * (ppt_spatial_index_bytes returns 0 otherwise; pass index = NULL then).
+ * result -- the outputs are bit-identical with and without it.  Supported for 512 <= N <= 32768
+ * (ppt_spatial_index_bytes returns 0 otherwise; pass index = NULL then); ppt_fps uses it up to 8192
+ * points (its state lives in shared memory) and runs its plain kernel above, ppt_knn* use it throughout.
  *   index: ppt_spatial_index_bytes(B, N) bytes of caller-owned scratch, valid until xyz changes. */
 int64_t ppt_spatial_index_bytes(int B, int N);
 int ppt_spatial_index_build(const float *xyz, void *index, int B, int N, void *stream);

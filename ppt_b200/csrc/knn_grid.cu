@@ -1,4 +1,4 @@
-// Exact kNN with spatial pruning for clouds of up to 8192 points (sm_100a).
+// Exact kNN with spatial pruning for clouds of 512 to 32768 points (sm_100a).
 //
 // Same contract as the brute-force scan in knn.cu (the k nearest under (distance, index) with the
 // reference's fp32 distance formula) -- but most of the cloud is never touched:
@@ -57,9 +57,13 @@ __global__ void __launch_bounds__(PREP_THREADS, 1)
 knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ workspace, int N) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = ((N + 31) / 32) * 32, rows = np / 32;
-  float4* spts = reinterpret_cast<float4*>(smem_raw);                  // [np]
-  int* sidx = reinterpret_cast<int*>(spts + np);                       // [np]
-  int* hist = sidx + np;                                               // [CELLS]  counts, then cursors
+  // clouds of up to 8192 points are sorted in shared memory and copied out; larger ones (up to 32768) are scattered
+  // straight into the record in global memory (`direct`), which then also feeds the row boxes
+  const bool direct = N > spidx::MAX_N;
+  const int nps = direct ? 0 : np;
+  float4* spts = reinterpret_cast<float4*>(smem_raw);                  // [np]   (direct: re-pointed below)
+  int* sidx = reinterpret_cast<int*>(spts + nps);                      // [np]
+  int* hist = sidx + nps;                                              // [CELLS]  counts, then cursors
   int* warp_tot = hist + CELLS;                                        // [32]
   float* red = reinterpret_cast<float*>(warp_tot + 32);                // [6][32]
   float* box = red + 6 * 32;                                           // lo[3], inv[3]
@@ -69,6 +73,10 @@ knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ wo
   const float* cloud = xyz + (size_t)b * N * 3;
   const GridLayout L(N);
   unsigned char* rec = workspace + (size_t)b * L.total;
+  if (direct) {
+    spts = reinterpret_cast<float4*>(rec + L.pts);
+    sidx = reinterpret_cast<int*>(rec + L.idx);
+  }
 
   // 1. bounding box of the cloud
   const float inf = __int_as_float(0x7f800000);
@@ -158,7 +166,8 @@ knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ wo
   // 5. sorted cloud, indices, per-row boxes and the header to the workspace
   float4* pts_out = reinterpret_cast<float4*>(rec + L.pts);
   int* idx_out = reinterpret_cast<int*>(rec + L.idx);
-  for (int n = tid; n < np; n += PREP_THREADS) { pts_out[n] = spts[n]; idx_out[n] = sidx[n]; }
+  if (!direct)
+    for (int n = tid; n < np; n += PREP_THREADS) { pts_out[n] = spts[n]; idx_out[n] = sidx[n]; }
   RowBox* boxes = reinterpret_cast<RowBox*>(rec + L.boxes);
   for (int r = warp; r < rows; r += PREP_THREADS / 32) {
     const float4 p = spts[r * 32 + lane];
@@ -287,7 +296,9 @@ __device__ __forceinline__ void scan_row(TopList& t, unsigned long long* __restr
   if (cnt >= 32) flush32(t, buf, cnt, k, lane);
 }
 
-template <bool GROUP>
+// RESIDENT = false (8192 < N <= 32768): the sorted points and their indices stay in the record (655 KB at 32768 points:
+// L2-resident) and rows are read with global loads; only the row and batch boxes live in shared memory.
+template <bool GROUP, bool RESIDENT>
 __global__ void __launch_bounds__(SEARCH_THREADS, 1)
 knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query,
                   const unsigned char* __restrict__ workspace, int64_t* __restrict__ idx_out,
@@ -298,14 +309,15 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   // than S.  (One CTA per (cloud, 128 queries) left the last of 3.46 waves at BASELINE configs[1] 54 % empty.)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = ((N + 31) / 32) * 32, rows = np / 32;
-  float4* pts = reinterpret_cast<float4*>(smem_raw);     // [np]
-  int* sidx = reinterpret_cast<int*>(pts + np);          // [np]
-  RowBox* boxes = reinterpret_cast<RowBox*>(sidx + np);  // [rows]
+  const int nps = RESIDENT ? np : 0;
+  const float4* pts = reinterpret_cast<const float4*>(smem_raw);     // [np]  (not RESIDENT: re-pointed per cloud)
+  const int* sidx = reinterpret_cast<const int*>(pts + nps);         // [np]
+  RowBox* boxes = reinterpret_cast<RowBox*>(smem_raw + (size_t)nps * 20);  // [rows]
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(boxes + rows) + (threadIdx.x >> 5) * CAND_CAP;
   // one box per BATCH of 32 consecutive rows (1024 Morton-ordered points): a query tests these first and only looks
   // at the row boxes of batches its tau-ball reaches
   RowBox* bbox = reinterpret_cast<RowBox*>(reinterpret_cast<unsigned long long*>(boxes + rows) + SEARCH_WARPS * CAND_CAP);
-  const int nbatch = (rows + 31) >> 5;  // <= 8
+  const int nbatch = (rows + 31) >> 5;  // <= 8 (RESIDENT) / <= 32
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const GridLayout L(N);
@@ -320,10 +332,17 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   const unsigned char* rec = workspace + (size_t)b * L.total;
   const float* cloud = xyz + (size_t)b * N * 3;
   if (base != q_lo) __syncthreads();  // every warp is done with the previous cloud
-  {  // contiguous in the record: pts | idx | boxes
+  if (RESIDENT) {  // contiguous in the record: pts | idx | boxes
     const uint4* src = reinterpret_cast<const uint4*>(rec + L.pts);
     uint4* dst = reinterpret_cast<uint4*>(smem_raw);
     const int n16 = (int)((L.cells - L.pts) / 16);
+    for (int i = tid; i < n16; i += SEARCH_THREADS) dst[i] = __ldg(src + i);
+  } else {
+    pts = reinterpret_cast<const float4*>(rec + L.pts);
+    sidx = reinterpret_cast<const int*>(rec + L.idx);
+    const uint4* src = reinterpret_cast<const uint4*>(rec + L.boxes);
+    uint4* dst = reinterpret_cast<uint4*>(boxes);
+    const int n16 = (int)((L.cells - L.boxes) / 16);
     for (int i = tid; i < n16; i += SEARCH_THREADS) dst[i] = __ldg(src + i);
   }
   const CloudHeader hdr = *reinterpret_cast<const CloudHeader*>(rec);
@@ -420,13 +439,13 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
 }
 
 size_t prep_smem(int N) {
-  const size_t np = (size_t)((N + 31) / 32) * 32;
+  const size_t np = N > spidx::MAX_N ? 0 : (size_t)((N + 31) / 32) * 32;
   return np * 20 + (CELLS + 32) * sizeof(int) + (6 * 32 + 8) * sizeof(float);
 }
 size_t search_smem(int N) {
   const size_t np = (size_t)((N + 31) / 32) * 32;
-  return np * 20 + (np / 32) * sizeof(RowBox) + (size_t)SEARCH_WARPS * CAND_CAP * sizeof(unsigned long long) +
-         8 * sizeof(RowBox);
+  return (N > spidx::MAX_N ? 0 : np * 20) + (np / 32) * sizeof(RowBox) +
+         (size_t)SEARCH_WARPS * CAND_CAP * sizeof(unsigned long long) + 32 * sizeof(RowBox);
 }
 
 }  // namespace
@@ -450,10 +469,14 @@ int ppt_knn_grid_search(const float* xyz, const float* query, const void* index,
                         float* nb_out, int B, int N, int S, int k, bool group, cudaStream_t st) {
   static PptOncePerDevice configured;
   if (configured.need()) {
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)search_smem(GRID_MAX_N)));
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)search_smem(GRID_MAX_N)));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)search_smem(spidx::MAX_N_INDEX)));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(knn_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)search_smem(spidx::MAX_N_INDEX)));
   }
   const unsigned char* ws = static_cast<const unsigned char*>(index);
   const long long total = (long long)B * S;
@@ -462,13 +485,10 @@ int ppt_knn_grid_search(const float* xyz, const float* query, const void* index,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // one CTA per SM at N = 8192 (the sorted cloud fills most of its shared memory); never fewer than 32 queries each
   const long long want = (total + SEARCH_WARPS - 1) / SEARCH_WARPS;
-  const int per_sm = search_smem(N) <= 100 * 1024 ? 2 : 1;  // small clouds: two CTAs (2048 threads) share an SM
-  const int grid = (int)(want < (long long)sms * per_sm ? want : (long long)sms * per_sm);
-  if (group)
-    knn_search_kernel<true><<<grid, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out, nb_out, N, S,
-                                                                         k, total);
-  else
-    knn_search_kernel<false><<<grid, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out, nb_out, N,
-                                                                          S, k, total);
+  const int grid = (int)(want < (long long)sms ? want : (long long)sms);  // 1024 threads x 64 registers: one CTA per SM
+  const bool res = N <= spidx::MAX_N;
+  auto kern = group ? (res ? knn_search_kernel<true, true> : knn_search_kernel<true, false>)
+                    : (res ? knn_search_kernel<false, true> : knn_search_kernel<false, false>);
+  kern<<<grid, SEARCH_THREADS, search_smem(N), st>>>(xyz, query, ws, idx_out, dist_out, nb_out, N, S, k, total);
   return ppt_launch_status();
 }

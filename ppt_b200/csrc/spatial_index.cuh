@@ -9,7 +9,8 @@
 
 namespace spidx {
 
-constexpr int MAX_N = 8192;   // the consumers keep a whole cloud in shared memory / registers
+constexpr int MAX_N = 8192;         // up to here the consumers keep a whole cloud in shared memory (bucketed FPS, kNN)
+constexpr int MAX_N_INDEX = 32768;  // up to here an index can be built; the kNN search then reads the sorted cloud from L2
 constexpr int MIN_N = 512;    // below this the plain kernels are already cheap
 constexpr int CELLS = 4096;   // 16^3
 
@@ -41,7 +42,8 @@ struct Layout {       // byte offsets inside one cloud's record
   }
 };
 
-inline bool supported(int N) { return N >= MIN_N && N <= MAX_N; }
+inline bool supported(int N) { return N >= MIN_N && N <= MAX_N_INDEX; }
+inline bool resident(int N) { return N >= MIN_N && N <= MAX_N; }
 
 }  // namespace spidx
 

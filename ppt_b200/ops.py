@@ -45,7 +45,7 @@ def _xyz3(name, t):
 def spatial_index(xyz):
     """Builds the per-cloud spatial index used by fps / knn / knn_group to skip far-away rows of the
     cloud (results are bit-identical with and without it).  Returns None where it does not apply
-    (N outside [512, 8192]).  The buffer is reused by the next call on the same device: build, use, discard."""
+    (N outside [512, 32768]; the bucketed FPS uses it up to 8192 points, the pruned kNN search up to 32768).  The buffer is reused by the next call on the same device: build, use, discard."""
     _need_cuda(xyz)
     xyz = _f32(xyz)
     B, N, _ = xyz.shape

@@ -61,6 +61,7 @@ KNN_CASES = [  # kind, B, N, S, k
     ("U", 2, 1024, 128, 32), ("U", 3, 1000, 37, 24), ("S", 1, 2048, 512, 32), ("U", 2, 8192, 512, 32),
     ("S", 3, 8192, 512, 32), ("U", 2, 8191, 100, 7), ("C", 2, 4096, 300, 32),
     ("U", 2, 256, 256, 4), ("S", 1, 512, 256, 4), ("U", 1, 32, 5, 32), ("U", 1, 33, 70, 1), ("S", 1, 20000, 65, 32),
+    ("U", 1, 32768, 512, 32), ("C", 2, 12000, 100, 24), ("S", 2, 8193, 64, 32),  # index built in place, cloud read from L2
 ]
 
 
