@@ -19,10 +19,60 @@
 //    tie-break (torch.max keeps the first index, F4) runs only when the ballot shows an actual tie.
 #include "common.cuh"
 #include "spatial_index.cuh"
+#include <type_traits>
+
+#ifdef FPS_TRACE
+// Measurement build only (tools/build_variant.py ... -DFPS_TRACE): warp 0 of cloud 0 accumulates the cycles of each
+// phase of an iteration; never compiled into the shipped library.
+__device__ unsigned long long fps_trace_phase[8];
+__device__ unsigned fps_trace_rows[1024];   // rows touched per iteration, whole CTA
+__device__ unsigned fps_trace_rowsmax[1024];  // ... most rows any one warp had
+__device__ unsigned fps_trace_rows0[1024];  // ... by warp 0
+__device__ unsigned fps_trace_iter[1024];   // cycles per iteration (warp 0)
+#define FPS_T(k)                                                                         \
+  do {                                                                                   \
+    if (b == 0 && tid == 0) {                                                            \
+      const long long now = clock64();                                                   \
+      t_acc[k] += now - t_prev;                                                          \
+      if (k == 4) { fps_trace_iter[g] = (unsigned)(now - t_iter); t_iter = now; }        \
+      t_prev = now;                                                                      \
+    }                                                                                    \
+  } while (0)
+extern "C" PPT_EXPORT int ppt_debug_fps_trace(void* dst, void* stream) {  // dst: 8 u64 + 4 x 1024 u32, device memory
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* d = static_cast<unsigned char*>(dst);
+  cudaMemcpyFromSymbolAsync(d, fps_trace_phase, 64, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyFromSymbolAsync(d + 64, fps_trace_rows, 4096, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyFromSymbolAsync(d + 64 + 4096, fps_trace_rows0, 4096, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyFromSymbolAsync(d + 64 + 8192, fps_trace_iter, 4096, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyFromSymbolAsync(d + 64 + 12288, fps_trace_rowsmax, 4096, 0, cudaMemcpyDeviceToDevice, st);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbolAsync(fps_trace_phase, z, 64, 0, cudaMemcpyHostToDevice, st);
+  static unsigned zr[1024];
+  cudaMemcpyToSymbolAsync(fps_trace_rows, zr, 4096, 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(fps_trace_rowsmax, zr, 4096, 0, cudaMemcpyHostToDevice, st);
+  return (int)cudaGetLastError();
+}
+#else
+#define FPS_T(k) do { } while (0)
+#endif
 
 namespace {
 
-template <int FG_WARPS>
+#ifndef FPS_GRID_MICRO
+#define FPS_GRID_MICRO 1
+#endif
+#ifndef FPS_GRID_HYBRID
+#define FPS_GRID_HYBRID 1
+#endif
+// index of a set bit of x != 0: every mask this is applied to either holds a single bit or may be walked in any order
+#if FPS_GRID_MICRO
+#define FPS_BIT(x) (31 - __clz((int)(x)))   // one FLO
+#else
+#define FPS_BIT(x) (__ffs((int)(x)) - 1)    // BREV + FLO
+#endif
+
+template <int FG_WARPS, int RPP>
 __global__ void __launch_bounds__(FG_WARPS * 32, 1)
 fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start,
                 const unsigned char* __restrict__ index, int64_t* __restrict__ idx_out,
@@ -52,8 +102,15 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
     smind[i] = o != 0x7fffffff ? 1e10f : -1.0f;
   }
 
-  // lane j: state of row (warp + FG_WARPS * j)
-  const int myrow = warp + FG_WARPS * lane;
+  // lane j: state of row row_of(j).  Rows are dealt to the warps in groups of FG_WARPS consecutive rows, each group
+  // rotated by its own number: a run of consecutive Morton rows still lands on distinct warps, and so do rows that
+  // are a power of two apart (the Morton neighbours across a y / z cell boundary), which "row % FG_WARPS" would
+  // all hand to the same warp.
+#ifndef FPS_GRID_ROT
+#define FPS_GRID_ROT 1
+#endif
+  auto row_of = [&](int j) { return FG_WARPS * j + (FPS_GRID_ROT ? ((warp - j) & (FG_WARPS - 1)) : warp); };
+  const int myrow = row_of(lane);
   const bool owner = lane < FG_RPW && myrow < rows;
   float blo0 = 0.f, blo1 = 0.f, blo2 = 0.f, bhi0 = 0.f, bhi1 = 0.f, bhi2 = 0.f;
   float rmax = -1.0f;          // largest running min-distance in the row (-1: nothing to pick)
@@ -72,13 +129,23 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   int64_t* out = idx_out + (size_t)b * G;
   float* cout = centers_out ? centers_out + (size_t)b * G * 3 : nullptr;
   const int neg1 = __float_as_int(-1.0f);
+  int wmax = neg1, wpos = 0;  // this warp's best row: (value bits, sorted position)
 
+#ifdef FPS_TRACE
+  long long t_prev = clock64(), t_iter = t_prev, t_acc[5] = {0, 0, 0, 0, 0};
+#endif
   for (int g = 0; g < G; ++g) {
     if (tid == 0) {
       out[g] = (int64_t)far;
       if (cout) { cout[g * 3 + 0] = cx; cout[g * 3 + 1] = cy; cout[g * 3 + 2] = cz; }
     }
-    if (g == G - 1) break;
+    if (g == G - 1) {
+#ifdef FPS_TRACE
+      if (b == 0 && tid == 0)
+        for (int k = 0; k < 5; ++k) fps_trace_phase[k] = (unsigned long long)t_acc[k];
+#endif
+      break;
+    }
 
     // which of this warp's rows can the new centre still affect?
     const float gx = fmaxf(fmaxf(__fsub_rn(blo0, cx), __fsub_rn(cx, bhi0)), 0.f);
@@ -86,47 +153,78 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
     const float gz = fmaxf(fmaxf(__fsub_rn(blo2, cz), __fsub_rn(cz, bhi2)), 0.f);
     const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
     unsigned mask = __ballot_sync(PPT_FULL_MASK, owner && lb < rmax);
+    FPS_T(0);
+#ifdef FPS_TRACE
+    if (lane == 0 && b == 0) atomicAdd(&fps_trace_rows[g], (unsigned)__popc(mask));
+    if (lane == 0 && b == 0) atomicMax(&fps_trace_rowsmax[g], (unsigned)__popc(mask));
+    if (b == 0 && warp == 0 && lane == 0) fps_trace_rows0[g] = (unsigned)__popc(mask);
+#endif
 
-    // Two rows per pass: their load -> distance -> reduce chains are independent and overlap.
+    // R rows per pass: their load -> distance -> reduce chains are independent and overlap.
+    const bool touched = mask != 0;  // warp-uniform
+    auto pass = [&](auto rc) {
+      constexpr int R = decltype(rc)::value;
+      int j[R], pos[R], vb[R], w[R];
+      bool on[R];
+      unsigned eq[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        on[r] = mask != 0;  // r == 0: always; a slot past the last set bit repeats row j[0] and stores nothing
+        j[r] = on[r] ? FPS_BIT(mask) : j[0];
+        mask = on[r] ? mask ^ (1u << j[r]) : 0u;
+        pos[r] = row_of(j[r]) * 32 + lane;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 p = spts[pos[r]];
+        const float m = fminf(smind[pos[r]], ppt_fps_dist(p.x, p.y, p.z, cx, cy, cz));  // torch.min(distance, dist)
+        if (on[r]) smind[pos[r]] = m;                                                    // padding stays -1
+        vb[r] = __float_as_int(m);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = __reduce_max_sync(PPT_FULL_MASK, vb[r]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) eq[r] = __ballot_sync(PPT_FULL_MASK, vb[r] == w[r]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (eq[r] & (eq[r] - 1)) {  // several lanes hold the maximum: the smallest original index wins
+          const unsigned cand = vb[r] == w[r] ? soid[pos[r]] : 0xffffffffu;
+          eq[r] = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+        }
+        const bool me = on[r] && lane == j[r];
+        rmax = me ? __int_as_float(w[r]) : rmax;
+        rpos = me ? pos[r] - lane + FPS_BIT(eq[r]) : rpos;
+      }
+    };
     while (mask) {  // warp-uniform
-      const int j0 = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const bool two = mask != 0;
-      const int j1 = two ? __ffs(mask) - 1 : j0;
-      mask &= mask - 1;  // no-op when it is already 0
-      const int pos0 = (warp + FG_WARPS * j0) * 32 + lane, pos1 = (warp + FG_WARPS * j1) * 32 + lane;
-      const float4 p0 = spts[pos0], p1 = spts[pos1];
-      const float m0 = fminf(smind[pos0], ppt_fps_dist(p0.x, p0.y, p0.z, cx, cy, cz));  // torch.min(distance, dist)
-      const float m1 = fminf(smind[pos1], ppt_fps_dist(p1.x, p1.y, p1.z, cx, cy, cz));  // padding stays -1
-      smind[pos0] = m0;
-      if (two) smind[pos1] = m1;
-      const int vb0 = __float_as_int(m0), vb1 = __float_as_int(m1);
-      const int w0 = __reduce_max_sync(PPT_FULL_MASK, vb0), w1 = __reduce_max_sync(PPT_FULL_MASK, vb1);
-      unsigned eq0 = __ballot_sync(PPT_FULL_MASK, vb0 == w0), eq1 = __ballot_sync(PPT_FULL_MASK, vb1 == w1);
-      if (eq0 & (eq0 - 1)) {  // several lanes hold the maximum: the smallest original index wins
-        const unsigned cand = vb0 == w0 ? soid[pos0] : 0xffffffffu;
-        eq0 = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
-      }
-      if (eq1 & (eq1 - 1)) {
-        const unsigned cand = vb1 == w1 ? soid[pos1] : 0xffffffffu;
-        eq1 = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
-      }
-      if (lane == j0) { rmax = __int_as_float(w0); rpos = pos0 - lane + __ffs(eq0) - 1; }
-      if (two && lane == j1) { rmax = __int_as_float(w1); rpos = pos1 - lane + __ffs(eq1) - 1; }
+#if FPS_GRID_HYBRID
+      const int nrow = __popc(mask);
+      if (nrow >= 3) pass(std::integral_constant<int, 4>{});
+      else if (nrow == 2) pass(std::integral_constant<int, 2>{});
+      else pass(std::integral_constant<int, 1>{});
+#else
+      pass(std::integral_constant<int, RPP>{});
+#endif
     }
+    FPS_T(1);
 
     // best row of this warp, then of the block (one barrier per iteration, double-buffered slots)
-    const int vb = owner ? __float_as_int(rmax) : neg1;
-    const int wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
-    unsigned eq = __ballot_sync(PPT_FULL_MASK, owner && vb == wmax);
-    if (eq & (eq - 1)) {
-      const unsigned cand = (owner && vb == wmax) ? soid[rpos] : 0xffffffffu;
-      eq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+    // (a warp none of whose rows was touched keeps last iteration's answer)
+    if (!FPS_GRID_MICRO || touched) {
+      const int vb = owner ? __float_as_int(rmax) : neg1;
+      wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
+      unsigned eq = __ballot_sync(PPT_FULL_MASK, owner && vb == wmax);
+      if (eq & (eq - 1)) {
+        const unsigned cand = (owner && vb == wmax) ? soid[rpos] : 0xffffffffu;
+        eq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+      }
+      wpos = __shfl_sync(PPT_FULL_MASK, rpos, eq ? FPS_BIT(eq) : 0);
     }
-    const int wpos = __shfl_sync(PPT_FULL_MASK, rpos, eq ? __ffs(eq) - 1 : 0);
     const int par = g & 1;
     if (lane == 0) slot[par * FG_WARPS + warp] = make_int2(wmax, wpos);
+    FPS_T(2);
     __syncthreads();
+    FPS_T(3);
     const int2 s = lane < FG_WARPS ? slot[par * FG_WARPS + lane] : make_int2(neg1, 0);
     const int cmax = __reduce_max_sync(PPT_FULL_MASK, s.x);
     unsigned ceq = __ballot_sync(PPT_FULL_MASK, s.x == cmax);
@@ -134,24 +232,25 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
       const unsigned cand = s.x == cmax ? soid[s.y] : 0xffffffffu;
       ceq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
     }
-    const int cpos = __shfl_sync(PPT_FULL_MASK, s.y, __ffs(ceq) - 1);
+    const int cpos = __shfl_sync(PPT_FULL_MASK, s.y, FPS_BIT(ceq));
     far = soid[cpos];
     const float4 c = spts[cpos];
     cx = c.x; cy = c.y; cz = c.z;
+    FPS_T(4);
   }
 }
 
-template <int W>
+template <int W, int RPP>
 int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                     int B, int N, int G, cudaStream_t st) {
   static PptOncePerDevice configured;
   const size_t slots = 2 * W * sizeof(int2);
   if (configured.need()) {
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel<W, RPP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)spidx::MAX_N * 24 + slots)));
   }
   const size_t smem = (size_t)((N + 31) & ~31) * 24 + slots;
-  fps_grid_kernel<W><<<B, W * 32, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,
+  fps_grid_kernel<W, RPP><<<B, W * 32, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,
                                              centers_out, N, G);
   return ppt_launch_status();
 }
@@ -161,5 +260,11 @@ int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, i
 int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                  int B, int N, int G, cudaStream_t st) {
   // 16 warps: what measured best on B200 (8 and 32 were within 5 % and slower)
-  return launch_fps_grid<16>(xyz, start, index, idx_out, centers_out, B, N, G, st);
+#ifndef FPS_GRID_WARPS
+#define FPS_GRID_WARPS 16
+#endif
+#ifndef FPS_GRID_RPP
+#define FPS_GRID_RPP 2
+#endif
+  return launch_fps_grid<FPS_GRID_WARPS, FPS_GRID_RPP>(xyz, start, index, idx_out, centers_out, B, N, G, st);
 }
