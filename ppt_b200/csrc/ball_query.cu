@@ -86,7 +86,7 @@ ball_query_warp_kernel(const float* __restrict__ xyz, const float* __restrict__ 
                   float thr, int N, int S, int nsample, int tiles_per_cloud) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* pts = reinterpret_cast<float4*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // shuffle: provably warp-uniform
   const int b = blockIdx.x / tiles_per_cloud;
   const int q0 = (blockIdx.x - b * tiles_per_cloud) * BQW_QPB + warp * BQW_QW;
   const float* cloud = xyz + (size_t)b * N * 3;

@@ -230,7 +230,7 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
   float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [128]
   long long* clk0 = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(bars) + 192);  // [2], see below
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform
   const BlobLayout L{(uint32_t)SPLIT};
   const float* sc = reinterpret_cast<const float*>(blob + L.scales());
   // measurement aid (ppt_set_clock_trace): CTA 0 adds its lifetime in ns and in SM cycles to clock_acc[0..1];
@@ -562,7 +562,7 @@ encoder_stage1_tc_kernel(const float* __restrict__ nbhd, const unsigned char* __
   uint64_t* gram_full = w1_full + 1;       // [1] TRAIN: every Gram product of this CTA is complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gram_full + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform
   const BlobLayout L{(uint32_t)SPLIT};
   const float* sc = reinterpret_cast<const float*>(blob + L.scales());
 
@@ -811,7 +811,7 @@ group_linear_kernel(const unsigned char* __restrict__ act_img, const unsigned ch
   uint64_t* b_empty = b_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -980,7 +980,7 @@ group_c_stats_kernel(const unsigned char* __restrict__ g_img, const unsigned cha
   uint64_t* b_full = acc_empty + 2;
   uint64_t* b_empty = b_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }

@@ -209,7 +209,7 @@ extern "C" PPT_EXPORT int ppt_fps(const float* xyz, const int64_t* start, int64_
   if (!xyz || !start || !idx_out || B < 0 || N < 1 || G < 1) return PPT_EINVAL;
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (index && spidx::resident(N)) return ppt_fps_grid(xyz, start, index, idx_out, centers_out, B, N, G, st);
+  if (index && spidx::resident(N) && G <= N) return ppt_fps_grid(xyz, start, index, idx_out, centers_out, B, N, G, st);
   if (N <= 512) return launch_fps<128, 4, 1>(xyz, start, idx_out, centers_out, B, N, G, st);
   if (N <= 1024) return launch_fps<256, 4, 1>(xyz, start, idx_out, centers_out, B, N, G, st);
   if (N <= 2048) return launch_fps<512, 4, 1>(xyz, start, idx_out, centers_out, B, N, G, st);

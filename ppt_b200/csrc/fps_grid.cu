@@ -8,15 +8,23 @@
 // evaluated with the very same rounded operations.  If lb >= the row's largest running min-distance,
 // min(mind, d) leaves every point of the row unchanged and the row (and its cached argmax) is skipped.
 //
-// One CTA per cloud, 32 warps.  The kernel is bound by the dependent-latency chain of one iteration
-// (skip test -> row updates -> warp argmax -> barrier -> block argmax -> centroid), not by work, so:
-//  * the sorted cloud, running min-distances and original indices live in shared memory (one point
-//    per lane per row: conflict-free) and the rows a centre touches are visited with a loop over the
-//    set bits of a ballot; warp w owns rows w, w+32, ... (a centre's neighbourhood is a run of
-//    consecutive Morton rows, so interleaving leaves at most one or two per warp);
-//  * lane j keeps row (w + 32 j)'s box, max and argmax POSITION, so the skip test of all rows of a
-//    warp is one pass and every argmax level is ONE max-reduction plus a ballot; the original-index
-//    tie-break (torch.max keeps the first index, F4) runs only when the ballot shows an actual tie.
+// One CTA per cloud, 16 warps.  128 clouds occupy 128 SMs for 511 dependent iterations, so the kernel's time IS the
+// latency of one iteration (skip test -> row passes of the busiest warp -> warp argmax -> barrier -> block argmax ->
+// centre), about half of it dependent-instruction latency and half issue contention among the 16 warps that all run
+// the same phase at the same time.  What that led to (each step measured on B200 at 128 x 8192 -> 512):
+//  * the sorted cloud, running min-distances and original indices live in shared memory (one point per lane per
+//    row: conflict-free); lane j of a warp keeps the box, max and argmax POSITION of one of the warp's rows, so the
+//    skip test of all rows of a warp is one pass and a ballot;
+//  * rows are dealt to the warps in rotated groups (row_of), touched rows are visited 1, 2 or 4 per pass depending
+//    on how many the warp has (independent load -> distance -> reduce chains overlap; padding a pass with repeated
+//    rows costs issue slots that other warps need);
+//  * every argmax level is a max-reduction of the value bits, a second max-reduction of the position over the
+//    lanes that hold the maximum, and a ballot that only feeds the tie test; the original-index tie-break
+//    (torch.max keeps the first index, F4) runs only on an actual tie;
+//  * a warp none of whose rows was touched re-publishes last iteration's (max, position) without recomputing it;
+//  * long-latency bit scans are avoided (one FLO per visited row; __ffs would be BREV + FLO.SH) and nothing is
+//    stored to global memory inside the loop: the winners are remembered as 16-bit sorted positions in shared
+//    memory and written out by the whole block at the end.
 #include "common.cuh"
 #include "spatial_index.cuh"
 #include <type_traits>
@@ -59,20 +67,12 @@ extern "C" PPT_EXPORT int ppt_debug_fps_trace(void* dst, void* stream) {  // dst
 
 namespace {
 
-#ifndef FPS_GRID_MICRO
-#define FPS_GRID_MICRO 1
-#endif
-#ifndef FPS_GRID_HYBRID
-#define FPS_GRID_HYBRID 1
-#endif
-// index of a set bit of x != 0: every mask this is applied to either holds a single bit or may be walked in any order
-#if FPS_GRID_MICRO
-#define FPS_BIT(x) (31 - __clz((int)(x)))   // one FLO
-#else
-#define FPS_BIT(x) (__ffs((int)(x)) - 1)    // BREV + FLO
-#endif
+// index of the highest set bit of x != 0 (the row masks may be walked in any order).  Measured: this (FLO + 2 ALU)
+// 282 us, lowest-bit-first (__ffs: BREV + FLO.SH, two dependent long-latency ops per use) 340 us; a bfind.u32 in
+// inline asm makes ptxas guard every *_sync of the loop with WARPSYNC.
+#define FPS_BIT(x) (31 - __clz((int)(x)))
 
-template <int FG_WARPS, int RPP>
+template <int FG_WARPS>
 __global__ void __launch_bounds__(FG_WARPS * 32, 1)
 fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start,
                 const unsigned char* __restrict__ index, int64_t* __restrict__ idx_out,
@@ -81,10 +81,11 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = (N + 31) & ~31, rows = np / 32;
-  float4* spts = reinterpret_cast<float4*>(smem_raw);       // [np] sorted {x,y,z,|p|^2}
+  int2* slot = reinterpret_cast<int2*>(smem_raw);           // [2][FG_WARPS] (value bits, sorted position)
+  float4* spts = reinterpret_cast<float4*>(slot + 2 * FG_WARPS);  // [np] sorted {x,y,z,|p|^2}
   float* smind = reinterpret_cast<float*>(spts + np);       // [np] running min-distance (-1: padding)
   unsigned* soid = reinterpret_cast<unsigned*>(smind + np); // [np] original index
-  int2* slot = reinterpret_cast<int2*>(soid + np);          // [2][FG_WARPS] (value bits, sorted position)
+  unsigned short* sel = reinterpret_cast<unsigned short*>(soid + np);  // [G] sorted position of sample g >= 1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -106,10 +107,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   // rotated by its own number: a run of consecutive Morton rows still lands on distinct warps, and so do rows that
   // are a power of two apart (the Morton neighbours across a y / z cell boundary), which "row % FG_WARPS" would
   // all hand to the same warp.
-#ifndef FPS_GRID_ROT
-#define FPS_GRID_ROT 1
-#endif
-  auto row_of = [&](int j) { return FG_WARPS * j + (FPS_GRID_ROT ? ((warp - j) & (FG_WARPS - 1)) : warp); };
+  auto row_of = [&](int j) { return FG_WARPS * j + ((warp - j) & (FG_WARPS - 1)); };
   const int myrow = row_of(lane);
   const bool owner = lane < FG_RPW && myrow < rows;
   float blo0 = 0.f, blo1 = 0.f, blo2 = 0.f, bhi0 = 0.f, bhi1 = 0.f, bhi2 = 0.f;
@@ -130,23 +128,19 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   float* cout = centers_out ? centers_out + (size_t)b * G * 3 : nullptr;
   const int neg1 = __float_as_int(-1.0f);
   int wmax = neg1, wpos = 0;  // this warp's best row: (value bits, sorted position)
+  int wr_slot = warp, rd_slot = lane < FG_WARPS ? lane : 0;  // double-buffered by iteration parity (one barrier each)
 
 #ifdef FPS_TRACE
   long long t_prev = clock64(), t_iter = t_prev, t_acc[5] = {0, 0, 0, 0, 0};
 #endif
-  for (int g = 0; g < G; ++g) {
-    if (tid == 0) {
-      out[g] = (int64_t)far;
-      if (cout) { cout[g * 3 + 0] = cx; cout[g * 3 + 1] = cy; cout[g * 3 + 2] = cz; }
-    }
-    if (g == G - 1) {
-#ifdef FPS_TRACE
-      if (b == 0 && tid == 0)
-        for (int k = 0; k < 5; ++k) fps_trace_phase[k] = (unsigned long long)t_acc[k];
-#endif
-      break;
-    }
-
+  // Sample 0 is the start point; samples 1 .. G-1 are remembered as sorted positions in shared memory and written out
+  // by the whole block after the loop (the sorted copy holds the cloud's own bits), so that an iteration carries no
+  // global store and no thread-0 branch.
+  if (tid == 0) {
+    out[0] = (int64_t)far;
+    if (cout) { cout[0] = cx; cout[1] = cy; cout[2] = cz; }
+  }
+  for (int g = 0; g < G - 1; ++g) {
     // which of this warp's rows can the new centre still affect?
     const float gx = fmaxf(fmaxf(__fsub_rn(blo0, cx), __fsub_rn(cx, bhi0)), 0.f);
     const float gy = fmaxf(fmaxf(__fsub_rn(blo1, cy), __fsub_rn(cy, bhi1)), 0.f);
@@ -164,14 +158,14 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
     const bool touched = mask != 0;  // warp-uniform
     auto pass = [&](auto rc) {
       constexpr int R = decltype(rc)::value;
-      int j[R], pos[R], vb[R], w[R];
+      int j[R], pos[R], vb[R], w[R], best[R];
       bool on[R];
       unsigned eq[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         on[r] = mask != 0;  // r == 0: always; a slot past the last set bit repeats row j[0] and stores nothing
         j[r] = on[r] ? FPS_BIT(mask) : j[0];
-        mask = on[r] ? mask ^ (1u << j[r]) : 0u;
+        if (on[r]) mask ^= 1u << j[r];
         pos[r] = row_of(j[r]) * 32 + lane;
       }
 #pragma unroll
@@ -186,71 +180,87 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
 #pragma unroll
       for (int r = 0; r < R; ++r) eq[r] = __ballot_sync(PPT_FULL_MASK, vb[r] == w[r]);
 #pragma unroll
+      for (int r = 0; r < R; ++r) best[r] = __reduce_max_sync(PPT_FULL_MASK, vb[r] == w[r] ? pos[r] : 0);
+#pragma unroll
       for (int r = 0; r < R; ++r) {
         if (eq[r] & (eq[r] - 1)) {  // several lanes hold the maximum: the smallest original index wins
           const unsigned cand = vb[r] == w[r] ? soid[pos[r]] : 0xffffffffu;
-          eq[r] = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+          const unsigned mn = __reduce_min_sync(PPT_FULL_MASK, cand);
+          best[r] = __reduce_max_sync(PPT_FULL_MASK, cand == mn ? pos[r] : 0);
         }
         const bool me = on[r] && lane == j[r];
+        rpos = me ? best[r] : rpos;
         rmax = me ? __int_as_float(w[r]) : rmax;
-        rpos = me ? pos[r] - lane + FPS_BIT(eq[r]) : rpos;
       }
     };
     while (mask) {  // warp-uniform
-#if FPS_GRID_HYBRID
-      const int nrow = __popc(mask);
-      if (nrow >= 3) pass(std::integral_constant<int, 4>{});
-      else if (nrow == 2) pass(std::integral_constant<int, 2>{});
+      const unsigned m2 = mask & (mask - 1);  // at least two / three rows left?  (plain ALU: no POPC)
+      if (m2 & (m2 - 1)) pass(std::integral_constant<int, 4>{});
+      else if (m2) pass(std::integral_constant<int, 2>{});
       else pass(std::integral_constant<int, 1>{});
-#else
-      pass(std::integral_constant<int, RPP>{});
-#endif
     }
     FPS_T(1);
 
     // best row of this warp, then of the block (one barrier per iteration, double-buffered slots)
-    // (a warp none of whose rows was touched keeps last iteration's answer)
-    if (!FPS_GRID_MICRO || touched) {
+    if (touched) {
       const int vb = owner ? __float_as_int(rmax) : neg1;
       wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
-      unsigned eq = __ballot_sync(PPT_FULL_MASK, owner && vb == wmax);
+      const bool hit = owner && vb == wmax;
+      const unsigned eq = __ballot_sync(PPT_FULL_MASK, hit);
+      wpos = __reduce_max_sync(PPT_FULL_MASK, hit ? rpos : 0);
       if (eq & (eq - 1)) {
-        const unsigned cand = (owner && vb == wmax) ? soid[rpos] : 0xffffffffu;
-        eq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+        const unsigned cand = hit ? soid[rpos] : 0xffffffffu;
+        const unsigned mn = __reduce_min_sync(PPT_FULL_MASK, cand);
+        wpos = __reduce_max_sync(PPT_FULL_MASK, cand == mn ? rpos : 0);
       }
-      wpos = __shfl_sync(PPT_FULL_MASK, rpos, eq ? FPS_BIT(eq) : 0);
     }
-    const int par = g & 1;
-    if (lane == 0) slot[par * FG_WARPS + warp] = make_int2(wmax, wpos);
+    if (lane == 0) slot[wr_slot] = make_int2(wmax, wpos);
     FPS_T(2);
     __syncthreads();
     FPS_T(3);
-    const int2 s = lane < FG_WARPS ? slot[par * FG_WARPS + lane] : make_int2(neg1, 0);
+    const int2 s = lane < FG_WARPS ? slot[rd_slot] : make_int2(neg1, 0);
+    wr_slot ^= FG_WARPS;  // the other parity
+    rd_slot ^= FG_WARPS;
     const int cmax = __reduce_max_sync(PPT_FULL_MASK, s.x);
     unsigned ceq = __ballot_sync(PPT_FULL_MASK, s.x == cmax);
+    int cpos = __reduce_max_sync(PPT_FULL_MASK, s.x == cmax ? s.y : 0);
     if (ceq & (ceq - 1)) {
       const unsigned cand = s.x == cmax ? soid[s.y] : 0xffffffffu;
-      ceq = __ballot_sync(PPT_FULL_MASK, cand == __reduce_min_sync(PPT_FULL_MASK, cand));
+      const unsigned mn = __reduce_min_sync(PPT_FULL_MASK, cand);
+      cpos = __reduce_max_sync(PPT_FULL_MASK, cand == mn ? s.y : 0);
     }
-    const int cpos = __shfl_sync(PPT_FULL_MASK, s.y, FPS_BIT(ceq));
-    far = soid[cpos];
+    if (tid == 0) sel[g + 1] = (unsigned short)cpos;
     const float4 c = spts[cpos];
     cx = c.x; cy = c.y; cz = c.z;
     FPS_T(4);
   }
+#ifdef FPS_TRACE
+  if (b == 0 && tid == 0)
+    for (int k = 0; k < 5; ++k) fps_trace_phase[k] = (unsigned long long)t_acc[k];
+#endif
+  __syncthreads();
+  for (int g = 1 + tid; g < G; g += FG_THREADS) {
+    const int p = sel[g];
+    out[g] = (int64_t)soid[p];
+    if (cout) {
+      const float4 c = spts[p];
+      cout[g * 3 + 0] = c.x; cout[g * 3 + 1] = c.y; cout[g * 3 + 2] = c.z;
+    }
+  }
 }
 
-template <int W, int RPP>
+template <int W>
 int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                     int B, int N, int G, cudaStream_t st) {
   static PptOncePerDevice configured;
   const size_t slots = 2 * W * sizeof(int2);
+  const size_t sel = ((size_t)G * sizeof(unsigned short) + 15) & ~(size_t)15;
   if (configured.need()) {
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel<W, RPP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)((size_t)spidx::MAX_N * 24 + slots)));
+    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)spidx::MAX_N * 26 + slots + 16)));
   }
-  const size_t smem = (size_t)((N + 31) & ~31) * 24 + slots;
-  fps_grid_kernel<W, RPP><<<B, W * 32, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,
+  const size_t smem = (size_t)((N + 31) & ~31) * 24 + slots + sel;  // G <= N
+  fps_grid_kernel<W><<<B, W * 32, smem, st>>>(xyz, start, static_cast<const unsigned char*>(index), idx_out,
                                              centers_out, N, G);
   return ppt_launch_status();
 }
@@ -259,12 +269,9 @@ int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, i
 
 int ppt_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                  int B, int N, int G, cudaStream_t st) {
-  // 16 warps: what measured best on B200 (8 and 32 were within 5 % and slower)
+  // 16 warps: what measured best on B200 (8 and 32 warps: 5-15 % slower, before and after the round-2 rework)
 #ifndef FPS_GRID_WARPS
 #define FPS_GRID_WARPS 16
 #endif
-#ifndef FPS_GRID_RPP
-#define FPS_GRID_RPP 2
-#endif
-  return launch_fps_grid<FPS_GRID_WARPS, FPS_GRID_RPP>(xyz, start, index, idx_out, centers_out, B, N, G, st);
+  return launch_fps_grid<FPS_GRID_WARPS>(xyz, start, index, idx_out, centers_out, B, N, G, st);
 }

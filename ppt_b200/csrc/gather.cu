@@ -115,7 +115,7 @@ gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ new_
                    const int64_t* __restrict__ idx, float* __restrict__ out, long long total_rows, int rows_per_cloud,
                    int N, int K, int D, int xyz_first) {
   // CONCAT: out row = [xyz - centre | feats] (or feats first), C = 3 + D; else: out row = points row, C = D
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // shuffle: provably warp-uniform
   const int C = CONCAT ? D + 3 : D;
   const int xyz_lo = xyz_first ? 0 : D, feat_lo = (CONCAT && xyz_first) ? 3 : 0;
   const float nanv = __int_as_float(0x7fc00000);

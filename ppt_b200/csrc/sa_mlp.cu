@@ -101,7 +101,7 @@ pointwise_linear_kernel(const unsigned char* __restrict__ act_img, const unsigne
   uint64_t* b_empty = b_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < SA_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -247,7 +247,7 @@ pointwise_linear_kblock_kernel(const unsigned char* __restrict__ act_img, const 
   uint64_t* acc_empty = acc_full + 1;      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform
   const int nkb = (KC + KB_CHUNKS - 1) / KB_CHUNKS;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
@@ -473,7 +473,7 @@ sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ feats, 
   uint64_t* act_ready = in_ready + 1;   // [2] layer 1 / layer 2 output written (all units)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
