@@ -57,3 +57,36 @@ __device__ __forceinline__ float ppt_pair_sqdist(float sx, float sy, float sz, f
 }
 
 __device__ __forceinline__ int ppt_lane() { return threadIdx.x & 31; }
+
+// ---- shared memory through explicit 32-bit shared-window addresses ----
+// With pointers derived from `extern __shared__`, ptxas re-derives the window base (S2R SR_CgaCtaId; MOV 0x400; LEA)
+// in front of shared accesses inside loops instead of keeping it in a register: three extra instructions and an S2R
+// latency per access in latency-bound loops (bucketed FPS: three times per iteration).  Taking the address once and
+// issuing ld/st.shared on integers keeps it out of the loops.  (volatile: ordered among themselves and against
+// barriers, like the pointer accesses they replace.)
+__device__ __forceinline__ uint32_t ppt_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 ppt_lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int2 ppt_lds64(uint32_t a) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float ppt_lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t ppt_lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void ppt_sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void ppt_sts64(uint32_t a, int x, int y) {
+  asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y));
+}
+__device__ __forceinline__ void ppt_sts_u16(uint32_t a, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v)); }

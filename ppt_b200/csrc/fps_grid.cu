@@ -81,8 +81,8 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = (N + 31) & ~31, rows = np / 32;
-  int2* slot = reinterpret_cast<int2*>(smem_raw);           // [2][FG_WARPS] (value bits, sorted position)
-  float4* spts = reinterpret_cast<float4*>(slot + 2 * FG_WARPS);  // [np] sorted {x,y,z,|p|^2}
+  int2* slot = reinterpret_cast<int2*>(smem_raw);           // [2][32] (value bits, sorted position); unused: (-1, 0)
+  float4* spts = reinterpret_cast<float4*>(slot + 64);      // [np] sorted {x,y,z,|p|^2}
   float* smind = reinterpret_cast<float*>(spts + np);       // [np] running min-distance (-1: padding)
   unsigned* soid = reinterpret_cast<unsigned*>(smind + np); // [np] original index
   unsigned short* sel = reinterpret_cast<unsigned short*>(soid + np);  // [G] sorted position of sample g >= 1
@@ -96,6 +96,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   const int* sidx = reinterpret_cast<const int*>(rec + L.idx);
   const spidx::RowBox* boxes = reinterpret_cast<const spidx::RowBox*>(rec + L.boxes);
 
+  if (tid < 64) slot[tid] = make_int2(__float_as_int(-1.0f), 0);
   for (int i = tid; i < np; i += FG_THREADS) {
     spts[i] = __ldg(pts + i);
     const int o = __ldg(sidx + i);
@@ -121,6 +122,12 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   }
   __syncthreads();
 
+  // shared-window addresses, taken once (common.cuh)
+  // (through a shuffle: otherwise ptxas treats the base as a constant and re-derives it at every use all the same)
+  const uint32_t a_slot = __shfl_sync(PPT_FULL_MASK, ppt_smem_addr(smem_raw), 0);
+  const uint32_t a_pts = a_slot + 64 * 8, a_mind = a_pts + np * 16, a_oid = a_mind + np * 4,
+                 a_sel = a_oid + np * 4;
+
   const int64_t s0 = start[b];  // the reference indexes xyz[start] (raises when out of range): clamp instead
   unsigned far = (unsigned)(s0 < 0 ? 0 : (s0 >= N ? N - 1 : s0));
   float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
@@ -128,7 +135,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   float* cout = centers_out ? centers_out + (size_t)b * G * 3 : nullptr;
   const int neg1 = __float_as_int(-1.0f);
   int wmax = neg1, wpos = 0;  // this warp's best row: (value bits, sorted position)
-  int wr_slot = warp, rd_slot = lane < FG_WARPS ? lane : 0;  // double-buffered by iteration parity (one barrier each)
+  int wr_slot = warp, rd_slot = lane;  // double-buffered by iteration parity (one barrier each)
 
 #ifdef FPS_TRACE
   long long t_prev = clock64(), t_iter = t_prev, t_acc[5] = {0, 0, 0, 0, 0};
@@ -170,9 +177,9 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float4 p = spts[pos[r]];
-        const float m = fminf(smind[pos[r]], ppt_fps_dist(p.x, p.y, p.z, cx, cy, cz));  // torch.min(distance, dist)
-        if (on[r]) smind[pos[r]] = m;                                                    // padding stays -1
+        const float4 p = ppt_lds128(a_pts + pos[r] * 16);
+        const float m = fminf(ppt_lds_f32(a_mind + pos[r] * 4), ppt_fps_dist(p.x, p.y, p.z, cx, cy, cz));  // torch.min
+        if (on[r]) ppt_sts_f32(a_mind + pos[r] * 4, m);                                  // padding stays -1
         vb[r] = __float_as_int(m);
       }
 #pragma unroll
@@ -184,7 +191,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (eq[r] & (eq[r] - 1)) {  // several lanes hold the maximum: the smallest original index wins
-          const unsigned cand = vb[r] == w[r] ? soid[pos[r]] : 0xffffffffu;
+          const unsigned cand = vb[r] == w[r] ? ppt_lds_u32(a_oid + pos[r] * 4) : 0xffffffffu;
           const unsigned mn = __reduce_min_sync(PPT_FULL_MASK, cand);
           best[r] = __reduce_max_sync(PPT_FULL_MASK, cand == mn ? pos[r] : 0);
         }
@@ -209,28 +216,28 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
       const unsigned eq = __ballot_sync(PPT_FULL_MASK, hit);
       wpos = __reduce_max_sync(PPT_FULL_MASK, hit ? rpos : 0);
       if (eq & (eq - 1)) {
-        const unsigned cand = hit ? soid[rpos] : 0xffffffffu;
+        const unsigned cand = hit ? ppt_lds_u32(a_oid + rpos * 4) : 0xffffffffu;
         const unsigned mn = __reduce_min_sync(PPT_FULL_MASK, cand);
         wpos = __reduce_max_sync(PPT_FULL_MASK, cand == mn ? rpos : 0);
       }
     }
-    if (lane == 0) slot[wr_slot] = make_int2(wmax, wpos);
+    if (lane == 0) ppt_sts64(a_slot + wr_slot * 8, wmax, wpos);
     FPS_T(2);
     __syncthreads();
     FPS_T(3);
-    const int2 s = lane < FG_WARPS ? slot[rd_slot] : make_int2(neg1, 0);
-    wr_slot ^= FG_WARPS;  // the other parity
-    rd_slot ^= FG_WARPS;
+    const int2 s = ppt_lds64(a_slot + rd_slot * 8);
+    wr_slot ^= 32;  // the other parity
+    rd_slot ^= 32;
     const int cmax = __reduce_max_sync(PPT_FULL_MASK, s.x);
     unsigned ceq = __ballot_sync(PPT_FULL_MASK, s.x == cmax);
     int cpos = __reduce_max_sync(PPT_FULL_MASK, s.x == cmax ? s.y : 0);
     if (ceq & (ceq - 1)) {
-      const unsigned cand = s.x == cmax ? soid[s.y] : 0xffffffffu;
+      const unsigned cand = s.x == cmax ? ppt_lds_u32(a_oid + s.y * 4) : 0xffffffffu;
       const unsigned mn = __reduce_min_sync(PPT_FULL_MASK, cand);
       cpos = __reduce_max_sync(PPT_FULL_MASK, cand == mn ? s.y : 0);
     }
-    if (tid == 0) sel[g + 1] = (unsigned short)cpos;
-    const float4 c = spts[cpos];
+    if (tid == 0) ppt_sts_u16(a_sel + (g + 1) * 2, (unsigned short)cpos);
+    const float4 c = ppt_lds128(a_pts + cpos * 16);
     cx = c.x; cy = c.y; cz = c.z;
     FPS_T(4);
   }
@@ -253,7 +260,7 @@ template <int W>
 int launch_fps_grid(const float* xyz, const int64_t* start, const void* index, int64_t* idx_out, float* centers_out,
                     int B, int N, int G, cudaStream_t st) {
   static PptOncePerDevice configured;
-  const size_t slots = 2 * W * sizeof(int2);
+  const size_t slots = 2 * 32 * sizeof(int2);
   const size_t sel = ((size_t)G * sizeof(unsigned short) + 15) & ~(size_t)15;
   if (configured.need()) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(fps_grid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
