@@ -105,8 +105,8 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   }
 
   // lane j: state of row row_of(j).  Rows are dealt to the warps in groups of FG_WARPS consecutive rows, each group
-  // rotated by its own number: a run of consecutive Morton rows still lands on distinct warps, and so do rows that
-  // are a power of two apart (the Morton neighbours across a y / z cell boundary), which "row % FG_WARPS" would
+  // rotated by its own number: a run of consecutive rows (neighbours along the Hilbert curve) still lands on distinct warps, and so do rows that
+  // are a power of two apart (where the curve comes back next to itself), which "row % FG_WARPS" would
   // all hand to the same warp.
   auto row_of = [&](int j) { return FG_WARPS * j + ((warp - j) & (FG_WARPS - 1)); };
   const int myrow = row_of(lane);

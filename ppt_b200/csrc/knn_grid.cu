@@ -3,7 +3,7 @@
 // Same contract as the brute-force scan in knn.cu (the k nearest under (distance, index) with the
 // reference's fp32 distance formula) -- but most of the cloud is never touched:
 //
-//   knn_prepare_kernel  one CTA per cloud: bounding box -> 16x16x16 Morton cells -> counting sort in
+//   knn_prepare_kernel  one CTA per cloud: bounding box -> 16x16x16 cells in Hilbert order -> counting sort in
 //                       shared memory -> the cloud in cell order as float4 {x,y,z,|p|^2} + original
 //                       indices, one bounding box (+ max |p|^2) per row of 32 consecutive sorted points,
 //                       and the first sorted position of every cell.
@@ -31,14 +31,40 @@ constexpr int PREP_THREADS = 1024;
 constexpr int SEARCH_THREADS = 1024;     // 32 warps: the per-query work is latency-bound (shuffles), so
 constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;  // occupancy is what hides it
 
-__device__ __forceinline__ unsigned spread4(unsigned v) {  // 4 bits -> every third bit
-  return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
-}
+// Cell of a point: 16 x 16 x 16 grid over the cloud's bounding box, as the linear id x | y << 4 | z << 8.
 __device__ __forceinline__ int cell_of(float x, float y, float z, const float* lo, const float* inv) {
   const int cx = min(15, max(0, (int)((x - lo[0]) * inv[0])));
   const int cy = min(15, max(0, (int)((y - lo[1]) * inv[1])));
   const int cz = min(15, max(0, (int)((z - lo[2]) * inv[2])));
-  return (int)(spread4((unsigned)cx) | (spread4((unsigned)cy) << 1) | (spread4((unsigned)cz) << 2));
+  return cx | (cy << 4) | (cz << 8);
+}
+// Position of cell (x, y, z) along the 3-D Hilbert curve of order 4 (Skilling's transpose algorithm).  The cloud is
+// sorted in this order: consecutive cells are always face neighbours, so a row of 32 consecutive points is a compact
+// blob.  (Round 1 used Morton order, whose jumps at power-of-two boundaries give the rows that straddle them large
+// bounding boxes: more rows touched per FPS iteration, more rows scanned per kNN query.)
+__device__ __forceinline__ int hilbert4(int lin) {
+  unsigned X[3] = {(unsigned)lin & 15u, ((unsigned)lin >> 4) & 15u, ((unsigned)lin >> 8) & 15u};
+#pragma unroll
+  for (unsigned Q = 8; Q > 1; Q >>= 1) {
+    const unsigned P = Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q) X[0] ^= P;
+      else { const unsigned t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+    }
+  }
+  X[1] ^= X[0]; X[2] ^= X[1];
+  unsigned t = 0;
+#pragma unroll
+  for (unsigned Q = 8; Q > 1; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  unsigned h = 0;
+#pragma unroll
+  for (int bit = 3; bit >= 0; --bit)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) h = (h << 1) | ((X[i] >> bit) & 1u);
+  return (int)h;
 }
 
 __device__ __forceinline__ float warp_min(float v) {
@@ -67,6 +93,7 @@ knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ wo
   int* warp_tot = hist + CELLS;                                        // [32]
   float* red = reinterpret_cast<float*>(warp_tot + 32);                // [6][32]
   float* box = red + 6 * 32;                                           // lo[3], inv[3]
+  unsigned short* lut = reinterpret_cast<unsigned short*>(box + 8);    // [CELLS] linear cell id -> Hilbert position
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -94,7 +121,7 @@ knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ wo
     const float a = warp_min(mn[c]), z = warp_max(mx[c]);
     if (lane == 0) { red[c * 32 + warp] = a; red[(3 + c) * 32 + warp] = z; }
   }
-  for (int i = tid; i < CELLS; i += PREP_THREADS) hist[i] = 0;
+  for (int i = tid; i < CELLS; i += PREP_THREADS) { hist[i] = 0; lut[i] = (unsigned short)hilbert4(i); }
   __syncthreads();
   if (warp == 0) {
 #pragma unroll
@@ -113,7 +140,7 @@ knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ wo
   // 2. histogram of cells
   for (int n = tid; n < N; n += PREP_THREADS) {
     const float x = cloud[(size_t)n * 3], y = cloud[(size_t)n * 3 + 1], z = cloud[(size_t)n * 3 + 2];
-    atomicAdd(&hist[cell_of(x, y, z, lo, inv)], 1);
+    atomicAdd(&hist[lut[cell_of(x, y, z, lo, inv)]], 1);
   }
   __syncthreads();
 
@@ -140,20 +167,22 @@ knn_prepare_kernel(const float* __restrict__ xyz, unsigned char* __restrict__ wo
   }
   __syncthreads();
   int run = warp_tot[warp] + incl - sum;
-  int* cells_out = reinterpret_cast<int*>(rec + L.cells);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    hist[tid * 4 + i] = run;       // becomes the scatter cursor
-    cells_out[tid * 4 + i] = run;
+    hist[tid * 4 + i] = run;       // first sorted position of Hilbert cell tid * 4 + i; becomes the scatter cursor
     run += c4[i];
   }
-  if (tid == PREP_THREADS - 1) cells_out[CELLS] = run;  // = N
+  __syncthreads();
+  // the searches look a cell up by its linear id
+  int* cells_out = reinterpret_cast<int*>(rec + L.cells);
+  for (int i = tid; i < CELLS; i += PREP_THREADS) cells_out[i] = hist[lut[i]];
+  if (tid == 0) cells_out[CELLS] = N;
   __syncthreads();
 
   // 4. scatter into cell order (order inside a cell is whatever the atomics give; see header comment)
   for (int n = tid; n < N; n += PREP_THREADS) {
     const float x = cloud[(size_t)n * 3], y = cloud[(size_t)n * 3 + 1], z = cloud[(size_t)n * 3 + 2];
-    const int pos = atomicAdd(&hist[cell_of(x, y, z, lo, inv)], 1);
+    const int pos = atomicAdd(&hist[lut[cell_of(x, y, z, lo, inv)]], 1);
     spts[pos] = make_float4(x, y, z, ppt_sqnorm3(x, y, z));
     sidx[pos] = n;
   }
@@ -315,7 +344,7 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
   const int* sidx = reinterpret_cast<const int*>(pts + nps);         // [np]
   RowBox* boxes = reinterpret_cast<RowBox*>(smem_raw + (size_t)nps * 20);  // [rows]
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(boxes + rows) + (threadIdx.x >> 5) * CAND_CAP;
-  // one box per BATCH of 32 consecutive rows (1024 Morton-ordered points): a query tests these first and only looks
+  // one box per BATCH of 32 consecutive rows (1024 consecutive points of the Hilbert order): a query tests these first and only looks
   // at the row boxes of batches its tau-ball reaches
   RowBox* bbox = reinterpret_cast<RowBox*>(reinterpret_cast<unsigned long long*>(boxes + rows) + SEARCH_WARPS * CAND_CAP);
   const int nbatch = (rows + 31) >> 5;  // <= 8 (RESIDENT) / <= 32
@@ -442,7 +471,7 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
 
 size_t prep_smem(int N) {
   const size_t np = N > spidx::MAX_N ? 0 : (size_t)((N + 31) / 32) * 32;
-  return np * 20 + (CELLS + 32) * sizeof(int) + (6 * 32 + 8) * sizeof(float);
+  return np * 20 + (CELLS + 32) * sizeof(int) + (6 * 32 + 8) * sizeof(float) + CELLS * sizeof(unsigned short);
 }
 size_t search_smem(int N) {
   const size_t np = (size_t)((N + 31) / 32) * 32;

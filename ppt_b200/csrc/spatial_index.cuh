@@ -1,6 +1,6 @@
 // Per-cloud spatial index shared by the pruned kNN search and the bucketed FPS (sm_100a).
 //
-// Built by spatial_index_build (knn_grid.cu): the cloud in 16x16x16 Morton-cell order as float4
+// Built by spatial_index_build (knn_grid.cu): the cloud sorted by 16x16x16 cell along a Hilbert curve, as float4
 // {x,y,z,|p|^2} with the original indices, one bounding box per ROW of 32 consecutive sorted points,
 // and the first sorted position of every cell.  One record per cloud in a caller-owned buffer.
 #pragma once
