@@ -45,7 +45,8 @@ def _xyz3(name, t):
 def spatial_index(xyz):
     """Builds the per-cloud spatial index used by fps / knn / knn_group to skip far-away rows of the
     cloud (results are bit-identical with and without it).  Returns None where it does not apply
-    (N outside [512, 32768]; the bucketed FPS uses it up to 8192 points, the pruned kNN search up to 32768).  The buffer is reused by the next call on the same device: build, use, discard."""
+    (N outside [512, 32768]; the bucketed FPS uses it up to 8192 points, the pruned kNN search up to 32768).
+    The buffer is reused by the next call on the same device and stream: build, use, discard."""
     _need_cuda(xyz)
     xyz = _f32(xyz)
     B, N, _ = xyz.shape
@@ -57,6 +58,9 @@ def spatial_index(xyz):
     with torch.cuda.device(xyz.device):
         _lib.check(lib.ppt_spatial_index_build(_ptr(xyz), _ptr(buf), B, N, _stream(xyz)), "ppt_spatial_index_build")
     return buf
+
+
+FPS_INDEX_MAX_N = 8192  # csrc/spatial_index.cuh MAX_N: the bucketed FPS keeps a cloud's state in shared memory
 
 
 def _resolve_index(index, xyz):
@@ -73,7 +77,10 @@ def fps(xyz, npoint, start, return_centers=False, index=AUTO):
     start = _i64(start)
     idx = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
     centers = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device) if return_centers else None
-    index = _resolve_index(index, xyz) if npoint > 8 else (None if isinstance(index, str) else index)
+    # AUTO: an index pays for itself from a handful of samples on, and only up to FPS_INDEX_MAX_N points (above that
+    # ppt_fps runs its plain cluster kernel and would ignore it)
+    use = npoint > 8 and N <= FPS_INDEX_MAX_N and npoint <= N
+    index = (_resolve_index(index, xyz) if use else None) if isinstance(index, str) else index
     with torch.cuda.device(xyz.device):
         _lib.check(_lib.load().ppt_fps(_ptr(xyz), _ptr(start), _ptr(idx), _ptr(centers), _ptr(index), B, N, npoint,
                                        _stream(xyz)), "ppt_fps")
