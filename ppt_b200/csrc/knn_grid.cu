@@ -287,7 +287,8 @@ __device__ __forceinline__ void flush32(TopList& t, unsigned long long* __restri
   cnt = rest;
 }
 
-// measured at 128 x 8192 / 512 queries / k = 32: 4 and 10 equal (0.170 ms), 20: 0.179; seeding with 1 row 0.300, 5 rows 0.179
+// measured at 128 x 8192 / 512 queries / k = 32 (Hilbert order): 4 and 10 equal (0.121 ms), 20: 0.127; seeding with 1 row 0.148,
+// 2 rows 0.126, 3 rows 0.121, 5 rows 0.132
 constexpr int INSERT_MAX = 10;  // pending keys up to which serial insertion (~12 instructions each) beats sort + merge (~210)
 
 __device__ __forceinline__ void flush_all(TopList& t, unsigned long long* __restrict__ buf, int& cnt, int k, int lane) {
