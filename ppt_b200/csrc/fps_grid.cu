@@ -21,7 +21,8 @@
 //  * every argmax level is a max-reduction of the value bits, a second max-reduction of the position over the
 //    lanes that hold the maximum, and a ballot that only feeds the tie test; the original-index tie-break
 //    (torch.max keeps the first index, F4) runs only on an actual tie;
-//  * a warp none of whose rows was touched re-publishes last iteration's (max, position) without recomputing it;
+//  * min-distances only decrease, so a warp recomputes its best row only when that very row was touched and
+//    otherwise re-publishes last iteration's (max, position);
 //  * long-latency bit scans are avoided (one FLO per visited row; __ffs would be BREV + FLO.SH) and nothing is
 //    stored to global memory inside the loop: the winners are remembered as 16-bit sorted positions in shared
 //    memory and written out by the whole block at the end.
@@ -79,6 +80,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
                 float* __restrict__ centers_out, int N, int G) {
   constexpr int FG_THREADS = FG_WARPS * 32;
   constexpr int FG_RPW = spidx::MAX_N / 32 / FG_WARPS;  // rows per warp at most
+  static_assert(spidx::MIN_N / 32 >= FG_WARPS, "every warp must own a row through lane 0 (wlane starts at 0)");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = (N + 31) & ~31, rows = np / 32;
   int2* slot = reinterpret_cast<int2*>(smem_raw);           // [2][32] (value bits, sorted position); unused: (-1, 0)
@@ -135,6 +137,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
   float* cout = centers_out ? centers_out + (size_t)b * G * 3 : nullptr;
   const int neg1 = __float_as_int(-1.0f);
   int wmax = neg1, wpos = 0;  // this warp's best row: (value bits, sorted position)
+  int wlane = 0;              // ... and the lane that owns it (lane 0 owns a row in every warp: rows >= FG_WARPS)
   int wr_slot = warp, rd_slot = lane;  // double-buffered by iteration parity (one barrier each)
 
 #ifdef FPS_TRACE
@@ -162,7 +165,8 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
 #endif
 
     // R rows per pass: their load -> distance -> reduce chains are independent and overlap.
-    const bool touched = mask != 0;  // warp-uniform
+    // Running min-distances only decrease, so the warp's best row changes only when that very row is touched.
+    const bool redo_best = (mask >> wlane) & 1u;  // warp-uniform
     auto pass = [&](auto rc) {
       constexpr int R = decltype(rc)::value;
       int j[R], pos[R], vb[R], w[R], best[R];
@@ -208,8 +212,9 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
     }
     FPS_T(1);
 
-    // best row of this warp, then of the block (one barrier per iteration, double-buffered slots)
-    if (touched) {
+    // best row of this warp (only when it may have changed), then of the block (one barrier per iteration,
+    // double-buffered slots)
+    if (redo_best) {
       const int vb = owner ? __float_as_int(rmax) : neg1;
       wmax = __reduce_max_sync(PPT_FULL_MASK, vb);
       const bool hit = owner && vb == wmax;
@@ -220,6 +225,7 @@ fps_grid_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start
         const unsigned mn = __reduce_min_sync(PPT_FULL_MASK, cand);
         wpos = __reduce_max_sync(PPT_FULL_MASK, cand == mn ? rpos : 0);
       }
+      wlane = (wpos >> 5) / FG_WARPS;  // the lane that owns that row (row_of)
     }
     if (lane == 0) ppt_sts64(a_slot + wr_slot * 8, wmax, wpos);
     FPS_T(2);
