@@ -406,13 +406,9 @@ knn_search_kernel(const float* __restrict__ xyz, const float* __restrict__ query
     const int r0 = min(rows - 1, __ldg(cell_start + cell_of(qx, qy, qz, hdr.lo, hdr.inv)) >> 5);
     const int ra = max(0, r0 - 1), rz = min(rows - 1, r0 + 1);
     int cnt = 0;
-#ifdef KNN_SEED_OWN_FIRST
     scan_row(t, cand, cnt, pts, sidx, r0, qx, qy, qz, qn, k, lane);  // the query's own row first: the tightest first tau
     if (ra < r0) scan_row(t, cand, cnt, pts, sidx, ra, qx, qy, qz, qn, k, lane);
     if (rz > r0) scan_row(t, cand, cnt, pts, sidx, rz, qx, qy, qz, qn, k, lane);
-#else
-    for (int r = ra; r <= rz; ++r) scan_row(t, cand, cnt, pts, sidx, r, qx, qy, qz, qn, k, lane);
-#endif
     flush_all(t, cand, cnt, k, lane);  // a tight tau before the pruning pass
 
     // batches of 32 rows the tau-ball reaches (tau only shrinks from here on, so a batch rejected now stays rejected)
