@@ -12,12 +12,13 @@ namespace {
 using namespace tc05;
 
 constexpr int ST_THREADS = 128;
-constexpr int ST_TMEM_COLS = 256;
+constexpr int ST_TMEM_COLS = 512;
+constexpr int ST_A_COL = 256;  // A-in-TMEM mode: the A operand lives at columns [256, 256 + K / 2)
 
 template <uint32_t FMT>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restrict__ a_packed,
-                     const float* __restrict__ b, float* __restrict__ d, int N, int K, int b_mn, int split) {
+                     const float* __restrict__ b, float* __restrict__ d, int N, int K, int b_mn, int split, int a_tmem) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kchunks = K / 64;
@@ -42,7 +43,23 @@ umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restric
   const uint32_t tbase = *tmem_slot;
 
   // ---- operands into shared memory ----
-  if (a_packed) {
+  if (a_tmem) {
+    // A in TENSOR MEMORY (tcgen05.mma with [a_tmem]): row m of A = lane m, two consecutive K elements per 32-bit
+    // column (element k in the low half).  Thread m (warp w owns lanes 32 w .. 32 w + 31) converts its row and
+    // stores it 8 columns (K = 16) at a time.
+    const int m = tid;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint32_t r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t lo = to_operand<FMT>(a[(size_t)m * K + k0 + 2 * j]);
+        const uint32_t hi = to_operand<FMT>(a[(size_t)m * K + k0 + 2 * j + 1]);
+        r[j] = lo | (hi << 16);
+      }
+      tmem_st8(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ST_A_COL + k0 / 2), r);
+    }
+    tmem_wait_st();
+  } else if (a_packed) {
     if (tid == 0) {
       mbar_arrive_expect_tx(&bars[0], (uint32_t)split * a_bytes);
       for (int s = 0; s < split; ++s)
@@ -71,6 +88,7 @@ umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restric
     if (split == 2) *reinterpret_cast<uint16_t*>(sB + b_bytes + off) = to_operand<FMT>(v - from_operand<FMT>(hi));
   }
   fence_proxy_async_smem();
+  fence_before_sync();  // (orders the tcgen05.st of the A-in-TMEM mode before the barrier)
   __syncthreads();
 
   // ---- MMA: one thread issues ----
@@ -85,6 +103,7 @@ umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restric
         for (int pass = 0; pass < (split == 2 ? 3 : 1); ++pass) {
           const int sa = pass == 2 ? 1 : 0, sb = pass == 1 ? 1 : 0;  // hi*hi, hi*lo, lo*hi
           const uint64_t adesc = make_sdesc(aaddr + sa * a_bytes + kc * 16384u + k16 * 32u, 16u, 1024u);
+          const uint32_t a_taddr = tbase + (uint32_t)(ST_A_COL + (kc * 64 + k16 * 16) / 2);
           uint64_t bdesc;
           if (b_mn) {
             const uint32_t k0 = (uint32_t)kc * 64u + (uint32_t)k16 * 16u;
@@ -92,7 +111,8 @@ umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restric
           } else {
             bdesc = make_sdesc(baddr + sb * b_bytes + kc * ((uint32_t)N * 128u) + k16 * 32u, 16u, 1024u);
           }
-          umma_f16(tbase, adesc, bdesc, idesc, acc);
+          if (a_tmem) umma_f16_ta(tbase, a_taddr, bdesc, idesc, acc);
+          else umma_f16(tbase, adesc, bdesc, idesc, acc);
           acc = 1;
         }
     umma_commit(&bars[1]);
@@ -116,11 +136,13 @@ umma_selftest_kernel(const float* __restrict__ a, const unsigned char* __restric
 }  // namespace
 
 // mode: bits [0,2) = PPT_ENC_FP16 / PPT_ENC_BF16 / PPT_ENC_FP16X3; bit 2 = B operand MN-major;
-// bit 3 = `a` points at a packed operand image (ppt_b200/encoder_pack.py: pack_kmajor) instead of fp32.
+// bit 3 = `a` points at a packed operand image (ppt_b200/encoder_pack.py: pack_kmajor) instead of fp32;
+// bit 4 = the A operand is placed in tensor memory (tcgen05.st) and the MMA reads it from there.
 extern "C" PPT_EXPORT int ppt_selftest_umma(const float* a, const float* b, float* d, int N, int K, int mode,
                                             void* stream) {
   if (!a || !b || !d) return PPT_EINVAL;
-  const int prec = mode & 3, b_mn = (mode >> 2) & 1, packed = (mode >> 3) & 1;
+  const int prec = mode & 3, b_mn = (mode >> 2) & 1, packed = (mode >> 3) & 1, a_tmem = (mode >> 4) & 1;
+  if (a_tmem && (packed || prec == PPT_ENC_FP16X3 || K > 512)) return PPT_EINVAL;
   if (prec > PPT_ENC_FP16X3) return PPT_EINVAL;
   if (N < 32 || N > 256 || (N % 32) != 0 || K < 64 || (K % 64) != 0) return PPT_ERANGE;
   if (b_mn && (N % 64) != 0) return PPT_ERANGE;
@@ -133,11 +155,11 @@ extern "C" PPT_EXPORT int ppt_selftest_umma(const float* a, const float* b, floa
   if (prec != PPT_ENC_BF16) {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel<tc05::FMT_F16>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    umma_selftest_kernel<tc05::FMT_F16><<<1, ST_THREADS, smem, st>>>(af, ap, b, d, N, K, b_mn, split);
+    umma_selftest_kernel<tc05::FMT_F16><<<1, ST_THREADS, smem, st>>>(af, ap, b, d, N, K, b_mn, split, a_tmem);
   } else {
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel<tc05::FMT_BF16>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    umma_selftest_kernel<tc05::FMT_BF16><<<1, ST_THREADS, smem, st>>>(af, ap, b, d, N, K, b_mn, split);
+    umma_selftest_kernel<tc05::FMT_BF16><<<1, ST_THREADS, smem, st>>>(af, ap, b, d, N, K, b_mn, split, a_tmem);
   }
   return ppt_launch_status();
 }

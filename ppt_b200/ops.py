@@ -434,13 +434,13 @@ def sa_mlp_forward(xyz, feats, new_xyz, idx, packed, dims, mode=ENC_FP16, per_la
     return out
 
 
-def selftest_umma(a, b, mode=ENC_FP16, b_mn_major=False, a_packed=None):
+def selftest_umma(a, b, mode=ENC_FP16, b_mn_major=False, a_packed=None, a_in_tmem=False):
     """D[128,N] = A[128,K] @ B[N,K]^T through the Encoder's tcgen05 building blocks."""
     _need_cuda(a, b)
     a, b = _f32(a), _f32(b)
     N, K = b.shape
     d = torch.empty((128, N), dtype=torch.float32, device=a.device)
-    flags = mode | (4 if b_mn_major else 0) | (8 if a_packed is not None else 0)
+    flags = mode | (4 if b_mn_major else 0) | (8 if a_packed is not None else 0) | (16 if a_in_tmem else 0)
     src = a if a_packed is None else a_packed
     with torch.cuda.device(a.device):
         _lib.check(_lib.load().ppt_selftest_umma(_ptr(src), _ptr(b), _ptr(d), N, K, flags, _stream(a)),

@@ -19,10 +19,15 @@ VARIANTS = [
 ]
 
 
-@pytest.mark.parametrize("N,K,mode,b_mn,packed", VARIANTS)
-def test_umma_selftest(N, K, mode, b_mn, packed):
+# the A operand read from TENSOR MEMORY (written there with tcgen05.st): N, K, mode, B MN-major
+TMEM_A_VARIANTS = [(128, 64, 0, 0), (64, 128, 0, 0), (64, 512, 0, 0), (64, 256, 1, 0), (256, 128, 0, 0), (128, 128, 0, 1)]
+VARIANTS = [v + (0,) for v in VARIANTS] + [(n, k, m, b, 0, 1) for n, k, m, b in TMEM_A_VARIANTS]
+
+
+@pytest.mark.parametrize("N,K,mode,b_mn,packed,a_tmem", VARIANTS)
+def test_umma_selftest(N, K, mode, b_mn, packed, a_tmem):
     try:
-        out = subprocess.run([sys.executable, CHILD] + [str(v) for v in (N, K, mode, b_mn, packed)],
+        out = subprocess.run([sys.executable, CHILD] + [str(v) for v in (N, K, mode, b_mn, packed, a_tmem)],
                              capture_output=True, text=True, timeout=120)
     except subprocess.TimeoutExpired:
         pytest.fail("tcgen05 self-test hung (killed after 120 s)")
