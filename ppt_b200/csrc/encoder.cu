@@ -524,27 +524,30 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
 // ======================================================================================
 // stage 2 with the ACTIVATIONS as the A operand and h3 in TENSOR MEMORY (single-part operands, eval mode)
 // ======================================================================================
-// encoder_stage_kernel<2> is bound by shared-memory bandwidth, not by the tensor pipe: an
-// M128 x N128 x K16 instruction with both operands in shared memory reads 8 KB in its 64 tensor cycles -- all of the
-// 128 B/clk an SM's shared memory delivers -- while the weight ring (384 KB per tile) and the h3 / h1 stores
-// (160 KB) compete for the same port: 1.3 MB per 128-point tile = 10.3 k cycles for 6.1 k cycles of MMA.
-// This kernel swaps the operand roles: D[point, channel] = act[point, K] . W[channel, K]^T, the points are the M
-// dimension (TMEM lanes) and the weights the B operand.  Then
-//   * the ReLU'd hidden layer h3 (512 channels) never touches shared memory: the epilogue writes it back into
-//     tensor memory as fp16 pairs (tcgen05.st, 256 columns) and the W4 units read it from there as their A operand
-//     (tcgen05.mma [a_tmem]; layout pinned by tests/test_gpu_umma.py) -- those instructions read only their 4 KB of
-//     weights from shared memory;
-//   * W32 (128 KB) stays RESIDENT in shared memory for the CTA's lifetime (the 128 KB the h3 buffer used to take), so
-//     only W4 streams through the ring: 256 KB per tile instead of 384.
-// Per tile: W32 units 32 x 8 KB + W4 units 64 x 4 KB + ring 256 KB + h1 32 KB = 800 KB = 6.25 k cycles of
-// shared-memory time against 6.1 k of MMA.  Tensor memory: two 128-column accumulators + h3 = 512 columns; an
-// accumulator is released as soon as its values are in registers (tcgen05.wait::ld), before the convert / store
-// work, so two suffice.  An epilogue thread owns a POINT (lane): the per-group bias c is warp-uniform per column
-// (read with broadcast loads), ReLU + conversion pack two channels per F2FP, and the group max of the last layer --
-// a maximum over the 32 lanes of a warp -- is a transposing butterfly (64 columns -> 2 per lane in 5 exchange steps).
+// encoder_stage_kernel<2> re-streams all 384 KB of W32 and W4 from L2 for every 128-point tile: 6.3 GB per 128-cloud
+// step, 11.3 TB/s at 0.555 ms -- the L2 -> SM path of the chip (~42 B/clk per SM when every SM streams), not the
+// tensor pipe and not shared memory (tools/ta_trace.py: the issuing warp spends 40 % of a tile waiting for weights).
+// This kernel swaps the operand roles, D[point, channel] = act[point, K] . W[channel, K]^T (points = TMEM lanes,
+// weights = B operand), so that
+//   * the ReLU'd hidden layer h3 lives in tensor memory as fp16 pairs (tcgen05.st) and is the A operand of the W4
+//     products straight from there (tcgen05.mma [a_tmem]; layout pinned by tests/test_gpu_umma.py) -- the 128 KB of
+//     shared memory it used to take now hold W32 for the CTA's whole lifetime, and only W4 streams: 256 KB per tile;
+//   * the schedule is a rolling one over the 64-channel K-chunks of h3, so that W4 is consumed at a UNIFORM rate
+//     (32 KB per 896 tensor cycles, just under what L2 delivers) instead of in one burst at the end of a tile:
+//         U0 U1 C0 U2 C1 U3 C2 U4 C3 U5 C4 U6 C5 U7 C6 C7        (per tile, in tensor-pipe order)
+//     U_j = W32 unit j: h3 channels [64 j, 64 j + 64) into a 64-column accumulator (A = h1 in shared memory, B = 64
+//     rows of the resident W32 image); C_j = W4 K-chunk j for BOTH 128-channel output units (A = h3 chunk j in
+//     tensor memory, B = two ring stages).  Only two 32-column h3 slots are alive at a time.
+// Tensor memory: 2 x 128 (W4 accumulators) + 2 x 64 (W32 accumulators) + 2 x 32 (h3 slots) = 448 columns.
+// Sixteen epilogue warps in two roles (a warp reads only its TMEM lane quadrant, so roles come in fours; a thread
+// owns a POINT = lane): warps 2-9 turn U_j into h3 chunk j (+ per-group bias c, warp-uniform per column: fetched one
+// float per lane a tile ahead, broadcast by shuffle; ReLU; F2FP) and rebuild h1 for the next tile; warps 10-17
+// reduce the W4 accumulators over each group's 32 points = over the lanes of a warp with a transposing butterfly on
+// packed pairs.  Each role has its own hand-off barriers (a warp that skipped phases of a shared barrier would be
+// fooled by the parity test).  An accumulator is released as soon as its values are in registers.
 // The split (3-MMA) precision mode and the train-mode BN_APPLY variant keep encoder_stage_kernel<2>.
 template <uint32_t FMT>
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(576, 1)
 encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
                          const float* __restrict__ cbuf,          // [groups_pad, 512]
                          unsigned char* __restrict__ out_img,     // t images
@@ -552,7 +555,7 @@ encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __
                          long long num_groups, int num_tiles) {
   constexpr int NT = 128, EPI_THREADS = 256, NSTAGE = 4;
   constexpr uint32_t H1_BYTES = 2u * NT * 128u;
-  constexpr uint32_t H3COL = 256, TCOLS = 512;
+  constexpr uint32_t ACC_R = 256, H3COL = 384, TCOLS = 512;  // W4 accumulators at columns 0 and 128
 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* w32s = smem;                          // [4 units][2 chunks][16 KB], resident
@@ -561,17 +564,16 @@ encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * IMG);
   uint64_t* full = bars;                  // [NSTAGE]
   uint64_t* empty = full + NSTAGE;        // [NSTAGE]
-  // Accumulator hand-offs, one set per epilogue role: a warp that skipped phases of a shared barrier would be fooled
-  // by the parity test (the phase two completions back has the parity it is waiting for).
-  uint64_t* full_r = empty + NSTAGE;      // [2] W32 unit complete in accumulator b   (ReLU warps wait)
-  uint64_t* full_m = full_r + 2;          // [2] W4 unit complete in accumulator b    (max warps wait)
-  uint64_t* empty_r = full_m + 2;         // [2] ReLU warps have read accumulator b   (256 arrivals)
-  uint64_t* empty_m = empty_r + 2;        // [2] max warps have read accumulator b    (128 arrivals)
-  uint64_t* h1_ready = empty_m + 2;       // [1]
-  uint64_t* h3_ready = h1_ready + 1;      // [4]
-  uint64_t* w32_full = h3_ready + 4;      // [1]
-  uint64_t* h1_free = w32_full + 1;       // [1] the W32 units of a tile have completed: h1 may be rebuilt
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h1_free + 1);
+  uint64_t* full_r = empty + NSTAGE;      // [2] U_j complete in W32 accumulator j & 1        (ReLU warps wait)
+  uint64_t* empty_r = full_r + 2;         // [2] ... and read out                              (256 arrivals)
+  uint64_t* slot_ready = empty_r + 2;     // [2] h3 chunk j written to slot j & 1              (256 arrivals)
+  uint64_t* slot_free = slot_ready + 2;   // [2] C_j has read slot j & 1
+  uint64_t* full_m = slot_free + 2;       // [2] W4 output unit v complete                     (max warps wait)
+  uint64_t* empty_m = full_m + 2;         // [2] ... and read out                              (256 arrivals)
+  uint64_t* h1_ready = empty_m + 2;       // [1] (256 arrivals)
+  uint64_t* h1_free = h1_ready + 1;       // [1] U_7 complete: h1 may be rebuilt
+  uint64_t* w32_full = h1_free + 1;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w32_full + 1);
   float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [128]
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -582,13 +584,13 @@ encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full_r[i], 1); mbar_init(&full_m[i], 1);
-      mbar_init(&empty_r[i], EPI_THREADS); mbar_init(&empty_m[i], 128);
+      mbar_init(&full_r[i], 1); mbar_init(&empty_r[i], EPI_THREADS);
+      mbar_init(&slot_ready[i], EPI_THREADS); mbar_init(&slot_free[i], 1);
+      mbar_init(&full_m[i], 1); mbar_init(&empty_m[i], EPI_THREADS);
     }
     mbar_init(h1_ready, EPI_THREADS);
-    for (int i = 0; i < 4; ++i) mbar_init(&h3_ready[i], EPI_THREADS);
-    mbar_init(w32_full, 1);
     mbar_init(h1_free, 1);
+    mbar_init(w32_full, 1);
     mbar_fence_init();
   }
   if (tid < 128) {  // W1' rows pre-multiplied by the activation scale (a power of two: exact)
@@ -611,11 +613,11 @@ encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __
       Ring r;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
-        for (int i = 0; i < 16; ++i) {  // W4: 2 units x 8 chunks, in blob order
+        for (int i = 0; i < 16; ++i) {  // W4 in consumption order: K-chunk i / 2 of output unit i & 1
           const uint32_t s = r.stage<NSTAGE>();
           mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
           mbar_arrive_expect_tx(&full[s], IMG);
-          bulk_g2s(ring + s * IMG, blob + L.W4() + (size_t)i * IMG, IMG, &full[s]);
+          bulk_g2s(ring + s * IMG, blob + L.W4() + (size_t)((i & 1) * 8 + (i >> 1)) * IMG, IMG, &full[s]);
           ++r.it;
         }
       }
@@ -624,90 +626,91 @@ encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __
     // ===================== MMA issuer: converged warp, one elected lane issues =====================
     if ((int)blockIdx.x < num_tiles) {
       constexpr uint32_t HI = sdesc_hi(1024u);
-      const uint32_t idesc = make_idesc(FMT, 128, 128, 0);
+      const uint32_t idesc_u = make_idesc(FMT, 128, 64, 0), idesc_c = make_idesc(FMT, 128, 128, 0);
       const uint32_t w32_lo0 = sdesc_lo(smem_u32(w32s), 16u);
       const uint32_t h1_lo0 = sdesc_lo(smem_u32(h1buf), 16u);
       const uint32_t ring_lo0 = sdesc_lo(smem_u32(ring), 16u);
       mbar_wait(w32_full, 0);
       uint32_t it = 0, tile_it = 0;
       TA_T0();
+      // U_j: accumulator j & 1 (four uses per tile: the previous one has parity ((j >> 1) & 1) ^ 1)
+      auto issue_u = [&](int j) {
+        const uint32_t b = (uint32_t)j & 1u;
+        mbar_wait(&empty_r[b], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        TA_T(2);
+        fence_after_sync();
+        const uint32_t d_tmem = tbase + ACC_R + b * 64u;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint64_t ad = sdesc_join(h1_lo0 + (uint32_t)kc * ((NT * 128u) >> 4) + (uint32_t)k16 * 2u, HI);
+            const uint64_t bd = sdesc_join(w32_lo0 + (uint32_t)((j >> 1) * 2 + kc) * (IMG >> 4) + b * (8192u >> 4) +
+                                               (uint32_t)k16 * 2u, HI);  // rows 64 (j & 1) .. of the image
+            umma_f16_elect(d_tmem, ad, bd, idesc_u, (kc | k16) ? 1u : 0u);
+          }
+        umma_commit_elect(&full_r[b]);
+        if (j == 7) umma_commit_elect(h1_free);
+        TA_T(3);
+      };
+      // C_j: both W4 output units += h3 chunk j (slot j & 1) . W4[:, 64 j ..]^T
+      auto issue_c = [&](int j, uint32_t tile_par) {
+        const uint32_t sl = (uint32_t)j & 1u;
+        mbar_wait(&slot_ready[sl], ((uint32_t)j >> 1) & 1u);
+        TA_T(5);
+#pragma unroll
+        for (int v = 0; v < 2; ++v, ++it) {
+          if (j == 0) { mbar_wait(&empty_m[v], tile_par ^ 1u); TA_T(1); }
+          const uint32_t s = it % NSTAGE;
+          mbar_wait(&full[s], (it / NSTAGE) & 1u);
+          TA_T(6);
+          fence_after_sync();
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint32_t a_tmem = tbase + H3COL + sl * 32u + (uint32_t)(k16 * 8);  // 16 channels = 8 columns
+            const uint64_t bd = sdesc_join(ring_lo0 + s * (IMG >> 4) + (uint32_t)k16 * 2u, HI);
+            umma_f16_ta_elect(tbase + (uint32_t)v * 128u, a_tmem, bd, idesc_c, (j | k16) ? 1u : 0u);
+          }
+          umma_commit_elect(&empty[s]);
+          TA_T(7);
+        }
+        umma_commit_elect(&slot_free[sl]);
+        if (j == 7) { umma_commit_elect(&full_m[0]); umma_commit_elect(&full_m[1]); }
+      };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         mbar_wait(h1_ready, tile_it & 1u);
         TA_T(0);
+        issue_u(0);
+        issue_u(1);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {  // h3[:, 128 u ..] = relu(h1 . W32_u^T + c): A = h1 (smem), B = W32 (resident)
-          // accumulator u & 1: last used by the previous tile's W4 unit (u < 2) or by W32 unit u - 2 of this tile
-          const uint32_t buf = (uint32_t)u & 1u;
-          if (u < 2) mbar_wait(&empty_m[buf], (tile_it & 1u) ^ 1u);
-          else mbar_wait(&empty_r[buf], 0u);
-          TA_T(u < 2 ? 1 : 2);
-          fence_after_sync();
-          const uint32_t d_tmem = tbase + buf * 128u;
-#pragma unroll
-          for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
-              const uint64_t ad = sdesc_join(h1_lo0 + (uint32_t)kc * ((NT * 128u) >> 4) + (uint32_t)k16 * 2u, HI);
-              const uint64_t bd = sdesc_join(w32_lo0 + (uint32_t)(u * 2 + kc) * (IMG >> 4) + (uint32_t)k16 * 2u, HI);
-              umma_f16_elect(d_tmem, ad, bd, idesc, (kc | k16) ? 1u : 0u);
-            }
-          umma_commit_elect(&full_r[buf]);
-          if (u == 3) umma_commit_elect(h1_free);
-          TA_T(3);
-        }
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {  // out[:, 128 v ..] = h3 . W4_v^T: A = h3 (tensor memory), B = W4 (ring)
-          const uint32_t buf = (uint32_t)v;  // last used by W32 unit 2 + v of this tile (its second ReLU release)
-          mbar_wait(&empty_r[buf], 1u);
-          TA_T(4);
-          fence_after_sync();
-          const uint32_t d_tmem = tbase + buf * 128u;
-#pragma unroll
-          for (int kc = 0; kc < 8; ++kc, ++it) {
-            if (v == 0 && (kc & 1) == 0) mbar_wait(&h3_ready[kc >> 1], tile_it & 1u);  // channels 128 (kc/2) ..
-            TA_T(5);
-            const uint32_t s = it % NSTAGE;
-            mbar_wait(&full[s], (it / NSTAGE) & 1u);
-            TA_T(6);
-            fence_after_sync();
-#pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
-              const uint32_t a_tmem = tbase + H3COL + (uint32_t)(kc * 32 + k16 * 8);  // 16 channels = 8 columns
-              const uint64_t bd = sdesc_join(ring_lo0 + s * (IMG >> 4) + (uint32_t)k16 * 2u, HI);
-              umma_f16_ta_elect(d_tmem, a_tmem, bd, idesc, (kc | k16) ? 1u : 0u);
-            }
-            umma_commit_elect(&empty[s]);
-            TA_T(7);
-          }
-          umma_commit_elect(&full_m[buf]);
+        for (int j = 0; j < 8; ++j) {
+          issue_c(j, tile_it & 1u);
+          if (j + 2 < 8) issue_u(j + 2);
         }
       }
       TA_DUMP();
     }
   } else if (warp < 10) {
-    // ===================== ReLU warps (2 .. 9): W32 units -> h3 in tensor memory; a thread owns a point =========
+    // ===================== ReLU warps (2 .. 9): U_j -> h3 chunk j in tensor memory; h1 of the next tile =========
     const int quad = warp & 3;              // TMEM lane quadrant = group of the tile (32 points)
-    const int half = (warp - 2) >> 2;       // which 64 of an accumulator's 128 columns (channels)
+    const int half = (warp - 2) >> 2;       // which 32 of an accumulator's 64 columns (channels)
     const float act_scale = __ldg(sc + 5);
     const float inv_p2s = __ldg(sc + 2) * act_scale;  // accumulator -> scaled activation, one FFMA per element
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
-    // The per-group bias c of a warp's group is the same for all its lanes; lane j fetches the two values of columns
-    // 2 j, 2 j + 1 of each unit (one coalesced 256-byte row per warp and unit) a whole tile ahead, and the epilogue
-    // broadcasts them with shuffles.  (Loading all 64 values per thread at the point of use left the FMAs waiting
-    // ~800 cycles for DRAM at every unit: 0.76 ms; through L1 with a tile-ahead prefetch: 0.73 ms.)
-    float2 cnext[4];
+    // per-group bias: lane l holds c[group][64 j + 32 half + l] for the eight units, fetched a whole tile ahead
+    // (at the point of use the FMAs waited ~800 cycles for DRAM at every unit)
+    float cnext[8];
     auto load_c = [&](int tile) {
       const long long gg = (long long)tile * 4 + quad;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        cnext[u] = make_float2(0.f, 0.f);
-        if (tile < num_tiles && gg < num_groups)
-          cnext[u] = __ldg(reinterpret_cast<const float2*>(cbuf + gg * 512 + u * 128 + half * 64) + lane);
+      for (int j = 0; j < 8; ++j) {
+        cnext[j] = 0.f;
+        if (tile < num_tiles && gg < num_groups) cnext[j] = __ldg(cbuf + gg * 512 + j * 64 + half * 32 + lane);
       }
     };
-    // h1 = relu(W1' x + b1') on the CUDA cores, written as the K-major A operand of the W32 units: two threads per
-    // point, 64 channels each, built for the NEXT tile while the tensor pipe runs this tile's W4 units
+    // h1 = relu(W1' x + b1') on the CUDA cores, written as the K-major A operand of the U units: two threads per
+    // point, 64 channels each, built for the NEXT tile while the tensor pipe runs the last chunks of this one
     const int e = tid - 64;                          // 0 .. 255
     const int p = e % NT, ch0 = (e / NT) * 64;       // ch0 is warp-uniform: w1s reads broadcast
     float nx = 0.f, ny = 0.f, nz = 0.f;              // coordinates for the NEXT build_h1 call
@@ -744,44 +747,43 @@ encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __
 
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      float2 ccur[4];
+      float ccur[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) ccur[u] = make_float2(cnext[u].x * act_scale, cnext[u].y * act_scale);
+      for (int j = 0; j < 8; ++j) ccur[j] = cnext[j] * act_scale;
       load_c(tile + gridDim.x);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t buf = (uint32_t)u & 1u;
-        mbar_wait(&full_r[buf], (uint32_t)(u >> 1));  // two W32 units per accumulator and tile
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t b = (uint32_t)j & 1u, par = ((uint32_t)j >> 1) & 1u;
+        mbar_wait(&full_r[b], par);
         fence_after_sync();
-        const uint32_t t_addr = tbase + lane_base + buf * 128u + (uint32_t)(half * 64);
-        uint32_t raw[2][32];
-        tmem_ld32_async(t_addr, raw[0]);
-        tmem_ld32_async(t_addr + 32, raw[1]);
+        uint32_t raw[32];
+        tmem_ld32_async(tbase + lane_base + ACC_R + b * 64u + (uint32_t)(half * 32), raw);
         tmem_wait_ld();
         fence_before_sync();
-        mbar_arrive(&empty_r[buf]);  // the values are in registers: the accumulator can be overwritten
-        uint32_t outw[32];
+        mbar_arrive(&empty_r[b]);  // the values are in registers: the accumulator can be overwritten
+        uint32_t outw[16];
         const float2 a2 = make_float2(inv_p2s, inv_p2s);
-        const float2 cl = ccur[u];
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          const float2 c01 = make_float2(__shfl_sync(PPT_FULL_MASK, cl.x, i >> 1), __shfl_sync(PPT_FULL_MASK, cl.y, i >> 1));
-          const uint32_t* r = raw[i >> 5] + (i & 31);
-          const float2 y01 = __ffma2_rn(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), a2, c01);
+        for (int i = 0; i < 32; i += 2) {
+          const float2 c01 = make_float2(__shfl_sync(PPT_FULL_MASK, ccur[j], i), __shfl_sync(PPT_FULL_MASK, ccur[j], i + 1));
+          const float2 y01 = __ffma2_rn(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), a2, c01);
           outw[i >> 1] = pack2<FMT, true>(y01.x, y01.y);  // channels i, i+1 -> one 32-bit column
         }
-        tmem_st32(tbase + lane_base + H3COL + (uint32_t)(u * 64 + half * 32), outw);
+        mbar_wait(&slot_free[b], par ^ 1u);  // C_{j-2} has read this slot
+        fence_after_sync();
+        tmem_st16(tbase + lane_base + H3COL + b * 32u + (uint32_t)(half * 16), outw);
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&h3_ready[u]);
+        mbar_arrive(&slot_ready[b]);
       }
-      // every MMA that reads h1 has completed once the W32 units have (h1_free): rebuild it for the next tile
+      // every MMA that reads h1 has completed once U_7 has (h1_free): rebuild it for the next tile
       mbar_wait(h1_free, tile_it & 1u);
       if (tile + (int)gridDim.x < num_tiles) build_h1(tile + 2 * gridDim.x);
     }
   } else {
-    // ===================== max warps (10 .. 13): group max of the W4 units =================
-    const int quad = warp & 3;              // warps 10, 11, 12, 13 -> quadrants 2, 3, 0, 1
+    // ===================== max warps (10 .. 17): group max of the two W4 output units =================
+    const int quad = warp & 3;              // TMEM lane quadrant = group of the tile
+    const int half = (warp - 10) >> 2;      // which 64 of an accumulator's 128 columns
     const float* bias_b4 = reinterpret_cast<const float*>(blob + L.b4());
     const float inv_g3 = __ldg(sc + 3), grp_scale = __ldg(sc + 6);
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -792,64 +794,58 @@ encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __
       const bool live = g < num_groups;
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        const uint32_t buf = (uint32_t)v;
-        mbar_wait(&full_m[buf], tile_it & 1u);
+        mbar_wait(&full_m[v], tile_it & 1u);
         fence_after_sync();
+        const uint32_t t_addr = tbase + lane_base + (uint32_t)v * 128u + (uint32_t)(half * 64);
+        uint32_t raw[2][32];
+        tmem_ld32_async(t_addr, raw[0]);
+        tmem_ld32_async(t_addr + 32, raw[1]);
+        tmem_wait_ld();
+        fence_before_sync();
+        mbar_arrive(&empty_m[v]);
+        const int ch = v * 128 + half * 64 + 2 * lane;  // the two columns this lane ends up with (even)
+        const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * IMG;
+        unsigned char* tdst = out_img + img + sw128_kmajor_off((int)(g & 127), ch & 63);
+        // The max over the group's 32 points = over the warp's lanes, for 64 columns, as a transposing butterfly:
+        // at the step with lane-bit b a lane keeps the half of its columns selected by that bit and takes the
+        // partner's values for them; after the five steps lane l holds columns 2 l and 2 l + 1.
+        if (features_out == nullptr) {
+          // tokens only: convert to operand precision FIRST (rounding is monotone, so max and conversion commute:
+          // the stored t values are bit-identical) and run the butterfly on packed pairs
+          const float sc2 = inv_g3 * grp_scale;
+          uint32_t h[32];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t t_addr = tbase + lane_base + buf * 128u + (uint32_t)(half * 64);
-          uint32_t raw[2][32];
-          tmem_ld32_async(t_addr, raw[0]);
-          tmem_ld32_async(t_addr + 32, raw[1]);
-          tmem_wait_ld();
-          if (half == 1) {
-            fence_before_sync();
-            mbar_arrive(&empty_m[buf]);
+          for (int i = 0; i < 32; ++i)
+            h[i] = pack2<FMT, false>(__uint_as_float(raw[i >> 4][(2 * i) & 31]) * sc2,
+                                     __uint_as_float(raw[i >> 4][(2 * i + 1) & 31]) * sc2);
+#pragma unroll
+          for (int w = 16, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+              const uint32_t keep = up ? h[i + w] : h[i], send = up ? h[i] : h[i + w];
+              h[i] = max2_operand<FMT>(keep, __shfl_xor_sync(PPT_FULL_MASK, send, bit));
+            }
           }
-          const int ch = v * 128 + half * 64 + 2 * lane;  // the two columns this lane ends up with (even)
-          const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * IMG;
-          unsigned char* tdst = out_img + img + sw128_kmajor_off((int)(g & 127), ch & 63);
-          // The max over the group's 32 points = over the warp's lanes, for 64 columns, as a transposing butterfly:
-          // at the step with lane-bit b a lane keeps the half of its columns selected by that bit and takes the
-          // partner's values for them; after the five steps lane l holds columns 2 l and 2 l + 1.
-          if (features_out == nullptr) {
-            // tokens only: convert to operand precision FIRST (rounding is monotone, so max and conversion commute:
-            // the stored t values are bit-identical) and run the butterfly on packed pairs
-            const float sc2 = inv_g3 * grp_scale;
-            uint32_t h[32];
+          if (live) *reinterpret_cast<uint32_t*>(tdst) = h[0];
+        } else {
+          float x[64];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              h[i] = pack2<FMT, false>(__uint_as_float(raw[i >> 4][(2 * i) & 31]) * sc2,
-                                       __uint_as_float(raw[i >> 4][(2 * i + 1) & 31]) * sc2);
+          for (int i = 0; i < 64; ++i) x[i] = __uint_as_float(raw[i >> 5][i & 31]);
 #pragma unroll
-            for (int w = 16, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-              const bool up = (lane & bit) != 0;
+          for (int w = 32, bit = 16; w >= 2; w >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
 #pragma unroll
-              for (int i = 0; i < w; ++i) {
-                const uint32_t keep = up ? h[i + w] : h[i], send = up ? h[i] : h[i + w];
-                h[i] = max2_operand<FMT>(keep, __shfl_xor_sync(PPT_FULL_MASK, send, bit));
-              }
+            for (int i = 0; i < w; ++i) {
+              const float keep = up ? x[i + w] : x[i], send = up ? x[i] : x[i + w];
+              x[i] = fmaxf(keep, __shfl_xor_sync(PPT_FULL_MASK, send, bit));
             }
-            if (live) *reinterpret_cast<uint32_t*>(tdst) = h[0];
-          } else {
-            float x[64];
-#pragma unroll
-            for (int i = 0; i < 64; ++i) x[i] = __uint_as_float(raw[i >> 5][i & 31]);
-#pragma unroll
-            for (int w = 32, bit = 16; w >= 2; w >>= 1, bit >>= 1) {
-              const bool up = (lane & bit) != 0;
-#pragma unroll
-              for (int i = 0; i < w; ++i) {
-                const float keep = up ? x[i + w] : x[i], send = up ? x[i] : x[i + w];
-                x[i] = fmaxf(keep, __shfl_xor_sync(PPT_FULL_MASK, send, bit));
-              }
-            }
-            if (live) {
-              const float m0 = x[0] * inv_g3, m1 = x[1] * inv_g3;  // exact: power of two
-              *reinterpret_cast<uint32_t*>(tdst) = pack2<FMT, false>(m0 * grp_scale, m1 * grp_scale);
-              const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_b4 + ch));
-              *reinterpret_cast<float2*>(features_out + g * 256 + ch) = make_float2(m0 + bb.x, m1 + bb.y);
-            }
+          }
+          if (live) {
+            const float m0 = x[0] * inv_g3, m1 = x[1] * inv_g3;  // exact: power of two
+            *reinterpret_cast<uint32_t*>(tdst) = pack2<FMT, false>(m0 * grp_scale, m1 * grp_scale);
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_b4 + ch));
+            *reinterpret_cast<float2*>(features_out + g * 256 + ch) = make_float2(m0 + bb.x, m1 + bb.y);
           }
         }
       }
@@ -1767,7 +1763,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
                                         scales + 1, cbuf, groups, tiles128, 0, 0);
   if ((phases & 4) && use_ta && !clock_acc)
-    k2ta<<<grid_t, 448, s2ta, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
+    k2ta<<<grid_t, 576, s2ta, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
   else if (phases & 4)
     (clock_acc ? k2clk : k2)<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups,
                                                                   tiles, nullptr, nullptr, clock_acc);

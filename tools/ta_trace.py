@@ -28,8 +28,9 @@ fn(buf.data_ptr(), None)
 torch.cuda.synchronize()
 acc = buf.cpu().numpy().astype(np.float64)
 tiles = (128 * 512 * 32 // 128 + 147) // 148
-names = ["wait h1_ready", "wait empty_m (W32 u0,u1: the max warps' release)", "wait empty_r (W32 u2,u3)",
-         "issue 8 MMAs + commit (W32 unit)", "wait empty_r (W4 unit)", "wait h3_ready", "wait ring full", "issue 4 MMAs + commit (W4 chunk)"]
+names = ["wait h1_ready", "wait empty_m (C_0: the max warps' release)", "wait empty_r (U_j: accumulator free)",
+         "issue 8 MMAs + commits (U_j)", "-", "wait slot_ready (C_j: h3 chunk written)", "wait ring full",
+         "issue 4 MMAs + commit (C_j, one output unit)"]
 print("cycles per tile in the MMA warp of CTA 0 (%d tiles): total %.0f" % (tiles, acc.sum() / tiles))
 for n, v in zip(names, acc):
     print("  %-52s %8.0f" % (n, v / tiles))
