@@ -37,21 +37,6 @@
 #include "common.cuh"
 #include "tc05.cuh"
 
-#ifdef TA_TRACE
-// Measurement build only: the MMA warp of CTA 0 accumulates the cycles it spends up to each marker.
-__device__ unsigned long long ta_trace_acc[8];
-#define TA_T0() long long ta_prev = clock64(); unsigned long long ta_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define TA_T(kk) do { const long long now_ = clock64(); ta_acc[kk] += (unsigned long long)(now_ - ta_prev); ta_prev = now_; } while (0)
-#define TA_DUMP() do { if (blockIdx.x == 0 && lane == 0) for (int q_ = 0; q_ < 8; ++q_) ta_trace_acc[q_] = ta_acc[q_]; } while (0)
-extern "C" PPT_EXPORT int ppt_debug_ta_trace(void* dst, void* stream) {
-  return (int)cudaMemcpyFromSymbolAsync(dst, ta_trace_acc, 64, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-}
-#else
-#define TA_T0() do { } while (0)
-#define TA_T(kk) do { } while (0)
-#define TA_DUMP() do { } while (0)
-#endif
-
 namespace {
 
 using namespace tc05;
@@ -519,342 +504,6 @@ encoder_stage_kernel(const float* __restrict__ nbhd, const unsigned char* __rest
     atomicAdd(reinterpret_cast<unsigned long long*>(clock_acc), (unsigned long long)(ns1 - clk0[0]));
     atomicAdd(reinterpret_cast<unsigned long long*>(clock_acc) + 1, (unsigned long long)(clock64() - clk0[1]));
   }
-}
-
-// ======================================================================================
-// stage 2 with the ACTIVATIONS as the A operand and h3 in TENSOR MEMORY (single-part operands, eval mode)
-// ======================================================================================
-// encoder_stage_kernel<2> re-streams all 384 KB of W32 and W4 from L2 for every 128-point tile: 6.3 GB per 128-cloud
-// step, 11.3 TB/s at 0.555 ms -- the L2 -> SM path of the chip (~42 B/clk per SM when every SM streams), not the
-// tensor pipe and not shared memory (tools/ta_trace.py: the issuing warp spends 40 % of a tile waiting for weights).
-// This kernel swaps the operand roles, D[point, channel] = act[point, K] . W[channel, K]^T (points = TMEM lanes,
-// weights = B operand), so that
-//   * the ReLU'd hidden layer h3 lives in tensor memory as fp16 pairs (tcgen05.st) and is the A operand of the W4
-//     products straight from there (tcgen05.mma [a_tmem]; layout pinned by tests/test_gpu_umma.py) -- the 128 KB of
-//     shared memory it used to take now hold W32 for the CTA's whole lifetime, and only W4 streams: 256 KB per tile;
-//   * the schedule is a rolling one over the 64-channel K-chunks of h3, so that W4 is consumed at a UNIFORM rate
-//     (32 KB per 896 tensor cycles, just under what L2 delivers) instead of in one burst at the end of a tile:
-//         U0 U1 C0 U2 C1 U3 C2 U4 C3 U5 C4 U6 C5 U7 C6 C7        (per tile, in tensor-pipe order)
-//     U_j = W32 unit j: h3 channels [64 j, 64 j + 64) into a 64-column accumulator (A = h1 in shared memory, B = 64
-//     rows of the resident W32 image); C_j = W4 K-chunk j for BOTH 128-channel output units (A = h3 chunk j in
-//     tensor memory, B = two ring stages).  Only two 32-column h3 slots are alive at a time.
-// Tensor memory: 2 x 128 (W4 accumulators) + 2 x 64 (W32 accumulators) + 2 x 32 (h3 slots) = 448 columns.
-// Sixteen epilogue warps in two roles (a warp reads only its TMEM lane quadrant, so roles come in fours; a thread
-// owns a POINT = lane): warps 2-9 turn U_j into h3 chunk j (+ per-group bias c, warp-uniform per column: fetched one
-// float per lane a tile ahead, broadcast by shuffle; ReLU; F2FP) and rebuild h1 for the next tile; warps 10-17
-// reduce the W4 accumulators over each group's 32 points = over the lanes of a warp with a transposing butterfly on
-// packed pairs.  Each role has its own hand-off barriers (a warp that skipped phases of a shared barrier would be
-// fooled by the parity test).  An accumulator is released as soon as its values are in registers.
-// The split (3-MMA) precision mode and the train-mode BN_APPLY variant keep encoder_stage_kernel<2>.
-template <uint32_t FMT>
-__global__ void __launch_bounds__(576, 1)
-encoder_stage2_ta_kernel(const float* __restrict__ nbhd, const unsigned char* __restrict__ blob,
-                         const float* __restrict__ cbuf,          // [groups_pad, 512]
-                         unsigned char* __restrict__ out_img,     // t images
-                         float* __restrict__ features_out,        // nullable: [groups, 256]
-                         long long num_groups, int num_tiles) {
-  constexpr int NT = 128, EPI_THREADS = 256, NSTAGE = 4;
-  constexpr uint32_t H1_BYTES = 2u * NT * 128u;
-  constexpr uint32_t ACC_R = 256, H3COL = 384, TCOLS = 512;  // W4 accumulators at columns 0 and 128
-
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* w32s = smem;                          // [4 units][2 chunks][16 KB], resident
-  unsigned char* h1buf = w32s + 8 * IMG;               // [2 chunks][NT x 128 B], K-major
-  unsigned char* ring = h1buf + H1_BYTES;              // [NSTAGE][16 KB]: W4 chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * IMG);
-  uint64_t* full = bars;                  // [NSTAGE]
-  uint64_t* empty = full + NSTAGE;        // [NSTAGE]
-  uint64_t* full_r = empty + NSTAGE;      // [2] U_j complete in W32 accumulator j & 1        (ReLU warps wait)
-  uint64_t* empty_r = full_r + 2;         // [2] ... and read out                              (256 arrivals)
-  uint64_t* slot_ready = empty_r + 2;     // [2] h3 chunk j written to slot j & 1              (256 arrivals)
-  uint64_t* slot_free = slot_ready + 2;   // [2] C_j has read slot j & 1
-  uint64_t* full_m = slot_free + 2;       // [2] W4 output unit v complete                     (max warps wait)
-  uint64_t* empty_m = full_m + 2;         // [2] ... and read out                              (256 arrivals)
-  uint64_t* h1_ready = empty_m + 2;       // [1] (256 arrivals)
-  uint64_t* h1_free = h1_ready + 1;       // [1] U_7 complete: h1 may be rebuilt
-  uint64_t* w32_full = h1_free + 1;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w32_full + 1);
-  float4* w1s = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [128]
-
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const BlobLayout L{1u};
-  const float* sc = reinterpret_cast<const float*>(blob + L.scales());
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full_r[i], 1); mbar_init(&empty_r[i], EPI_THREADS);
-      mbar_init(&slot_ready[i], EPI_THREADS); mbar_init(&slot_free[i], 1);
-      mbar_init(&full_m[i], 1); mbar_init(&empty_m[i], EPI_THREADS);
-    }
-    mbar_init(h1_ready, EPI_THREADS);
-    mbar_init(h1_free, 1);
-    mbar_init(w32_full, 1);
-    mbar_fence_init();
-  }
-  if (tid < 128) {  // W1' rows pre-multiplied by the activation scale (a power of two: exact)
-    float4 w = __ldg(reinterpret_cast<const float4*>(blob + L.w1()) + tid);
-    const float s = __ldg(sc + 5);
-    w.x *= s; w.y *= s; w.z *= s; w.w *= s;
-    w1s[tid] = w;
-  }
-  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tbase = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== weight producer =====================
-    if (lane == 0 && (int)blockIdx.x < num_tiles) {
-      mbar_arrive_expect_tx(w32_full, 8 * IMG);
-      for (int i = 0; i < 8; ++i) bulk_g2s(w32s + i * IMG, blob + L.W32() + (size_t)i * IMG, IMG, w32_full);
-      Ring r;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-#pragma unroll 1
-        for (int i = 0; i < 16; ++i) {  // W4 in consumption order: K-chunk i / 2 of output unit i & 1
-          const uint32_t s = r.stage<NSTAGE>();
-          mbar_wait_relaxed(&empty[s], r.parity<NSTAGE>() ^ 1u);
-          mbar_arrive_expect_tx(&full[s], IMG);
-          bulk_g2s(ring + s * IMG, blob + L.W4() + (size_t)((i & 1) * 8 + (i >> 1)) * IMG, IMG, &full[s]);
-          ++r.it;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: converged warp, one elected lane issues =====================
-    if ((int)blockIdx.x < num_tiles) {
-      constexpr uint32_t HI = sdesc_hi(1024u);
-      const uint32_t idesc_u = make_idesc(FMT, 128, 64, 0), idesc_c = make_idesc(FMT, 128, 128, 0);
-      const uint32_t w32_lo0 = sdesc_lo(smem_u32(w32s), 16u);
-      const uint32_t h1_lo0 = sdesc_lo(smem_u32(h1buf), 16u);
-      const uint32_t ring_lo0 = sdesc_lo(smem_u32(ring), 16u);
-      mbar_wait(w32_full, 0);
-      uint32_t it = 0, tile_it = 0;
-      TA_T0();
-      // U_j: accumulator j & 1 (four uses per tile: the previous one has parity ((j >> 1) & 1) ^ 1)
-      auto issue_u = [&](int j) {
-        const uint32_t b = (uint32_t)j & 1u;
-        mbar_wait(&empty_r[b], (((uint32_t)j >> 1) & 1u) ^ 1u);
-        TA_T(2);
-        fence_after_sync();
-        const uint32_t d_tmem = tbase + ACC_R + b * 64u;
-#pragma unroll
-        for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            const uint64_t ad = sdesc_join(h1_lo0 + (uint32_t)kc * ((NT * 128u) >> 4) + (uint32_t)k16 * 2u, HI);
-            const uint64_t bd = sdesc_join(w32_lo0 + (uint32_t)((j >> 1) * 2 + kc) * (IMG >> 4) + b * (8192u >> 4) +
-                                               (uint32_t)k16 * 2u, HI);  // rows 64 (j & 1) .. of the image
-            umma_f16_elect(d_tmem, ad, bd, idesc_u, (kc | k16) ? 1u : 0u);
-          }
-        umma_commit_elect(&full_r[b]);
-        if (j == 7) umma_commit_elect(h1_free);
-        TA_T(3);
-      };
-      // C_j: both W4 output units += h3 chunk j (slot j & 1) . W4[:, 64 j ..]^T
-      auto issue_c = [&](int j, uint32_t tile_par) {
-        const uint32_t sl = (uint32_t)j & 1u;
-        mbar_wait(&slot_ready[sl], ((uint32_t)j >> 1) & 1u);
-        TA_T(5);
-#pragma unroll
-        for (int v = 0; v < 2; ++v, ++it) {
-          if (j == 0) { mbar_wait(&empty_m[v], tile_par ^ 1u); TA_T(1); }
-          const uint32_t s = it % NSTAGE;
-          mbar_wait(&full[s], (it / NSTAGE) & 1u);
-          TA_T(6);
-          fence_after_sync();
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            const uint32_t a_tmem = tbase + H3COL + sl * 32u + (uint32_t)(k16 * 8);  // 16 channels = 8 columns
-            const uint64_t bd = sdesc_join(ring_lo0 + s * (IMG >> 4) + (uint32_t)k16 * 2u, HI);
-            umma_f16_ta_elect(tbase + (uint32_t)v * 128u, a_tmem, bd, idesc_c, (j | k16) ? 1u : 0u);
-          }
-          umma_commit_elect(&empty[s]);
-          TA_T(7);
-        }
-        umma_commit_elect(&slot_free[sl]);
-        if (j == 7) { umma_commit_elect(&full_m[0]); umma_commit_elect(&full_m[1]); }
-      };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-        mbar_wait(h1_ready, tile_it & 1u);
-        TA_T(0);
-        issue_u(0);
-        issue_u(1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          issue_c(j, tile_it & 1u);
-          if (j + 2 < 8) issue_u(j + 2);
-        }
-      }
-      TA_DUMP();
-    }
-  } else if (warp < 10) {
-    // ===================== ReLU warps (2 .. 9): U_j -> h3 chunk j in tensor memory; h1 of the next tile =========
-    const int quad = warp & 3;              // TMEM lane quadrant = group of the tile (32 points)
-    const int half = (warp - 2) >> 2;       // which 32 of an accumulator's 64 columns (channels)
-    const float act_scale = __ldg(sc + 5);
-    const float inv_p2s = __ldg(sc + 2) * act_scale;  // accumulator -> scaled activation, one FFMA per element
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-
-    // per-group bias: lane l holds c[group][64 j + 32 half + l] for the eight units, fetched a whole tile ahead
-    // (at the point of use the FMAs waited ~800 cycles for DRAM at every unit)
-    float cnext[8];
-    auto load_c = [&](int tile) {
-      const long long gg = (long long)tile * 4 + quad;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        cnext[j] = 0.f;
-        if (tile < num_tiles && gg < num_groups) cnext[j] = __ldg(cbuf + gg * 512 + j * 64 + half * 32 + lane);
-      }
-    };
-    // h1 = relu(W1' x + b1') on the CUDA cores, written as the K-major A operand of the U units: two threads per
-    // point, 64 channels each, built for the NEXT tile while the tensor pipe runs the last chunks of this one
-    const int e = tid - 64;                          // 0 .. 255
-    const int p = e % NT, ch0 = (e / NT) * 64;       // ch0 is warp-uniform: w1s reads broadcast
-    float nx = 0.f, ny = 0.f, nz = 0.f;              // coordinates for the NEXT build_h1 call
-    auto fetch_point = [&](int tile) {
-      nx = ny = nz = 0.f;
-      const long long gp = (long long)tile * NT + p;
-      if (tile < num_tiles && gp < num_groups * 32) {
-        const float* src = nbhd + gp * 3;
-        nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
-      }
-    };
-    auto build_h1 = [&](int tile_after) {
-      const float x = nx, y = ny, z = nz;
-      fetch_point(tile_after);
-#pragma unroll 4
-      for (int c8 = 0; c8 < 64; c8 += 8) {
-        float v[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 w = w1s[ch0 + c8 + t];
-          v[t] = fmaf(w.z, z, fmaf(w.y, y, fmaf(w.x, x, w.w)));
-        }
-        const int ch = ch0 + c8;
-        store_relu8<FMT, 1>(h1buf, (uint32_t)(ch >> 6) * (NT * 128u) + sw128_kmajor_off(p, ch & 63), H1_BYTES, v);
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(h1_ready);
-    };
-    if ((int)blockIdx.x < num_tiles) {
-      load_c(blockIdx.x);
-      fetch_point(blockIdx.x);
-      build_h1(blockIdx.x + gridDim.x);
-    }
-
-    uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      float ccur[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ccur[j] = cnext[j] * act_scale;
-      load_c(tile + gridDim.x);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t b = (uint32_t)j & 1u, par = ((uint32_t)j >> 1) & 1u;
-        mbar_wait(&full_r[b], par);
-        fence_after_sync();
-        uint32_t raw[32];
-        tmem_ld32_async(tbase + lane_base + ACC_R + b * 64u + (uint32_t)(half * 32), raw);
-        tmem_wait_ld();
-        fence_before_sync();
-        mbar_arrive(&empty_r[b]);  // the values are in registers: the accumulator can be overwritten
-        uint32_t outw[16];
-        const float2 a2 = make_float2(inv_p2s, inv_p2s);
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 c01 = make_float2(__shfl_sync(PPT_FULL_MASK, ccur[j], i), __shfl_sync(PPT_FULL_MASK, ccur[j], i + 1));
-          const float2 y01 = __ffma2_rn(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), a2, c01);
-          outw[i >> 1] = pack2<FMT, true>(y01.x, y01.y);  // channels i, i+1 -> one 32-bit column
-        }
-        mbar_wait(&slot_free[b], par ^ 1u);  // C_{j-2} has read this slot
-        fence_after_sync();
-        tmem_st16(tbase + lane_base + H3COL + b * 32u + (uint32_t)(half * 16), outw);
-        tmem_wait_st();
-        fence_before_sync();
-        mbar_arrive(&slot_ready[b]);
-      }
-      // every MMA that reads h1 has completed once U_7 has (h1_free): rebuild it for the next tile
-      mbar_wait(h1_free, tile_it & 1u);
-      if (tile + (int)gridDim.x < num_tiles) build_h1(tile + 2 * gridDim.x);
-    }
-  } else {
-    // ===================== max warps (10 .. 17): group max of the two W4 output units =================
-    const int quad = warp & 3;              // TMEM lane quadrant = group of the tile
-    const int half = (warp - 10) >> 2;      // which 64 of an accumulator's 128 columns
-    const float* bias_b4 = reinterpret_cast<const float*>(blob + L.b4());
-    const float inv_g3 = __ldg(sc + 3), grp_scale = __ldg(sc + 6);
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-
-    uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      const long long g = (long long)tile * 4 + quad;  // this thread's group
-      const bool live = g < num_groups;
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        mbar_wait(&full_m[v], tile_it & 1u);
-        fence_after_sync();
-        const uint32_t t_addr = tbase + lane_base + (uint32_t)v * 128u + (uint32_t)(half * 64);
-        uint32_t raw[2][32];
-        tmem_ld32_async(t_addr, raw[0]);
-        tmem_ld32_async(t_addr + 32, raw[1]);
-        tmem_wait_ld();
-        fence_before_sync();
-        mbar_arrive(&empty_m[v]);
-        const int ch = v * 128 + half * 64 + 2 * lane;  // the two columns this lane ends up with (even)
-        const size_t img = ((size_t)(g >> 7) * 4 + (size_t)(ch >> 6)) * IMG;
-        unsigned char* tdst = out_img + img + sw128_kmajor_off((int)(g & 127), ch & 63);
-        // The max over the group's 32 points = over the warp's lanes, for 64 columns, as a transposing butterfly:
-        // at the step with lane-bit b a lane keeps the half of its columns selected by that bit and takes the
-        // partner's values for them; after the five steps lane l holds columns 2 l and 2 l + 1.
-        if (features_out == nullptr) {
-          // tokens only: convert to operand precision FIRST (rounding is monotone, so max and conversion commute:
-          // the stored t values are bit-identical) and run the butterfly on packed pairs
-          const float sc2 = inv_g3 * grp_scale;
-          uint32_t h[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            h[i] = pack2<FMT, false>(__uint_as_float(raw[i >> 4][(2 * i) & 31]) * sc2,
-                                     __uint_as_float(raw[i >> 4][(2 * i + 1) & 31]) * sc2);
-#pragma unroll
-          for (int w = 16, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-            const bool up = (lane & bit) != 0;
-#pragma unroll
-            for (int i = 0; i < w; ++i) {
-              const uint32_t keep = up ? h[i + w] : h[i], send = up ? h[i] : h[i + w];
-              h[i] = max2_operand<FMT>(keep, __shfl_xor_sync(PPT_FULL_MASK, send, bit));
-            }
-          }
-          if (live) *reinterpret_cast<uint32_t*>(tdst) = h[0];
-        } else {
-          float x[64];
-#pragma unroll
-          for (int i = 0; i < 64; ++i) x[i] = __uint_as_float(raw[i >> 5][i & 31]);
-#pragma unroll
-          for (int w = 32, bit = 16; w >= 2; w >>= 1, bit >>= 1) {
-            const bool up = (lane & bit) != 0;
-#pragma unroll
-            for (int i = 0; i < w; ++i) {
-              const float keep = up ? x[i + w] : x[i], send = up ? x[i] : x[i + w];
-              x[i] = fmaxf(keep, __shfl_xor_sync(PPT_FULL_MASK, send, bit));
-            }
-          }
-          if (live) {
-            const float m0 = x[0] * inv_g3, m1 = x[1] * inv_g3;  // exact: power of two
-            *reinterpret_cast<uint32_t*>(tdst) = pack2<FMT, false>(m0 * grp_scale, m1 * grp_scale);
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_b4 + ch));
-            *reinterpret_cast<float2*>(features_out + g * 256 + ch) = make_float2(m0 + bb.x, m1 + bb.y);
-          }
-        }
-      }
-    }
-  }
-
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<TCOLS>(tbase);
 }
 
 // ======================================================================================
@@ -1727,13 +1376,6 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   static_assert(s1tc <= 232448, "shared memory budget (227 KB per CTA)");
   auto k2 = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2>;
   auto k2clk = encoder_stage_kernel<FMT, SPLIT, NT, 2, EPW2, BN_EVAL, true>;
-  auto k2ta = encoder_stage2_ta_kernel<FMT>;  // single-part operands: h3 in tensor memory (see the kernel)
-  constexpr size_t s2ta = 8 * (size_t)IMG + 2 * 128 * 128 + 4 * (size_t)IMG + 256 + 2048;
-  static_assert(s2ta <= 232448, "shared memory budget (227 KB per CTA)");
-#ifndef PPT_STAGE2_TA
-#define PPT_STAGE2_TA 1
-#endif
-  constexpr bool use_ta = PPT_STAGE2_TA && SPLIT == 1 && NT == 128;
   auto kb = group_linear_kernel<FMT, SPLIT, 4>;
   auto kd = group_linear_kernel<FMT, SPLIT, 3>;
   auto kda = group_linear_kernel<FMT, SPLIT, 3, 4, true>;
@@ -1744,7 +1386,6 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k1tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1tc));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2clk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-    PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(k2ta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2ta));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
     PPT_RETURN_IF_CUDA(cudaFuncSetAttribute(kda, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl));
@@ -1762,9 +1403,7 @@ int run_encoder(const float* nbhd, const unsigned char* blob, unsigned char* ws,
   if (phases & 2)
     kb<<<grid_g, LIN_THREADS, sl, st>>>(ws + W.g_img, blob + L.W3A(), reinterpret_cast<const float*>(blob + L.bias_c()),
                                         scales + 1, cbuf, groups, tiles128, 0, 0);
-  if ((phases & 4) && use_ta && !clock_acc)
-    k2ta<<<grid_t, 576, s2ta, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups, tiles);
-  else if (phases & 4)
+  if (phases & 4)
     (clock_acc ? k2clk : k2)<<<grid_t, (EPW2 + 2) * 32, s2, st>>>(nbhd, blob, cbuf, ws + W.t_img, features_out, groups,
                                                                   tiles, nullptr, nullptr, clock_acc);
   if ((phases & 8) && tokens_out)
