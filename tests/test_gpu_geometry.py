@@ -229,6 +229,18 @@ def test_three_nn_and_interpolate_bit_exact(ops, N, S, D):
     assert np.array_equal(bits(got), bits(want))  # includes negative / ~0 distances (F3)
 
 
+@pytest.mark.parametrize("B,N,S,D", [(12, 2048, 512, 384), (24, 1000, 300, 128), (11, 257, 800, 384)])
+def test_three_interpolate_large_batch_bit_exact(ops, B, N, S, D):
+    """Wide rows from few source points at part-seg batch sizes (and a ragged N)."""
+    unknown = cloud("S", B, N, 70 + N)
+    known = cloud("S", B, S, 71 + S)
+    feats = torch.randn(B, S, D, generator=torch.Generator().manual_seed(D + B))
+    gd, gi = ops.three_nn(dev(unknown), dev(known))
+    want = cpu.three_interpolate(feats.numpy(), gi.cpu().numpy(), gd.cpu().numpy())
+    got = ops.three_interpolate(dev(feats), gi, gd)
+    assert np.array_equal(bits(got), bits(want))
+
+
 def test_feature_propagation_fixture(ops, golden):
     f = golden("msg_fp_small")
     xyz = dev(f["xyz"])
