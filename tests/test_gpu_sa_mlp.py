@@ -12,7 +12,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CHILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_sa_mlp_child.py")
-TOL = {"fp16": 2e-3, "bf16": 1.5e-2}  # three chained layers with 16-bit operands, norm-relative
+# three chained layers with 16-bit operands.  fp16: the token path's 1e-3 (measured 2.9e-4 .. 4.6e-4, which IS the
+# arithmetic floor: tests/test_host_cpu.py emulates the same rounding on the CPU and lands on 4.56e-4 for ssg2)
+TOL = {"fp16": 1e-3, "bf16": 1.5e-2}
 
 
 @pytest.mark.parametrize("single_kernel", ["1", "0"])  # activations in shared memory / per-layer kernels (PPT_SA_PER_LAYER)

@@ -283,3 +283,37 @@ def test_custom_ops_are_registered_with_fake_shapes():
         assert d.shape == (2, 100, 3) and i.dtype == torch.int64
         assert torch.ops.ppt_b200.three_interpolate(torch.empty(2, 8, 6, device="cuda"), i, d).shape == (2, 100, 6)
         assert torch.ops.ppt_b200.encoder_tokens(nb.new_empty(2, 8, 32, 3), torch.empty(10, dtype=torch.uint8, device="cuda"), 0).shape == (2, 8, 384)
+
+
+def test_f1_error_floor_of_three_fp16_layers():
+    """What error do three chained layers with fp16 operands have by construction?  This emulates the arithmetic of
+    the tensor-core path on the CPU -- operands rounded to fp16 before each layer, fp32 accumulation, fp32 bias / ReLU --
+    on the SSG level-2 fixture and measures its distance from an fp64 evaluation of the same module with the metric of
+    tests/test_gpu_sa_mlp.py: 4.56e-4 max / 2.49e-4 rms.  The kernel measures 4.56e-4 / 2.49e-4 on the same case
+    (B200), i.e. it adds nothing of its own, and the GPU test holds it to 1e-3 like the token path."""
+    import numpy as np
+    from oracle import torch_port as tp
+    f = np.load(os.path.join(ROOT, "tests", "golden", "sa_mlp.npz"))
+    xyz, feats = torch.from_numpy(f["ssg2.xyz"]), torch.from_numpy(f["ssg2.feats"])
+    sd = tp.make_sa_state(131, [128, 128, 256], 11)
+    fidx = tp.fps_indices(xyz, 128, 0)
+    new_xyz = tp.take_rows(xyz, fidx)
+    idx = tp.ball_indices(0.4, 64, xyz, new_xyz)
+    grouped = torch.cat([tp.take_rows(xyz, idx) - new_xyz.unsqueeze(2), tp.take_rows(feats, idx)], dim=-1)
+    ref32 = tp.sa_mlp_max(grouped, sd, 3)
+    assert float((ref32 - torch.from_numpy(f["ssg2.out"])).abs().max()) < 1e-5  # the grouping above is the module's
+    sd64 = {k: v.double() for k, v in sd.items()}
+    ref = tp.sa_mlp_max(grouped.double(), sd64, 3)
+
+    x = grouped.reshape(-1, 131).float()                       # [points, C]
+    for i in range(3):
+        w = sd64["mlp_convs.%d.weight" % i][:, :, 0, 0]
+        s = sd64["mlp_bns.%d.weight" % i] / torch.sqrt(sd64["mlp_bns.%d.running_var" % i] + 1e-5)
+        wf = (w * s[:, None]).float()                          # BatchNorm folded (fp64), stored in fp32
+        bf = ((sd64["mlp_convs.%d.bias" % i] - sd64["mlp_bns.%d.running_mean" % i]) * s + sd64["mlp_bns.%d.bias" % i]).float()
+        y = x.half().float() @ wf.half().float().T + bf        # fp16 operands, fp32 accumulate
+        x = torch.relu(y)
+    emu = x.reshape(1, 128, 64, 256).max(dim=2)[0].permute(0, 2, 1).double()
+    d = emu - ref
+    e_max, e_rms = float(d.abs().max() / ref.abs().max()), float(d.norm() / ref.norm())
+    assert 2e-4 < e_max < 6e-4 and e_rms < 4e-4, (e_max, e_rms)
